@@ -1,0 +1,82 @@
+"""ctypes binding of libcdra (include/cdra.h).  PyTorch is used only for device memory / streams.
+
+The product path loads `cdra/libcdra.so` (nvcc, sm_100a) and fails loudly when it is missing — there
+is no CPU fallback.  The CPU logic-check build (`tests/emu/libcdra_emu.so`) can only be selected
+explicitly by the CPU test-suite through `load(emulated=True)`; it is never used by bench / smoke.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libcdra.so')
+EMU_PATH = os.path.join(os.path.dirname(os.path.dirname(HERE)), 'tests', 'emu', 'libcdra_emu.so')
+
+F32, BF16 = 0, 1
+ARENA_DYN_PARAMS, ARENA_DYN_STATE, ARENA_POL_PARAMS, ARENA_POL_STATE, ARENA_VAL_PARAMS, ARENA_VAL_STATE = range(6)
+
+
+class CdraError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('height', C.c_int32), ('width', C.c_int32), ('dtype', C.c_int32),
+                ('image_u8', C.c_int32)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    'cdra_last_error': (C.c_char_p, []),
+    'cdra_version': (C.c_int, []),
+    'cdra_plan_create': (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    'cdra_plan_destroy': (None, [_P]),
+    'cdra_plan_workspace_bytes': (C.c_size_t, [_P]),
+    'cdra_arena_size': (C.c_int64, [_P, C.c_int]),
+    'cdra_arena_num_tensors': (C.c_int, [_P, C.c_int]),
+    'cdra_arena_tensor': (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'cdra_plan_tensor': (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'cdra_dynamics_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
+    'cdra_dynamics_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'cdra_policy_head_loss_fwd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int,
+                                                C.c_float, _P, _P, _P, _P, _P, _P]),
+    'cdra_value_head_loss_fwd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P, _P, _P]),
+    'cdra_gae': (C.c_int, [_P, _P, _P, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, _P, _P, _P]),
+    'cdra_clip_adam': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, C.c_int64, C.c_float, _P, _P]),
+    'cdra_gather_rows': (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
+}
+
+_loaded = {}
+
+
+def load(emulated=False):
+    """Load the shared library and declare every symbol of include/cdra.h."""
+    key = bool(emulated)
+    if key in _loaded:
+        return _loaded[key]
+    path = EMU_PATH if emulated else LIB_PATH
+    if not os.path.exists(path):
+        raise CdraError(f'{path} is missing: build it with `python carla-driving-rl-agent_b200/build.py` '
+                        '(there is no fallback path)')
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)           # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _loaded[key] = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(lib, code, what=''):
+    if code != 0:
+        raise CdraError(f'{what} failed ({code}): {lib.cdra_last_error().decode()}')
+
+
+def ptr(t):
+    """Raw pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,180 @@
+"""Thin object layer over the C ABI: owns the plan, the flat parameter / state / gradient / Adam arenas
+(torch tensors: device memory only) and the workspace, and exposes one method per ABI entry point.
+
+`core.networks.CARLANetwork` / `core.carla_agent.CARLAgent` (the reference-facing API) are built on it.
+"""
+import ctypes as C
+import torch
+
+from . import _lib
+
+
+class Arena:
+    """Flat fp32 buffer + named views, mirroring Keras get_weights()/set_weights() bookkeeping."""
+
+    def __init__(self, lib, plan, which, device):
+        self.which = which
+        self.size = int(lib.cdra_arena_size(plan, which))
+        self.flat = torch.zeros(self.size, dtype=torch.float32, device=device)
+        self.names, self.offsets, self.shapes = [], [], []
+        n = lib.cdra_arena_num_tensors(plan, which)
+        name = C.create_string_buffer(128)
+        off, nd, dims = C.c_int64(), C.c_int32(), (C.c_int32 * 4)()
+        for i in range(n):
+            _lib.check(lib, lib.cdra_arena_tensor(plan, which, i, name, 128, C.byref(off), C.byref(nd), dims), 'arena_tensor')
+            self.names.append(name.value.decode())
+            self.offsets.append(off.value)
+            self.shapes.append(tuple(dims[j] for j in range(nd.value)))
+        self.index = {n_: i for i, n_ in enumerate(self.names)}
+        self.offsets_dev = torch.tensor(self.offsets + [self.size], dtype=torch.int64, device=device)
+
+    def view(self, name, flat=None):
+        i = self.index[name]
+        flat = self.flat if flat is None else flat
+        n = 1
+        for s in self.shapes[i]:
+            n *= s
+        return flat[self.offsets[i]:self.offsets[i] + n].view(self.shapes[i])
+
+    def items(self, flat=None):
+        return [(n, self.view(n, flat)) for n in self.names]
+
+    def load_dict(self, d, strict=True):
+        for n in self.names:
+            if n in d:
+                self.view(n).copy_(d[n].to(self.flat.dtype))
+            elif strict:
+                raise KeyError(n)
+
+    def to_dict(self, flat=None):
+        return {n: v.clone() for n, v in self.items(flat)}
+
+
+class Engine:
+    def __init__(self, batch, height=90, width=120, dtype='bf16', image_u8=True, device='cuda', emulated=False):
+        self.lib = _lib.load(emulated=emulated)
+        self.device = torch.device(device)
+        if not emulated and self.device.type != 'cuda':
+            raise _lib.CdraError('libcdra runs on CUDA devices only (no CPU fallback)')
+        self.emulated = emulated
+        self.B, self.H, self.W = batch, height, width
+        self.dtype = dtype
+        self.image_u8 = bool(image_u8)
+        cfg = _lib.Config(batch, height, width, _lib.BF16 if dtype == 'bf16' else _lib.F32, 1 if image_u8 else 0)
+        self.plan = C.c_void_p()
+        _lib.check(self.lib, self.lib.cdra_plan_create(C.byref(cfg), C.byref(self.plan)), 'plan_create')
+        self.ws_bytes = int(self.lib.cdra_plan_workspace_bytes(self.plan))
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        mk = lambda w: Arena(self.lib, self.plan, w, self.device)
+        self.dyn, self.dyn_state = mk(_lib.ARENA_DYN_PARAMS), mk(_lib.ARENA_DYN_STATE)
+        self.pol, self.pol_state = mk(_lib.ARENA_POL_PARAMS), mk(_lib.ARENA_POL_STATE)
+        self.val, self.val_state = mk(_lib.ARENA_VAL_PARAMS), mk(_lib.ARENA_VAL_STATE)
+        z = lambda a: torch.zeros_like(a.flat)
+        self.g_dyn, self.g_pol, self.g_val = z(self.dyn), z(self.pol), z(self.val)
+        self.adam = {k: (z(a), z(a)) for k, a in (('dyn', self.dyn), ('pol', self.pol), ('val', self.val))}
+        self.adam_step = dict(dyn=0, pol=0, val=0)
+        self.norms = {k: torch.zeros(len(a.names), dtype=torch.float32, device=self.device)
+                      for k, a in (('pol', self.pol), ('val', self.val), ('dyn', self.dyn))}
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+        self.x512, self.d_x512 = f(batch, 512), f(batch, 512)
+        self.scalars, self.head_out = f(16), f(batch, 8)
+
+    def __del__(self):
+        try:
+            if self.plan:
+                self.lib.cdra_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        if self.emulated:
+            return None
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def tensor(self, name):
+        """View of a named intermediate tensor inside the workspace (parity taps)."""
+        off, dims, es = C.c_int64(), (C.c_int32 * 4)(), C.c_int32()
+        _lib.check(self.lib, self.lib.cdra_plan_tensor(self.plan, name.encode(), C.byref(off), dims, C.byref(es)), 'plan_tensor')
+        shape = [d for d in dims]
+        while len(shape) > 1 and shape[-1] == 1:
+            shape.pop()
+        n = 1
+        for s in shape:
+            n *= s
+        dt = torch.float32 if es.value == 4 else torch.bfloat16
+        raw = self.ws[off.value: off.value + n * es.value]
+        return raw.view(dt).view(shape)
+
+    def _check_obs(self, obs):
+        img = obs['state_image']
+        want = torch.uint8 if self.image_u8 else torch.float32
+        assert img.dtype == want and tuple(img.shape) == (self.B, 4, self.H, self.W, 3), (img.dtype, img.shape)
+        for k, d in (('state_road', 9), ('state_vehicle', 4), ('state_navigation', 5)):
+            assert obs[k].dtype == torch.float32 and tuple(obs[k].shape) == (self.B, 4, d), (k, obs[k].shape)
+            assert obs[k].is_contiguous()
+        assert img.is_contiguous()
+
+    # ------------------------------------------------------------------ ABI calls
+    def dynamics_forward(self, obs, training=True, out=None):
+        self._check_obs(obs)
+        out = self.x512 if out is None else out
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_dynamics_forward(
+            self.plan, p(self.dyn.flat), p(self.dyn_state.flat), p(obs['state_image']), p(obs['state_road']),
+            p(obs['state_vehicle']), p(obs['state_navigation']), 1 if training else 0, p(out), p(self.ws),
+            self._stream()), 'dynamics_forward')
+        return out
+
+    def dynamics_backward(self, obs, d_out):
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_dynamics_backward(
+            self.plan, p(self.dyn.flat), p(obs['state_image']), p(obs['state_road']), p(obs['state_vehicle']),
+            p(obs['state_navigation']), p(d_out), p(self.g_dyn), p(self.ws), self._stream()), 'dynamics_backward')
+        return self.g_dyn
+
+    def policy_head(self, x512, actions_eval, logp_old, adv, true_speed, true_sim, clip_ratio=0.2, ent_coef=1.0,
+                    training=True, grad_scale=1.0, backward=True):
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_policy_head_loss_fwd_bwd(
+            self.plan, p(self.pol.flat), p(self.pol_state.flat), p(x512), p(actions_eval), p(logp_old), p(adv),
+            p(true_speed), p(true_sim), clip_ratio, ent_coef, 1 if training else 0, grad_scale, p(self.scalars),
+            p(self.head_out), p(self.d_x512) if backward else None, p(self.g_pol) if backward else None, p(self.ws),
+            self._stream()), 'policy_head')
+        return self.scalars
+
+    def value_head(self, x512, returns_be, true_speed, true_sim, training=True, grad_scale=1.0, backward=True):
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_value_head_loss_fwd_bwd(
+            self.plan, p(self.val.flat), p(self.val_state.flat), p(x512), p(returns_be), p(true_speed), p(true_sim),
+            1 if training else 0, grad_scale, p(self.scalars), p(self.head_out), p(self.d_x512) if backward else None,
+            p(self.g_val) if backward else None, p(self.ws), self._stream()), 'value_head')
+        return self.scalars
+
+    def gae(self, rewards, values_be, last_value_be, gamma, lambda_, scale):
+        bs, T = rewards.shape
+        returns_be = torch.empty(bs, T, 2, dtype=torch.float32, device=rewards.device)
+        adv = torch.empty(bs, T, dtype=torch.float32, device=rewards.device)
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_gae(p(rewards), p(values_be), p(last_value_be), float(gamma), float(lambda_),
+                                               float(scale), bs, T, p(returns_be), p(adv), self._stream()), 'gae')
+        return returns_be, adv
+
+    def clip_adam(self, which, lr, clip_norm=None, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-7):
+        arena = dict(dyn=self.dyn, pol=self.pol, val=self.val)[which]
+        grads = dict(dyn=self.g_dyn, pol=self.g_pol, val=self.g_val)[which]
+        m, v = self.adam[which]
+        self.adam_step[which] += 1
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_clip_adam(
+            p(arena.flat), p(grads), p(m), p(v), p(arena.offsets_dev), len(arena.names), arena.size,
+            float(clip_norm) if clip_norm else 0.0, float(lr), beta1, beta2, eps, self.adam_step[which],
+            float(grad_scale), p(self.norms[which]), self._stream()), 'clip_adam')
+
+    def gather_rows(self, src, index, out):
+        row_bytes = src[0].numel() * src.element_size()
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_gather_rows(p(src), p(index), index.numel(), row_bytes, p(out),
+                                                       self._stream()), 'gather_rows')
+        return out

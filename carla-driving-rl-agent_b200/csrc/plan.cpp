@@ -1,0 +1,185 @@
+// Plan construction (host only).  See plan.h.
+#include "plan.h"
+#include <cstdio>
+
+namespace cdra {
+
+static const int kStageC[3] = {116, 232, 464};      // core/architectures.py:34 (g = 1.0)
+static const int kStageBlocks[3] = {4, 8, 4};       // core/architectures.py:165-167
+static const int kStemC = 24, kLastC = 768;         // :159 ; core/carla_agent.py:66
+static const int kFeatUnits = 16, kTrunkIn = 352, kTrunkUnits = 512, kHeadUnits = 320;
+
+static void same_pad(int n, int k, int s, int& out, int& before) {
+    out = (n + s - 1) / s;
+    int total = (out - 1) * s + k - n;
+    if (total < 0) total = 0;
+    before = total / 2;                               // TF puts the extra cell after
+}
+
+static BnConv add_bnconv(Plan& p, const std::string& name, std::initializer_list<int> wdims, int K, int N) {
+    BnConv l; l.name = name; l.K = K; l.N = N;
+    l.w = p.dyn_params.add(name + ".w", wdims);
+    l.b = p.dyn_params.add(name + ".b", {N});
+    l.g = p.dyn_params.add(name + ".g", {N});
+    l.be = p.dyn_params.add(name + ".be", {N});
+    l.mm = p.dyn_state.add(name + ".mm", {N});
+    l.mv = p.dyn_state.add(name + ".mv", {N});
+    l.counter = p.n_counters++;
+    return l;
+}
+
+static int add_tensor(Plan& p, const std::string& name, int H, int W, int C, bool tables, bool has_grad = true) {
+    WsTensor t; t.name = name; t.H = H; t.W = W; t.C = C; t.Rt = p.B * H * W; t.elem = p.elem;
+    t.tables = tables; t.has_grad = has_grad;
+    p.tensor_index[name] = (int)p.tensors.size();
+    p.tensors.push_back(t);
+    return (int)p.tensors.size() - 1;
+}
+
+static void build_head(HeadSpec& h, bool policy) {
+    h.bn1_g = h.params.add("bn1.g", {kTrunkUnits}); h.bn1_be = h.params.add("bn1.be", {kTrunkUnits});
+    h.bn1_mm = h.state.add("bn1.mm", {kTrunkUnits}); h.bn1_mv = h.state.add("bn1.mv", {kTrunkUnits});
+    h.d1_w = h.params.add("d1.w", {kTrunkUnits, kHeadUnits}); h.d1_b = h.params.add("d1.b", {kHeadUnits});
+    h.bn2_g = h.params.add("bn2.g", {kHeadUnits}); h.bn2_be = h.params.add("bn2.be", {kHeadUnits});
+    h.bn2_mm = h.state.add("bn2.mm", {kHeadUnits}); h.bn2_mv = h.state.add("bn2.mv", {kHeadUnits});
+    h.d2_w = h.params.add("d2.w", {kHeadUnits, kHeadUnits}); h.d2_b = h.params.add("d2.b", {kHeadUnits});
+    const char* pn[4] = {"alpha", "beta", "similarity", "speed"};
+    const char* vn[4] = {"base", "exp", "speed", "similarity"};
+    const int pnn[4] = {2, 2, 1, 1}, vnn[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) {
+        std::string n = policy ? pn[i] : vn[i];
+        h.out_n[i] = policy ? pnn[i] : vnn[i];
+        h.out_w[i] = h.params.add(n + ".w", {kHeadUnits, h.out_n[i]});
+        h.out_b[i] = h.params.add(n + ".b", {h.out_n[i]});
+    }
+}
+
+Plan* build_plan(const cdra_config& cfg, std::string& err) {
+    if (cfg.batch < 1 || cfg.height < 19 || cfg.width < 19) { err = "bad batch / image size"; return nullptr; }
+    if (cfg.dtype != CDRA_DTYPE_F32 && cfg.dtype != CDRA_DTYPE_BF16) { err = "bad dtype"; return nullptr; }
+    Plan* pp = new Plan();
+    Plan& p = *pp;
+    p.cfg = cfg; p.B = cfg.batch; p.H = cfg.height; p.W = cfg.width;
+    p.elem = cfg.dtype == CDRA_DTYPE_BF16 ? 2 : 4;
+
+    // ---- layer graph + arenas (order == oracle/spec.py::dynamics_params)
+    p.stem = add_bnconv(p, "tower.stem", {3, 3, 3, kStemC}, 27, kStemC);
+    p.Hs = (p.H - 3) / 2 + 1; p.Ws = (p.W - 3) / 2 + 1;
+    same_pad(p.Hs, 3, 2, p.Hp, p.pool_pad_t); same_pad(p.Ws, 3, 2, p.Wp, p.pool_pad_l);
+    p.t_stem = add_tensor(p, "tower.stem", p.Hs, p.Ws, kStemC, true);
+    p.t_pool = add_tensor(p, "tower.pool", p.Hp, p.Wp, kStemC, false);
+    int cin = kStemC, h = p.Hp, w = p.Wp, t_prev = p.t_pool;
+    for (int s = 0; s < 3; ++s) {
+        const int c = kStageC[s];
+        for (int u = 0; u < kStageBlocks[s]; ++u) {
+            Unit un; char buf[64]; snprintf(buf, sizeof buf, "tower.s%d.u%d", s + 1, u);
+            un.name = buf; un.stride = u == 0 ? 2 : 1; un.cin = cin; un.c = c; un.half = c / 2;
+            un.Hi = h; un.Wi = w;
+            if (un.stride == 2) { same_pad(h, 3, 2, un.Ho, un.pad_t); same_pad(w, 3, 2, un.Wo, un.pad_l); }
+            else { un.Ho = h; un.Wo = w; un.pad_t = un.pad_l = 1; }
+            const int sc = un.stride == 2 ? cin : cin / 2;       // shortcut_channels, :127
+            const int kin = un.stride == 2 ? cin : cin / 2;
+            un.pw1 = add_bnconv(p, un.name + ".pw1", {kin, un.half}, kin, un.half);
+            un.dw = add_bnconv(p, un.name + ".dw", {3, 3, un.half}, 9, un.half);
+            un.pw2 = add_bnconv(p, un.name + ".pw2", {un.half, c - sc}, un.half, c - sc);
+            if (un.stride == 2) {
+                un.scdw = add_bnconv(p, un.name + ".scdw", {3, 3, sc}, 9, sc);
+                un.scpw = add_bnconv(p, un.name + ".scpw", {sc, sc}, sc, sc);
+            }
+            un.t_in = t_prev;
+            un.t_r1 = add_tensor(p, un.name + ".pw1", h, w, un.half, true);
+            un.t_r2 = add_tensor(p, un.name + ".dw", un.Ho, un.Wo, un.half, true);
+            un.t_rs = un.stride == 2 ? add_tensor(p, un.name + ".scdw", un.Ho, un.Wo, sc, true) : -1;
+            un.t_out = add_tensor(p, un.name + ".out", un.Ho, un.Wo, c, true);
+            p.units.push_back(un);
+            t_prev = un.t_out; cin = c; h = un.Ho; w = un.Wo;
+        }
+    }
+    p.head = add_bnconv(p, "tower.head", {kStageC[2], kLastC}, kStageC[2], kLastC);
+    p.t_head = add_tensor(p, "tower.head", h, w, kLastC, true);
+
+    const char* fnames[3] = {"road", "vehicle", "navigation"};
+    const int fd[3] = {9, 4, 5};
+    for (int m = 0; m < 3; ++m) {
+        FeatSpec f; f.name = fnames[m]; f.d = fd[m];
+        f.d1 = add_bnconv(p, std::string("feat.") + fnames[m] + ".d1", {fd[m], kFeatUnits}, fd[m], kFeatUnits);
+        f.d2 = add_bnconv(p, std::string("feat.") + fnames[m] + ".d2", {kFeatUnits, kFeatUnits}, kFeatUnits, kFeatUnits);
+        p.feats.push_back(f);
+    }
+    const char* gnames[4] = {"image", "road", "vehicle", "navigation"};
+    const int gdin[4] = {kLastC, 16, 16, 16}, gun[4] = {256, 32, 32, 32};
+    for (int g = 0; g < 4; ++g) {
+        GruSpec s; s.name = gnames[g]; s.din = gdin[g]; s.units = gun[g];
+        s.k = p.dyn_params.add(std::string("gru.") + gnames[g] + ".k", {gdin[g], 3 * gun[g]});
+        s.r = p.dyn_params.add(std::string("gru.") + gnames[g] + ".r", {gun[g], 3 * gun[g]});
+        s.b = p.dyn_params.add(std::string("gru.") + gnames[g] + ".b", {2, 3 * gun[g]});
+        p.grus.push_back(s);
+    }
+    p.trunk_g = p.dyn_params.add("trunk.bn.g", {kTrunkIn});
+    p.trunk_be = p.dyn_params.add("trunk.bn.be", {kTrunkIn});
+    p.trunk_mm = p.dyn_state.add("trunk.bn.mm", {kTrunkIn});
+    p.trunk_mv = p.dyn_state.add("trunk.bn.mv", {kTrunkIn});
+    p.trunk_w = p.dyn_params.add("trunk.dense.w", {kTrunkIn, kTrunkUnits});
+    p.trunk_b = p.dyn_params.add("trunk.dense.b", {kTrunkUnits});
+    build_head(p.policy, true);
+    build_head(p.value, false);
+
+    // ---- workspace map
+    size_t off = 0;
+    auto alloc = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    for (auto& t : p.tensors) if (t.tables) { t.fst = alloc((size_t)4 * t.C * 16); t.bst = alloc((size_t)4 * t.C * 16); }
+    p.zero_bytes = off;
+    p.counters_off = alloc((size_t)(p.n_counters + 16) * 4);
+    for (auto& t : p.tensors) if (t.tables) { t.aff = alloc((size_t)4 * t.C * 8); t.bnp = alloc((size_t)4 * t.C * 8); }
+    for (auto& t : p.tensors) { t.data = alloc(t.bytes()); }
+    for (auto& t : p.tensors) { t.grad = t.has_grad ? alloc(t.bytes()) : 0; }
+    auto f32 = [&](const std::string& name, std::vector<int> dims) {
+        size_t n = 1; for (int d : dims) n *= d;
+        size_t o = alloc(n * 4);
+        p.named[name] = {o, dims};
+        return o;
+    };
+    const int B = p.B;
+    p.gap = f32("tower.gap", {4, B, kLastC});
+    p.dgap = f32("d.tower.gap", {4, B, kLastC});
+    for (auto& f : p.feats) {
+        f.h1 = f32("feat." + f.name + ".h1", {4, B, kFeatUnits});
+        f.h2 = f32("feat." + f.name + ".h2", {4, B, kFeatUnits});
+        f.n1 = f32("feat." + f.name + ".n1", {4, B, kFeatUnits});
+        f.out = f32("feat." + f.name + ".out", {4, B, kFeatUnits});
+        f.dbuf1 = f32("d.feat." + f.name + ".out", {4, B, kFeatUnits});
+        f.dbuf2 = f32("d.feat." + f.name + ".tmp", {4, B, kFeatUnits});
+        f.st1 = f32("feat." + f.name + ".st1", {4, kFeatUnits, 2});
+        f.st2 = f32("feat." + f.name + ".st2", {4, kFeatUnits, 2});
+    }
+    for (size_t g = 0; g < p.grus.size(); ++g) {
+        GruSpec& s = p.grus[g];
+        const int u3 = 3 * s.units;
+        s.xp = f32("gru." + s.name + ".xp", {4, B, u3});
+        s.hp = f32("gru." + s.name + ".hp", {4, B, u3});
+        s.hs = f32("gru." + s.name + ".hs", {4, B, s.units});
+        s.dxp = f32("d.gru." + s.name + ".xp", {4, B, u3});
+        s.dhp = f32("d.gru." + s.name + ".hp", {4, B, u3});
+        s.dh = f32("d.gru." + s.name + ".h", {2, B, s.units});
+        s.x_in = g == 0 ? p.gap : p.feats[g - 1].out;
+        s.dx_in = g == 0 ? p.dgap : p.feats[g - 1].dbuf1;
+    }
+    p.dyn_in = f32("dynamics_in", {B, kTrunkIn});
+    p.ddyn_in = f32("d.dynamics_in", {B, kTrunkIn});
+    p.trunk_n = f32("trunk.n", {B, kTrunkIn});
+    f32("d.trunk.n", {B, kTrunkIn});
+    p.trunk_stat = f32("trunk.stat", {kTrunkIn, 2});
+    // head scratch: n1[512] pre1 a1 n2 pre2 a2 [320 each] + their gradients + stats
+    f32("head.n1", {B, kTrunkUnits}); f32("head.pre1", {B, kHeadUnits}); f32("head.a1", {B, kHeadUnits});
+    f32("head.n2", {B, kHeadUnits}); f32("head.pre2", {B, kHeadUnits}); f32("head.a2", {B, kHeadUnits});
+    f32("head.st1", {kTrunkUnits, 2}); f32("head.st2", {kHeadUnits, 2});
+    f32("d.head.a2", {B, kHeadUnits}); f32("d.head.pre2", {B, kHeadUnits}); f32("d.head.n2", {B, kHeadUnits});
+    f32("d.head.a1", {B, kHeadUnits}); f32("d.head.pre1", {B, kHeadUnits}); f32("d.head.n1", {B, kTrunkUnits});
+    f32("head.dlogits", {B, 8});
+    f32("head.acc", {64});          // fp64 x 32 loss accumulators
+    p.scratch = f32("scratch", {4, B < 4 ? 4 : B, kLastC});
+    p.ws_bytes = off;
+    return pp;
+}
+
+}  // namespace cdra

@@ -1,0 +1,126 @@
+// Host-side launch sequences for the image tower (forward and backward).
+#pragma once
+#include "plan.h"
+#include "tower_fwd.cuh"
+#include "tower_bwd.cuh"
+
+namespace cdra {
+
+struct RunCtx {
+    const Plan* p;
+    char* ws;
+    const float* params;     // dynamics trainable arena
+    float* state;            // dynamics state arena (moving stats); may be null in backward
+    float* grads;            // dynamics gradient arena (backward)
+    cudaStream_t stream;
+    int training;
+};
+
+inline unsigned* counter_ptr(const RunCtx& c, int idx) { return (unsigned*)(c.ws + c.p->counters_off) + idx; }
+
+inline BnTables tables_of(const RunCtx& c, const WsTensor& t) {
+    BnTables tb;
+    tb.fst = (double2*)(c.ws + t.fst); tb.bst = (double2*)(c.ws + t.bst);
+    tb.aff = (float2*)(c.ws + t.aff); tb.bnp = (float2*)(c.ws + t.bnp);
+    return tb;
+}
+inline BnLayer bn_of(const RunCtx& c, const BnConv& l, int unbiased = 1) {
+    BnLayer b;
+    b.gamma = c.params + l.g; b.beta = c.params + l.be;
+    b.mov_mean = c.state ? c.state + l.mm : nullptr; b.mov_var = c.state ? c.state + l.mv : nullptr;
+    b.counter = counter_ptr(c, l.counter); b.training = c.training; b.unbiased = unbiased;
+    return b;
+}
+inline ActView view_of(const RunCtx& c, const WsTensor& t, int coff, bool clamp) {
+    ActView v; v.data = c.ws + t.data; v.ld = t.C; v.coff = coff;
+    v.aff = t.tables ? (const float2*)(c.ws + t.aff) : nullptr; v.clamp = clamp ? 1 : 0;
+    return v;
+}
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+template <typename T>
+void launch_pw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, int Rt, const WsTensor& dst, const ColMap& cm) {
+    PwArgs<T> a;
+    a.in = in; a.K = l.K; a.Rt = Rt; a.w = c.params + l.w; a.bias = c.params + l.b; a.cm = cm;
+    a.out = (T*)(c.ws + dst.data); a.ldo = dst.C; a.tb = tables_of(c, dst); a.bn = bn_of(c, l); a.do_stats = 1;
+    dim3 grid(cdiv(Rt, kPwTM), kT, cdiv(cm.n, kPwTN));
+    auto k = pw_fwd_kernel<T>;
+    CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
+}
+
+template <typename T>
+void launch_dw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, const Unit& u, int C, const WsTensor& dst) {
+    DwArgs<T> a;
+    a.in = in; a.B = c.p->B; a.Hi = u.Hi; a.Wi = u.Wi; a.Ho = u.Ho; a.Wo = u.Wo; a.C = C; a.stride = u.stride;
+    a.pad_t = u.pad_t; a.pad_l = u.pad_l; a.w = c.params + l.w; a.bias = c.params + l.b;
+    a.out = (T*)(c.ws + dst.data); a.tb = tables_of(c, dst); a.bn = bn_of(c, l);
+    const long long items = (long long)a.B * u.Ho * u.Wo * (C / 2);
+    dim3 grid(cdiv(items, 256 * kDwItems), kT);
+    auto k = dw_fwd_kernel<T>;
+    CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
+}
+
+template <typename T, typename TIn>
+void tower_forward(const RunCtx& c, const TIn* image) {
+    const Plan& p = *c.p;
+    const int B = p.B;
+    {   // stem conv (+BN statistics)                                  core/architectures.py:159-160
+        const WsTensor& ts = p.tensors[p.t_stem];
+        StemArgs<T, TIn> a;
+        a.img = image; a.B = B; a.H = p.H; a.W = p.W; a.Ho = p.Hs; a.Wo = p.Ws;
+        a.w = c.params + p.stem.w; a.bias = c.params + p.stem.b; a.out = (T*)(c.ws + ts.data);
+        a.tb = tables_of(c, ts); a.bn = bn_of(c, p.stem);
+        dim3 grid(cdiv(ts.Rt, 128 * kStemPPT), kT);
+        auto k = stem_fwd_kernel<T, TIn>;
+        CDRA_LAUNCH(k, grid, dim3(128), 0, c.stream, a);
+    }
+    {   // BN + ReLU6 on load, maxpool 3x3 s2 SAME                      :160-161
+        const WsTensor& ts = p.tensors[p.t_stem];
+        const WsTensor& tp = p.tensors[p.t_pool];
+        PoolArgs<T> a;
+        a.in = view_of(c, ts, 0, true); a.B = B; a.Hi = p.Hs; a.Wi = p.Ws; a.Ho = p.Hp; a.Wo = p.Wp; a.C = kStemC;
+        a.pad_t = p.pool_pad_t; a.pad_l = p.pool_pad_l; a.out = (T*)(c.ws + tp.data);
+        dim3 grid(cdiv((long long)tp.Rt * (kStemC / 2), 256), kT);
+        auto k = pool_fwd_kernel<T>;
+        CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
+    }
+    for (const Unit& u : p.units) {                                     // :120-151
+        const WsTensor& tin = p.tensors[u.t_in];
+        const WsTensor& r1 = p.tensors[u.t_r1];
+        const WsTensor& r2 = p.tensors[u.t_r2];
+        const WsTensor& out = p.tensors[u.t_out];
+        const bool in_clamp = tin.tables;        // unit outputs are BN+ReLU6 outputs; the pool output is plain
+        const int sc = u.stride == 2 ? u.cin : u.cin / 2;
+        // branch: pw1 -> BN/ReLU6 -> dw -> BN -> pw2 -> BN/ReLU6
+        ActView x = view_of(c, tin, u.stride == 2 ? 0 : u.cin / 2, in_clamp);
+        launch_pw_fwd<T>(c, u.pw1, x, tin.Rt, r1, ColMap{u.half, 0, 0, 0});
+        launch_dw_fwd<T>(c, u.dw, view_of(c, r1, 0, true), u, u.half, r2);
+        launch_pw_fwd<T>(c, u.pw2, view_of(c, r2, 0, false), r2.Rt, out, ColMap{u.c - sc, 1, sc / 2, u.half});
+        if (u.stride == 2) {
+            const WsTensor& rs = p.tensors[u.t_rs];
+            launch_dw_fwd<T>(c, u.scdw, view_of(c, tin, 0, in_clamp), u, sc, rs);
+            launch_pw_fwd<T>(c, u.scpw, view_of(c, rs, 0, false), rs.Rt, out, ColMap{sc, 1, 0, u.half});
+        } else {
+            PassArgs<T> a;
+            a.in = (const T*)(c.ws + tin.data); a.ldi = tin.C; a.out = (T*)(c.ws + out.data); a.ldo = out.C;
+            a.half = u.half; a.Rt = out.Rt;
+            a.aff_in = tin.tables ? (const float2*)(c.ws + tin.aff) : nullptr; a.aff_out = (float2*)(c.ws + out.aff);
+            a.bnp_in = tin.tables ? (const float2*)(c.ws + tin.bnp) : nullptr; a.bnp_out = (float2*)(c.ws + out.bnp);
+            dim3 grid(cdiv((long long)out.Rt * (u.half / 2), 256), kT);
+            auto k = pass_fwd_kernel<T>;
+            CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
+        }
+    }
+    {   // head conv 464 -> 768, BN, ReLU6, global average pool        :169-172
+        const WsTensor& tin = p.tensors[p.units.back().t_out];
+        const WsTensor& th = p.tensors[p.t_head];
+        launch_pw_fwd<T>(c, p.head, view_of(c, tin, 0, true), tin.Rt, th, ColMap{p.head.N, 0, 0, 0});
+        GapArgs<T> a;
+        a.in = view_of(c, th, 0, true); a.B = B; a.HW = th.H * th.W; a.C = th.C; a.out = (float*)(c.ws + p.gap);
+        dim3 grid(cdiv((long long)B * th.C, 256), kT);
+        auto k = gap_fwd_kernel<T>;
+        CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
+    }
+}
+
+}  // namespace cdra

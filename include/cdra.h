@@ -1,0 +1,127 @@
+/* libcdra — C ABI of the B200-native PPO-update hot path of Luca96/carla-driving-rl-agent.
+ *
+ * The reference has no native boundary (it is pure Python on TF2/Keras); the functions below are what
+ * a drop-in replacement of its numeric layer binds (see INTEGRATION.md for the Python-side stub).
+ * Each entry cites the reference code it replaces.  Conventions:
+ *   - every function returns 0 on success or a negative CDRA_ERR_* code; cdra_last_error() returns a
+ *     thread-local description of the last failure.  No exceptions cross the boundary.
+ *   - all tensor arguments are raw DEVICE pointers owned by the caller (torch.Tensor.data_ptr());
+ *     `stream` is a cudaStream_t passed as void*.  All work is enqueued asynchronously on it.
+ *   - the library allocates nothing after cdra_plan_create; scratch memory is one caller-owned
+ *     workspace of cdra_plan_workspace_bytes() bytes that must be zeroed once before first use.
+ *   - a plan is thread-compatible, not thread-safe: one plan per (process, device).
+ */
+#ifndef CDRA_H_
+#define CDRA_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDRA_OK 0
+#define CDRA_ERR_BADARG (-1)
+#define CDRA_ERR_SHAPE (-2)
+#define CDRA_ERR_WORKSPACE (-3)
+#define CDRA_ERR_CUDA (-4)
+#define CDRA_ERR_NCCL (-5)
+
+#define CDRA_DTYPE_F32 0   /* parity mode: fp32 activations */
+#define CDRA_DTYPE_BF16 1  /* perf mode: bf16 activation storage, fp32 accumulate / statistics */
+
+/* arenas (flat fp32 buffers owned by the caller) */
+#define CDRA_ARENA_DYN_PARAMS 0   /* dynamics trainable (2,128,450 floats)  */
+#define CDRA_ARENA_DYN_STATE 1    /* dynamics BN moving mean/var (16,564)   */
+#define CDRA_ARENA_POL_PARAMS 2   /* policy head trainable (270,470)        */
+#define CDRA_ARENA_POL_STATE 3    /* policy head BN moving stats (1,664)    */
+#define CDRA_ARENA_VAL_PARAMS 4   /* value head trainable (269,828)         */
+#define CDRA_ARENA_VAL_STATE 5    /* value head BN moving stats (1,664)     */
+
+typedef struct cdra_config {
+    int32_t batch;      /* B: samples per call on this device (SGD minibatch shard)             */
+    int32_t height;     /* image H (90)                                                         */
+    int32_t width;      /* image W (120)                                                        */
+    int32_t dtype;      /* CDRA_DTYPE_*                                                         */
+    int32_t image_u8;   /* 1: state_image is uint8 0..255 (scaled by 1/255 on load); 0: float32 */
+} cdra_config;
+
+typedef struct cdra_plan cdra_plan_t;
+
+const char* cdra_last_error(void);
+int cdra_version(void);
+
+/* Builds the layer graph of core/networks.py:37-56 (dynamics_layers) + core/architectures.py:30-173
+ * for a fixed (B, H, W, dtype).  Host-only; does not touch the GPU. */
+int cdra_plan_create(const cdra_config* cfg, cdra_plan_t** out);
+void cdra_plan_destroy(cdra_plan_t* plan);
+size_t cdra_plan_workspace_bytes(const cdra_plan_t* plan);
+
+/* Arena layout introspection (mirrors Keras `model.get_weights()` bookkeeping of core/networks.py:297-310). */
+int64_t cdra_arena_size(const cdra_plan_t* plan, int arena);             /* floats */
+int cdra_arena_num_tensors(const cdra_plan_t* plan, int arena);
+int cdra_arena_tensor(const cdra_plan_t* plan, int arena, int index, char* name, int name_cap,
+                      int64_t* offset, int32_t* ndim, int32_t dims[4]);
+/* Location of a named intermediate tensor inside the workspace (parity tests read taps through it). */
+int cdra_plan_tensor(const cdra_plan_t* plan, const char* name, int64_t* byte_offset, int32_t dims[4],
+                     int32_t* elem_size);
+
+/* CARLANetwork.dynamics_predict_train / dynamics_predict (core/networks.py:206-212) on
+ * dynamics_layers (core/networks.py:37-56).  image [B,4,H,W,3] (u8 or f32), road [B,4,9],
+ * vehicle [B,4,4], navigation [B,4,5] f32; out512 [B,512] f32.  training!=0 uses batch statistics and
+ * updates the moving statistics in `state` exactly like 4 sequential Keras BN calls per layer. */
+int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, const void* image,
+                          const float* road, const float* vehicle, const float* navigation, int training,
+                          float* out512, void* workspace, void* stream);
+
+/* tape.gradient(loss, dynamics.trainable_variables) (core/carla_agent.py:361-365,440-444): consumes
+ * d loss / d out512 [B,512] and the activations cdra_dynamics_forward left in `workspace`; writes
+ * (overwrites) the flat gradient arena `grads` (same layout as CDRA_ARENA_DYN_PARAMS). */
+int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* image, const float* road,
+                           const float* vehicle, const float* navigation, const float* d_out512,
+                           float* grads, void* workspace, void* stream);
+
+/* CARLAgent.policy_objective (core/carla_agent.py:394-428) on PolicyNetwork.call
+ * (core/networks.py:96-137) + its backward.  x512 [B,512]; actions_eval [B,2] (decision D2: the action
+ * the new policy's log-prob is evaluated at, clipped to [eps,1-eps] like _clip_actions :139-144);
+ * logp_old [B,2]; adv [B]; true_speed/true_sim [B,1].  scalars_out (16 floats): 0 total, 1 loss_policy,
+ * 2 loss_entropy(=coef*H), 3 loss_speed, 4 loss_similarity, 5 ratio mean, 6 log_prob mean, 7 entropy,
+ * 8 speed mean, 9 similarity mean.  d_x512 [B,512]; grads = policy gradient arena (overwritten).
+ * grad_scale multiplies every gradient (1/world_size under data parallelism). */
+int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
+                                  const float* actions_eval, const float* logp_old, const float* adv,
+                                  const float* true_speed, const float* true_sim, float clip_ratio,
+                                  float ent_coef, int training, float grad_scale, float* scalars_out,
+                                  float* head_out, float* d_x512, float* grads, void* workspace, void* stream);
+
+/* CARLAgent.value_objective (core/carla_agent.py:469-486) on CARLANetwork.value_branch/value_head
+ * (core/networks.py:255-275) + backward.  returns_be [B,2] (base, exp).  scalars_out: 0 total, 1 loss_v,
+ * 2 loss_speed, 3 loss_similarity, 4 speed mean, 5 similarity mean.  head_out [B,4] = (base, exp, speed, sim). */
+int cdra_value_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
+                                 const float* returns_be, const float* true_speed, const float* true_sim,
+                                 int training, float grad_scale, float* scalars_out, float* head_out,
+                                 float* d_x512, float* grads, void* workspace, void* stream);
+
+/* PPOMemory.end_trajectory + compute_returns + compute_advantages (rl/agents/ppo.py:692-727) with
+ * utils.gae / rewards_to_go / discount_cumsum / decompose_number / tf_sp_norm
+ * (rl/utils.py:57-84,140-151,344-349) for `bs` independent trajectories of length T.
+ * rewards [bs][T]; values_be [bs][T][2]; last_value_be [bs][2] (zeros for terminal states);
+ * outputs returns_be [bs][T][2], adv [bs][T] (sp-normalised * scale).  gamma / lambda_ are doubles because the
+ * reference hands python floats to scipy.signal.lfilter, which filters in float64. */
+int cdra_gae(const float* rewards, const float* values_be, const float* last_value_be, double gamma,
+             double lambda_, float scale, int bs, int T, float* returns_be_out, float* adv_out, void* stream);
+
+/* utils.clip_gradients (rl/utils.py:120-121; per-tensor tf.clip_by_norm) followed by Keras
+ * Adam.apply_gradients (rl/agents/ppo.py:246-250,270-273; core/carla_agent.py:386-388) over a flat
+ * arena of `total` floats.  tensor_offsets [n_tensors+1] (device, int64) delimits the tensors; clip_norm<=0 disables
+ * clipping.  step is the 1-based Adam iteration.  grad_scale is applied to the gradient first. */
+int cdra_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* tensor_offsets,
+                   int n_tensors, int64_t total, float clip_norm, float lr, float beta1, float beta2, float eps,
+                   int64_t step, float grad_scale, float* norms_out, void* stream);
+
+/* utils.data_to_batches gather (rl/utils.py:365-393): dst[i] = src[index[i]] for rows of row_bytes. */
+int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDRA_H_ */

@@ -97,8 +97,9 @@ class BNState:
             mm = params[name + '.mm'].clone()
             mv = params[name + '.mv'].clone()
             for mean, var in calls:
-                mm = mm * m + mean.to(mm.dtype) * (1.0 - m)
-                mv = mv * m + var.to(mv.dtype) * (1.0 - m)
+                # Keras assign_moving_average: variable -= (variable - value) * (1 - momentum) [lib]
+                mm = mm - (mm - mean.to(mm.dtype)) * (1.0 - m)
+                mv = mv - (mv - var.to(mv.dtype)) * (1.0 - m)
             new[name + '.mm'] = mm
             new[name + '.mv'] = mv
         return new
