@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""PPO update-step throughput of the B200-native hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libcdra, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle restatement of the
+                                                             # reference's TF/Keras path on the host cores
+
+A "step" is one SGD minibatch index of the PPO update over the global minibatch (bs samples per GPU):
+policy pass (shared-trunk forward+backward, policy head + clipped-surrogate/entropy/aux loss, gradient
+all-reduce, per-tensor clip + Adam on head and trunk) AND value pass (the same with the value head), i.e.
+every sample goes through both passes like `PPOAgent.update` (rl/agents/ppo.py:190-226); GAE / returns for
+all bs x T transitions run once per update inside the timed region.  Rollout tensors (bs x T samples,
+uint8 frames) are resident in HBM before the clock starts; every step gathers its minibatch from them.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'carla-driving-rl-agent_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = 'ppo_update_samples_per_sec'
+BYTES_PER_SAMPLE = {('bf16', 90, 120): 41.43e6, ('f32', 90, 120): 82.60e6, ('bf16', 180, 240): 164.33e6}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=12)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--bs', type=int, default=512, help='samples per GPU per SGD step (BASELINE config 2: 512)')
+    ap.add_argument('--T', type=int, default=256)
+    ap.add_argument('--height', type=int, default=90)
+    ap.add_argument('--width', type=int, default=120)
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--cpu-batch', type=int, default=32)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_rollout(torch, bs, T, H, W, device, seed):
+    """Synthetic rollout tensors with the value distributions of SURVEY §8(d), generated on the device."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    N = bs * T
+    img = torch.empty(N, 4, H, W, 3, dtype=torch.uint8, device=device)
+    chunk = 2048
+    for s in range(0, N, chunk):
+        e = min(N, s + chunk)
+        img[s:e] = torch.randint(0, 256, (e - s, 4, H, W, 3), dtype=torch.uint8, device=device, generator=g)
+    r = lambda *shape: torch.rand(*shape, device=device, generator=g)
+    road = torch.cat([(r(N, 4, 3) < 0.2).float(), 0.3 + 0.6 * r(N, 4, 1),
+                      torch.nn.functional.one_hot(torch.randint(0, 5, (N, 4), device=device, generator=g), 5).float()], -1)
+    veh = torch.cat([r(N, 4, 1) * 2 - 1, r(N, 4, 3)], -1)
+    nav = torch.sort(r(N, 4, 5) * 25, dim=-1).values
+    d = dict(state_image=img, state_road=road.contiguous(), state_vehicle=veh.contiguous(), state_navigation=nav.contiguous(),
+             actions=r(N, 2).clamp(1e-4, 1 - 1e-4), logp_old=0.5 * torch.randn(N, 2, device=device, generator=g),
+             true_speed=0.3 * r(N, 1), true_sim=r(N, 1) * 2 - 1,
+             rewards=(torch.randn(bs, T, device=device, generator=g) * 2 + 1).clamp(-10, 30),
+             values_be=torch.stack([r(bs, T) * 2 - 1, r(bs, T) * 6], -1).contiguous(),
+             last_be=torch.stack([r(bs) * 2 - 1, r(bs) * 6], -1).contiguous())
+    return d
+
+
+class ClockSampler(threading.Thread):
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(',')])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_rate(steps, warmup, batch, H, W, threads=None):
+    """Times the oracle's policy pass + value pass (+ clip + Adam) on `batch` samples per step on the host."""
+    import torch
+    from oracle import model, ppo, spec
+    from tests import common as C
+    if threads:
+        torch.set_num_threads(threads)
+    dyn, pol, val = C.fresh_params(torch.float32)
+    obs, bt = C.synthetic_obs(batch, H, W, seed=1), C.synthetic_batch(batch, seed=2)
+    st = {k: ({n: torch.zeros_like(t) for n, t in d.items()}, {n: torch.zeros_like(t) for n, t in d.items()})
+          for k, d in (('dyn', dyn), ('pol', pol), ('val', val))}
+    n_step = [0]
+
+    def step():
+        n_step[0] += 1
+        r = C.policy_step_oracle(dyn, pol, obs, bt, dtype=torch.float32)
+        ppo.apply_step(dyn, r['g_dyn'], st['dyn'][0], st['dyn'][1], 2 * n_step[0] - 1, 3e-4)
+        ppo.apply_step(pol, r['g_head'], st['pol'][0], st['pol'][1], n_step[0], 3e-4, clip=1.0)
+        r = C.value_step_oracle(dyn, val, obs, bt, dtype=torch.float32)
+        ppo.apply_step(dyn, r['g_dyn'], st['dyn'][0], st['dyn'][1], 2 * n_step[0], 3e-4)
+        ppo.apply_step(val, r['g_head'], st['val'][0], st['val'][1], n_step[0], 3e-4, clip=1.0)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rate, sec, cores = cpu_reference_rate(args.steps, max(1, min(args.warmup, 2)), args.cpu_batch, args.height, args.width)
+    sample = f'{args.cpu_batch}-sample SGD minibatch per step (policy pass + value pass + clip + Adam), fp32, torch-CPU restatement'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'PPO update, {args.height}x{args.width}x3 x4-frame obs, bs={args.bs}/GPU, T={args.T}',
+                   'note': 'TF 2.3.1 is not installable here; the CPU arm is the oracle port of the reference path'},
+        'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from cdra.engine import Engine
+    from cdra.init import init_engine
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    bs, T, H, W = args.bs, args.T, args.height, args.width
+    eng = Engine(bs, H, W, dtype=args.dtype, image_u8=True, device=dev)
+    init_engine(eng, seed=42)                                       # Keras-default random init, same on every rank
+    old_pol = eng.pol.flat.clone()
+    roll = synthetic_rollout(torch, bs, T, H, W, dev, 1234 + rank)
+    N = bs * T
+    perm_p = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+    perm_v = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(8 + rank))
+    keys = ('state_image', 'state_road', 'state_vehicle', 'state_navigation', 'actions', 'logp_old', 'true_speed', 'true_sim')
+    mb = {k: torch.empty((bs,) + tuple(roll[k].shape[1:]), dtype=roll[k].dtype, device=dev) for k in keys}
+    mb['adv'] = torch.empty(bs, device=dev); mb['returns'] = torch.empty(bs, 2, device=dev)
+    gscale = 1.0 / world
+    state = dict(adv=None, ret=None)
+
+    def gae():
+        ret, adv = eng.gae(roll['rewards'], roll['values_be'], roll['last_be'], 0.9999, 0.999, 2.0)
+        state['ret'], state['adv'] = ret.view(N, 2), adv.view(N, 1)
+
+    def gather(idx, what):
+        for k in keys:
+            eng.gather_rows(roll[k], idx, mb[k])
+        if what == 'policy':
+            eng.gather_rows(state['adv'], idx, mb['adv'])
+        else:
+            eng.gather_rows(state['ret'], idx, mb['returns'])
+
+    def allreduce(*ts):
+        if world > 1:
+            for t in ts:
+                dist.all_reduce(t)
+
+    def sgd_step(i, host=None):
+        if i % T == 0:
+            gae()                                                     # once per update (PPOAgent.end_episode)
+        lo = (i % T) * bs
+        if host is None:
+            gather(perm_p[lo:lo + bs], 'policy')
+        else:
+            for k in host[0]:
+                mb[k].copy_(host[0][k], non_blocking=True)
+        # ---- policy pass (rl/agents/ppo.py:199-210, core/carla_agent.py:351-388)
+        x = eng.dynamics_forward(mb)
+        eng.policy_head(x, mb['actions'], mb['logp_old'], mb['adv'], mb['true_speed'], mb['true_sim'], 0.2, 1.0)
+        eng.dynamics_backward(mb, eng.d_x512)
+        allreduce(eng.g_dyn, eng.g_pol)
+        eng.clip_adam('dyn', 3e-4, None, gscale)
+        old_pol.copy_(eng.pol.flat)                                   # update_old_policy before the Adam step (ppo.py:249)
+        eng.clip_adam('pol', 3e-4, 1.0, gscale)
+        loss_p = eng.scalars[0].clone()
+        # ---- value pass (rl/agents/ppo.py:213-224, core/carla_agent.py:430-463)
+        if host is None:
+            gather(perm_v[lo:lo + bs], 'value')
+        else:
+            for k in host[1]:
+                mb[k].copy_(host[1][k], non_blocking=True)
+        x = eng.dynamics_forward(mb)
+        eng.value_head(x, mb['returns'], mb['true_speed'], mb['true_sim'])
+        eng.dynamics_backward(mb, eng.d_x512)
+        allreduce(eng.g_dyn, eng.g_val)
+        eng.clip_adam('dyn', 3e-4, None, gscale)
+        eng.clip_adam('val', 3e-4, 1.0, gscale)
+        return loss_p, eng.scalars[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, first, host_bufs=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            if host_bufs is None:
+                sgd_step(first + i)
+            else:
+                lp, lv = sgd_step(first + i, host_bufs[i % len(host_bufs)])
+                host_loss[0].copy_(lp, non_blocking=False); host_loss[1].copy_(lv, non_blocking=False)   # D2H read of the step's result
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    launches0 = eng.lib.cdra_launch_count()
+    for i in range(args.warmup):
+        sgd_step(i)
+    torch.cuda.synchronize()
+    per_step_launches = (eng.lib.cdra_launch_count() - launches0) / max(1, args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = eng.lib.cdra_launch_count()
+    ms = timed(args.steps, args.warmup)
+    launches = eng.lib.cdra_launch_count() - l0
+    clocks = sampler.finish() if sampler else None
+    value = world * bs * args.steps / (ms / 1e3)
+
+    # ---- end-to-end: same step through the public call with HOST buffers (pinned), H2D + D2H inside the clock
+    e2e_keys = keys + ('adv', 'returns')
+    gather(perm_p[:bs], 'policy'); gather(perm_v[:bs], 'value'); torch.cuda.synchronize()
+    host_bufs = []
+    for j in range(2):                                                # (policy-pass minibatch, value-pass minibatch) pairs
+        gather(perm_p[j * bs:(j + 1) * bs], 'policy')
+        hp = {k: mb[k].cpu().pin_memory() for k in keys + ('adv',)}
+        gather(perm_v[j * bs:(j + 1) * bs], 'value')
+        hv = {k: mb[k].cpu().pin_memory() for k in keys + ('returns',)}
+        host_bufs.append((hp, hv))
+    host_loss = [torch.empty((), pin_memory=True), torch.empty((), pin_memory=True)]
+    h2d = sum(t.numel() * t.element_size() for h in host_bufs[0] for t in h.values())
+    e2e_steps = max(2, args.steps // 2)
+    timed(1, 1, host_bufs)
+    ms_e2e = timed(e2e_steps, 1, host_bufs)
+    e2e_value = world * bs * e2e_steps / (ms_e2e / 1e3)
+
+    out = {
+        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
+        'data': 'synthetic',
+        'config': {'workload': f'PPO update (policy pass + value pass), obs {H}x{W}x3 x4-frame stack + road/vehicle/nav vectors, '
+                               f'bs={bs}/GPU (global {bs * world}), T={T}, N=bs*T rollout resident in HBM',
+                   'step': 'one SGD minibatch index = bs samples/GPU through both passes; GAE once per T steps',
+                   'l2': f'inputs ({roll["state_image"].numel() / 1e9:.1f} GB rollout) and activations exceed L2; no flush needed',
+                   'parallelism': f'dp{world}', 'optimizer': 'Keras-style Adam x3, per-tensor clip 1.0 on heads'},
+        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
+                'ms_per_step': ms_e2e / e2e_steps},
+        'gpu_launches': int(launches), 'launches_per_step': per_step_launches, 'clocks': clocks,
+    }
+    peak, peak_src = measured_peaks()
+    bps = BYTES_PER_SAMPLE.get((args.dtype, H, W))
+    if bps:
+        out['roofline_step'] = {'bound': 'hbm', 'achieved': value / world * bps / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                'frac': value / world * bps / 1e9 / peak, 'bytes_per_sample': bps,
+                                'note': 'canonical algorithmic bytes of SURVEY 8(d) x samples/s/GPU; peak ' + peak_src}
+    if rank == 0 and not args.no_profile:
+        out['roofline'] = kernel_roofline(eng, sgd_step, args.warmup + args.steps, peak, peak_src)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores = cpu_reference_rate(2, 1, args.cpu_batch, H, W)
+        out['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                               'sample': f'2 timed SGD steps of {args.cpu_batch} samples (both passes + clip + Adam), fp32 oracle on the host'}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(eng, sgd_step, first, peak, peak_src):
+    """Per-kernel CUDA-event timing on the launch stream (serialised; outside the timed region)."""
+    import ctypes
+    import torch
+    lib = eng.lib
+    lib.cdra_profile_reset(); lib.cdra_profile_enable(1)
+    sgd_step(first); sgd_step(first + 1)
+    torch.cuda.synchronize()
+    lib.cdra_profile_enable(0)
+    n = lib.cdra_profile_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.cdra_profile_report(buf, n + 16)
+    rows = []
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms, by = line.split('\t')
+        short = name
+        for tag in ('stem_fwd', 'pool_fwd', 'pw_fwd', 'dw_fwd', 'pass_fwd', 'gap_fwd', 'bstat', 'pw_dgrad', 'pw_wgrad', 'dw_dgrad',
+                    'dw_wgrad', 'pass_bwd', 'pool_bwd', 'stem_wgrad', 'gap_bwd', 'sgemm', 'colsum', 'bn1d_fwd', 'bn1d_bwd',
+                    'swish6_fwd', 'swish6_bwd', 'gru_gate_fwd', 'gru_gate_bwd', 'featnet_fwd', 'featnet_bwd', 'head_loss', 'gae',
+                    'sqnorm', 'adam', 'gather_rows'):
+            if tag in name:
+                short = tag
+        rows.append((short, int(cnt), float(ms), float(by)))
+    agg = {}
+    for s, c, m, b in rows:
+        a = agg.setdefault(s, [0, 0.0, 0.0]); a[0] += c; a[1] += m; a[2] += b
+    total = sum(a[1] for a in agg.values())
+    top = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    name, (cnt, ms, by) = top[0]
+    ach = by / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+    return {'bound': 'hbm', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+            'launches': cnt, 'avg_ms': ms / max(cnt, 1), 'share_of_step': ms / total if total else None, 'peak_source': peak_src,
+            'by_kernel': {k: {'launches': v[0], 'ms': round(v[1], 3), 'share': round(v[1] / total, 4),
+                              'GBps': round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None} for k, v in top[:14]}}
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -45,6 +45,10 @@ _SIGNATURES = {
     'cdra_clip_adam': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int64, C.c_float, _P, _P]),
     'cdra_gather_rows': (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
+    'cdra_launch_count': (C.c_int64, []),
+    'cdra_profile_enable': (None, [C.c_int]),
+    'cdra_profile_reset': (None, []),
+    'cdra_profile_report': (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 _loaded = {}

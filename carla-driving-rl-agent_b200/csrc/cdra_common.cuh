@@ -21,11 +21,21 @@
 #define CDRA_DEV __device__ __forceinline__
 #define CDRA_SHARED __shared__
 #define CDRA_LAUNCH_BOUNDS(n) __launch_bounds__(n)
-#define CDRA_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+namespace cdra {
+// launch accounting / optional per-kernel CUDA-event timing (cdra_profile_* in include/cdra.h)
+void prof_pre(const void* func, cudaStream_t stream);
+void prof_post(cudaStream_t stream);
+}
+#define CDRA_LAUNCH(kernel, grid, block, smem, stream, ...)          \
+    do {                                                              \
+        cdra::prof_pre((const void*)(kernel), stream);                \
+        kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);           \
+        cdra::prof_post(stream);                                      \
+    } while (0)
 #define CDRA_DYN_SMEM(name) extern __shared__ __align__(1024) char name[]
 #define CDRA_RESTRICT __restrict__
 #endif
+namespace cdra { void prof_bytes(double algorithmic_bytes); }   // bytes of the next launch (for the roofline)
 
 typedef __nv_bfloat16 bf16;
 

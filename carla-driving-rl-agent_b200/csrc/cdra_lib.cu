@@ -26,6 +26,42 @@ static void zero_async(void* p, size_t n, cudaStream_t s) { cudaMemsetAsync(p, 0
 
 struct cdra_plan { Plan* p; };
 
+// ----------------------------------------------------------------------------------------------- launch accounting
+#include <atomic>
+#include <map>
+#include <mutex>
+namespace {
+struct ProfEntry { long long count = 0; double ms = 0.0, bytes = 0.0; };
+std::atomic<long long> g_launches{0};
+bool g_prof = false;
+double g_pending_bytes = 0.0;
+std::map<const void*, ProfEntry> g_entries;
+#ifndef CDRA_EMU
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+const void* g_cur = nullptr;
+#endif
+}
+namespace cdra {
+void prof_bytes(double b) { g_pending_bytes = b; }
+#ifndef CDRA_EMU
+void prof_pre(const void* func, cudaStream_t stream) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof) return;
+    if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+    g_cur = func;
+    cudaEventRecord(g_ev0, stream);
+}
+void prof_post(cudaStream_t stream) {
+    if (!g_prof) { g_pending_bytes = 0.0; return; }
+    cudaEventRecord(g_ev1, stream);
+    cudaEventSynchronize(g_ev1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+    ProfEntry& e = g_entries[g_cur];
+    e.count++; e.ms += ms; e.bytes += g_pending_bytes; g_pending_bytes = 0.0;
+}
+#endif
+}
+
 // ----------------------------------------------------------------------------------------------- small launch helpers
 static void gemm(cudaStream_t st, bool ta, bool tb, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                  const float* bias, int M, int N, int K, bool accumulate) {
@@ -110,6 +146,7 @@ static void launch_bstat(const RunCtx& c, const WsTensor& t, int coff, int C, bo
     a.clamp = clamp ? 1 : 0; a.tb = tables_of(c, t);
     int rows = 4096 / C; if (rows < 8) rows = 8;
     a.rows_per_block = rows;
+    prof_bytes(4.0 * t.Rt * C * 2 * sizeof(T));                // read dA and R once
     auto k = bstat_kernel<T>;
     CDRA_LAUNCH(k, dim3(cdiv(t.Rt, rows), kT), dim3(256), 0, c.stream, a);
 }
@@ -126,9 +163,11 @@ static void launch_pw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
     int splits = (int)cdiv(Rt, 2048); if (splits < 1) splits = 1; if (splits > 64) splits = 64;
     a.row_splits = splits;
     if (need_dx) {
+        prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));  // read dA, R; write dX
         auto k = pw_dgrad_kernel<T>;
         CDRA_LAUNCH(k, dim3(cdiv(Rt, kPwTM), kT, cdiv(l.K, kPwTN)), dim3(256), 0, c.stream, a);
     }
+    prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));      // read dA, R, X
     auto k2 = pw_wgrad_kernel<T>;
     CDRA_LAUNCH(k2, dim3(cdiv(l.K + 1, kPwTM), cdiv(cm.n, kPwTN), kT * splits), dim3(256), 0, c.stream, a);
 }
@@ -142,8 +181,10 @@ static void launch_dw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
     a.pad_t = u.pad_t; a.pad_l = u.pad_l; a.w = c.params + l.w;
     a.dx = dx; a.ldx = ldx; a.coffx = coffx; a.accumulate = accumulate ? 1 : 0;
     a.dw = c.grads + l.w; a.db = c.grads + l.b; a.dgamma = c.grads + l.g; a.dbeta = c.grads + l.be;
+    prof_bytes(4.0 * a.B * (2.0 * u.Ho * u.Wo + (double)u.Hi * u.Wi) * C * sizeof(T));
     auto k1 = dw_dgrad_kernel<T>;
     CDRA_LAUNCH(k1, dim3(cdiv((long long)a.B * u.Hi * u.Wi * (C / 2), 256), kT), dim3(256), 0, c.stream, a);
+    prof_bytes(4.0 * a.B * (2.0 * u.Ho * u.Wo + (double)u.Hi * u.Wi) * C * sizeof(T));
     auto k2 = dw_wgrad_kernel<T>;
     CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho * u.Wo * (C / 2), 256 * kDwItems), kT), dim3(256), 0, c.stream, a);
 }
@@ -483,6 +524,24 @@ int cdra_clip_adam(float* params, const float* grads, float* m, float* v, const 
     }
     CDRA_LAUNCH(adam_kernel, dim3(blocks), dim3(256), 0, st, a);
     return check_launch("clip_adam");
+}
+
+int64_t cdra_launch_count(void) { return (int64_t)g_launches.load(); }
+void cdra_profile_enable(int on) { g_prof = on != 0; }
+void cdra_profile_reset(void) { g_entries.clear(); }
+int cdra_profile_report(char* buf, int cap) {
+    std::string s;
+#ifndef CDRA_EMU
+    for (auto& kv : g_entries) {
+        const char* name = nullptr;
+        if (cudaFuncGetName(&name, kv.first) != cudaSuccess || !name) name = "?";
+        char line[640];
+        snprintf(line, sizeof line, "%s\t%lld\t%.6f\t%.0f\n", name, kv.second.count, kv.second.ms, kv.second.bytes);
+        s += line;
+    }
+#endif
+    if (buf && cap > 0) { strncpy(buf, s.c_str(), cap - 1); buf[cap - 1] = 0; }
+    return (int)s.size();
 }
 
 int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst, void* stream) {

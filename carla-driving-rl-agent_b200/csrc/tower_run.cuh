@@ -44,6 +44,7 @@ void launch_pw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, int Rt, 
     a.in = in; a.K = l.K; a.Rt = Rt; a.w = c.params + l.w; a.bias = c.params + l.b; a.cm = cm;
     a.out = (T*)(c.ws + dst.data); a.ldo = dst.C; a.tb = tables_of(c, dst); a.bn = bn_of(c, l); a.do_stats = 1;
     dim3 grid(cdiv(Rt, kPwTM), kT, cdiv(cm.n, kPwTN));
+    prof_bytes(4.0 * Rt * (l.K + cm.n) * sizeof(T));          // read input once, write raw output once
     auto k = pw_fwd_kernel<T>;
     CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
 }
@@ -56,6 +57,7 @@ void launch_dw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, const Un
     a.out = (T*)(c.ws + dst.data); a.tb = tables_of(c, dst); a.bn = bn_of(c, l);
     const long long items = (long long)a.B * u.Ho * u.Wo * (C / 2);
     dim3 grid(cdiv(items, 256 * kDwItems), kT);
+    prof_bytes(4.0 * a.B * ((double)u.Hi * u.Wi + (double)u.Ho * u.Wo) * C * sizeof(T));
     auto k = dw_fwd_kernel<T>;
     CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
 }
@@ -71,6 +73,7 @@ void tower_forward(const RunCtx& c, const TIn* image) {
         a.w = c.params + p.stem.w; a.bias = c.params + p.stem.b; a.out = (T*)(c.ws + ts.data);
         a.tb = tables_of(c, ts); a.bn = bn_of(c, p.stem);
         dim3 grid(cdiv(ts.Rt, 128 * kStemPPT), kT);
+        prof_bytes(4.0 * B * ((double)p.H * p.W * 3 * sizeof(TIn) + (double)p.Hs * p.Ws * kStemC * sizeof(T)));
         auto k = stem_fwd_kernel<T, TIn>;
         CDRA_LAUNCH(k, grid, dim3(128), 0, c.stream, a);
     }

@@ -121,6 +121,15 @@ int cdra_clip_adam(float* params, const float* grads, float* m, float* v, const 
 /* utils.data_to_batches gather (rl/utils.py:365-393): dst[i] = src[index[i]] for rows of row_bytes. */
 int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst, void* stream);
 
+/* Launch accounting (bench.py's `gpu_launches`) and optional per-kernel CUDA-event timing on the launch
+ * stream (bench.py's live roofline numbers).  Profiling serialises every launch; never leave it on
+ * inside a timed region.  cdra_profile_report writes "name\tcount\ttotal_ms\talgorithmic_bytes\n" lines
+ * and returns the number of bytes the full report needs. */
+int64_t cdra_launch_count(void);
+void cdra_profile_enable(int on);
+void cdra_profile_reset(void);
+int cdra_profile_report(char* buf, int cap);
+
 #ifdef __cplusplus
 }
 #endif

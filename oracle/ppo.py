@@ -76,13 +76,20 @@ def end_trajectory(rewards, values_be, last_value_be, gamma, lambda_, scale):
     rewards = np.asarray(rewards, np.float32)
     values_be = np.asarray(values_be, np.float32)
     last = np.asarray(last_value_be, np.float32)
-    v_T = np.float32(last[0] * np.power(np.float32(10.0), last[1], dtype=np.float32))
+
+    def pow10(e):
+        # tf.pow(10.0, e) on CPU is Eigen's scalar std::pow(float, float) [lib], i.e. glibc powf, which is
+        # correctly rounded; numpy's float32 `power` is a SIMD kernel that is up to 1 ulp off, so the
+        # oracle evaluates in float64 and rounds once.
+        return np.power(10.0, np.asarray(e, np.float64)).astype(np.float32)
+
+    v_T = np.float32(last[0] * pow10(last[1]))
     r = np.concatenate([rewards, [v_T]]).astype(np.float32)
     vbe = np.concatenate([values_be, last[None]], axis=0)
     returns = discount_cumsum(r, gamma)[:-1].astype(np.float32)
     dec = [decompose_number(x) for x in returns]
     returns_be = np.array(dec, np.float32).reshape(-1, 2)
-    v = (vbe[:, 0] * np.power(np.float32(10.0), vbe[:, 1], dtype=np.float32)).astype(np.float32)
+    v = (vbe[:, 0] * pow10(vbe[:, 1])).astype(np.float32)
     g = np.float32(gamma)
     deltas = ((r[:-1] + g * v[1:]).astype(np.float32) - v[:-1]).astype(np.float32)
     adv = discount_cumsum(deltas, gamma * lambda_).astype(np.float32)

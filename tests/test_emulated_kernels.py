@@ -1,0 +1,146 @@
+"""CPU logic checks of the library's plain-CUDA kernels through the SIMT emulator (tests/emu/), against
+the oracle, at sizes the emulator finishes in seconds.  These exercise indexing / tiling / channel-map /
+BatchNorm bookkeeping logic only; the parity tests proper run on the GPU (test_gpu_parity.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model, ppo, spec
+from tests import common as C
+
+B, H, W = 3, 42, 58      # stem 20x28 -> pool 10x14 -> 5x7 -> 3x4 -> 2x2
+
+
+@pytest.fixture(scope='module')
+def eng(built_libs):
+    from cdra.engine import Engine
+    e = Engine(B, H, W, dtype='f32', image_u8=True, device='cpu', emulated=True)
+    return e
+
+
+@pytest.fixture(scope='module')
+def params():
+    return C.fresh_params(torch.float64)
+
+
+def test_arena_layout_matches_oracle_spec(eng):
+    for arena, state, pspec in ((eng.dyn, eng.dyn_state, spec.dynamics_params()), (eng.pol, eng.pol_state, spec.head_params('policy')),
+                                (eng.val, eng.val_state, spec.head_params('value'))):
+        tr, nt, st, ns = spec.split_layout(pspec)
+        assert arena.names == list(tr) and arena.size == nt
+        assert state.names == list(st) and state.size == ns
+        for n, (off, shape) in tr.items():
+            i = arena.index[n]
+            assert arena.offsets[i] == off and arena.shapes[i] == tuple(shape)
+
+
+def test_forward_taps_and_moving_stats(eng, params):
+    dyn, pol, val = params
+    C.load_engine(eng, dyn, pol, val)
+    obs = C.synthetic_obs(B, H, W, seed=5)
+    out = eng.dynamics_forward(obs).clone()
+    taps, bs = {}, model.BNState()
+    ref = model.dynamics_forward(dyn, C.oracle_obs(obs), True, bs, taps)
+    for k in ('tower.stem', 'tower.pool', 'tower.s1.u0.pw1', 'tower.s1.u0.dw', 'tower.s1.u0.scdw', 'tower.s1.u1.pw1',
+              'tower.s2.u0.pw1', 'tower.s3.u3.dw', 'tower.head'):
+        assert C.rel_max(eng.tensor(k)[:B], taps[k]) < 2e-4, k
+    assert C.rel_max(eng.tensor('tower.gap'), taps['tower.gap']) < 5e-4
+    assert C.rel_max(eng.tensor('dynamics_in'), taps['dynamics_in']) < 5e-4
+    assert C.rel_max(out, ref) < 1e-3
+    new = bs.apply_moving(dyn)
+    got = eng.dyn_state.to_dict()
+    assert max((got[k].double() - new[k]).abs().max().item() for k in got) < 1e-5
+
+
+def test_channel_shuffle_is_bit_exact(eng, params):
+    """the shortcut half of a stride-1 unit is a pure index permutation of the input's left half"""
+    dyn, pol, val = params
+    C.load_engine(eng, dyn, pol, val)
+    eng.dynamics_forward(C.synthetic_obs(B, H, W, seed=6))
+    x, y = eng.tensor('tower.s1.u0.out'), eng.tensor('tower.s1.u1.out')
+    c = x.shape[-1]
+    perm = model.shuffle_perm(c)                       # out[j] = concat[perm[j]]
+    for j, q in enumerate(perm):
+        if q < c // 2:                                  # concat position q < C/2 is the shortcut = x[..., q]
+            assert torch.equal(y[..., j], x[..., q])
+
+
+def test_policy_pass_gradients(eng, params):
+    dyn, pol, val = params
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = C.synthetic_obs(B, H, W, seed=7), C.synthetic_batch(B, seed=8)
+    sc = C.policy_step_engine(eng, obs, bt)
+    ref = C.policy_step_oracle(dyn, pol, obs, bt)
+    assert abs(sc[0].item() - ref['loss'].item()) < 1e-4 * max(1.0, abs(ref['loss'].item()))
+    names = ['loss_total', 'loss_policy', 'loss_entropy', 'loss_speed_policy', 'loss_similarity_policy', 'ratio', 'log_prob',
+             'entropy', 'speed_pi', 'similarity_pi']
+    for i, n in enumerate(names):
+        assert abs(sc[i].item() - ref['scalars'][n].item()) < 2e-4 * max(1.0, abs(ref['scalars'][n].item())), n
+    rows = C.grad_report(eng.pol, eng.g_pol, ref['g_head'])
+    assert max(r[2] for r in rows) < 1e-2      # BatchNorm over B = 3 rows amplifies fp32 rounding
+    rows = C.grad_report(eng.dyn, eng.g_dyn, ref['g_dyn'])
+    tail = [r for r in rows if not r[0].startswith('tower.')]
+    assert max(r[2] for r in tail) < 2e-2, sorted(tail, key=lambda r: -r[2])[:3]
+    # ReLU6 masks can flip between fp32 kernels and the fp64 oracle at this tiny batch (BatchNorm over
+    # <= 12 values amplifies rounding): judge the tower by relative L2, which a single flip barely moves
+    l2 = sorted(r[1] for r in rows)
+    assert l2[len(l2) // 2] < 2e-2 and l2[-1] < 0.25, (l2[len(l2) // 2], l2[-1])
+
+
+def test_value_pass_gradients(eng, params):
+    dyn, pol, val = params
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = C.synthetic_obs(B, H, W, seed=9), C.synthetic_batch(B, seed=10)
+    sc = C.value_step_engine(eng, obs, bt)
+    ref = C.value_step_oracle(dyn, val, obs, bt)
+    assert abs(sc[0].item() - ref['loss'].item()) < 1e-4 * max(1.0, abs(ref['loss'].item()))
+    rows = C.grad_report(eng.val, eng.g_val, ref['g_head'])
+    assert max(r[2] for r in rows) < 1e-2
+    rows = C.grad_report(eng.dyn, eng.g_dyn, ref['g_dyn'])
+    l2 = sorted(r[1] for r in rows)
+    assert l2[len(l2) // 2] < 2e-2 and l2[-1] < 0.25
+
+
+def test_gae_returns_exponents_bit_exact(eng):
+    rng = np.random.RandomState(0)
+    bs, T = 6, 41
+    rew = (rng.randn(bs, T) * 2 + 1).clip(-10, 30).astype('f')
+    vbe = np.stack([rng.rand(bs, T) * 2 - 1, rng.rand(bs, T) * 6], -1).astype('f')
+    last = np.stack([rng.rand(bs) * 2 - 1, rng.rand(bs) * 6], -1).astype('f')
+    last[0] = 0                                         # terminal state: CARLANetwork.last_value zeros (networks.py:171)
+    rb, adv = eng.gae(torch.tensor(rew), torch.tensor(vbe), torch.tensor(last), 0.9999, 0.999, 2.0)
+    for i in range(bs):
+        r_ref, a_ref, _ = ppo.end_trajectory(rew[i], vbe[i], last[i], 0.9999, 0.999, 2.0)
+        assert np.array_equal(rb[i].numpy(), r_ref)     # base and exponent bit-exact (sequential fp64 filter)
+        assert np.abs(adv[i].numpy() - a_ref).max() < 5e-7 * 2.0
+
+
+def test_clip_adam_three_steps(eng):
+    arena = eng.val
+    g = torch.Generator().manual_seed(3)
+    p0 = {n: torch.randn(s, generator=g) for n, s in zip(arena.names, arena.shapes)}
+    g0 = {n: torch.randn(s, generator=g) * (3.0 if i % 2 else 0.01) for i, (n, s) in enumerate(zip(arena.names, arena.shapes))}
+    arena.load_dict(p0)
+    for n in arena.names:
+        arena.view(n, eng.g_val).copy_(g0[n])
+    eng.adam['val'][0].zero_(); eng.adam['val'][1].zero_(); eng.adam_step['val'] = 0
+    pr = {k: v.clone().double() for k, v in p0.items()}
+    m = {k: torch.zeros_like(v) for k, v in pr.items()}
+    v = {k: torch.zeros_like(t) for k, t in pr.items()}
+    for step in (1, 2, 3):
+        eng.clip_adam('val', 3e-4, clip_norm=1.0)
+        ppo.apply_step(pr, {k: t.double() for k, t in g0.items()}, m, v, step, 3e-4, clip=1.0)
+    got = arena.to_dict()
+    assert max((got[k].double() - pr[k]).abs().max().item() for k in got) < 2e-6
+
+
+def test_gather_rows(eng):
+    src = torch.arange(7 * 48, dtype=torch.uint8).view(7, 48).contiguous()
+    idx = torch.tensor([5, 0, 3, 3], dtype=torch.int64)
+    out = torch.empty(4, 48, dtype=torch.uint8)
+    eng.gather_rows(src, idx, out)
+    assert torch.equal(out, src[idx])
+    src = torch.randn(9, 5)
+    out = torch.empty(3, 5)
+    eng.gather_rows(src, torch.tensor([8, 1, 4]), out)
+    assert torch.equal(out, src[[8, 1, 4]])

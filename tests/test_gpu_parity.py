@@ -1,0 +1,221 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI, against the oracle on the same
+seeded inputs (SURVEY §8c,d).  fp32 "parity mode" is compared with the fp64 oracle; bf16 "perf mode"
+against the same oracle with bf16-level tolerances; full-size runs are checked through
+size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model, ppo, spec
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+
+H, W = 90, 120
+
+
+def _engine(B, dtype, h=H, w=W):
+    from cdra.engine import Engine
+    return Engine(B, h, w, dtype=dtype, image_u8=True, device='cuda')
+
+
+def _dev(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+@pytest.fixture(scope='module')
+def params():
+    return C.fresh_params(torch.float64)
+
+
+TAPS = ('tower.stem', 'tower.pool', 'tower.s1.u0.pw1', 'tower.s1.u0.dw', 'tower.s1.u0.scdw', 'tower.s1.u1.pw1', 'tower.s1.u3.dw',
+        'tower.s2.u0.pw1', 'tower.s2.u4.dw', 'tower.s3.u0.scdw', 'tower.s3.u3.dw', 'tower.head')
+
+
+def test_forward_fp32_matches_oracle(built_libs, params):
+    B = 8
+    dyn, pol, val = params
+    eng = _engine(B, 'f32')
+    C.load_engine(eng, dyn, pol, val)
+    obs = C.synthetic_obs(B, H, W, seed=1234)
+    out = eng.dynamics_forward(_dev(obs)).clone()
+    torch.cuda.synchronize()
+    taps, bs = {}, model.BNState()
+    ref = model.dynamics_forward(dyn, C.oracle_obs(obs), True, bs, taps)
+    for k in TAPS:
+        assert C.rel_max(eng.tensor(k)[:B], taps[k]) < 1e-4, k             # fp32 tolerance: 1e-4 of the tensor's max
+    assert C.rel_max(eng.tensor('tower.gap'), taps['tower.gap']) < 1e-4
+    assert C.rel_max(out, ref) < 2e-4
+    new, got = bs.apply_moving(dyn), eng.dyn_state.to_dict()
+    assert max(C.rel_max(got[k], new[k]) for k in got) < 1e-5
+    # index ops are bit-exact: the shortcut half of a stride-1 unit is a permutation of the input's left half
+    x, y = eng.tensor('tower.s2.u0.out'), eng.tensor('tower.s2.u1.out')
+    c = x.shape[-1]
+    for j, q in enumerate(model.shuffle_perm(c)):
+        if q < c // 2:
+            assert torch.equal(y[..., j], x[..., q])
+
+
+def test_forward_fp32_trained_weights(built_libs):
+    """same check on the reference's shipped stage-s5-curriculum agent (realistic BN statistics / saturation)"""
+    B = 4
+    dyn, pol, val = C.trained_params(torch.float64)
+    eng = _engine(B, 'f32')
+    C.load_engine(eng, dyn, pol, val)
+    obs = C.synthetic_obs(B, H, W, seed=77)
+    out = eng.dynamics_forward(_dev(obs)).clone()
+    ref = model.dynamics_forward(dyn, C.oracle_obs(obs), True)
+    assert C.rel_max(out, ref) < 1e-3
+
+
+def _check_grads(eng, arena, flat, ref_grads, head):
+    rows = C.grad_report(arena, flat, ref_grads)
+    if head:
+        assert max(r[2] for r in rows) < 1e-3, sorted(rows, key=lambda r: -r[2])[:3]
+        return
+    tail = [r for r in rows if not r[0].startswith('tower.')]
+    assert max(r[2] for r in tail) < 2e-3, sorted(tail, key=lambda r: -r[2])[:3]
+    # tower: ReLU6 / max-pool decisions that sit within rounding distance of a boundary may flip between
+    # the fp32 kernels and the fp64 oracle (any two implementations differ there); relative L2 is robust
+    l2 = sorted(r[1] for r in rows)
+    assert l2[len(l2) // 2] < 2e-3 and l2[int(len(l2) * 0.9)] < 2e-2 and l2[-1] < 0.2, (l2[len(l2) // 2], l2[-1])
+
+
+def test_policy_pass_fp32(built_libs, params):
+    B = 8
+    dyn, pol, val = params
+    eng = _engine(B, 'f32')
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = C.synthetic_obs(B, H, W, seed=21), C.synthetic_batch(B, seed=22)
+    sc = C.policy_step_engine(eng, _dev(obs), _dev(bt)).cpu()
+    ref = C.policy_step_oracle(dyn, pol, obs, bt)
+    # north-star tolerance: PPO loss within rtol 1e-4 of the reference arithmetic
+    assert abs(sc[0].item() - ref['loss'].item()) <= 1e-4 * abs(ref['loss'].item()) + 1e-6
+    names = ['loss_total', 'loss_policy', 'loss_entropy', 'loss_speed_policy', 'loss_similarity_policy', 'ratio', 'log_prob',
+             'entropy', 'speed_pi', 'similarity_pi']
+    for i, n in enumerate(names):
+        assert abs(sc[i].item() - ref['scalars'][n].item()) <= 1e-4 * abs(ref['scalars'][n].item()) + 2e-6, n
+    _check_grads(eng, eng.pol, eng.g_pol, ref['g_head'], True)
+    _check_grads(eng, eng.dyn, eng.g_dyn, ref['g_dyn'], False)
+
+
+def test_value_pass_fp32(built_libs, params):
+    B = 8
+    dyn, pol, val = params
+    eng = _engine(B, 'f32')
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = C.synthetic_obs(B, H, W, seed=31), C.synthetic_batch(B, seed=32)
+    sc = C.value_step_engine(eng, _dev(obs), _dev(bt)).cpu()
+    ref = C.value_step_oracle(dyn, val, obs, bt)
+    assert abs(sc[0].item() - ref['loss'].item()) <= 1e-4 * abs(ref['loss'].item()) + 1e-6
+    _check_grads(eng, eng.val, eng.g_val, ref['g_head'], True)
+    _check_grads(eng, eng.dyn, eng.g_dyn, ref['g_dyn'], False)
+
+
+def test_bf16_mode_tracks_oracle(built_libs, params):
+    """perf mode: bf16 activation storage, fp32 accumulate -> bf16-level agreement with the fp64 oracle"""
+    B = 8
+    dyn, pol, val = params
+    eng = _engine(B, 'bf16')
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = C.synthetic_obs(B, H, W, seed=41), C.synthetic_batch(B, seed=42)
+    sc = C.policy_step_engine(eng, _dev(obs), _dev(bt)).cpu()
+    ref = C.policy_step_oracle(dyn, pol, obs, bt)
+    assert C.rel_l2(eng.x512, ref['x512']) < 5e-2
+    assert abs(sc[0].item() - ref['loss'].item()) < 5e-2 * max(1.0, abs(ref['loss'].item()))
+    rows = C.grad_report(eng.dyn, eng.g_dyn, ref['g_dyn'])
+    l2 = sorted(r[1] for r in rows)
+    assert l2[len(l2) // 2] < 0.15, l2[len(l2) // 2]
+
+
+def test_gae_full_size_bit_exact(built_libs):
+    """BASELINE config sizes: bs 512 x T 256 trajectories; exponents and bases bit-exact vs scipy.lfilter path"""
+    eng = _engine(2, 'f32', 42, 58)
+    rng = np.random.RandomState(0)
+    bs, T = 512, 256
+    rew = (rng.randn(bs, T) * 2 + 1).clip(-10, 30).astype('f')
+    vbe = np.stack([rng.rand(bs, T) * 2 - 1, rng.rand(bs, T) * 6], -1).astype('f')
+    last = np.stack([rng.rand(bs) * 2 - 1, rng.rand(bs) * 6], -1).astype('f')
+    last[::7] = 0
+    rb, adv = eng.gae(torch.tensor(rew).cuda(), torch.tensor(vbe).cuda(), torch.tensor(last).cuda(), 0.9999, 0.999, 2.0)
+    rb, adv = rb.cpu().numpy(), adv.cpu().numpy()
+    for i in range(0, bs, 3):
+        r_ref, a_ref, _ = ppo.end_trajectory(rew[i], vbe[i], last[i], 0.9999, 0.999, 2.0)
+        assert np.array_equal(rb[i][:, 1], r_ref[:, 1])                     # integer exponents: exact
+        assert np.abs(rb[i][:, 0] - r_ref[:, 0]).max() <= 1.2e-7           # bases: <= 1 ulp (device pow)
+        assert np.abs(adv[i] - a_ref).max() < 1e-6
+    # long-horizon stress (config 5): T = 512
+    rb2, adv2 = eng.gae(torch.tensor(np.tile(rew[:8], (1, 2))).cuda(), torch.tensor(np.tile(vbe[:8], (1, 2, 1))).cuda(),
+                        torch.tensor(last[:8]).cuda(), 0.9999, 0.999, 2.0)
+    r_ref, a_ref, _ = ppo.end_trajectory(np.tile(rew[3], 2), np.tile(vbe[3], (2, 1)), last[3], 0.9999, 0.999, 2.0)
+    assert np.array_equal(rb2[3].cpu().numpy()[:, 1], r_ref[:, 1])
+    assert np.abs(adv2[3].cpu().numpy() - a_ref).max() < 1e-6
+
+
+def test_clip_adam_and_gather(built_libs):
+    eng = _engine(2, 'f32', 42, 58)
+    arena = eng.pol
+    g = torch.Generator().manual_seed(3)
+    p0 = {n: torch.randn(s, generator=g) for n, s in zip(arena.names, arena.shapes)}
+    g0 = {n: torch.randn(s, generator=g) * (3.0 if i % 2 else 0.01) for i, (n, s) in enumerate(zip(arena.names, arena.shapes))}
+    arena.load_dict(p0)
+    for n in arena.names:
+        arena.view(n, eng.g_pol).copy_(g0[n])
+    pr = {k: v.clone().double() for k, v in p0.items()}
+    m = {k: torch.zeros_like(v) for k, v in pr.items()}
+    v = {k: torch.zeros_like(t) for k, t in pr.items()}
+    for step in (1, 2, 3):
+        eng.clip_adam('pol', 3e-4, clip_norm=1.0)
+        ppo.apply_step(pr, {k: t.double() for k, t in g0.items()}, m, v, step, 3e-4, clip=1.0)
+    got = arena.to_dict()
+    assert max((got[k].double().cpu() - pr[k]).abs().max().item() for k in got) < 2e-6
+    # dynamics optimiser: no clipping (core/carla_agent.py:386-388)
+    eng.g_dyn.normal_(generator=None)
+    before = eng.dyn.flat.clone()
+    eng.clip_adam('dyn', 1e-3)
+    step = (eng.dyn.flat - before).abs()
+    assert abs(step.max().item() - 1e-3) < 1e-5           # first Adam step has magnitude lr for every coordinate
+    src = torch.randint(0, 256, (64, 4 * 90 * 120 * 3), dtype=torch.uint8, device='cuda')
+    idx = torch.randperm(64, device='cuda')[:32]
+    out = torch.empty(32, src.shape[1], dtype=torch.uint8, device='cuda')
+    eng.gather_rows(src, idx, out)
+    assert torch.equal(out, src[idx])
+
+
+def test_full_size_properties_bf16(built_libs, params):
+    """BASELINE config 2 minibatch (B = 512, 90x120, bf16): size-independent properties"""
+    B = 512
+    dyn, pol, val = params
+    eng = _engine(B, 'bf16')
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = _dev(C.synthetic_obs(B, H, W, seed=51)), _dev(C.synthetic_batch(B, seed=52))
+    sc = C.policy_step_engine(eng, obs, bt)
+    assert torch.isfinite(sc[:10]).all() and torch.isfinite(eng.g_dyn).all() and torch.isfinite(eng.g_pol).all()
+    # (1) every BatchNorm output is normalised per (slice, channel): mean 0 / variance 1 before gamma, beta
+    raw = eng.tensor('tower.s2.u3.pw1').float().view(4, B * 6 * 8, -1)
+    mu, var = raw.mean(1), raw.var(1, unbiased=False)
+    g_, b_ = eng.dyn.view('tower.s2.u3.pw1.g'), eng.dyn.view('tower.s2.u3.pw1.be')
+    z = (raw - mu[:, None]) * torch.rsqrt(var[:, None] + 1e-3)
+    assert z.mean(1).abs().max() < 1e-3 and (z.var(1, unbiased=False) - var / (var + 1e-3)).abs().max() < 1e-2
+    # (2) channel shuffle / pass-through is bit-exact at full size
+    x, y = eng.tensor('tower.s3.u1.out'), eng.tensor('tower.s3.u2.out')
+    c = x.shape[-1]
+    perm = model.shuffle_perm(c)
+    for j in range(0, c, 7):
+        if perm[j] < c // 2:
+            assert torch.equal(y[..., j], x[..., perm[j]])
+    # (3) gradients of parameters that only shift a BatchNorm input are (numerically) zero
+    gb = eng.dyn.view('tower.s1.u1.pw1.b', eng.g_dyn).abs().max().item()
+    gw = eng.dyn.view('tower.s1.u1.pw1.w', eng.g_dyn).abs().max().item()
+    assert gb < 2e-2 * gw
+    # (4) backward is linear in d_out: scaling the upstream gradient scales every parameter gradient
+    g1 = eng.g_dyn.clone()
+    eng.dynamics_backward(obs, eng.d_x512 * 2.0)
+    assert C.rel_l2(eng.g_dyn, 2.0 * g1) < 2e-2
+    # (5) a few SGD steps on a fixed minibatch reduce the value loss
+    losses = []
+    for _ in range(4):
+        s = C.value_step_engine(eng, obs, bt)
+        losses.append(s[0].item())
+        eng.clip_adam('dyn', 3e-4); eng.clip_adam('val', 3e-4, clip_norm=1.0)
+    assert losses[-1] < losses[0]
