@@ -51,7 +51,11 @@ class Arena:
 
 
 class Engine:
-    def __init__(self, batch, height=90, width=120, dtype='bf16', image_u8=True, device='cuda', emulated=False):
+    def __init__(self, batch, height=90, width=120, dtype='bf16', image_u8=True, device='cuda', emulated=False,
+                 share=None):
+        """`share`: another Engine whose parameter / state / gradient / Adam arenas this one reuses (a plan is
+        specific to one batch size; siblings let one network serve several, e.g. a remainder minibatch or B=1
+        rollout inference)."""
         self.lib = _lib.load(emulated=emulated)
         self.device = torch.device(device)
         if not emulated and self.device.type != 'cuda':
@@ -65,19 +69,28 @@ class Engine:
         _lib.check(self.lib, self.lib.cdra_plan_create(C.byref(cfg), C.byref(self.plan)), 'plan_create')
         self.ws_bytes = int(self.lib.cdra_plan_workspace_bytes(self.plan))
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
-        mk = lambda w: Arena(self.lib, self.plan, w, self.device)
-        self.dyn, self.dyn_state = mk(_lib.ARENA_DYN_PARAMS), mk(_lib.ARENA_DYN_STATE)
-        self.pol, self.pol_state = mk(_lib.ARENA_POL_PARAMS), mk(_lib.ARENA_POL_STATE)
-        self.val, self.val_state = mk(_lib.ARENA_VAL_PARAMS), mk(_lib.ARENA_VAL_STATE)
-        z = lambda a: torch.zeros_like(a.flat)
-        self.g_dyn, self.g_pol, self.g_val = z(self.dyn), z(self.pol), z(self.val)
-        self.adam = {k: (z(a), z(a)) for k, a in (('dyn', self.dyn), ('pol', self.pol), ('val', self.val))}
-        self.adam_step = dict(dyn=0, pol=0, val=0)
-        self.norms = {k: torch.zeros(len(a.names), dtype=torch.float32, device=self.device)
-                      for k, a in (('pol', self.pol), ('val', self.val), ('dyn', self.dyn))}
+        if share is not None:
+            for k in ('dyn', 'dyn_state', 'pol', 'pol_state', 'val', 'val_state', 'g_dyn', 'g_pol', 'g_val', 'adam',
+                      'adam_step', 'norms'):
+                setattr(self, k, getattr(share, k))
+        else:
+            mk = lambda w: Arena(self.lib, self.plan, w, self.device)
+            self.dyn, self.dyn_state = mk(_lib.ARENA_DYN_PARAMS), mk(_lib.ARENA_DYN_STATE)
+            self.pol, self.pol_state = mk(_lib.ARENA_POL_PARAMS), mk(_lib.ARENA_POL_STATE)
+            self.val, self.val_state = mk(_lib.ARENA_VAL_PARAMS), mk(_lib.ARENA_VAL_STATE)
+            z = lambda a: torch.zeros_like(a.flat)
+            self.g_dyn, self.g_pol, self.g_val = z(self.dyn), z(self.pol), z(self.val)
+            self.adam = {k: (z(a), z(a)) for k, a in (('dyn', self.dyn), ('pol', self.pol), ('val', self.val))}
+            self.adam_step = dict(dyn=0, pol=0, val=0)
+            self.norms = {k: torch.zeros(len(a.names), dtype=torch.float32, device=self.device)
+                          for k, a in (('pol', self.pol), ('val', self.val), ('dyn', self.dyn))}
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
         self.x512, self.d_x512 = f(batch, 512), f(batch, 512)
         self.scalars, self.head_out = f(16), f(batch, 8)
+
+    def sibling(self, batch):
+        return Engine(batch, self.H, self.W, dtype=self.dtype, image_u8=self.image_u8, device=self.device,
+                      emulated=self.emulated, share=self)
 
     def __del__(self):
         try:

@@ -54,6 +54,12 @@ CDRA_DEV void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 CDRA_DEV float rnd(float v, const float*) { return v; }
 CDRA_DEV float rnd(float v, const bf16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// two adjacent channels in one access (element index must be even)
+CDRA_DEV float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+CDRA_DEV float2 ld2(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+CDRA_DEV void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+CDRA_DEV void st2(bf16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+
 CDRA_DEV float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6.f); }
 
 // A channel sub-range of an NHWC activation tensor whose values are stored *raw* (pre-BatchNorm);

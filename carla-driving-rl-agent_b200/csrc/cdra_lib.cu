@@ -4,6 +4,7 @@
 #include <cmath>
 #include "plan.h"
 #include "tower_run.cuh"
+#include "tower_opt.cuh"
 #include "tail.cuh"
 #include "ppo.cuh"
 
@@ -144,7 +145,7 @@ static void launch_bstat(const RunCtx& c, const WsTensor& t, int coff, int C, bo
     BstatArgs<T> a;
     a.dA = (const T*)(c.ws + t.grad); a.R = (const T*)(c.ws + t.data); a.ld = t.C; a.coff = coff; a.C = C; a.Rt = t.Rt;
     a.clamp = clamp ? 1 : 0; a.tb = tables_of(c, t);
-    int rows = 4096 / C; if (rows < 8) rows = 8;
+    int rows = 16384 / C; if (rows < 64) rows = 64;
     a.rows_per_block = rows;
     prof_bytes(4.0 * t.Rt * C * 2 * sizeof(T));                // read dA and R once
     auto k = bstat_kernel<T>;
@@ -162,6 +163,18 @@ static void launch_pw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
     a.dw = c.grads + l.w; a.db = c.grads + l.b; a.dgamma = c.grads + l.g; a.dbeta = c.grads + l.be;
     int splits = (int)cdiv(Rt, 2048); if (splits < 1) splits = 1; if (splits > 64) splits = 64;
     a.row_splits = splits;
+#ifndef CDRA_EMU
+    if constexpr (std::is_same<T, bf16>::value) {               // tensor-core path (pw_mma.cuh)
+        if (need_dx) {
+            PwMmaBwdArgs pa; pa.a = a; pa.wn = (const bf16*)(c.ws + l.wn); pa.Np = l.Np;
+            prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));
+            CDRA_LAUNCH(pw_dgrad_mma_kernel, dim3(cdiv(Rt, kMmTM), kT, cdiv(l.K, kMmTN)), dim3(256), 0, c.stream, pa);
+        }
+        prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));
+        CDRA_LAUNCH(pw_wgrad_mma_kernel, dim3(cdiv(l.K + 1, kWgKT), cdiv(cm.n, kWgNT), kT * splits), dim3(256), 0, c.stream, a);
+        return;
+    }
+#endif
     if (need_dx) {
         prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));  // read dA, R; write dX
         auto k = pw_dgrad_kernel<T>;
@@ -181,12 +194,14 @@ static void launch_dw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
     a.pad_t = u.pad_t; a.pad_l = u.pad_l; a.w = c.params + l.w;
     a.dx = dx; a.ldx = ldx; a.coffx = coffx; a.accumulate = accumulate ? 1 : 0;
     a.dw = c.grads + l.w; a.db = c.grads + l.b; a.dgamma = c.grads + l.g; a.dbeta = c.grads + l.be;
+    int lanes_c = ((C / 2) + 31) & ~31; if (lanes_c > 256) lanes_c = 256;
+    a.ppb = 16 * (256 / lanes_c); a.ppb_w = 64 * (256 / lanes_c);
     prof_bytes(4.0 * a.B * (2.0 * u.Ho * u.Wo + (double)u.Hi * u.Wi) * C * sizeof(T));
     auto k1 = dw_dgrad_kernel<T>;
-    CDRA_LAUNCH(k1, dim3(cdiv((long long)a.B * u.Hi * u.Wi * (C / 2), 256), kT), dim3(256), 0, c.stream, a);
+    CDRA_LAUNCH(k1, dim3(cdiv((long long)a.B * u.Hi * u.Wi, a.ppb), kT), dim3(256), 0, c.stream, a);
     prof_bytes(4.0 * a.B * (2.0 * u.Ho * u.Wo + (double)u.Hi * u.Wi) * C * sizeof(T));
     auto k2 = dw_wgrad_kernel<T>;
-    CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho * u.Wo * (C / 2), 256 * kDwItems), kT), dim3(256), 0, c.stream, a);
+    CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho * u.Wo, a.ppb_w), kT), dim3(256), 0, c.stream, a);
 }
 
 template <typename T, typename TIn>
@@ -236,11 +251,13 @@ static void tower_backward(const RunCtx& c, const TIn* image) {
     {   // maxpool + stem
         const WsTensor& ts = p.tensors[p.t_stem];
         const WsTensor& tp = p.tensors[p.t_pool];
-        PoolBwdArgs<T> a;
-        a.in = view_of(c, ts, 0, true); a.dpool = (const T*)(c.ws + tp.grad); a.dstem = (T*)(c.ws + ts.grad);
+        PoolBwd2Args<T> a;
+        a.in = view_of(c, ts, 0, true); a.pool = (const T*)(c.ws + tp.data); a.dpool = (const T*)(c.ws + tp.grad);
+        a.dstem = (T*)(c.ws + ts.grad);
         a.B = B; a.Hi = p.Hs; a.Wi = p.Ws; a.Ho = p.Hp; a.Wo = p.Wp; a.C = kStemC; a.pad_t = p.pool_pad_t; a.pad_l = p.pool_pad_l;
-        auto k = pool_bwd_kernel<T>;
-        CDRA_LAUNCH(k, dim3(cdiv((long long)ts.Rt * kStemC, 256), kT), dim3(256), 0, c.stream, a);
+        prof_bytes(4.0 * B * ((double)p.Hs * p.Ws * 2 + (double)p.Hp * p.Wp * 2) * kStemC * sizeof(T));
+        auto k = pool_bwd2_kernel<T>;
+        CDRA_LAUNCH(k, dim3(cdiv((long long)ts.Rt * (kStemC / 2), 256), kT), dim3(256), 0, c.stream, a);
         launch_bstat<T>(c, ts, 0, kStemC, true);
         StemBwdArgs<T, TIn> s;
         s.img = image; s.B = B; s.H = p.H; s.W = p.W; s.Ho = p.Hs; s.Wo = p.Ws;

@@ -131,6 +131,18 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
     p.zero_bytes = off;
     p.counters_off = alloc((size_t)(p.n_counters + 16) * 4);
     for (auto& t : p.tensors) if (t.tables) { t.aff = alloc((size_t)4 * t.C * 8); t.bnp = alloc((size_t)4 * t.C * 8); }
+    {   // bf16 weight copies for the tensor-core pointwise kernels
+        auto pw = [&](BnConv& l, int split) {
+            l.is_pw = true; l.split = split;
+            l.Kp = (l.K + 31) / 32 * 32; l.Np = (l.N + 31) / 32 * 32;
+            if (p.elem == 2) {
+                l.wt = alloc((size_t)((l.N + 7) / 8 * 8) * l.Kp * 2);
+                l.wn = alloc((size_t)((l.K + 7) / 8 * 8) * l.Np * 2);
+            }
+        };
+        for (auto& u : p.units) { pw(u.pw1, 0); pw(u.pw2, 1); if (u.stride == 2) pw(u.scpw, 1); }
+        pw(p.head, 0);
+    }
     for (auto& t : p.tensors) { t.data = alloc(t.bytes()); }
     for (auto& t : p.tensors) { t.grad = t.has_grad ? alloc(t.bytes()) : 0; }
     auto f32 = [&](const std::string& name, std::vector<int> dims) {

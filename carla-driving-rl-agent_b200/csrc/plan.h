@@ -35,6 +35,10 @@ struct BnConv {
     int64_t w = -1, b = -1, g = -1, be = -1;   // trainable arena
     int64_t mm = -1, mv = -1;                  // state arena
     int counter = -1;                          // ticket counter index
+    // pointwise convs in bf16 mode: per-step bf16 copies of the weights (workspace byte offsets), see pw_mma.cuh
+    bool is_pw = false;
+    int split = 0, Kp = 0, Np = 0;
+    size_t wt = 0, wn = 0;
 };
 
 struct WsTensor {       // activation tensor living in the workspace

@@ -1,0 +1,390 @@
+// bf16 tensor-core versions of the three pointwise-conv (1x1) kernels: forward, data gradient, weight
+// gradient (core/architectures.py:130,134,140,170 and their tape gradients).  Legacy-path MMA
+// (mma.sync.m16n8k16, fp32 accumulate) with register-staged, software-pipelined operand loads so that
+// the BatchNorm affine / ReLU6 / BN-backward transforms are applied on the way into shared memory.
+// Only compiled for the device (no emulator counterpart): the CUDA-core kernels in tower_fwd.cuh /
+// tower_bwd.cuh are the logic reference, and GPU tests compare both against the oracle.
+#pragma once
+#ifndef CDRA_EMU
+#include "tower_fwd.cuh"
+#include "tower_bwd.cuh"
+
+namespace cdra {
+
+CDRA_DEV uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+CDRA_DEV float2 unpack_bf16(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+CDRA_DEV void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+CDRA_DEV void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+CDRA_DEV void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// ---- bf16 copies of the pointwise weights, rebuilt once per forward (weights change every SGD step)
+//   wt [Np8][Kp32] : wt[j][k] = W[k][colmap_w(j)]   (B operand of the forward GEMM, k contiguous)
+//   wn [Kp8][Np32] : wn[k][j] = W[k][colmap_w(j)]   (B operand of the data-gradient GEMM, j contiguous)
+struct WPrepLayer { const float* w; bf16* wt; bf16* wn; int K, N, Kp, Np, split; };
+constexpr int kWPrepMax = 40;
+struct WPrepArgs { WPrepLayer l[kWPrepMax]; int n; };
+
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) wprep_kernel(WPrepArgs a) {
+    const WPrepLayer L = a.l[blockIdx.x];
+    ColMap cm{L.N, L.split, 0, 0};
+    const int Np8 = (L.N + 7) & ~7, Kp8 = (L.K + 7) & ~7;
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < Np8 * L.Kp; i += gridDim.y * 256) {
+        const int j = i / L.Kp, k = i - j * L.Kp;
+        L.wt[i] = __float2bfloat16_rn((j < L.N && k < L.K) ? L.w[(size_t)k * L.N + colmap_w(cm, j)] : 0.f);
+    }
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < Kp8 * L.Np; i += gridDim.y * 256) {
+        const int k = i / L.Np, j = i - k * L.Np;
+        L.wn[i] = __float2bfloat16_rn((j < L.N && k < L.K) ? L.w[(size_t)k * L.N + colmap_w(cm, j)] : 0.f);
+    }
+}
+
+constexpr int kMmTM = 128, kMmTN = 128, kMmKC = 32, kMmLd = kMmKC + 8;
+
+// ======================================================================================== forward
+struct PwMmaFwdArgs {
+    PwArgs<bf16> a;
+    const bf16* wt; int Kp;
+};
+
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
+    const PwArgs<bf16>& a = pa.a;
+    __shared__ __align__(16) bf16 smem[2 * kMmTM * kMmLd + 2 * kMmTN * kMmLd];     // As[2] | Bs[2]; reused as Cs
+    __shared__ float s_scale[480], s_shift[480];
+    __shared__ float s_sum[kMmTN], s_sq[kMmTN];
+    bf16* As = smem;
+    bf16* Bs = smem + 2 * kMmTM * kMmLd;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.y, row0 = blockIdx.x * kMmTM, col0 = blockIdx.z * kMmTN;
+    const int N = a.cm.n, K = a.K;
+    const int ncols = min(kMmTN, N - col0), nblk = (ncols + 7) >> 3;
+    for (int k = tid; k < pa.Kp; k += 256) {
+        float sc = 1.f, sh = 0.f;
+        if (a.in.aff && k < K) { const float2 f = a.in.aff[(size_t)t * a.in.ld + a.in.coff + k]; sc = f.x; sh = f.y; }
+        s_scale[k] = sc; s_shift[k] = sh;
+    }
+    if (tid < kMmTN) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+    __syncthreads();
+
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+    const int p = tid & 15, rb = tid >> 4;               // loader: k pair p, rows rb + 16 i
+    const bf16* in = (const bf16*)a.in.data;
+    const int clampf = a.in.clamp;
+    uint32_t ra[8], rbw[8];
+    auto load_chunk = [&](int k0) {
+        const int k = k0 + 2 * p;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row0 + rb + 16 * i;
+            uint32_t v = 0u;
+            if (r < a.Rt && k < K) {
+                const uint32_t raw = *reinterpret_cast<const uint32_t*>(in + ((size_t)t * a.Rt + r) * a.in.ld + a.in.coff + k);
+                float2 f = unpack_bf16(raw);
+                f.x = fmaf(f.x, s_scale[k], s_shift[k]); f.y = fmaf(f.y, s_scale[k + 1], s_shift[k + 1]);
+                if (clampf) { f.x = relu6f(f.x); f.y = relu6f(f.y); }
+                v = pack_bf16(f.x, f.y);
+            }
+            ra[i] = v;
+            const int n = col0 + rb + 16 * i;
+            rbw[i] = (rb + 16 * i < nblk * 8 && k < pa.Kp) ? *reinterpret_cast<const uint32_t*>(pa.wt + (size_t)n * pa.Kp + k) : 0u;
+        }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            *reinterpret_cast<uint32_t*>(As + (size_t)buf * kMmTM * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = ra[i];
+            *reinterpret_cast<uint32_t*>(Bs + (size_t)buf * kMmTN * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = rbw[i];
+        }
+    };
+    const int nchunks = (K + kMmKC - 1) / kMmKC;
+    load_chunk(0);
+    store_chunk(0);
+    __syncthreads();
+    for (int kc = 0; kc < nchunks; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < nchunks) load_chunk((kc + 1) * kMmKC);
+        const bf16* Ab = As + (size_t)buf * kMmTM * kMmLd;
+        const bf16* Bb = Bs + (size_t)buf * kMmTN * kMmLd;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t af[4];
+            ldsm_x4(af, Ab + (warp * 16 + (lane & 15)) * kMmLd + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+            for (int nb2 = 0; nb2 < 8; ++nb2) {
+                if (nb2 * 2 < nblk) {
+                    uint32_t bf[4];
+                    const int mi = lane >> 3;
+                    ldsm_x4(bf, Bb + (nb2 * 16 + (mi >> 1) * 8 + (lane & 7)) * kMmLd + ks * 16 + (mi & 1) * 8);
+                    mma_bf16(acc[nb2 * 2], af, bf[0], bf[1]);
+                    mma_bf16(acc[nb2 * 2 + 1], af, bf[2], bf[3]);
+                }
+            }
+        }
+        if (kc + 1 < nchunks) store_chunk(buf ^ 1);
+        __syncthreads();
+    }
+    // ---- epilogue: bias, stage the bf16 tile in shared memory, column statistics, coalesced store
+    constexpr int kCLd = kMmTN + 8;
+    bf16* Cs = smem;
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb) {
+        if (nb < nblk) {
+            const int j = nb * 8 + 2 * tg;
+            const float b0 = (col0 + j < N) ? a.bias[colmap_w(a.cm, col0 + j)] : 0.f;
+            const float b1 = (col0 + j + 1 < N) ? a.bias[colmap_w(a.cm, col0 + j + 1)] : 0.f;
+            *reinterpret_cast<uint32_t*>(Cs + (warp * 16 + g) * kCLd + j) = pack_bf16(acc[nb][0] + b0, acc[nb][1] + b1);
+            *reinterpret_cast<uint32_t*>(Cs + (warp * 16 + g + 8) * kCLd + j) = pack_bf16(acc[nb][2] + b0, acc[nb][3] + b1);
+        }
+    }
+    __syncthreads();
+    const int rows = min(kMmTM, a.Rt - row0);
+    {   // statistics over the stored (rounded) values: 2 threads per column
+        const int j = tid & 127, half = tid >> 7;
+        if (j < ncols) {
+            float s = 0.f, q = 0.f;
+            for (int r = half; r < rows; r += 2) { const float v = __bfloat162float(Cs[r * kCLd + j]); s += v; q = fmaf(v, v, q); }
+            atomicAdd(&s_sum[j], s); atomicAdd(&s_sq[j], q);
+        }
+    }
+    for (int i = tid; i < rows * ncols; i += 256) {
+        const int r = i / ncols, j = i - r * ncols;
+        a.out[((size_t)t * a.Rt + row0 + r) * a.ldo + colmap_c(a.cm, col0 + j)] = Cs[r * kCLd + j];
+    }
+    __syncthreads();
+    if (tid < ncols) {
+        double2* dst = a.tb.fst + (size_t)t * a.ldo + colmap_c(a.cm, col0 + tid);
+        atomicAdd(&dst->x, (double)s_sum[tid]);
+        atomicAdd(&dst->y, (double)s_sq[tid]);
+    }
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    if (last_block_ticket(a.bn.counter, total))
+        bn_finalize(a.cm, a.tb, a.ldo, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)a.Rt,
+                    a.bn.unbiased, a.bn.training, 256, tid);
+}
+
+// ======================================================================================== data gradient
+struct PwMmaBwdArgs {
+    PwBwdArgs<bf16> a;
+    const bf16* wn; int Np;          // [Kp8][Np] bf16
+};
+
+// dR for output column pair (j, j+1) of row `grow` (global row index), as packed bf16x2
+CDRA_DEV uint32_t load_dr_pair(const PwBwdArgs<bf16>& a, size_t grow, int j, int N, const BnCol& c0, const BnCol& c1, int ch0, int ch1) {
+    float d0 = 0.f, d1 = 0.f;
+    const size_t o = grow * a.ldo;
+    if (j < N) d0 = make_dr(__bfloat162float(a.dout[o + ch0]), __bfloat162float(a.out[o + ch0]), c0, a.clamp);
+    if (j + 1 < N) d1 = make_dr(__bfloat162float(a.dout[o + ch1]), __bfloat162float(a.out[o + ch1]), c1, a.clamp);
+    return pack_bf16(d0, d1);
+}
+
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
+    const PwBwdArgs<bf16>& a = pa.a;
+    __shared__ __align__(16) bf16 smem[2 * kMmTM * kMmLd + 2 * kMmTN * kMmLd];
+    bf16* As = smem;                                   // dR chunk   [row][n]
+    bf16* Bs = smem + 2 * kMmTM * kMmLd;               // W chunk    [k][n]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.y, row0 = blockIdx.x * kMmTM, k0t = blockIdx.z * kMmTN;
+    const int N = a.cm.n, K = a.K;
+    const int kcols = min(kMmTN, K - k0t), kblk = (kcols + 7) >> 3;
+    const double inv_n = 1.0 / (double)a.Rt;
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    const int p = tid & 15, rb = tid >> 4;
+    uint32_t ra[8], rbw[8];
+    auto load_chunk = [&](int n0) {
+        const int j = n0 + 2 * p;
+        BnCol c0, c1; int ch0 = 0, ch1 = 0;
+        if (j < N) { ch0 = colmap_c(a.cm, j); c0 = load_bncol(a.tb, a.ldo, t, ch0, inv_n); }
+        if (j + 1 < N) { ch1 = colmap_c(a.cm, j + 1); c1 = load_bncol(a.tb, a.ldo, t, ch1, inv_n); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row0 + rb + 16 * i;
+            ra[i] = (r < a.Rt && j < N) ? load_dr_pair(a, (size_t)t * a.Rt + r, j, N, c0, c1, ch0, ch1) : 0u;
+            const int kk = k0t + rb + 16 * i;
+            rbw[i] = (rb + 16 * i < kblk * 8 && j < pa.Np) ? *reinterpret_cast<const uint32_t*>(pa.wn + (size_t)kk * pa.Np + j) : 0u;
+        }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            *reinterpret_cast<uint32_t*>(As + (size_t)buf * kMmTM * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = ra[i];
+            *reinterpret_cast<uint32_t*>(Bs + (size_t)buf * kMmTN * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = rbw[i];
+        }
+    };
+    const int nchunks = (N + kMmKC - 1) / kMmKC;
+    load_chunk(0);
+    store_chunk(0);
+    __syncthreads();
+    for (int nc = 0; nc < nchunks; ++nc) {
+        const int buf = nc & 1;
+        if (nc + 1 < nchunks) load_chunk((nc + 1) * kMmKC);
+        const bf16* Ab = As + (size_t)buf * kMmTM * kMmLd;
+        const bf16* Bb = Bs + (size_t)buf * kMmTN * kMmLd;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t af[4];
+            ldsm_x4(af, Ab + (warp * 16 + (lane & 15)) * kMmLd + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+            for (int nb2 = 0; nb2 < 8; ++nb2) {
+                if (nb2 * 2 < kblk) {
+                    uint32_t bf[4];
+                    const int mi = lane >> 3;
+                    ldsm_x4(bf, Bb + (nb2 * 16 + (mi >> 1) * 8 + (lane & 7)) * kMmLd + ks * 16 + (mi & 1) * 8);
+                    mma_bf16(acc[nb2 * 2], af, bf[0], bf[1]);
+                    mma_bf16(acc[nb2 * 2 + 1], af, bf[2], bf[3]);
+                }
+            }
+        }
+        if (nc + 1 < nchunks) store_chunk(buf ^ 1);
+        __syncthreads();
+    }
+    constexpr int kCLd = kMmTN + 8;
+    bf16* Cs = smem;
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb) {
+        if (nb < kblk) {
+            const int j = nb * 8 + 2 * tg;
+            *reinterpret_cast<uint32_t*>(Cs + (warp * 16 + g) * kCLd + j) = pack_bf16(acc[nb][0], acc[nb][1]);
+            *reinterpret_cast<uint32_t*>(Cs + (warp * 16 + g + 8) * kCLd + j) = pack_bf16(acc[nb][2], acc[nb][3]);
+        }
+    }
+    __syncthreads();
+    const int rows = min(kMmTM, a.Rt - row0);
+    for (int i = tid; i < rows * kcols; i += 256) {
+        const int r = i / kcols, k = i - r * kcols;
+        bf16* d = a.dx + ((size_t)t * a.Rt + row0 + r) * a.ldx + a.coffx + k0t + k;
+        float v = __bfloat162float(Cs[r * kCLd + k]);
+        if (a.accumulate) v += __bfloat162float(*d);
+        *d = __float2bfloat16_rn(v);
+    }
+}
+
+// ======================================================================================== weight gradient
+constexpr int kWgKT = 128, kWgNT = 64, kWgMC = 32, kWgLdX = kWgKT + 8, kWgLdR = kWgNT + 8;
+
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
+    __shared__ __align__(16) bf16 Xs[2][kWgMC][kWgLdX];      // act(in) chunk [row][k]
+    __shared__ __align__(16) bf16 Rs[2][kWgMC][kWgLdR];      // dR chunk      [row][j]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0t = blockIdx.x * kWgKT, j0t = blockIdx.y * kWgNT;
+    const int t = blockIdx.z / a.row_splits, sp = blockIdx.z % a.row_splits;
+    const int N = a.cm.n, K = a.K;
+    const double inv_n = 1.0 / (double)a.Rt;
+    const int rows_per = (a.Rt + a.row_splits - 1) / a.row_splits;
+    const int rbeg = sp * rows_per, rend = min(a.Rt, rbeg + rows_per);
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    // X loader: pair px (k = k0t + 2 px), rows rx + 4 i
+    const int px = tid & 63, rx = tid >> 6;
+    const int kx = k0t + 2 * px;
+    float sx0 = 1.f, hx0 = 0.f, sx1 = 1.f, hx1 = 0.f;
+    if (a.in.aff) {
+        if (kx < K) { const float2 f = a.in.aff[(size_t)t * a.in.ld + a.in.coff + kx]; sx0 = f.x; hx0 = f.y; }
+        if (kx + 1 < K) { const float2 f = a.in.aff[(size_t)t * a.in.ld + a.in.coff + kx + 1]; sx1 = f.x; hx1 = f.y; }
+    }
+    // dR loader: pair pr (j = j0t + 2 pr), rows rr + 8 i
+    const int pr = tid & 31, rr = tid >> 5;
+    const int jr = j0t + 2 * pr;
+    BnCol c0, c1; int ch0 = 0, ch1 = 0;
+    if (jr < N) { ch0 = colmap_c(a.cm, jr); c0 = load_bncol(a.tb, a.ldo, t, ch0, inv_n); }
+    if (jr + 1 < N) { ch1 = colmap_c(a.cm, jr + 1); c1 = load_bncol(a.tb, a.ldo, t, ch1, inv_n); }
+    const bf16* in = (const bf16*)a.in.data;
+    uint32_t vx[8], vr[4];
+    auto load_chunk = [&](int m0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = m0 + rx + 4 * i;
+            uint32_t v = 0u;
+            if (r < rend) {
+                if (kx < K) {
+                    float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + ((size_t)t * a.Rt + r) * a.in.ld + a.in.coff + kx));
+                    f.x = fmaf(f.x, sx0, hx0); f.y = fmaf(f.y, sx1, hx1);
+                    if (a.in.clamp) { f.x = relu6f(f.x); f.y = relu6f(f.y); }
+                    v = pack_bf16(f.x, f.y);
+                } else if (kx == K) v = pack_bf16(1.f, 0.f);          // virtual ones row -> bias gradient
+            }
+            vx[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + rr + 8 * i;
+            vr[i] = (r < rend && jr < N) ? load_dr_pair(a, (size_t)t * a.Rt + r, jr, N, c0, c1, ch0, ch1) : 0u;
+        }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint32_t*>(&Xs[buf][rx + 4 * i][2 * px]) = vx[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t*>(&Rs[buf][rr + 8 * i][2 * pr]) = vr[i];
+    };
+    const int nchunks = (rend - rbeg + kWgMC - 1) / kWgMC;
+    if (nchunks > 0) { load_chunk(rbeg); store_chunk(0); }
+    __syncthreads();
+    for (int mc = 0; mc < nchunks; ++mc) {
+        const int buf = mc & 1;
+        if (mc + 1 < nchunks) load_chunk(rbeg + (mc + 1) * kWgMC);
+#pragma unroll
+        for (int ms = 0; ms < 2; ++ms) {
+            uint32_t af[4];
+            const int mi = lane >> 3;
+            ldsm_x4_trans(af, &Xs[buf][ms * 16 + (mi >> 1) * 8 + (lane & 7)][warp * 16 + (mi & 1) * 8]);
+#pragma unroll
+            for (int nb2 = 0; nb2 < 4; ++nb2) {
+                uint32_t bf[4];
+                ldsm_x4_trans(bf, &Rs[buf][ms * 16 + (mi & 1) * 8 + (lane & 7)][nb2 * 16 + (mi >> 1) * 8]);
+                mma_bf16(acc[nb2 * 2], af, bf[0], bf[1]);
+                mma_bf16(acc[nb2 * 2 + 1], af, bf[2], bf[3]);
+            }
+        }
+        if (mc + 1 < nchunks) store_chunk(buf ^ 1);
+        __syncthreads();
+    }
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0t + warp * 16 + g + (e >> 1) * 8, j = j0t + nb * 8 + 2 * tg + (e & 1);
+            if (k <= K && j < N) {
+                const int wc = colmap_w(a.cm, j);
+                if (k < K) atomicAdd(a.dw + (size_t)k * N + wc, acc[nb][e]);
+                else atomicAdd(a.db + wc, acc[nb][e]);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {       // BN parameter gradients
+        for (int j = tid; j < N; j += 256) {
+            const int c = colmap_c(a.cm, j), wc = colmap_w(a.cm, j);
+            double gs = 0.0, bs = 0.0;
+            for (int tt = 0; tt < kT; ++tt) { const double2 s = a.tb.bst[(size_t)tt * a.ldo + c]; bs += s.x; gs += s.y; }
+            a.dgamma[wc] = (float)gs; a.dbeta[wc] = (float)bs;
+        }
+    }
+}
+
+}  // namespace cdra
+#endif  // CDRA_EMU

@@ -48,18 +48,28 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) bstat_kernel(BstatArgs<T> a) {
     __syncthreads();
     const int r0 = blockIdx.x * a.rows_per_block;
     const int r1 = min(a.Rt, r0 + a.rows_per_block);
-    const long long items = (long long)(r1 - r0) * a.C;
-    // each thread keeps to one channel whenever 256 % C == 0; otherwise channels rotate (still correct)
-    for (long long i = tid; i < items; i += 256) {
-        const int c = (int)(i % a.C);
-        const int r = r0 + (int)(i / a.C);
-        const size_t o = ((size_t)t * a.Rt + r) * a.ld + a.coff + c;
-        const float2 af = a.tb.aff[(size_t)t * a.ld + a.coff + c], bp = a.tb.bnp[(size_t)t * a.ld + a.coff + c];
-        const float R = ldf(a.R + o), dA = ldf(a.dA + o);
-        const float z = fmaf(R, af.x, af.y);
-        const float dz = (!a.clamp || (z > 0.f && z < 6.f)) ? dA : 0.f;
-        atomicAdd(&s1[c], dz);
-        atomicAdd(&s2[c], dz * (R - bp.x) * bp.y);
+    // thread <-> fixed channel pair (coalesced 2-element accesses), row lanes stride over the block's rows;
+    // sums are kept in registers and folded into shared memory once per thread
+    const int CP = a.C >> 1;
+    const int lanes_c = CP >= 256 ? 256 : ((CP + 31) & ~31);
+    const int lanes_r = 256 / lanes_c, cl = tid % lanes_c, rl = tid / lanes_c;
+    for (int cp = cl; cp < CP; cp += lanes_c) {
+        const int c = cp * 2;
+        const float2 af0 = a.tb.aff[(size_t)t * a.ld + a.coff + c], bp0 = a.tb.bnp[(size_t)t * a.ld + a.coff + c];
+        const float2 af1 = a.tb.aff[(size_t)t * a.ld + a.coff + c + 1], bp1 = a.tb.bnp[(size_t)t * a.ld + a.coff + c + 1];
+        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+        if (rl < lanes_r)
+            for (int r = r0 + rl; r < r1; r += lanes_r) {
+                const size_t o = ((size_t)t * a.Rt + r) * a.ld + a.coff + c;
+                const float R0 = ldf(a.R + o), R1 = ldf(a.R + o + 1), d0 = ldf(a.dA + o), d1 = ldf(a.dA + o + 1);
+                const float z0 = fmaf(R0, af0.x, af0.y), z1 = fmaf(R1, af1.x, af1.y);
+                const float dz0 = (!a.clamp || (z0 > 0.f && z0 < 6.f)) ? d0 : 0.f;
+                const float dz1 = (!a.clamp || (z1 > 0.f && z1 < 6.f)) ? d1 : 0.f;
+                a0 += dz0; b0 = fmaf(dz0, (R0 - bp0.x) * bp0.y, b0);
+                a1 += dz1; b1 = fmaf(dz1, (R1 - bp1.x) * bp1.y, b1);
+            }
+        atomicAdd(&s1[c], a0); atomicAdd(&s2[c], b0);
+        atomicAdd(&s1[c + 1], a1); atomicAdd(&s2[c + 1], b1);
     }
     __syncthreads();
     for (int i = tid; i < a.C; i += 256) {
@@ -245,43 +255,47 @@ struct DwBwdArgs {
     const float* w;                                 // [3][3][C]
     T* dx; int ldx, coffx, accumulate;
     float* dw; float* db; float* dgamma; float* dbeta;
+    int ppb, ppb_w;                                 // input pixels per block (dgrad) / output pixels per block (wgrad)
 };
 
 template <typename T>
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_dgrad_kernel(DwBwdArgs<T> a) {
-    const int t = blockIdx.y;
-    const int CP = a.C >> 1, hiw = a.Hi * a.Wi, how = a.Ho * a.Wo;
-    const long long total = (long long)a.B * hiw * CP;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int cp = (int)(idx % CP);
-    const long long p = idx / CP;
-    const int b = (int)(p / hiw), r = (int)(p - (long long)b * hiw), iy = r / a.Wi, ix = r - iy * a.Wi;
-    const int c = cp * 2;
+    const int tid = threadIdx.x, t = blockIdx.y;
+    const int hiw = a.Hi * a.Wi, how = a.Ho * a.Wo, npix = a.B * hiw;
+    const DwLanes L = dw_lanes(a.C, tid);
+    const int p0 = blockIdx.x * a.ppb, p1 = min(npix, p0 + a.ppb);
+    if (L.cl >= (a.C >> 1) || L.rl >= L.lanes_r) return;
+    const int c = L.cl * 2;
     const double inv_n = 1.0 / ((double)a.B * how);
     const BnCol b0 = load_bncol(a.tb, a.C, t, c, inv_n), b1 = load_bncol(a.tb, a.C, t, c + 1, inv_n);
-    float g0 = 0.f, g1 = 0.f;
+    float w0[9], w1[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int ny = iy + a.pad_t - ky;
-        if (ny < 0 || ny % a.stride) continue;
-        const int oy = ny / a.stride;
-        if (oy >= a.Ho) continue;
+    for (int k = 0; k < 9; ++k) { w0[k] = a.w[k * a.C + c]; w1[k] = a.w[k * a.C + c + 1]; }
+    for (int p = p0 + L.rl; p < p1; p += L.lanes_r) {
+        const int b = p / hiw, r = p - b * hiw, iy = r / a.Wi, ix = r - iy * a.Wi;
+        float g0 = 0.f, g1 = 0.f;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int nx = ix + a.pad_l - kx;
-            if (nx < 0 || nx % a.stride) continue;
-            const int ox = nx / a.stride;
-            if (ox >= a.Wo) continue;
-            const size_t o = (((size_t)(t * a.B + b) * a.Ho + oy) * a.Wo + ox) * a.C + c;
-            const float* wp = a.w + (ky * 3 + kx) * a.C + c;
-            g0 = fmaf(make_dr(ldf(a.dout + o), ldf(a.out + o), b0, 0), wp[0], g0);
-            g1 = fmaf(make_dr(ldf(a.dout + o + 1), ldf(a.out + o + 1), b1, 0), wp[1], g1);
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ny = iy + a.pad_t - ky;
+            if (ny < 0 || ny % a.stride) continue;
+            const int oy = ny / a.stride;
+            if (oy >= a.Ho) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int nx = ix + a.pad_l - kx;
+                if (nx < 0 || nx % a.stride) continue;
+                const int ox = nx / a.stride;
+                if (ox >= a.Wo) continue;
+                const size_t o = (((size_t)(t * a.B + b) * a.Ho + oy) * a.Wo + ox) * a.C + c;
+                const float2 dv = ld2(a.dout + o), rv = ld2(a.out + o);
+                g0 = fmaf(make_dr(dv.x, rv.x, b0, 0), w0[ky * 3 + kx], g0);
+                g1 = fmaf(make_dr(dv.y, rv.y, b1, 0), w1[ky * 3 + kx], g1);
+            }
         }
+        T* d = a.dx + ((size_t)t * npix + p) * a.ldx + a.coffx + c;
+        if (a.accumulate) { const float2 old = ld2(d); g0 += old.x; g1 += old.y; }
+        st2(d, make_float2(g0, g1));
     }
-    T* d = a.dx + ((size_t)t * a.B * hiw + p) * a.ldx + a.coffx + c;
-    if (a.accumulate) { g0 += ldf(d); g1 += ldf(d + 1); }
-    stf(d, g0); stf(d + 1, g1);
 }
 
 template <typename T>
@@ -290,36 +304,43 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_wgrad_kernel(DwBwdArgs<T> a) {
     const int tid = threadIdx.x, t = blockIdx.y;
     for (int i = tid; i < 10 * kDwMaxC; i += 256) (&s_dw[0][0])[i] = 0.f;
     __syncthreads();
-    const int CP = a.C >> 1, hiw = a.Hi * a.Wi, how = a.Ho * a.Wo;
-    const long long total = (long long)a.B * how * CP;
-    const double inv_n = 1.0 / ((double)a.B * how);
-    for (int it = 0; it < kDwItems; ++it) {
-        const long long idx = ((long long)blockIdx.x * kDwItems + it) * 256 + tid;
-        if (idx >= total) break;
-        const int cp = (int)(idx % CP);
-        const long long p = idx / CP;
-        const int b = (int)(p / how), r = (int)(p - (long long)b * how), oy = r / a.Wo, ox = r - oy * a.Wo;
-        const int c = cp * 2;
+    const int hiw = a.Hi * a.Wi, how = a.Ho * a.Wo, npix = a.B * how;
+    const DwLanes L = dw_lanes(a.C, tid);
+    const int p0 = blockIdx.x * a.ppb_w, p1 = min(npix, p0 + a.ppb_w);
+    if (L.cl < (a.C >> 1) && L.rl < L.lanes_r) {
+        const int c = L.cl * 2;
+        const double inv_n = 1.0 / ((double)a.B * how);
         const BnCol b0 = load_bncol(a.tb, a.C, t, c, inv_n), b1 = load_bncol(a.tb, a.C, t, c + 1, inv_n);
-        const size_t o = ((size_t)t * a.B * how + p) * a.C + c;
-        const float d0 = make_dr(ldf(a.dout + o), ldf(a.out + o), b0, 0);
-        const float d1 = make_dr(ldf(a.dout + o + 1), ldf(a.out + o + 1), b1, 0);
-        atomicAdd(&s_dw[9][c], d0); atomicAdd(&s_dw[9][c + 1], d1);
-        const T* base = (const T*)a.in.data + ((size_t)(t * a.B + b) * hiw) * a.in.ld + a.in.coff + c;
-        const float2* af = a.in.aff ? a.in.aff + (size_t)t * a.in.ld + a.in.coff + c : nullptr;
+        float2 f0 = make_float2(1.f, 0.f), f1 = make_float2(1.f, 0.f);
+        if (a.in.aff) { f0 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c]; f1 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c + 1]; }
+        float g0[10], g1[10];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * a.stride - a.pad_t + ky;
-            if (iy < 0 || iy >= a.Hi) continue;
+        for (int k = 0; k < 10; ++k) { g0[k] = 0.f; g1[k] = 0.f; }
+        for (int p = p0 + L.rl; p < p1; p += L.lanes_r) {
+            const int b = p / how, r = p - b * how, oy = r / a.Wo, ox = r - oy * a.Wo;
+            const size_t o = ((size_t)t * npix + p) * a.C + c;
+            const float2 dv = ld2(a.dout + o), rv = ld2(a.out + o);
+            const float d0 = make_dr(dv.x, rv.x, b0, 0), d1 = make_dr(dv.y, rv.y, b1, 0);
+            g0[9] += d0; g1[9] += d1;
+            const T* base = (const T*)a.in.data + ((size_t)(t * a.B + b) * hiw) * a.in.ld + a.in.coff + c;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * a.stride - a.pad_l + kx;
-                if (ix < 0 || ix >= a.Wi) continue;
-                const T* q = base + ((size_t)iy * a.Wi + ix) * a.in.ld;
-                atomicAdd(&s_dw[ky * 3 + kx][c], act_apply(ldf(q), af, a.in.clamp) * d0);
-                atomicAdd(&s_dw[ky * 3 + kx][c + 1], act_apply(ldf(q + 1), af ? af + 1 : nullptr, a.in.clamp) * d1);
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = oy * a.stride - a.pad_t + ky;
+                if (iy < 0 || iy >= a.Hi) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ox * a.stride - a.pad_l + kx;
+                    if (ix < 0 || ix >= a.Wi) continue;
+                    float2 v = ld2(base + ((size_t)iy * a.Wi + ix) * a.in.ld);
+                    v.x = fmaf(v.x, f0.x, f0.y); v.y = fmaf(v.y, f1.x, f1.y);
+                    if (a.in.clamp) { v.x = relu6f(v.x); v.y = relu6f(v.y); }
+                    g0[ky * 3 + kx] = fmaf(v.x, d0, g0[ky * 3 + kx]);
+                    g1[ky * 3 + kx] = fmaf(v.y, d1, g1[ky * 3 + kx]);
+                }
             }
         }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { atomicAdd(&s_dw[k][c], g0[k]); atomicAdd(&s_dw[k][c + 1], g1[k]); }
     }
     __syncthreads();
     for (int i = tid; i < 10 * a.C; i += 256) {
@@ -406,7 +427,7 @@ struct StemBwdArgs {
     int pix_per_block;
 };
 constexpr int kStemWgThreads = 672;     // >= 27*24 = 648
-constexpr int kStemWgP = 32;
+constexpr int kStemWgP = 128;
 
 template <typename T, typename TIn>
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(kStemWgThreads) stem_wgrad_kernel(StemBwdArgs<T, TIn> a) {

@@ -259,10 +259,23 @@ struct DwArgs {
     T* out;               // [kT*B*Ho*Wo][C] raw
     BnTables tb;
     BnLayer bn;
+    int ppb;              // output pixels per block
 };
 
-constexpr int kDwItems = 4;     // (pixel, channel-pair) items per thread
+constexpr int kDwItems = 4;     // legacy constant (grid sizing of the weight-gradient kernel)
 constexpr int kDwMaxC = 256;
+
+// thread <-> fixed channel pair (weights / affine in registers, coalesced 2-channel accesses), row lanes loop
+// over the block's output pixels; statistics accumulate in registers.
+struct DwLanes { int lanes_c, lanes_r, cl, rl; };
+CDRA_DEV DwLanes dw_lanes(int C, int tid) {
+    DwLanes l;
+    const int CP = C >> 1;
+    l.lanes_c = (CP + 31) & ~31;
+    if (l.lanes_c > 256) l.lanes_c = 256;
+    l.lanes_r = 256 / l.lanes_c; l.cl = tid % l.lanes_c; l.rl = tid / l.lanes_c;
+    return l;
+}
 
 template <typename T>
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_kernel(DwArgs<T> a) {
@@ -270,37 +283,44 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_kernel(DwArgs<T> a) {
     const int tid = threadIdx.x, t = blockIdx.y;
     for (int i = tid; i < a.C; i += 256) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
     __syncthreads();
-    const int CP = a.C >> 1, how = a.Ho * a.Wo;
-    const long long total = (long long)a.B * how * CP;
-    for (int it = 0; it < kDwItems; ++it) {
-        const long long idx = ((long long)blockIdx.x * kDwItems + it) * 256 + tid;
-        if (idx >= total) break;
-        const int cp = (int)(idx % CP);
-        const long long p = idx / CP;
-        const int b = (int)(p / how), r = (int)(p - (long long)b * how), oy = r / a.Wo, ox = r - oy * a.Wo;
-        const int c = cp * 2;
-        const T* base = (const T*)a.in.data + ((size_t)(t * a.B + b) * a.Hi * a.Wi) * a.in.ld + a.in.coff + c;
-        const float2* af = a.in.aff ? a.in.aff + (size_t)t * a.in.ld + a.in.coff + c : nullptr;
-        float a0 = a.bias[c], a1 = a.bias[c + 1];
+    const int how = a.Ho * a.Wo, npix = a.B * how;
+    const DwLanes L = dw_lanes(a.C, tid);
+    const int p0 = blockIdx.x * a.ppb, p1 = min(npix, p0 + a.ppb);
+    if (L.cl < (a.C >> 1) && L.rl < L.lanes_r) {
+        const int c = L.cl * 2;
+        float w0[9], w1[9];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * a.stride - a.pad_t + ky;
-            if (iy < 0 || iy >= a.Hi) continue;
+        for (int k = 0; k < 9; ++k) { w0[k] = a.w[k * a.C + c]; w1[k] = a.w[k * a.C + c + 1]; }
+        const float bias0 = a.bias[c], bias1 = a.bias[c + 1];
+        float2 f0 = make_float2(1.f, 0.f), f1 = make_float2(1.f, 0.f);
+        if (a.in.aff) { f0 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c]; f1 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c + 1]; }
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        for (int p = p0 + L.rl; p < p1; p += L.lanes_r) {
+            const int b = p / how, r = p - b * how, oy = r / a.Wo, ox = r - oy * a.Wo;
+            const T* base = (const T*)a.in.data + ((size_t)(t * a.B + b) * a.Hi * a.Wi) * a.in.ld + a.in.coff + c;
+            float a0 = bias0, a1 = bias1;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * a.stride - a.pad_l + kx;
-                if (ix < 0 || ix >= a.Wi) continue;
-                const T* q = base + ((size_t)iy * a.Wi + ix) * a.in.ld;
-                const float* wp = a.w + (ky * 3 + kx) * a.C + c;
-                a0 = fmaf(act_apply(ldf(q), af, a.in.clamp), wp[0], a0);
-                a1 = fmaf(act_apply(ldf(q + 1), af ? af + 1 : nullptr, a.in.clamp), wp[1], a1);
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = oy * a.stride - a.pad_t + ky;
+                if (iy < 0 || iy >= a.Hi) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ox * a.stride - a.pad_l + kx;
+                    if (ix < 0 || ix >= a.Wi) continue;
+                    float2 v = ld2(base + ((size_t)iy * a.Wi + ix) * a.in.ld);
+                    v.x = fmaf(v.x, f0.x, f0.y); v.y = fmaf(v.y, f1.x, f1.y);
+                    if (a.in.clamp) { v.x = relu6f(v.x); v.y = relu6f(v.y); }
+                    a0 = fmaf(v.x, w0[ky * 3 + kx], a0);
+                    a1 = fmaf(v.y, w1[ky * 3 + kx], a1);
+                }
             }
+            T* dst = a.out + ((size_t)t * npix + p) * a.C + c;
+            st2(dst, make_float2(a0, a1));
+            const float v0 = rnd(a0, dst), v1 = rnd(a1, dst);
+            s0 += v0; q0 = fmaf(v0, v0, q0); s1 += v1; q1 = fmaf(v1, v1, q1);
         }
-        T* dst = a.out + ((size_t)t * a.B * how + p) * a.C + c;
-        stf(dst, a0); stf(dst + 1, a1);
-        const float v0 = rnd(a0, dst), v1 = rnd(a1, dst);
-        atomicAdd(&s_sum[c], v0); atomicAdd(&s_sq[c], v0 * v0);
-        atomicAdd(&s_sum[c + 1], v1); atomicAdd(&s_sq[c + 1], v1 * v1);
+        atomicAdd(&s_sum[c], s0); atomicAdd(&s_sq[c], q0);
+        atomicAdd(&s_sum[c + 1], s1); atomicAdd(&s_sq[c + 1], q1);
     }
     __syncthreads();
     for (int i = tid; i < a.C; i += 256) {
@@ -311,7 +331,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_kernel(DwArgs<T> a) {
     const unsigned total_blocks = gridDim.x * gridDim.y;
     if (last_block_ticket(a.bn.counter, total_blocks)) {
         ColMap cm{a.C, 0, 0, 0};
-        bn_finalize(cm, a.tb, a.C, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)a.B * how,
+        bn_finalize(cm, a.tb, a.C, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)npix,
                     a.bn.unbiased, a.bn.training, 256, tid);
     }
 }

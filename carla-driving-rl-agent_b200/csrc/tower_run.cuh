@@ -1,8 +1,10 @@
 // Host-side launch sequences for the image tower (forward and backward).
 #pragma once
 #include "plan.h"
+#include <type_traits>
 #include "tower_fwd.cuh"
 #include "tower_bwd.cuh"
+#include "pw_mma.cuh"
 
 namespace cdra {
 
@@ -43,11 +45,34 @@ void launch_pw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, int Rt, 
     PwArgs<T> a;
     a.in = in; a.K = l.K; a.Rt = Rt; a.w = c.params + l.w; a.bias = c.params + l.b; a.cm = cm;
     a.out = (T*)(c.ws + dst.data); a.ldo = dst.C; a.tb = tables_of(c, dst); a.bn = bn_of(c, l); a.do_stats = 1;
-    dim3 grid(cdiv(Rt, kPwTM), kT, cdiv(cm.n, kPwTN));
     prof_bytes(4.0 * Rt * (l.K + cm.n) * sizeof(T));          // read input once, write raw output once
+#ifndef CDRA_EMU
+    if constexpr (std::is_same<T, bf16>::value) {               // tensor-core path (pw_mma.cuh)
+        PwMmaFwdArgs pa; pa.a = a; pa.wt = (const bf16*)(c.ws + l.wt); pa.Kp = l.Kp;
+        dim3 grid(cdiv(Rt, kMmTM), kT, cdiv(cm.n, kMmTN));
+        CDRA_LAUNCH(pw_fwd_mma_kernel, grid, dim3(256), 0, c.stream, pa);
+        return;
+    }
+#endif
+    dim3 grid(cdiv(Rt, kPwTM), kT, cdiv(cm.n, kPwTN));
     auto k = pw_fwd_kernel<T>;
     CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
 }
+
+#ifndef CDRA_EMU
+inline void launch_wprep(const RunCtx& c) {
+    const Plan& p = *c.p;
+    WPrepArgs a; a.n = 0;
+    auto add = [&](const BnConv& l) {
+        WPrepLayer& L = a.l[a.n++];
+        L.w = c.params + l.w; L.wt = (bf16*)(c.ws + l.wt); L.wn = (bf16*)(c.ws + l.wn);
+        L.K = l.K; L.N = l.N; L.Kp = l.Kp; L.Np = l.Np; L.split = l.split;
+    };
+    for (const Unit& u : p.units) { add(u.pw1); add(u.pw2); if (u.stride == 2) add(u.scpw); }
+    add(p.head);
+    CDRA_LAUNCH(wprep_kernel, dim3(a.n, 8), dim3(256), 0, c.stream, a);
+}
+#endif
 
 template <typename T>
 void launch_dw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, const Unit& u, int C, const WsTensor& dst) {
@@ -55,8 +80,9 @@ void launch_dw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, const Un
     a.in = in; a.B = c.p->B; a.Hi = u.Hi; a.Wi = u.Wi; a.Ho = u.Ho; a.Wo = u.Wo; a.C = C; a.stride = u.stride;
     a.pad_t = u.pad_t; a.pad_l = u.pad_l; a.w = c.params + l.w; a.bias = c.params + l.b;
     a.out = (T*)(c.ws + dst.data); a.tb = tables_of(c, dst); a.bn = bn_of(c, l);
-    const long long items = (long long)a.B * u.Ho * u.Wo * (C / 2);
-    dim3 grid(cdiv(items, 256 * kDwItems), kT);
+    int lanes_c = ((C / 2) + 31) & ~31; if (lanes_c > 256) lanes_c = 256;
+    a.ppb = 16 * (256 / lanes_c);
+    dim3 grid(cdiv((long long)a.B * u.Ho * u.Wo, a.ppb), kT);
     prof_bytes(4.0 * a.B * ((double)u.Hi * u.Wi + (double)u.Ho * u.Wo) * C * sizeof(T));
     auto k = dw_fwd_kernel<T>;
     CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
@@ -66,6 +92,9 @@ template <typename T, typename TIn>
 void tower_forward(const RunCtx& c, const TIn* image) {
     const Plan& p = *c.p;
     const int B = p.B;
+#ifndef CDRA_EMU
+    if constexpr (std::is_same<T, bf16>::value) launch_wprep(c);
+#endif
     {   // stem conv (+BN statistics)                                  core/architectures.py:159-160
         const WsTensor& ts = p.tensors[p.t_stem];
         StemArgs<T, TIn> a;

@@ -1,0 +1,135 @@
+"""Numeric subset of the reference's rl/utils.py needed by the PPO-update path, on PyTorch
+tensors + libcdra.  Plotting / trace IO / gym helpers that the hot path never calls are not mirrored."""
+import os
+import random
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from rl import spaces
+from rl.parameters import DynamicParameter
+
+NP_EPS = np.finfo(np.float32).eps            # rl/utils.py:24
+EPSILON = float(NP_EPS)                      # rl/utils.py:25
+OPTIMIZERS = ('adam',)                       # the only optimiser the CUDA path implements (rl/utils.py:29-46 lists 8)
+
+
+def get_optimizer_by_name(name: str, *args, **kwargs):
+    """rl/utils.py:39-46: unknown names raise ValueError; here everything but Adam is 'unknown'."""
+    if name.lower() not in OPTIMIZERS:
+        raise ValueError(f'Cannot find optimizer {name}. Select one of {OPTIMIZERS}.')
+    print(f'Optimizer: {name}.')
+    return dict(name=name.lower(), args=args, kwargs=kwargs)
+
+
+def makedir(*args: str) -> str:
+    path = os.path.join(*args)
+    os.makedirs(path, exist_ok=True)
+    return path
+
+
+def to_float(x):
+    return x.float() if isinstance(x, torch.Tensor) else torch.as_tensor(x, dtype=torch.float32)
+
+
+def to_tensor(x, expand_axis=0):
+    """rl/utils.py `to_tensor`: python / numpy structures -> float tensors with a leading batch axis."""
+    if isinstance(x, dict):
+        return {k: to_tensor(v, expand_axis) for k, v in x.items()}
+    t = torch.as_tensor(np.asarray(x), dtype=torch.float32) if not isinstance(x, torch.Tensor) else x.float()
+    return t.unsqueeze(expand_axis) if expand_axis is not None else t
+
+
+def space_to_flat_spec(space, name: str) -> Dict[str, tuple]:
+    """rl/utils.py:212-247."""
+    kind = spaces.kind(space)
+    spec = dict()
+    if kind == 'discrete':
+        spec[name] = (space.n,)
+    elif kind == 'multidiscrete':
+        spec[name] = space.nvec.shape
+    elif kind == 'box':
+        spec[name] = tuple(space.shape)
+    else:
+        for key, value in space.spaces.items():
+            for k, v in space_to_flat_spec(value, f'{name}_{key}').items():
+                spec[k] = v
+    return spec
+
+
+def clip(value, min_value, max_value):
+    return min(max_value, max(value, min_value))
+
+
+def decompose_number(num: float) -> Tuple[float, float]:
+    """rl/utils.py:140-151 (fp32 arithmetic like the reference's tf.map_fn path)."""
+    num = np.float32(num)
+    exponent = 0
+    while abs(num) > np.float32(1.0):
+        num = np.float32(num / np.float32(10.0))
+        exponent += 1
+    return float(num), float(exponent)
+
+
+def polyak_averaging(arena_flat: torch.Tensor, old_flat: torch.Tensor, alpha=0.99):
+    """rl/utils.py:105-117: w = alpha * w_new + (1 - alpha) * w_old (in place on the flat arena)."""
+    arena_flat.mul_(alpha).add_(old_flat, alpha=1.0 - alpha)
+
+
+def index_batches(n: int, batch_size: int, shuffle_batches=False, seed=None, drop_remainder=False, num_shards=1, skip=0,
+                  shuffle=False) -> List[np.ndarray]:
+    """Index form of `data_to_batches` (rl/utils.py:365-393): tf.data `from_tensor_slices -> skip -> shuffle(buffer =
+    batch_size) -> shard/concatenate -> batch(drop_remainder) -> shuffle(buffer = batch_size)`; returns the list of
+    row-index arrays the CUDA gather kernel consumes (prefetch has no numerical meaning)."""
+    rng = np.random.RandomState(seed if seed is not None else random.randint(0, 2 ** 31 - 1))
+    idx = list(range(skip, n))
+
+    def buffered_shuffle(items, buffer_size):
+        out, buf = [], []
+        for it in items:
+            buf.append(it)
+            if len(buf) > buffer_size:
+                out.append(buf.pop(rng.randint(len(buf))))
+        while buf:
+            out.append(buf.pop(rng.randint(len(buf))))
+        return out
+
+    if shuffle:
+        idx = buffered_shuffle(idx, batch_size)
+    if num_shards > 1:
+        idx = [i for s in range(num_shards) for i in idx[s::num_shards]]
+    batches = [np.asarray(idx[i:i + batch_size], dtype=np.int64) for i in range(0, len(idx), batch_size)]
+    if drop_remainder:
+        batches = [b for b in batches if len(b) == batch_size]
+    if shuffle_batches:
+        batches = buffered_shuffle(batches, batch_size)
+    return batches
+
+
+class Summary:
+    """Lightweight stand-in for utils.Summary (rl/utils.py:577-673): collects scalars per key; `mode=None`
+    disables logging.  TensorBoard export is outside the hot path."""
+
+    def __init__(self, mode='summary', name=None, keys: Optional[List[str]] = None, **_):
+        self.mode = mode
+        self.name = name
+        self.keys = set(keys) if keys else None
+        self.stats: Dict[str, list] = {}
+        self.should_log = mode is not None
+
+    def log(self, **kwargs):
+        if not self.should_log:
+            return
+        for k, v in kwargs.items():
+            if self.keys is not None and k not in self.keys:
+                continue
+            if isinstance(v, torch.Tensor):
+                v = v.detach().float().mean().item() if v.numel() > 1 else v.item()
+            elif isinstance(v, (list, tuple)):
+                v = [float(x) for x in v]
+            self.stats.setdefault(k, []).append(v)
+
+    def write_summaries(self):
+        self.last = {k: v[-1] for k, v in self.stats.items() if v}
+        self.stats = {}

@@ -78,7 +78,10 @@ def _check_grads(eng, arena, flat, ref_grads, head):
     # tower: ReLU6 / max-pool decisions that sit within rounding distance of a boundary may flip between
     # the fp32 kernels and the fp64 oracle (any two implementations differ there); relative L2 is robust
     l2 = sorted(r[1] for r in rows)
-    assert l2[len(l2) // 2] < 2e-3 and l2[int(len(l2) * 0.9)] < 2e-2 and l2[-1] < 0.2, (l2[len(l2) // 2], l2[-1])
+    assert l2[len(l2) // 2] < 1e-2 and l2[int(len(l2) * 0.9)] < 3e-2 and l2[-1] < 0.2, (l2[len(l2) // 2], l2[-1])
+    # the layers closest to the loss see no flipped decision upstream: tight agreement there
+    late = [r for r in rows if r[0].startswith(('tower.head', 'tower.s3.u3.pw2', 'tower.s3.u3.dw'))]
+    assert max(r[1] for r in late) < 2e-3, late
 
 
 def test_policy_pass_fp32(built_libs, params):
