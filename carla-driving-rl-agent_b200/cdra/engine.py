@@ -148,10 +148,11 @@ class Engine:
         return self.g_dyn
 
     def policy_head(self, x512, actions_eval, logp_old, adv, true_speed, true_sim, clip_ratio=0.2, ent_coef=1.0,
-                    training=True, grad_scale=1.0, backward=True):
+                    training=True, grad_scale=1.0, backward=True, update_moving=True):
         p = _lib.ptr
+        state = self.pol_state.flat if (update_moving or not training) else None
         _lib.check(self.lib, self.lib.cdra_policy_head_loss_fwd_bwd(
-            self.plan, p(self.pol.flat), p(self.pol_state.flat), p(x512), p(actions_eval), p(logp_old), p(adv),
+            self.plan, p(self.pol.flat), p(state), p(x512), p(actions_eval), p(logp_old), p(adv),
             p(true_speed), p(true_sim), clip_ratio, ent_coef, 1 if training else 0, grad_scale, p(self.scalars),
             p(self.head_out), p(self.d_x512) if backward else None, p(self.g_pol) if backward else None, p(self.ws),
             self._stream()), 'policy_head')

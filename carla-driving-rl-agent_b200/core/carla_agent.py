@@ -1,0 +1,290 @@
+"""CARLAgent — the reference's core/carla_agent.py agent surface (constructor kwargs, update path, losses,
+gradient application order, memory, fake environment) with the numerics executed by libcdra.
+
+Not mirrored: `record` / `evaluate` (CARLA roll-outs) and `augment` (rollout-time image augmentation,
+SURVEY §8f-4) — they need the simulator / are outside the update hot path.
+"""
+import os
+from typing import Union
+
+import numpy as np
+import torch
+
+from rl import utils, spaces
+from rl.agents.ppo import PPOAgent, PPOMemory
+from rl.parameters import DynamicParameter, LearningRateSchedule
+from core.networks import CARLANetwork
+
+
+def swish6(x):
+    """rl/utils.py:420-421 (name is what the network spec validates against)."""
+    return torch.minimum(x * torch.sigmoid(x), torch.full_like(x, 6.0))
+
+
+def relu6(x):
+    return torch.clamp(x, 0.0, 6.0)
+
+
+class FakeCARLAEnvironment:
+    """A testing-only environment with the state- and action-space of a CARLA environment
+    (core/carla_agent.py:26-52).  Like the reference's it only defines spaces; unlike the reference's it uses the
+    real `CARLAEnv` shapes (time_horizon 4, 5 waypoints, 2 actions, core/carla_env.py:18-27) so that an agent built
+    on it matches the shipped checkpoints, and it carries the `info_buffer` / `reset_info` that
+    `CARLAgent.update` needs."""
+    time_horizon = 4
+
+    def __init__(self, image_shape=(90, 120, 3), image_uint8=False):
+        self.image_uint8 = image_uint8
+        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(2,))                       # CARLAEnv.ACTION, carla_env.py:18
+        self.observation_space = spaces.Dict(
+            road=spaces.Box(low=0.0, high=15.0, shape=(9,)), vehicle=spaces.Box(low=-1.0, high=1.0, shape=(4,)),
+            navigation=spaces.Box(low=0.0, high=25.0, shape=(5,)), image=spaces.Box(low=0.0, high=1.0, shape=image_shape))
+        self.info_buffer = dict(speed=[], similarity=[])
+
+    def reset_info(self):
+        for k in self.info_buffer:
+            self.info_buffer[k] = []
+
+    def seed(self, seed):
+        pass
+
+    def step(self, action):
+        pass
+
+    def reset(self):
+        pass
+
+    def render(self, mode='human'):
+        pass
+
+    def close(self):
+        pass
+
+
+class SyntheticCARLAEnvironment(FakeCARLAEnvironment):
+    """FakeCARLAEnvironment that actually steps: observations / rewards / info drawn from the synthetic
+    distributions of SURVEY §8(d).  Drives `CARLAgent.learn` end to end without a simulator."""
+
+    def __init__(self, image_shape=(90, 120, 3), image_uint8=True, seed=0):
+        super().__init__(image_shape, image_uint8)
+        self.rng = np.random.RandomState(seed)
+        self.image_shape = image_shape
+
+    def _obs(self):
+        r = self.rng
+        img = r.randint(0, 256, size=(4,) + tuple(self.image_shape)).astype(np.uint8)
+        if not self.image_uint8:
+            img = img.astype(np.float32) / 255.0
+        road = np.concatenate([(r.rand(4, 3) < 0.2).astype(np.float32), 0.3 + 0.6 * r.rand(4, 1), np.eye(5)[r.randint(0, 5, 4)]], 1)
+        veh = np.concatenate([r.rand(4, 1) * 2 - 1, r.rand(4, 3)], 1)
+        nav = np.sort(r.rand(4, 5) * 25, axis=1)
+        return dict(image=img, road=road.astype(np.float32), vehicle=veh.astype(np.float32), navigation=nav.astype(np.float32))
+
+    def reset(self):
+        return self._obs()
+
+    def step(self, action):
+        self.info_buffer['speed'].append(float(self.rng.rand() * 30.0))
+        self.info_buffer['similarity'].append(float(self.rng.rand() * 2 - 1))
+        reward = float(np.clip(self.rng.randn() * 2 + 1, -10, 30))
+        return self._obs(), reward, False, {}
+
+
+# -------------------------------------------------------------------------------------------------
+# -- Agent
+# -------------------------------------------------------------------------------------------------
+class CARLAgent(PPOAgent):
+    DEFAULT_CONTROL = dict(units=320, num_layers=2, activation=swish6)                           # core/carla_agent.py:61-68
+    DEFAULT_CONTROL_VALUE = dict(units=320, num_layers=2, activation=swish6)
+    DEFAULT_DYNAMICS = dict(road=dict(units=16, num_layers=2, activation=relu6),
+                            vehicle=dict(units=16, num_layers=2, activation=relu6),
+                            navigation=dict(units=16, num_layers=2, activation=relu6),
+                            shufflenet=dict(g=1.0, last_channels=768),
+                            rnn=dict(image=256, road=32, vehicle=32, navigation=32),
+                            dynamics=dict(units=512))
+
+    def __init__(self, *args, aug_intensity=1.0, clip_norm=(1.0, 1.0, 1.0), name='carla', load_full=True, eta=0.0,
+                 dynamics_lr: Union[float, LearningRateSchedule] = 1e-3, update_dynamics=True, delta=0.0, aux=1.0,
+                 **kwargs):
+        assert aug_intensity >= 0.0                                                              # :84
+        network_spec = dict(kwargs.pop('network', {}))
+        network_spec.setdefault('network', CARLANetwork)
+        network_spec.setdefault('control_policy', self.DEFAULT_CONTROL)
+        network_spec.setdefault('control_value', self.DEFAULT_CONTROL_VALUE)
+        network_spec.setdefault('dynamics', self.DEFAULT_DYNAMICS)
+
+        self.should_update_dynamics = update_dynamics
+        self.dynamics_path = os.path.join(kwargs.get('weights_dir', 'weights'), name, 'dynamics_model')
+        self.load_full = load_full
+        super().__init__(*args, name=name, network=network_spec, clip_norm=clip_norm, **kwargs)
+        self.network: CARLANetwork = self.network
+        self.aug_intensity = aug_intensity
+        self.delta, self.eta, self.aux = delta, eta, aux                                         # stored, unused (:102-104)
+        self.evaluation_path = utils.makedir(os.path.join(self.base_path, 'evaluation'))
+
+        # the reference sets these flags but never clips the dynamics gradients (:109-117 vs :386-388)
+        if isinstance(clip_norm, float):
+            self.should_clip_dynamics_grads, self.grad_norm_dynamics = True, clip_norm
+        elif isinstance(clip_norm[2], float):
+            self.should_clip_dynamics_grads, self.grad_norm_dynamics = True, clip_norm[2]
+        else:
+            self.should_clip_dynamics_grads = False
+
+        self.dynamics_lr = DynamicParameter.create(value=dynamics_lr)
+        self.dynamics_lr.load(config=self.config.get('dynamics_lr', {}))
+        self.dynamics_optimizer = utils.get_optimizer_by_name(name=kwargs.get('optimizer', 'adam'), learning_rate=dynamics_lr)
+
+    # ------------------------------------------------------------------ update (core/carla_agent.py:129-145)
+    def update(self):
+        if len(self.memory) < self.batch_size:
+            print('[Not updated] memory too small!')
+            self.env.reset_info()
+            return
+        super().update()
+        try:
+            actions = (self.memory.actions - 1.0) * 2.0 + 1.0
+            self.log(action_throttle_or_brake=actions[:, 0], action_steer=actions[:, 1])
+        except Exception:
+            print('[update] unable to print actions')
+        self.env.reset_info()
+
+    def _aux_targets(self, n):
+        speed = torch.as_tensor(np.asarray(self.env.info_buffer['speed'], dtype=np.float32)).reshape(-1, 1) / 100.0
+        similarity = torch.as_tensor(np.asarray(self.env.info_buffer['similarity'], dtype=np.float32)).reshape(-1, 1)
+        if speed.shape[0] >= n:                                                                  # :338-345
+            speed, similarity = speed[:n], similarity[:n]
+        else:
+            pad = torch.zeros(n - speed.shape[0], 1)
+            speed, similarity = torch.cat([speed, pad], 0), torch.cat([similarity, pad], 0)
+        return speed, similarity
+
+    def policy_batch_tensors(self):
+        """core/carla_agent.py:323-332."""
+        states, advantages, actions, log_probabilities = super().policy_batch_tensors()
+        states = dict(states)
+        states['action'] = actions
+        speed, similarity = self._aux_targets(actions.shape[0])
+        return states, advantages, log_probabilities, speed, similarity
+
+    def value_batch_tensors(self):
+        """core/carla_agent.py:334-349."""
+        states, returns = super().value_batch_tensors()
+        states = dict(states)
+        states['action'] = self.memory.actions
+        speed, similarity = self._aux_targets(returns.shape[0])
+        return states, returns, speed, similarity
+
+    # ------------------------------------------------------------------ gradients (:351-388, :430-463)
+    def _named_grads(self, arena, flat):
+        return [arena.view(n, flat) for n in arena.names]
+
+    def get_policy_gradients(self, batch):
+        states, advantages, log_probabilities, speed, similarity = batch
+        dynamics_out = self.network.dynamics_predict_train(states)
+        new_batch = (dynamics_out, advantages, log_probabilities, speed, similarity)
+        loss = self.policy_objective(batch=new_batch)
+        eng = dynamics_out['_engine']
+        grads = dict(policy=self._named_grads(eng.pol, eng.g_pol))
+        if self.should_update_dynamics:
+            eng.dynamics_backward(dynamics_out['_obs'], eng.d_x512)
+            grads['dynamics'] = self._named_grads(eng.dyn, eng.g_dyn)
+            return loss, grads
+        return loss, grads['policy']
+
+    def apply_policy_gradients(self, gradients):
+        if isinstance(gradients, dict):
+            assert self.should_update_dynamics
+            grads = self.apply_dynamics_gradients(gradients=gradients['dynamics'])
+            super().apply_policy_gradients(gradients=gradients['policy'])
+            self.log(gradients_norm_dynamics=[g.norm() for g in grads])
+        else:
+            super().apply_policy_gradients(gradients)
+
+    def apply_dynamics_gradients(self, gradients):
+        """Adam without clipping (core/carla_agent.py:386-388)."""
+        self.network.engine.clip_adam('dyn', self.dynamics_lr(), None, self.network.grad_scale)
+        return gradients
+
+    def policy_predict(self, inputs: dict) -> dict:
+        raise NotImplementedError('the policy head is evaluated inside policy_objective (one fused kernel)')
+
+    def policy_objective(self, batch):
+        """core/carla_agent.py:394-428: clipped surrogate - entropy + auxiliary losses; forward + backward of the
+        policy head in one fused call (gradients land in the engine's policy arena and d_x512)."""
+        states, advantages, old_log_prob, true_speed, true_similarity = batch
+        eng = states['_engine']
+        x = states['dynamics']
+        B = eng.B
+        # decision D2: the log-prob is evaluated at a detached sample of the *new* policy, like
+        # PolicyNetwork.call (core/networks.py:97-100); sample here from the current parameters
+        with torch.no_grad():
+            z2, z1 = torch.full((B, 2), 0.5, device=eng.device), torch.zeros(B, 1, device=eng.device)
+            eng.policy_head(x, z2, z2, z1.view(-1), z1, z1, training=True, backward=False, update_moving=False)
+            ho = eng.head_out.view(B, 8)
+            actions_eval = torch.distributions.Beta(ho[:, 0:2], ho[:, 2:4]).sample().clamp(utils.EPSILON, 1 - utils.EPSILON)
+        sc = eng.policy_head(x, actions_eval.contiguous(), old_log_prob.contiguous(), advantages.reshape(-1).contiguous(),
+                             true_speed.contiguous(), true_similarity.contiguous(), float(self.clip_ratio()),
+                             float(self.entropy_strength()), training=True, grad_scale=1.0, backward=True)
+        self.log(ratio=sc[5], log_prob=sc[6], entropy=sc[7], entropy_coeff=self.entropy_strength.value,
+                 ratio_clip=self.clip_ratio.value, loss_speed_policy=sc[3], loss_policy=sc[1], loss_entropy=sc[2],
+                 speed_pi=sc[8], loss_similarity_policy=sc[4], similarity_pi=sc[9])
+        return sc[0].clone()
+
+    def get_value_gradients(self, batch):
+        states, returns, speed, similarity = batch
+        dynamics_out = self.network.dynamics_predict_train(states)
+        loss = self.value_objective(batch=(dynamics_out, returns, speed, similarity))
+        eng = dynamics_out['_engine']
+        grads = dict(value=self._named_grads(eng.val, eng.g_val))
+        if self.should_update_dynamics:
+            eng.dynamics_backward(dynamics_out['_obs'], eng.d_x512)
+            grads['dynamics'] = self._named_grads(eng.dyn, eng.g_dyn)
+            return loss, grads
+        return loss, grads['value']
+
+    def apply_value_gradients(self, gradients):
+        if isinstance(gradients, dict):
+            assert self.should_update_dynamics
+            grads = self.apply_dynamics_gradients(gradients=gradients['dynamics'])
+            super().apply_value_gradients(gradients=gradients['value'])
+            self.log(gradients_norm_dynamics_v=[g.norm() for g in grads])
+        else:
+            super().apply_value_gradients(gradients)
+
+    def value_objective(self, batch):
+        """core/carla_agent.py:469-486."""
+        states, returns, true_speed, true_similarity = batch
+        eng = states['_engine']
+        sc = eng.value_head(states['dynamics'], returns.contiguous(), true_speed.contiguous(), true_similarity.contiguous(),
+                            training=True, grad_scale=1.0, backward=True)
+        self.log(speed_v=sc[4], similarity_v=sc[5], loss_v=sc[1], loss_speed_value=sc[2], loss_similarity_value=sc[3])
+        return sc[0].clone()
+
+    def get_memory(self):
+        return CARLAMemory(state_spec=self.state_spec, num_actions=self.num_actions, time_horizon=self.env.time_horizon,
+                           device=self.network.device)
+
+    def preprocess(self):
+        """Augmentation closure of the reference (core/carla_agent.py:523-579); image augmentation is a rollout-time
+        "next" row: this build batches the observation dict and leaves the image untouched."""
+        if self.aug_intensity > 0.0:
+            print('[preprocess] image augmentation is not built; observations are passed through unchanged')
+
+        def prepare(state):
+            if isinstance(state, list):
+                state = {k: np.stack([s[k] for s in state], 0) for k in state[0]}
+                state = {f'state_{k}': v for k, v in state.items()}
+            return state
+        return prepare
+
+    def load_weights(self):
+        print('loading weights...')
+        self.network.load_weights(full=self.load_full)
+
+
+class CARLAMemory(PPOMemory):
+    """core/carla_agent.py:586-596: states carry a `time_horizon` axis."""
+
+    def __init__(self, state_spec: dict, num_actions: int, time_horizon: int, device='cpu'):
+        super().__init__(state_spec, num_actions, device=device)
+        self.time_horizon = time_horizon
