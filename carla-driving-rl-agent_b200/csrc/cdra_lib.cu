@@ -139,6 +139,34 @@ static void tail_forward(const RunCtx& c, const float* road, const float* vehicl
     }
 }
 
+// ----------------------------------------------------------------------------------------------- inference-mode tables
+static void eval_affine(const RunCtx& c) {
+    const Plan& p = *c.p;
+    EvalAffArgs a; a.n = 0;
+    auto flush = [&]() {
+        if (a.n) { CDRA_LAUNCH(eval_affine_kernel, dim3(a.n), dim3(256), 0, c.stream, a); a.n = 0; }
+    };
+    auto add = [&](const BnConv& l, const WsTensor& dst, ColMap cm) {
+        EvalAffLayer& L = a.l[a.n++];
+        L.gamma = c.params + l.g; L.beta = c.params + l.be; L.mm = c.state + l.mm; L.mv = c.state + l.mv;
+        L.aff = (float2*)(c.ws + dst.aff); L.bnp = (float2*)(c.ws + dst.bnp); L.ld = dst.C; L.cm = cm;
+        if (a.n == kEvalMax) flush();
+    };
+    add(p.stem, p.tensors[p.t_stem], ColMap{kStemC, 0, 0, 0});
+    for (const Unit& u : p.units) {
+        const int sc = u.stride == 2 ? u.cin : u.cin / 2;
+        add(u.pw1, p.tensors[u.t_r1], ColMap{u.half, 0, 0, 0});
+        add(u.dw, p.tensors[u.t_r2], ColMap{u.half, 0, 0, 0});
+        add(u.pw2, p.tensors[u.t_out], ColMap{u.c - sc, 1, sc / 2, u.half});
+        if (u.stride == 2) {
+            add(u.scdw, p.tensors[u.t_rs], ColMap{sc, 0, 0, 0});
+            add(u.scpw, p.tensors[u.t_out], ColMap{sc, 1, 0, u.half});
+        }
+    }
+    add(p.head, p.tensors[p.t_head], ColMap{p.head.N, 0, 0, 0});
+    flush();
+}
+
 // ----------------------------------------------------------------------------------------------- tower backward
 template <typename T>
 static void launch_bstat(const RunCtx& c, const WsTensor& t, int coff, int C, bool clamp) {
@@ -454,10 +482,10 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     if (!plan || !params || !image || !road || !vehicle || !navigation || !out512 || !workspace)
         return fail(CDRA_ERR_BADARG, "null argument");
     if (!training && !state) return fail(CDRA_ERR_BADARG, "inference needs the moving statistics");
-    if (!training) return fail(CDRA_ERR_BADARG, "inference-mode forward is not built yet (SURVEY 8f-1)");
     const Plan& p = *plan->p;
-    RunCtx c{&p, (char*)workspace, params, state, nullptr, (cudaStream_t)stream, training};
-    zero_async(c.ws, p.zero_bytes, c.stream);
+    RunCtx c{&p, (char*)workspace, params, state, nullptr, (cudaStream_t)stream, training ? 1 : 0};
+    if (training) zero_async(c.ws, p.zero_bytes, c.stream);
+    else eval_affine(c);                 // BN affine from the moving statistics (CARLANetwork.dynamics_predict)
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
     if (bf && u8) tower_forward<bf16, uint8_t>(c, (const uint8_t*)image);
     else if (bf) tower_forward<bf16, float>(c, (const float*)image);

@@ -171,6 +171,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
         const int r = i / ncols, j = i - r * ncols;
         a.out[((size_t)t * a.Rt + row0 + r) * a.ldo + colmap_c(a.cm, col0 + j)] = Cs[r * kCLd + j];
     }
+    if (!a.do_stats) return;           // inference (block-uniform)
     __syncthreads();
     if (tid < ncols) {
         double2* dst = a.tb.fst + (size_t)t * a.ldo + colmap_c(a.cm, col0 + tid);

@@ -86,6 +86,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(128) stem_fwd_kernel(StemArgs<T, TIn> a) {
             }
         }
     }
+    if (!a.bn.training) return;        // inference: moving statistics, no batch sums (block-uniform)
 #pragma unroll
     for (int c = 0; c < kStemC; ++c) {
         const float s = warp_sum(lsum[c]), q = warp_sum(lsq[c]);
@@ -322,6 +323,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_kernel(DwArgs<T> a) {
         atomicAdd(&s_sum[c], s0); atomicAdd(&s_sq[c], q0);
         atomicAdd(&s_sum[c + 1], s1); atomicAdd(&s_sq[c + 1], q1);
     }
+    if (!a.bn.training) return;        // inference (block-uniform)
     __syncthreads();
     for (int i = tid; i < a.C; i += 256) {
         double2* dst = a.tb.fst + (size_t)t * a.C + i;

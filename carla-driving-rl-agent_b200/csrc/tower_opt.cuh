@@ -67,4 +67,24 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pool_bwd2_kernel(PoolBwd2Args<T> a) {
     st2(a.dstem + ((size_t)t * a.B * hiw + p) * a.C + c, make_float2(g0, g1));
 }
 
+// --------------------------------------------------------------------------- inference-mode BatchNorm affine
+// training=False (CARLANetwork.dynamics_predict, core/networks.py:206-208): every conv's per-(slice, channel)
+// (scale, shift) comes from the moving statistics; one launch fills the tables of up to kEvalMax layers.
+struct EvalAffLayer { const float* gamma; const float* beta; const float* mm; const float* mv; float2* aff; float2* bnp; int ld; ColMap cm; };
+constexpr int kEvalMax = 28;
+struct EvalAffArgs { EvalAffLayer l[kEvalMax]; int n; };
+
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) eval_affine_kernel(EvalAffArgs a) {
+    const EvalAffLayer& L = a.l[blockIdx.x];
+    for (int j = threadIdx.x; j < L.cm.n; j += 256) {
+        const int c = colmap_c(L.cm, j), w = colmap_w(L.cm, j);
+        const float inv = (float)(1.0 / sqrt((double)L.mv[w] + (double)kBnEps));
+        const float scale = L.gamma[w] * inv;
+        for (int t = 0; t < kT; ++t) {
+            L.aff[(size_t)t * L.ld + c] = make_float2(scale, L.beta[w] - L.mm[w] * scale);
+            L.bnp[(size_t)t * L.ld + c] = make_float2(L.mm[w], inv);
+        }
+    }
+}
+
 }  // namespace cdra

@@ -44,7 +44,7 @@ template <typename T>
 void launch_pw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, int Rt, const WsTensor& dst, const ColMap& cm) {
     PwArgs<T> a;
     a.in = in; a.K = l.K; a.Rt = Rt; a.w = c.params + l.w; a.bias = c.params + l.b; a.cm = cm;
-    a.out = (T*)(c.ws + dst.data); a.ldo = dst.C; a.tb = tables_of(c, dst); a.bn = bn_of(c, l); a.do_stats = 1;
+    a.out = (T*)(c.ws + dst.data); a.ldo = dst.C; a.tb = tables_of(c, dst); a.bn = bn_of(c, l); a.do_stats = c.training ? 1 : 0;
     prof_bytes(4.0 * Rt * (l.K + cm.n) * sizeof(T));          // read input once, write raw output once
 #ifndef CDRA_EMU
     if constexpr (std::is_same<T, bf16>::value) {               // tensor-core path (pw_mma.cuh)

@@ -52,6 +52,28 @@ def test_forward_taps_and_moving_stats(eng, params):
     assert max((got[k].double() - new[k]).abs().max().item() for k in got) < 1e-5
 
 
+def test_inference_mode_uses_moving_statistics(eng, params):
+    """CARLANetwork.dynamics_predict (training=False, core/networks.py:206-208)"""
+    dyn, pol, val = params
+    C.load_engine(eng, dyn, pol, val)
+    obs = C.synthetic_obs(B, H, W, seed=15)
+    state_before = eng.dyn_state.flat.clone()
+    out = eng.dynamics_forward(obs, training=False).clone()
+    ref = model.dynamics_forward(dyn, C.oracle_obs(obs), training=False)
+    assert C.rel_max(out, ref) < 1e-4
+    assert torch.equal(eng.dyn_state.flat, state_before)           # inference never touches the moving averages
+    z = torch.zeros(B, 2)
+    eng.value_head(out, z, z[:, :1].contiguous(), z[:, :1].contiguous(), training=False, backward=False)
+    v = model.value_forward(val, ref, training=False)
+    assert C.rel_max(eng.head_out.view(-1)[:B * 4].view(B, 4)[:, :2], v['value']) < 1e-4
+    eng.policy_head(out, torch.full((B, 2), 0.5), z, z[:, 0].contiguous(), z[:, :1].contiguous(), z[:, :1].contiguous(),
+                    training=False, backward=False)
+    pi = model.policy_forward(pol, ref, torch.full((B, 2), 0.5, dtype=torch.float64), training=False)
+    ho = eng.head_out.view(B, 8)
+    assert C.rel_max(ho[:, 0:2], pi['alpha']) < 1e-4 and C.rel_max(ho[:, 2:4], pi['beta']) < 1e-4
+    assert C.rel_max(ho[:, 6:8], pi['log_prob']) < 1e-4
+
+
 def test_channel_shuffle_is_bit_exact(eng, params):
     """the shortcut half of a stride-1 unit is a pure index permutation of the input's left half"""
     dyn, pol, val = params
