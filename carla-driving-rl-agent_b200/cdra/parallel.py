@@ -1,0 +1,50 @@
+"""Data parallelism over the minibatch: one process per GPU, parameters / Adam state replicated,
+each rank computes gradients on its shard of the global minibatch (BatchNorm statistics per replica, decision
+D3), one all-reduce (sum) per gradient arena per SGD step over NCCL/NVLink, and the fused clip+Adam kernel applies
+`grad_scale = 1 / world_size` while it reads the reduced arena — so per-tensor clipping sees the global-batch
+gradient, exactly like tf.clip_by_norm on a single process (rl/utils.py:120-121).
+
+torch.distributed is the plumbing (NCCL on GPUs, gloo in the CPU tests); there is no data-path collective besides
+this exchange.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+class GradSync:
+    def __init__(self, engine):
+        self.engine = engine
+        self.world = world_size()
+        self.grad_scale = 1.0 / self.world
+
+    def broadcast_parameters(self, src=0):
+        """Make every replica start from rank `src`'s parameters, state and Adam moments."""
+        if self.world == 1:
+            return
+        e = self.engine
+        for t in (e.dyn.flat, e.dyn_state.flat, e.pol.flat, e.pol_state.flat, e.val.flat, e.val_state.flat):
+            dist.broadcast(t, src)
+        for m, v in e.adam.values():
+            dist.broadcast(m, src); dist.broadcast(v, src)
+
+    def allreduce(self, *which):
+        """Sum the named gradient arenas ('dyn', 'pol', 'val') across ranks, in place, on the current stream."""
+        if self.world == 1:
+            return
+        e = self.engine
+        for w in which:
+            dist.all_reduce(dict(dyn=e.g_dyn, pol=e.g_pol, val=e.g_val)[w], op=dist.ReduceOp.SUM)
+
+    def shard(self, n_trajectories):
+        """Trajectories [lo, hi) owned by this rank (rollouts never move between GPUs)."""
+        per = n_trajectories // self.world
+        r = rank()
+        return r * per, (r + 1) * per

@@ -202,6 +202,7 @@ class CARLAgent(PPOAgent):
 
     def apply_dynamics_gradients(self, gradients):
         """Adam without clipping (core/carla_agent.py:386-388)."""
+        self.network.sync.allreduce('dyn')
         self.network.engine.clip_adam('dyn', self.dynamics_lr(), None, self.network.grad_scale)
         return gradients
 

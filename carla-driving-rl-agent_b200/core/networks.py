@@ -172,7 +172,9 @@ class CARLANetwork(Network):
         self.image_u8 = bool(getattr(agent.env, 'image_uint8', False))
         self.engine = Engine(agent.batch_size, H, W, dtype=self.dtype, image_u8=self.image_u8, device=self.device, emulated=emulated)
         self._siblings: Dict[int, Engine] = {agent.batch_size: self.engine}
-        self.grad_scale = 1.0 / world_size
+        from cdra.parallel import GradSync
+        self.sync = GradSync(self.engine)            # one rank per GPU under torchrun; a no-op on a single process
+        self.grad_scale = self.sync.grad_scale
         seed = agent.seed if agent.seed is not None else 42
         init_arena(self.engine.dyn, self.engine.dyn_state, seed)
         init_arena(self.engine.pol, self.engine.pol_state, seed + 1)

@@ -192,14 +192,24 @@ static void launch_pw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
     int splits = (int)cdiv(Rt, 2048); if (splits < 1) splits = 1; if (splits > 64) splits = 64;
     a.row_splits = splits;
 #ifndef CDRA_EMU
-    if constexpr (std::is_same<T, bf16>::value) {               // tensor-core path (pw_mma.cuh)
+    if constexpr (std::is_same<T, bf16>::value) if (use_mma()) {               // tensor-core path (pw_mma.cuh)
         if (need_dx) {
             PwMmaBwdArgs pa; pa.a = a; pa.wn = (const bf16*)(c.ws + l.wn); pa.Np = l.Np;
             prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));
-            CDRA_LAUNCH(pw_dgrad_mma_kernel, dim3(cdiv(Rt, kMmTM), kT, cdiv(l.K, kMmTN)), dim3(256), 0, c.stream, pa);
+            if (l.K <= 64) {
+                auto k64 = pw_dgrad_mma_kernel<64>;
+                CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, 1), dim3(256), 0, c.stream, pa);
+            } else {
+                auto k128 = pw_dgrad_mma_kernel<128>;
+                CDRA_LAUNCH(k128, dim3(cdiv(Rt, kMmTM), kT, cdiv(l.K, 128)), dim3(256), 0, c.stream, pa);
+            }
         }
+        const int kt = (int)cdiv(l.K + 1, kWgKT), nt = (int)cdiv(cm.n, kWgNT);
+        int sp = 1184 / (kt * nt * kT); if (sp < 1) sp = 1;
+        const int max_sp = (int)cdiv(Rt, 64); if (sp > max_sp) sp = max_sp;
+        a.row_splits = sp;
         prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));
-        CDRA_LAUNCH(pw_wgrad_mma_kernel, dim3(cdiv(l.K + 1, kWgKT), cdiv(cm.n, kWgNT), kT * splits), dim3(256), 0, c.stream, a);
+        CDRA_LAUNCH(pw_wgrad_mma_kernel, dim3(kt, nt, kT * sp), dim3(256), 0, c.stream, a);
         return;
     }
 #endif
@@ -503,6 +513,7 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
     const Plan& p = *plan->p;
     RunCtx c{&p, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, 1};
     zero_async(grads, (size_t)p.dyn_params.size * 4, c.stream);
+    zero_async(c.ws, p.zero_bytes, c.stream);      // BN-backward sums (the forward sums are already folded into aff/bnp)
     tail_backward(c, road, vehicle, navigation, d_out512);
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
     if (bf && u8) tower_backward<bf16, uint8_t>(c, (const uint8_t*)image);

@@ -56,7 +56,9 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) wprep_kernel(WPrepArgs a) {
     }
 }
 
-constexpr int kMmTM = 128, kMmTN = 128, kMmKC = 32, kMmLd = kMmKC + 8;
+// tile: 128 rows x TN output columns per CTA (TN = 64 for narrow layers keeps registers / smem small so that more
+// CTAs are resident), reduction chunks of 32, 8 warps x 16 rows
+constexpr int kMmTM = 128, kMmKC = 32, kMmLd = kMmKC + 8;
 
 // ======================================================================================== forward
 struct PwMmaFwdArgs {
@@ -64,33 +66,36 @@ struct PwMmaFwdArgs {
     const bf16* wt; int Kp;
 };
 
+template <int TN>
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
+    constexpr int NB = TN / 8, kCLd = TN + 8;
+    constexpr int kAB = 2 * kMmTM * kMmLd + 2 * TN * kMmLd, kC = kMmTM * kCLd;
     const PwArgs<bf16>& a = pa.a;
-    __shared__ __align__(16) bf16 smem[2 * kMmTM * kMmLd + 2 * kMmTN * kMmLd];     // As[2] | Bs[2]; reused as Cs
+    __shared__ __align__(16) bf16 smem[kAB > kC ? kAB : kC];     // As[2] | Bs[2]; reused as the output tile Cs
     __shared__ float s_scale[480], s_shift[480];
-    __shared__ float s_sum[kMmTN], s_sq[kMmTN];
+    __shared__ float s_sum[TN], s_sq[TN];
     bf16* As = smem;
     bf16* Bs = smem + 2 * kMmTM * kMmLd;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = blockIdx.y, row0 = blockIdx.x * kMmTM, col0 = blockIdx.z * kMmTN;
+    const int t = blockIdx.y, row0 = blockIdx.x * kMmTM, col0 = blockIdx.z * TN;
     const int N = a.cm.n, K = a.K;
-    const int ncols = min(kMmTN, N - col0), nblk = (ncols + 7) >> 3;
+    const int ncols = min(TN, N - col0), nblk = (ncols + 7) >> 3;
     for (int k = tid; k < pa.Kp; k += 256) {
         float sc = 1.f, sh = 0.f;
         if (a.in.aff && k < K) { const float2 f = a.in.aff[(size_t)t * a.in.ld + a.in.coff + k]; sc = f.x; sh = f.y; }
         s_scale[k] = sc; s_shift[k] = sh;
     }
-    if (tid < kMmTN) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+    if (tid < TN) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
     __syncthreads();
 
-    float acc[16][4];
+    float acc[NB][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    for (int i = 0; i < NB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
 
     const int p = tid & 15, rb = tid >> 4;               // loader: k pair p, rows rb + 16 i
     const bf16* in = (const bf16*)a.in.data;
     const int clampf = a.in.clamp;
-    uint32_t ra[8], rbw[8];
+    uint32_t ra[8], rbw[TN / 16];
     auto load_chunk = [&](int k0) {
         const int k = k0 + 2 * p;
 #pragma unroll
@@ -105,16 +110,20 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
                 v = pack_bf16(f.x, f.y);
             }
             ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < TN / 16; ++i) {
             const int n = col0 + rb + 16 * i;
             rbw[i] = (rb + 16 * i < nblk * 8 && k < pa.Kp) ? *reinterpret_cast<const uint32_t*>(pa.wt + (size_t)n * pa.Kp + k) : 0u;
         }
     };
     auto store_chunk = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i)
             *reinterpret_cast<uint32_t*>(As + (size_t)buf * kMmTM * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = ra[i];
-            *reinterpret_cast<uint32_t*>(Bs + (size_t)buf * kMmTN * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = rbw[i];
-        }
+#pragma unroll
+        for (int i = 0; i < TN / 16; ++i)
+            *reinterpret_cast<uint32_t*>(Bs + (size_t)buf * TN * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = rbw[i];
     };
     const int nchunks = (K + kMmKC - 1) / kMmKC;
     load_chunk(0);
@@ -124,13 +133,13 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
         const int buf = kc & 1;
         if (kc + 1 < nchunks) load_chunk((kc + 1) * kMmKC);
         const bf16* Ab = As + (size_t)buf * kMmTM * kMmLd;
-        const bf16* Bb = Bs + (size_t)buf * kMmTN * kMmLd;
+        const bf16* Bb = Bs + (size_t)buf * TN * kMmLd;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             uint32_t af[4];
             ldsm_x4(af, Ab + (warp * 16 + (lane & 15)) * kMmLd + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
-            for (int nb2 = 0; nb2 < 8; ++nb2) {
+            for (int nb2 = 0; nb2 < NB / 2; ++nb2) {
                 if (nb2 * 2 < nblk) {
                     uint32_t bf[4];
                     const int mi = lane >> 3;
@@ -144,11 +153,10 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
         __syncthreads();
     }
     // ---- epilogue: bias, stage the bf16 tile in shared memory, column statistics, coalesced store
-    constexpr int kCLd = kMmTN + 8;
     bf16* Cs = smem;
     const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
-    for (int nb = 0; nb < 16; ++nb) {
+    for (int nb = 0; nb < NB; ++nb) {
         if (nb < nblk) {
             const int j = nb * 8 + 2 * tg;
             const float b0 = (col0 + j < N) ? a.bias[colmap_w(a.cm, col0 + j)] : 0.f;
@@ -159,17 +167,26 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
     }
     __syncthreads();
     const int rows = min(kMmTM, a.Rt - row0);
-    {   // statistics over the stored (rounded) values: 2 threads per column
-        const int j = tid & 127, half = tid >> 7;
+    if (a.do_stats) {   // statistics over the stored (rounded) values: 256/TN threads per column
+        constexpr int kPer = 256 / TN;
+        const int j = tid % TN, part = tid / TN;
         if (j < ncols) {
             float s = 0.f, q = 0.f;
-            for (int r = half; r < rows; r += 2) { const float v = __bfloat162float(Cs[r * kCLd + j]); s += v; q = fmaf(v, v, q); }
+            for (int r = part; r < rows; r += kPer) { const float v = __bfloat162float(Cs[r * kCLd + j]); s += v; q = fmaf(v, v, q); }
             atomicAdd(&s_sum[j], s); atomicAdd(&s_sq[j], q);
         }
     }
-    for (int i = tid; i < rows * ncols; i += 256) {
-        const int r = i / ncols, j = i - r * ncols;
-        a.out[((size_t)t * a.Rt + row0 + r) * a.ldo + colmap_c(a.cm, col0 + j)] = Cs[r * kCLd + j];
+    // store: 2-column (4-byte) accesses whenever the destination pair is adjacent and aligned
+    const int npair = (ncols + 1) >> 1;
+    for (int i = tid; i < rows * npair; i += 256) {
+        const int r = i / npair, j = (i - r * npair) * 2;
+        bf16* row = a.out + ((size_t)t * a.Rt + row0 + r) * a.ldo;
+        const int c0 = colmap_c(a.cm, col0 + j);
+        if (j + 1 < ncols) {
+            const int c1 = colmap_c(a.cm, col0 + j + 1);
+            if (c1 == c0 + 1 && !(c0 & 1)) *reinterpret_cast<uint32_t*>(row + c0) = *reinterpret_cast<const uint32_t*>(Cs + r * kCLd + j);
+            else { row[c0] = Cs[r * kCLd + j]; row[c1] = Cs[r * kCLd + j + 1]; }
+        } else row[c0] = Cs[r * kCLd + j];
     }
     if (!a.do_stats) return;           // inference (block-uniform)
     __syncthreads();
@@ -194,26 +211,35 @@ struct PwMmaBwdArgs {
 CDRA_DEV uint32_t load_dr_pair(const PwBwdArgs<bf16>& a, size_t grow, int j, int N, const BnCol& c0, const BnCol& c1, int ch0, int ch1) {
     float d0 = 0.f, d1 = 0.f;
     const size_t o = grow * a.ldo;
-    if (j < N) d0 = make_dr(__bfloat162float(a.dout[o + ch0]), __bfloat162float(a.out[o + ch0]), c0, a.clamp);
-    if (j + 1 < N) d1 = make_dr(__bfloat162float(a.dout[o + ch1]), __bfloat162float(a.out[o + ch1]), c1, a.clamp);
+    if (j + 1 < N && ch1 == ch0 + 1 && !(ch0 & 1)) {
+        const float2 dv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.dout + o + ch0));
+        const float2 rv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.out + o + ch0));
+        d0 = make_dr(dv.x, rv.x, c0, a.clamp); d1 = make_dr(dv.y, rv.y, c1, a.clamp);
+    } else {
+        if (j < N) d0 = make_dr(__bfloat162float(a.dout[o + ch0]), __bfloat162float(a.out[o + ch0]), c0, a.clamp);
+        if (j + 1 < N) d1 = make_dr(__bfloat162float(a.dout[o + ch1]), __bfloat162float(a.out[o + ch1]), c1, a.clamp);
+    }
     return pack_bf16(d0, d1);
 }
 
+template <int TK>
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
+    constexpr int NB = TK / 8, kCLd = TK + 8;
+    constexpr int kAB = 2 * kMmTM * kMmLd + 2 * TK * kMmLd, kC = kMmTM * kCLd;
     const PwBwdArgs<bf16>& a = pa.a;
-    __shared__ __align__(16) bf16 smem[2 * kMmTM * kMmLd + 2 * kMmTN * kMmLd];
+    __shared__ __align__(16) bf16 smem[kAB > kC ? kAB : kC];
     bf16* As = smem;                                   // dR chunk   [row][n]
     bf16* Bs = smem + 2 * kMmTM * kMmLd;               // W chunk    [k][n]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = blockIdx.y, row0 = blockIdx.x * kMmTM, k0t = blockIdx.z * kMmTN;
+    const int t = blockIdx.y, row0 = blockIdx.x * kMmTM, k0t = blockIdx.z * TK;
     const int N = a.cm.n, K = a.K;
-    const int kcols = min(kMmTN, K - k0t), kblk = (kcols + 7) >> 3;
+    const int kcols = min(TK, K - k0t), kblk = (kcols + 7) >> 3;
     const double inv_n = 1.0 / (double)a.Rt;
-    float acc[16][4];
+    float acc[NB][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    for (int i = 0; i < NB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
     const int p = tid & 15, rb = tid >> 4;
-    uint32_t ra[8], rbw[8];
+    uint32_t ra[8], rbw[TK / 16];
     auto load_chunk = [&](int n0) {
         const int j = n0 + 2 * p;
         BnCol c0, c1; int ch0 = 0, ch1 = 0;
@@ -223,16 +249,20 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
         for (int i = 0; i < 8; ++i) {
             const int r = row0 + rb + 16 * i;
             ra[i] = (r < a.Rt && j < N) ? load_dr_pair(a, (size_t)t * a.Rt + r, j, N, c0, c1, ch0, ch1) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < TK / 16; ++i) {
             const int kk = k0t + rb + 16 * i;
             rbw[i] = (rb + 16 * i < kblk * 8 && j < pa.Np) ? *reinterpret_cast<const uint32_t*>(pa.wn + (size_t)kk * pa.Np + j) : 0u;
         }
     };
     auto store_chunk = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i)
             *reinterpret_cast<uint32_t*>(As + (size_t)buf * kMmTM * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = ra[i];
-            *reinterpret_cast<uint32_t*>(Bs + (size_t)buf * kMmTN * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = rbw[i];
-        }
+#pragma unroll
+        for (int i = 0; i < TK / 16; ++i)
+            *reinterpret_cast<uint32_t*>(Bs + (size_t)buf * TK * kMmLd + (rb + 16 * i) * kMmLd + 2 * p) = rbw[i];
     };
     const int nchunks = (N + kMmKC - 1) / kMmKC;
     load_chunk(0);
@@ -242,13 +272,13 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
         const int buf = nc & 1;
         if (nc + 1 < nchunks) load_chunk((nc + 1) * kMmKC);
         const bf16* Ab = As + (size_t)buf * kMmTM * kMmLd;
-        const bf16* Bb = Bs + (size_t)buf * kMmTN * kMmLd;
+        const bf16* Bb = Bs + (size_t)buf * TK * kMmLd;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             uint32_t af[4];
             ldsm_x4(af, Ab + (warp * 16 + (lane & 15)) * kMmLd + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
-            for (int nb2 = 0; nb2 < 8; ++nb2) {
+            for (int nb2 = 0; nb2 < NB / 2; ++nb2) {
                 if (nb2 * 2 < kblk) {
                     uint32_t bf[4];
                     const int mi = lane >> 3;
@@ -261,11 +291,10 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
         if (nc + 1 < nchunks) store_chunk(buf ^ 1);
         __syncthreads();
     }
-    constexpr int kCLd = kMmTN + 8;
     bf16* Cs = smem;
     const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
-    for (int nb = 0; nb < 16; ++nb) {
+    for (int nb = 0; nb < NB; ++nb) {
         if (nb < kblk) {
             const int j = nb * 8 + 2 * tg;
             *reinterpret_cast<uint32_t*>(Cs + (warp * 16 + g) * kCLd + j) = pack_bf16(acc[nb][0], acc[nb][1]);
@@ -274,51 +303,53 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
     }
     __syncthreads();
     const int rows = min(kMmTM, a.Rt - row0);
-    for (int i = tid; i < rows * kcols; i += 256) {
-        const int r = i / kcols, k = i - r * kcols;
+    const int npair = kcols >> 1;                       // K is even for every layer of the tower
+    for (int i = tid; i < rows * npair; i += 256) {
+        const int r = i / npair, k = (i - r * npair) * 2;
         bf16* d = a.dx + ((size_t)t * a.Rt + row0 + r) * a.ldx + a.coffx + k0t + k;
-        float v = __bfloat162float(Cs[r * kCLd + k]);
-        if (a.accumulate) v += __bfloat162float(*d);
-        *d = __float2bfloat16_rn(v);
+        float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(Cs + r * kCLd + k));
+        if (a.accumulate) { const float2 o = unpack_bf16(*reinterpret_cast<const uint32_t*>(d)); v.x += o.x; v.y += o.y; }
+        *reinterpret_cast<uint32_t*>(d) = pack_bf16(v.x, v.y);
     }
 }
 
 // ======================================================================================== weight gradient
-constexpr int kWgKT = 128, kWgNT = 64, kWgMC = 32, kWgLdX = kWgKT + 8, kWgLdR = kWgNT + 8;
+// dW tile 64(k) x 64(j) per CTA; the 8 warps are 4 k-groups x 2 row halves of every 32-row chunk, the halves are
+// folded through shared memory before the (fp32) atomics; rows are split over many CTAs (grid.z) for parallelism.
+constexpr int kWgKT = 64, kWgNT = 64, kWgMC = 32, kWgLdX = kWgKT + 8, kWgLdR = kWgNT + 8;
 
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
     __shared__ __align__(16) bf16 Xs[2][kWgMC][kWgLdX];      // act(in) chunk [row][k]
     __shared__ __align__(16) bf16 Rs[2][kWgMC][kWgLdR];      // dR chunk      [row][j]
+    __shared__ float red[4][32][33];                          // cross-half reduction
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kg = warp & 3, mh = warp >> 2;
     const int k0t = blockIdx.x * kWgKT, j0t = blockIdx.y * kWgNT;
     const int t = blockIdx.z / a.row_splits, sp = blockIdx.z % a.row_splits;
     const int N = a.cm.n, K = a.K;
     const double inv_n = 1.0 / (double)a.Rt;
-    const int rows_per = (a.Rt + a.row_splits - 1) / a.row_splits;
+    const int rows_per = ((a.Rt + a.row_splits - 1) / a.row_splits + kWgMC - 1) / kWgMC * kWgMC;
     const int rbeg = sp * rows_per, rend = min(a.Rt, rbeg + rows_per);
     float acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-    // X loader: pair px (k = k0t + 2 px), rows rx + 4 i
-    const int px = tid & 63, rx = tid >> 6;
-    const int kx = k0t + 2 * px;
+    // loaders: pair p (2 columns), rows rq + 8 i
+    const int p = tid & 31, rq = tid >> 5;
+    const int kx = k0t + 2 * p, jr = j0t + 2 * p;
     float sx0 = 1.f, hx0 = 0.f, sx1 = 1.f, hx1 = 0.f;
     if (a.in.aff) {
         if (kx < K) { const float2 f = a.in.aff[(size_t)t * a.in.ld + a.in.coff + kx]; sx0 = f.x; hx0 = f.y; }
         if (kx + 1 < K) { const float2 f = a.in.aff[(size_t)t * a.in.ld + a.in.coff + kx + 1]; sx1 = f.x; hx1 = f.y; }
     }
-    // dR loader: pair pr (j = j0t + 2 pr), rows rr + 8 i
-    const int pr = tid & 31, rr = tid >> 5;
-    const int jr = j0t + 2 * pr;
     BnCol c0, c1; int ch0 = 0, ch1 = 0;
     if (jr < N) { ch0 = colmap_c(a.cm, jr); c0 = load_bncol(a.tb, a.ldo, t, ch0, inv_n); }
     if (jr + 1 < N) { ch1 = colmap_c(a.cm, jr + 1); c1 = load_bncol(a.tb, a.ldo, t, ch1, inv_n); }
     const bf16* in = (const bf16*)a.in.data;
-    uint32_t vx[8], vr[4];
+    uint32_t vx[4], vr[4];
     auto load_chunk = [&](int m0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = m0 + rx + 4 * i;
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + rq + 8 * i;
             uint32_t v = 0u;
             if (r < rend) {
                 if (kx < K) {
@@ -329,34 +360,30 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
                 } else if (kx == K) v = pack_bf16(1.f, 0.f);          // virtual ones row -> bias gradient
             }
             vx[i] = v;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = m0 + rr + 8 * i;
             vr[i] = (r < rend && jr < N) ? load_dr_pair(a, (size_t)t * a.Rt + r, jr, N, c0, c1, ch0, ch1) : 0u;
         }
     };
     auto store_chunk = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint32_t*>(&Xs[buf][rx + 4 * i][2 * px]) = vx[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t*>(&Rs[buf][rr + 8 * i][2 * pr]) = vr[i];
+        for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<uint32_t*>(&Xs[buf][rq + 8 * i][2 * p]) = vx[i];
+            *reinterpret_cast<uint32_t*>(&Rs[buf][rq + 8 * i][2 * p]) = vr[i];
+        }
     };
-    const int nchunks = (rend - rbeg + kWgMC - 1) / kWgMC;
+    const int nchunks = rend > rbeg ? (rend - rbeg + kWgMC - 1) / kWgMC : 0;
     if (nchunks > 0) { load_chunk(rbeg); store_chunk(0); }
     __syncthreads();
     for (int mc = 0; mc < nchunks; ++mc) {
         const int buf = mc & 1;
         if (mc + 1 < nchunks) load_chunk(rbeg + (mc + 1) * kWgMC);
-#pragma unroll
-        for (int ms = 0; ms < 2; ++ms) {
+        {
             uint32_t af[4];
             const int mi = lane >> 3;
-            ldsm_x4_trans(af, &Xs[buf][ms * 16 + (mi >> 1) * 8 + (lane & 7)][warp * 16 + (mi & 1) * 8]);
+            ldsm_x4_trans(af, &Xs[buf][mh * 16 + (mi >> 1) * 8 + (lane & 7)][kg * 16 + (mi & 1) * 8]);
 #pragma unroll
             for (int nb2 = 0; nb2 < 4; ++nb2) {
                 uint32_t bf[4];
-                ldsm_x4_trans(bf, &Rs[buf][ms * 16 + (mi & 1) * 8 + (lane & 7)][nb2 * 16 + (mi >> 1) * 8]);
+                ldsm_x4_trans(bf, &Rs[buf][mh * 16 + (mi & 1) * 8 + (lane & 7)][nb2 * 16 + (mi >> 1) * 8]);
                 mma_bf16(acc[nb2 * 2], af, bf[0], bf[1]);
                 mma_bf16(acc[nb2 * 2 + 1], af, bf[2], bf[3]);
             }
@@ -364,16 +391,27 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
         if (mc + 1 < nchunks) store_chunk(buf ^ 1);
         __syncthreads();
     }
-    const int g = lane >> 2, tg = lane & 3;
+    // fold the two row halves, then one atomic per output element
+    if (mh == 1) {
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+        for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = k0t + warp * 16 + g + (e >> 1) * 8, j = j0t + nb * 8 + 2 * tg + (e & 1);
-            if (k <= K && j < N) {
-                const int wc = colmap_w(a.cm, j);
-                if (k < K) atomicAdd(a.dw + (size_t)k * N + wc, acc[nb][e]);
-                else atomicAdd(a.db + wc, acc[nb][e]);
+            for (int e = 0; e < 4; ++e) red[kg][nb * 4 + e][lane] = acc[nb][e];
+    }
+    __syncthreads();
+    if (mh == 0) {
+        const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = acc[nb][e] + red[kg][nb * 4 + e][lane];
+                const int k = k0t + kg * 16 + g + (e >> 1) * 8, j = j0t + nb * 8 + 2 * tg + (e & 1);
+                if (k <= K && j < N) {
+                    const int wc = colmap_w(a.cm, j);
+                    if (k < K) atomicAdd(a.dw + (size_t)k * N + wc, v);
+                    else atomicAdd(a.db + wc, v);
+                }
             }
         }
     }

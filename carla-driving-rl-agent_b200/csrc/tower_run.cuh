@@ -2,6 +2,7 @@
 #pragma once
 #include "plan.h"
 #include <type_traits>
+#include <cstdlib>
 #include "tower_fwd.cuh"
 #include "tower_bwd.cuh"
 #include "pw_mma.cuh"
@@ -17,6 +18,9 @@ struct RunCtx {
     cudaStream_t stream;
     int training;
 };
+
+// debugging aid: CDRA_NO_MMA=1 routes bf16 pointwise convs through the CUDA-core kernels (A/B parity checks)
+inline bool use_mma() { static const bool v = getenv("CDRA_NO_MMA") == nullptr; return v; }
 
 inline unsigned* counter_ptr(const RunCtx& c, int idx) { return (unsigned*)(c.ws + c.p->counters_off) + idx; }
 
@@ -47,10 +51,15 @@ void launch_pw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, int Rt, 
     a.out = (T*)(c.ws + dst.data); a.ldo = dst.C; a.tb = tables_of(c, dst); a.bn = bn_of(c, l); a.do_stats = c.training ? 1 : 0;
     prof_bytes(4.0 * Rt * (l.K + cm.n) * sizeof(T));          // read input once, write raw output once
 #ifndef CDRA_EMU
-    if constexpr (std::is_same<T, bf16>::value) {               // tensor-core path (pw_mma.cuh)
+    if constexpr (std::is_same<T, bf16>::value) if (use_mma()) {               // tensor-core path (pw_mma.cuh)
         PwMmaFwdArgs pa; pa.a = a; pa.wt = (const bf16*)(c.ws + l.wt); pa.Kp = l.Kp;
-        dim3 grid(cdiv(Rt, kMmTM), kT, cdiv(cm.n, kMmTN));
-        CDRA_LAUNCH(pw_fwd_mma_kernel, grid, dim3(256), 0, c.stream, pa);
+        if (cm.n <= 64) {
+            auto k64 = pw_fwd_mma_kernel<64>;
+            CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, 1), dim3(256), 0, c.stream, pa);
+        } else {
+            auto k128 = pw_fwd_mma_kernel<128>;
+            CDRA_LAUNCH(k128, dim3(cdiv(Rt, kMmTM), kT, cdiv(cm.n, 128)), dim3(256), 0, c.stream, pa);
+        }
         return;
     }
 #endif

@@ -156,10 +156,12 @@ class PPOAgent(Agent):
         if self.should_polyak_average:
             old = net.policy.flat.clone()
             net.update_old_policy(old)
+            net.sync.allreduce('pol')
             net.engine.clip_adam('pol', self.policy_lr(), clip, net.grad_scale)
             utils.polyak_averaging(net.policy.flat, old, alpha=self.polyak_coeff)
         else:
             net.update_old_policy()
+            net.sync.allreduce('pol')
             net.engine.clip_adam('pol', self.policy_lr(), clip, net.grad_scale)
         return gradients
 
@@ -167,6 +169,7 @@ class PPOAgent(Agent):
         """rl/agents/ppo.py:264-275."""
         net = self.network
         clip = self.grad_norm_value if self.should_clip_value_grads else None
+        net.sync.allreduce('val')
         if self.should_polyak_average:
             old = net.value.flat.clone()
             net.engine.clip_adam('val', self.value_lr(), clip, net.grad_scale)

