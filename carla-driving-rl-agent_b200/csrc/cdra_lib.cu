@@ -196,13 +196,11 @@ static void launch_pw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
         if (need_dx) {
             PwMmaBwdArgs pa; pa.a = a; pa.wn = (const bf16*)(c.ws + l.wn); pa.Np = l.Np;
             prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));
-            if (l.K <= 64) {
-                auto k64 = pw_dgrad_mma_kernel<64>;
-                CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, 1), dim3(256), 0, c.stream, pa);
-            } else {
-                auto k128 = pw_dgrad_mma_kernel<128>;
-                CDRA_LAUNCH(k128, dim3(cdiv(Rt, kMmTM), kT, cdiv(l.K, 128)), dim3(256), 0, c.stream, pa);
-            }
+            auto k64 = pw_dgrad_mma_kernel<64>;
+            static bool carve = (cudaFuncSetAttribute(k64, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+                                 cudaFuncSetAttribute(pw_wgrad_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
+            (void)carve;
+            CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, cdiv(l.K, 64)), dim3(256), 0, c.stream, pa);
         }
         const int kt = (int)cdiv(l.K + 1, kWgKT), nt = (int)cdiv(cm.n, kWgNT);
         int sp = 1184 / (kt * nt * kT); if (sp < 1) sp = 1;
@@ -235,11 +233,17 @@ static void launch_dw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
     int lanes_c = ((C / 2) + 31) & ~31; if (lanes_c > 256) lanes_c = 256;
     a.ppb = 16 * (256 / lanes_c); a.ppb_w = 64 * (256 / lanes_c);
     prof_bytes(4.0 * a.B * (2.0 * u.Ho * u.Wo + (double)u.Hi * u.Wi) * C * sizeof(T));
-    auto k1 = dw_dgrad_kernel<T>;
-    CDRA_LAUNCH(k1, dim3(cdiv((long long)a.B * u.Hi * u.Wi, a.ppb), kT), dim3(256), 0, c.stream, a);
+    const int lanes_r = 256 / lanes_c;
+    if (u.stride == 1) {
+        auto k1 = dw_dgrad_row_kernel<T>;
+        CDRA_LAUNCH(k1, dim3(cdiv((long long)a.B * u.Hi, lanes_r), kT), dim3(256), 0, c.stream, a);
+    } else {
+        auto k1 = dw_dgrad_kernel<T>;
+        CDRA_LAUNCH(k1, dim3(cdiv((long long)a.B * u.Hi * u.Wi, a.ppb), kT), dim3(256), 0, c.stream, a);
+    }
     prof_bytes(4.0 * a.B * (2.0 * u.Ho * u.Wo + (double)u.Hi * u.Wi) * C * sizeof(T));
-    auto k2 = dw_wgrad_kernel<T>;
-    CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho * u.Wo, a.ppb_w), kT), dim3(256), 0, c.stream, a);
+    if (u.stride == 1) { auto k2 = dw_wgrad_row_kernel<T, 1>; CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho, lanes_r), kT), dim3(256), 0, c.stream, a); }
+    else { auto k2 = dw_wgrad_row_kernel<T, 2>; CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho, lanes_r), kT), dim3(256), 0, c.stream, a); }
 }
 
 template <typename T, typename TIn>
@@ -295,7 +299,7 @@ static void tower_backward(const RunCtx& c, const TIn* image) {
         a.B = B; a.Hi = p.Hs; a.Wi = p.Ws; a.Ho = p.Hp; a.Wo = p.Wp; a.C = kStemC; a.pad_t = p.pool_pad_t; a.pad_l = p.pool_pad_l;
         prof_bytes(4.0 * B * ((double)p.Hs * p.Ws * 2 + (double)p.Hp * p.Wp * 2) * kStemC * sizeof(T));
         auto k = pool_bwd2_kernel<T>;
-        CDRA_LAUNCH(k, dim3(cdiv((long long)ts.Rt * (kStemC / 2), 256), kT), dim3(256), 0, c.stream, a);
+        CDRA_LAUNCH(k, dim3(p.Hs, B, kT), dim3(256), 0, c.stream, a);
         launch_bstat<T>(c, ts, 0, kStemC, true);
         StemBwdArgs<T, TIn> s;
         s.img = image; s.B = B; s.H = p.H; s.W = p.W; s.Ho = p.Hs; s.Wo = p.Ws;

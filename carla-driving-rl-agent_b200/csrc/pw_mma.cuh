@@ -67,7 +67,7 @@ struct PwMmaFwdArgs {
 };
 
 template <int TN>
-CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
+CDRA_KERNEL __launch_bounds__(256, TN == 64 ? 3 : 2) pw_fwd_mma_kernel(PwMmaFwdArgs pa) {
     constexpr int NB = TN / 8, kCLd = TN + 8;
     constexpr int kAB = 2 * kMmTM * kMmLd + 2 * TN * kMmLd, kC = kMmTM * kCLd;
     const PwArgs<bf16>& a = pa.a;
@@ -223,7 +223,7 @@ CDRA_DEV uint32_t load_dr_pair(const PwBwdArgs<bf16>& a, size_t grow, int j, int
 }
 
 template <int TK>
-CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
+CDRA_KERNEL __launch_bounds__(256, TK == 64 ? 3 : 2) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
     constexpr int NB = TK / 8, kCLd = TK + 8;
     constexpr int kAB = 2 * kMmTM * kMmLd + 2 * TK * kMmLd, kC = kMmTM * kCLd;
     const PwBwdArgs<bf16>& a = pa.a;
@@ -318,7 +318,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_dgrad_mma_kernel(PwMmaBwdArgs pa) {
 // folded through shared memory before the (fp32) atomics; rows are split over many CTAs (grid.z) for parallelism.
 constexpr int kWgKT = 64, kWgNT = 64, kWgMC = 32, kWgLdX = kWgKT + 8, kWgLdR = kWgNT + 8;
 
-CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
+CDRA_KERNEL __launch_bounds__(256, 3) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
     __shared__ __align__(16) bf16 Xs[2][kWgMC][kWgLdX];      // act(in) chunk [row][k]
     __shared__ __align__(16) bf16 Rs[2][kWgMC][kWgLdR];      // dR chunk      [row][j]
     __shared__ float red[4][32][33];                          // cross-half reduction

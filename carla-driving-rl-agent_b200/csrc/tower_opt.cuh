@@ -1,5 +1,6 @@
 // Second-generation versions of tower kernels that replaced slow first implementations.
 #pragma once
+#include "tower_fwd.cuh"
 #include "tower_bwd.cuh"
 
 namespace cdra {
@@ -20,13 +21,13 @@ struct PoolBwd2Args {
 
 template <typename T>
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pool_bwd2_kernel(PoolBwd2Args<T> a) {
-    const int t = blockIdx.y;
-    const int hiw = a.Hi * a.Wi, CP = a.C >> 1;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= (long long)a.B * hiw * CP) return;
-    const int c = (int)(idx % CP) * 2;
-    const long long p = idx / CP;
-    const int b = (int)(p / hiw), r = (int)(p - (long long)b * hiw), y = r / a.Wi, x = r - y * a.Wi;
+    // grid = (Hi, B, kT): the row is the block index, so no per-thread index divisions by runtime values
+    const int t = blockIdx.z, b = blockIdx.y, y = blockIdx.x;
+    const int hiw = a.Hi * a.Wi;
+    constexpr int CP = kStemC / 2;
+  for (int i = threadIdx.x; i < a.Wi * CP; i += 256) {
+    const int x = i / CP, c = (i - x * CP) * 2;
+    const long long p = (long long)b * hiw + (long long)y * a.Wi + x;
     const T* base = (const T*)a.in.data + ((size_t)(t * a.B + b) * hiw) * a.in.ld + a.in.coff + c;
     float2 f0 = make_float2(1.f, 0.f), f1 = make_float2(1.f, 0.f);
     if (a.in.aff) { f0 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c]; f1 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c + 1]; }
@@ -65,6 +66,182 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pool_bwd2_kernel(PoolBwd2Args<T> a) {
             }
         }
     st2(a.dstem + ((size_t)t * a.B * hiw + p) * a.C + c, make_float2(g0, g1));
+  }
+}
+
+// --------------------------------------------------------------------------- depthwise 3x3, row-sweep versions
+// One thread owns a channel pair and sweeps one output row with a 3x3 register window: S new columns are
+// loaded per output pixel (3 loads for stride 1 instead of 9), no per-pixel index divisions.
+template <int S, typename LoadF, typename EmitF>
+CDRA_DEV void dw_row_sweep(int Wo, int pad_l, LoadF ld, EmitF emit) {
+    float2 win[3][3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = S; kx < 3; ++kx) win[ky][kx] = ld(ky, -S - pad_l + kx);
+    for (int ox = 0; ox < Wo; ++ox) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3 - S; ++kx) win[ky][kx] = win[ky][kx + S];
+#pragma unroll
+            for (int kx = 3 - S; kx < 3; ++kx) win[ky][kx] = ld(ky, ox * S - pad_l + kx);
+        }
+        emit(ox, win);
+    }
+}
+
+struct DwRow { int c, b, y; bool active; };
+CDRA_DEV DwRow dw_row_of(int C, int rows_per_image, int nrows, int tid, int block) {
+    const DwLanes L = dw_lanes(C, tid);
+    DwRow r;
+    const int row = block * L.lanes_r + L.rl;
+    r.active = L.cl < (C >> 1) && L.rl < L.lanes_r && row < nrows;
+    r.c = L.cl * 2; r.b = row / rows_per_image; r.y = row - r.b * rows_per_image;
+    return r;
+}
+
+template <typename T, int S>
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_row_kernel(DwArgs<T> a) {
+    CDRA_SHARED float s_sum[kDwMaxC], s_sq[kDwMaxC];
+    const int tid = threadIdx.x, t = blockIdx.y;
+    for (int i = tid; i < a.C; i += 256) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+    __syncthreads();
+    const DwRow R = dw_row_of(a.C, a.Ho, a.B * a.Ho, tid, blockIdx.x);
+    if (R.active) {
+        const int c = R.c;
+        float w0[9], w1[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { w0[k] = a.w[k * a.C + c]; w1[k] = a.w[k * a.C + c + 1]; }
+        const float bias0 = a.bias[c], bias1 = a.bias[c + 1];
+        float2 f0 = make_float2(1.f, 0.f), f1 = make_float2(1.f, 0.f);
+        if (a.in.aff) { f0 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c]; f1 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c + 1]; }
+        const T* img = (const T*)a.in.data + ((size_t)(t * a.B + R.b) * a.Hi * a.Wi) * a.in.ld + a.in.coff + c;
+        const int iy0 = R.y * S - a.pad_t;
+        const int clampf = a.in.clamp, Wi = a.Wi, Hi = a.Hi, ld = a.in.ld;
+        auto load = [&](int ky, int ix) {
+            const int iy = iy0 + ky;
+            if (iy < 0 || iy >= Hi || ix < 0 || ix >= Wi) return make_float2(0.f, 0.f);
+            float2 v = ld2(img + ((size_t)iy * Wi + ix) * ld);
+            v.x = fmaf(v.x, f0.x, f0.y); v.y = fmaf(v.y, f1.x, f1.y);
+            if (clampf) { v.x = relu6f(v.x); v.y = relu6f(v.y); }
+            return v;
+        };
+        T* orow = a.out + (((size_t)(t * a.B + R.b) * a.Ho + R.y) * a.Wo) * a.C + c;
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        const int C = a.C;
+        dw_row_sweep<S>(a.Wo, a.pad_l, load, [&](int ox, float2 (&win)[3][3]) {
+            float a0 = bias0, a1 = bias1;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { a0 = fmaf(win[k / 3][k % 3].x, w0[k], a0); a1 = fmaf(win[k / 3][k % 3].y, w1[k], a1); }
+            T* dst = orow + (size_t)ox * C;
+            st2(dst, make_float2(a0, a1));
+            const float v0 = rnd(a0, dst), v1 = rnd(a1, dst);
+            s0 += v0; q0 = fmaf(v0, v0, q0); s1 += v1; q1 = fmaf(v1, v1, q1);
+        });
+        atomicAdd(&s_sum[c], s0); atomicAdd(&s_sq[c], q0);
+        atomicAdd(&s_sum[c + 1], s1); atomicAdd(&s_sq[c + 1], q1);
+    }
+    if (!a.bn.training) return;        // inference (block-uniform)
+    __syncthreads();
+    for (int i = tid; i < a.C; i += 256) {
+        double2* dst = a.tb.fst + (size_t)t * a.C + i;
+        atomicAdd(&dst->x, (double)s_sum[i]);
+        atomicAdd(&dst->y, (double)s_sq[i]);
+    }
+    const unsigned total_blocks = gridDim.x * gridDim.y;
+    if (last_block_ticket(a.bn.counter, total_blocks)) {
+        ColMap cm{a.C, 0, 0, 0};
+        bn_finalize(cm, a.tb, a.C, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)a.B * a.Ho * a.Wo,
+                    a.bn.unbiased, a.bn.training, 256, tid);
+    }
+}
+
+// data gradient, stride 1: dX[y][x] = sum_{u,v} dR[y-1+u][x-1+v] * w[2-u][2-v]  (the same sweep with flipped taps)
+template <typename T>
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_dgrad_row_kernel(DwBwdArgs<T> a) {
+    const int tid = threadIdx.x, t = blockIdx.y;
+    const DwRow R = dw_row_of(a.C, a.Hi, a.B * a.Hi, tid, blockIdx.x);
+    if (!R.active) return;
+    const int c = R.c;
+    const double inv_n = 1.0 / ((double)a.B * a.Ho * a.Wo);
+    const BnCol b0 = load_bncol(a.tb, a.C, t, c, inv_n), b1 = load_bncol(a.tb, a.C, t, c + 1, inv_n);
+    float w0[9], w1[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w0[k] = a.w[(8 - k) * a.C + c]; w1[k] = a.w[(8 - k) * a.C + c + 1]; }   // flipped
+    const size_t img = ((size_t)(t * a.B + R.b) * a.Ho * a.Wo) * a.C + c;
+    const int oy0 = R.y - 1, Wo = a.Wo, Ho = a.Ho, C = a.C;
+    auto load = [&](int u, int ox) {
+        const int oy = oy0 + u;
+        if (oy < 0 || oy >= Ho || ox < 0 || ox >= Wo) return make_float2(0.f, 0.f);
+        const size_t o = img + ((size_t)oy * Wo + ox) * C;
+        const float2 dv = ld2(a.dout + o), rv = ld2(a.out + o);
+        return make_float2(make_dr(dv.x, rv.x, b0, 0), make_dr(dv.y, rv.y, b1, 0));
+    };
+    T* drow = a.dx + (((size_t)(t * a.B + R.b) * a.Hi + R.y) * a.Wi) * a.ldx + a.coffx + c;
+    const int ldx = a.ldx, accumulate = a.accumulate;
+    dw_row_sweep<1>(a.Wi, 1, load, [&](int ix, float2 (&win)[3][3]) {
+        float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { g0 = fmaf(win[k / 3][k % 3].x, w0[k], g0); g1 = fmaf(win[k / 3][k % 3].y, w1[k], g1); }
+        T* d = drow + (size_t)ix * ldx;
+        if (accumulate) { const float2 old = ld2(d); g0 += old.x; g1 += old.y; }
+        st2(d, make_float2(g0, g1));
+    });
+}
+
+template <typename T, int S>
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_wgrad_row_kernel(DwBwdArgs<T> a) {
+    CDRA_SHARED float s_dw[10][kDwMaxC];        // 9 taps + bias
+    const int tid = threadIdx.x, t = blockIdx.y;
+    for (int i = tid; i < 10 * kDwMaxC; i += 256) (&s_dw[0][0])[i] = 0.f;
+    __syncthreads();
+    const DwRow R = dw_row_of(a.C, a.Ho, a.B * a.Ho, tid, blockIdx.x);
+    if (R.active) {
+        const int c = R.c;
+        const double inv_n = 1.0 / ((double)a.B * a.Ho * a.Wo);
+        const BnCol b0 = load_bncol(a.tb, a.C, t, c, inv_n), b1 = load_bncol(a.tb, a.C, t, c + 1, inv_n);
+        float2 f0 = make_float2(1.f, 0.f), f1 = make_float2(1.f, 0.f);
+        if (a.in.aff) { f0 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c]; f1 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c + 1]; }
+        const T* img = (const T*)a.in.data + ((size_t)(t * a.B + R.b) * a.Hi * a.Wi) * a.in.ld + a.in.coff + c;
+        const int iy0 = R.y * S - a.pad_t;
+        const int clampf = a.in.clamp, Wi = a.Wi, Hi = a.Hi, ld = a.in.ld, C = a.C;
+        auto load = [&](int ky, int ix) {
+            const int iy = iy0 + ky;
+            if (iy < 0 || iy >= Hi || ix < 0 || ix >= Wi) return make_float2(0.f, 0.f);
+            float2 v = ld2(img + ((size_t)iy * Wi + ix) * ld);
+            v.x = fmaf(v.x, f0.x, f0.y); v.y = fmaf(v.y, f1.x, f1.y);
+            if (clampf) { v.x = relu6f(v.x); v.y = relu6f(v.y); }
+            return v;
+        };
+        const size_t orow = (((size_t)(t * a.B + R.b) * a.Ho + R.y) * a.Wo) * a.C + c;
+        float g0[10], g1[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { g0[k] = 0.f; g1[k] = 0.f; }
+        dw_row_sweep<S>(a.Wo, a.pad_l, load, [&](int ox, float2 (&win)[3][3]) {
+            const size_t o = orow + (size_t)ox * C;
+            const float2 dv = ld2(a.dout + o), rv = ld2(a.out + o);
+            const float d0 = make_dr(dv.x, rv.x, b0, 0), d1 = make_dr(dv.y, rv.y, b1, 0);
+            g0[9] += d0; g1[9] += d1;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { g0[k] = fmaf(win[k / 3][k % 3].x, d0, g0[k]); g1[k] = fmaf(win[k / 3][k % 3].y, d1, g1[k]); }
+        });
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { atomicAdd(&s_dw[k][c], g0[k]); atomicAdd(&s_dw[k][c + 1], g1[k]); }
+    }
+    __syncthreads();
+    for (int i = tid; i < 10 * a.C; i += 256) {
+        const int tap = i / a.C, c = i - tap * a.C;
+        const float v = s_dw[tap][c];
+        if (tap < 9) atomicAdd(a.dw + tap * a.C + c, v); else atomicAdd(a.db + c, v);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int c = tid; c < a.C; c += 256) {
+            double g = 0.0, b = 0.0;
+            for (int tt = 0; tt < kT; ++tt) { const double2 s = a.tb.bst[(size_t)tt * a.C + c]; b += s.x; g += s.y; }
+            a.dgamma[c] = (float)g; a.dbeta[c] = (float)b;
+        }
+    }
 }
 
 // --------------------------------------------------------------------------- inference-mode BatchNorm affine

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include "tower_fwd.cuh"
 #include "tower_bwd.cuh"
+#include "tower_opt.cuh"
 #include "pw_mma.cuh"
 
 namespace cdra {
@@ -53,13 +54,12 @@ void launch_pw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, int Rt, 
 #ifndef CDRA_EMU
     if constexpr (std::is_same<T, bf16>::value) if (use_mma()) {               // tensor-core path (pw_mma.cuh)
         PwMmaFwdArgs pa; pa.a = a; pa.wt = (const bf16*)(c.ws + l.wt); pa.Kp = l.Kp;
-        if (cm.n <= 64) {
-            auto k64 = pw_fwd_mma_kernel<64>;
-            CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, 1), dim3(256), 0, c.stream, pa);
-        } else {
-            auto k128 = pw_fwd_mma_kernel<128>;
-            CDRA_LAUNCH(k128, dim3(cdiv(Rt, kMmTM), kT, cdiv(cm.n, 128)), dim3(256), 0, c.stream, pa);
-        }
+        // 64-column tiles: 80 registers / 35 KB smem -> 3 CTAs per SM (the 128-wide variant is register-bound at 2);
+        // wide layers re-read their A tile from L2 once per 64 output columns
+        auto k64 = pw_fwd_mma_kernel<64>;
+        static bool carve = (cudaFuncSetAttribute(k64, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
+        (void)carve;
+        CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, cdiv(cm.n, 64)), dim3(256), 0, c.stream, pa);
         return;
     }
 #endif
@@ -91,10 +91,10 @@ void launch_dw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, const Un
     a.out = (T*)(c.ws + dst.data); a.tb = tables_of(c, dst); a.bn = bn_of(c, l);
     int lanes_c = ((C / 2) + 31) & ~31; if (lanes_c > 256) lanes_c = 256;
     a.ppb = 16 * (256 / lanes_c);
-    dim3 grid(cdiv((long long)a.B * u.Ho * u.Wo, a.ppb), kT);
     prof_bytes(4.0 * a.B * ((double)u.Hi * u.Wi + (double)u.Ho * u.Wo) * C * sizeof(T));
-    auto k = dw_fwd_kernel<T>;
-    CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
+    dim3 grid(cdiv((long long)a.B * u.Ho, 256 / lanes_c), kT);      // row-sweep kernels: one output row per thread
+    if (u.stride == 1) { auto k = dw_fwd_row_kernel<T, 1>; CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a); }
+    else { auto k = dw_fwd_row_kernel<T, 2>; CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a); }
 }
 
 template <typename T, typename TIn>
