@@ -7,6 +7,9 @@ from tests import common as C
 B, H, W = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 90, 120
 e32 = Engine(B, H, W, dtype='f32', image_u8=True, device='cuda'); init_engine(e32, 42)
 e16 = Engine(B, H, W, dtype='bf16', image_u8=True, device='cuda'); init_engine(e16, 42)
+if len(sys.argv) > 2 and sys.argv[2] == 'trained':      # the reference's shipped stage-s5-curriculum agent
+    dyn, pol, val = C.trained_params(torch.float32)
+    C.load_engine(e32, dyn, pol, val); C.load_engine(e16, dyn, pol, val)
 dev = lambda d: {k: v.cuda() for k, v in d.items()}
 obs, bt = dev(C.synthetic_obs(B, H, W, seed=41)), dev(C.synthetic_batch(B, seed=42))
 s32 = C.policy_step_engine(e32, obs, bt).cpu(); s16 = C.policy_step_engine(e16, obs, bt).cpu()
