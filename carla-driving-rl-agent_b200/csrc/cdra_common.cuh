@@ -87,6 +87,23 @@ struct BnTables {
     double2* bst;     // backward sums (sum dz, sum dz*xhat)
 };
 
+// The fp64 sums are the one place where thousands of CTAs hit the same addresses; they are spread over
+// kStatCopies replicas (chosen by block index) and folded by the last block, which cuts the same-address
+// atomic contention that otherwise puts a ~150 us floor under every kernel.
+constexpr int kStatCopies = 16;
+CDRA_DEV int stat_copy() { return (int)((blockIdx.x + 5u * blockIdx.z) & (kStatCopies - 1)); }
+CDRA_DEV double2* stat_slot(double2* table, int ld, int copy, int t, int c) {
+    return table + ((size_t)copy * kT + t) * ld + c;
+}
+CDRA_DEV double2 stat_fold(const double2* table, int ld, int t, int c) {
+    double sx = 0.0, sy = 0.0;
+    for (int k = 0; k < kStatCopies; ++k) {
+        const volatile double2* p = table + ((size_t)k * kT + t) * ld + c;
+        sx += p->x; sy += p->y;
+    }
+    return make_double2(sx, sy);
+}
+
 // Destination-channel map of a pointwise conv's output column j (split = channel-shuffle aware):
 //   split=0: weight column j   -> channel j
 //   split=1: j <  N/2: weight column 2j        -> channel off + j                (even outputs)
@@ -142,8 +159,8 @@ CDRA_DEV void bn_finalize(const ColMap& cm, const BnTables& tb, int ld, const fl
         const float g = gamma[w], b = beta[w];
         float mm = mov_mean ? mov_mean[w] : 0.f, mv = mov_var ? mov_var[w] : 1.f;
         for (int t = 0; t < kT; ++t) {
-            const volatile double2* sp = tb.fst + (size_t)t * ld + c;
-            const double sx = sp->x, sxx = sp->y;
+            const double2 sp = stat_fold(tb.fst, ld, t, c);
+            const double sx = sp.x, sxx = sp.y;
             double mean = sx / n;
             double var = sxx / n - mean * mean;
             if (var < 0.0) var = 0.0;

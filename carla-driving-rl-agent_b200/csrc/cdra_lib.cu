@@ -172,7 +172,7 @@ template <typename T>
 static void launch_bstat(const RunCtx& c, const WsTensor& t, int coff, int C, bool clamp) {
     BstatArgs<T> a;
     a.dA = (const T*)(c.ws + t.grad); a.R = (const T*)(c.ws + t.data); a.ld = t.C; a.coff = coff; a.C = C; a.Rt = t.Rt;
-    a.clamp = clamp ? 1 : 0; a.tb = tables_of(c, t);
+    a.clamp = clamp ? 1 : 0; a.tb = tables_of(c, t); a.counter = counter_ptr(c, t.bcounter);
     int rows = 16384 / C; if (rows < 64) rows = 64;
     a.rows_per_block = rows;
     prof_bytes(4.0 * t.Rt * C * 2 * sizeof(T));                // read dA and R once
@@ -190,7 +190,7 @@ static void launch_pw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
     a.dx = dx; a.ldx = ldx; a.coffx = coffx; a.accumulate = accumulate ? 1 : 0;
     a.dw = c.grads + l.w; a.db = c.grads + l.b; a.dgamma = c.grads + l.g; a.dbeta = c.grads + l.be;
     int splits = (int)cdiv(Rt, 2048); if (splits < 1) splits = 1; if (splits > 64) splits = 64;
-    a.row_splits = splits;
+    a.row_splits = splits; a.partials = nullptr;
 #ifndef CDRA_EMU
     if constexpr (std::is_same<T, bf16>::value) if (use_mma()) {               // tensor-core path (pw_mma.cuh)
         if (need_dx) {
@@ -203,11 +203,14 @@ static void launch_pw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
             CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, cdiv(l.K, 64)), dim3(256), 0, c.stream, pa);
         }
         const int kt = (int)cdiv(l.K + 1, kWgKT), nt = (int)cdiv(cm.n, kWgNT);
-        int sp = 1184 / (kt * nt * kT); if (sp < 1) sp = 1;
+        int sp = 888 / (kt * nt * kT); if (sp < 1) sp = 1;             // ~6 CTAs per SM in total
         const int max_sp = (int)cdiv(Rt, 64); if (sp > max_sp) sp = max_sp;
         a.row_splits = sp;
+        a.partials = F(c.ws, named_off(*c.p, "wgrad.partials"));      // kt*nt*4*sp <= 1024 tiles
         prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));
         CDRA_LAUNCH(pw_wgrad_mma_kernel, dim3(kt, nt, kT * sp), dim3(256), 0, c.stream, a);
+        PwWgReduceArgs ra{a, kt, nt, kT * sp};
+        CDRA_LAUNCH(pw_wgrad_reduce_kernel, dim3(kt, nt), dim3(256), 0, c.stream, ra);
         return;
     }
 #endif
@@ -242,8 +245,9 @@ static void launch_dw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
         CDRA_LAUNCH(k1, dim3(cdiv((long long)a.B * u.Hi * u.Wi, a.ppb), kT), dim3(256), 0, c.stream, a);
     }
     prof_bytes(4.0 * a.B * (2.0 * u.Ho * u.Wo + (double)u.Hi * u.Wi) * C * sizeof(T));
-    if (u.stride == 1) { auto k2 = dw_wgrad_row_kernel<T, 1>; CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho, lanes_r), kT), dim3(256), 0, c.stream, a); }
-    else { auto k2 = dw_wgrad_row_kernel<T, 2>; CDRA_LAUNCH(k2, dim3(cdiv((long long)a.B * u.Ho, lanes_r), kT), dim3(256), 0, c.stream, a); }
+    unsigned wg_blocks = cdiv((long long)a.B * u.Ho, lanes_r); if (wg_blocks > 148) wg_blocks = 148;   // persistent: 4 CTAs / SM over the 4 slices
+    if (u.stride == 1) { auto k2 = dw_wgrad_row_kernel<T, 1>; CDRA_LAUNCH(k2, dim3(wg_blocks, kT), dim3(256), 0, c.stream, a); }
+    else { auto k2 = dw_wgrad_row_kernel<T, 2>; CDRA_LAUNCH(k2, dim3(wg_blocks, kT), dim3(256), 0, c.stream, a); }
 }
 
 template <typename T, typename TIn>

@@ -31,6 +31,7 @@ static BnConv add_bnconv(Plan& p, const std::string& name, std::initializer_list
 static int add_tensor(Plan& p, const std::string& name, int H, int W, int C, bool tables, bool has_grad = true) {
     WsTensor t; t.name = name; t.H = H; t.W = W; t.C = C; t.Rt = p.B * H * W; t.elem = p.elem;
     t.tables = tables; t.has_grad = has_grad;
+    if (tables) t.bcounter = p.n_counters++;
     p.tensor_index[name] = (int)p.tensors.size();
     p.tensors.push_back(t);
     return (int)p.tensors.size() - 1;
@@ -127,7 +128,8 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
     // ---- workspace map
     size_t off = 0;
     auto alloc = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    for (auto& t : p.tensors) if (t.tables) { t.fst = alloc((size_t)4 * t.C * 16); t.bst = alloc((size_t)4 * t.C * 16); }
+    const size_t kCopies = 16;        // == cdra::kStatCopies (cdra_common.cuh): replicated fp64 sums
+    for (auto& t : p.tensors) if (t.tables) { t.fst = alloc(kCopies * 4 * t.C * 16); t.bst = alloc(kCopies * 4 * t.C * 16); }
     p.zero_bytes = off;
     p.counters_off = alloc((size_t)(p.n_counters + 16) * 4);
     for (auto& t : p.tensors) if (t.tables) { t.aff = alloc((size_t)4 * t.C * 8); t.bnp = alloc((size_t)4 * t.C * 8); }
@@ -190,6 +192,7 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
     f32("head.dlogits", {B, 8});
     f32("head.acc", {64});          // fp64 x 32 loss accumulators
     p.scratch = f32("scratch", {4, B < 4 ? 4 : B, kLastC});
+    f32("wgrad.partials", {1024, 64, 64});       // per-CTA partial weight-gradient tiles (pw_mma.cuh)
     p.ws_bytes = off;
     return pp;
 }

@@ -49,6 +49,7 @@ struct WsTensor {       // activation tensor living in the workspace
     size_t data = 0, grad = 0;          // byte offsets
     size_t fst = 0, bst = 0, aff = 0, bnp = 0;
     bool tables = false, has_grad = true;
+    int bcounter = -1;   // ticket counter of the BN-backward-sums kernel
     size_t bytes() const { return (size_t)4 * Rt * C * elem; }
 };
 

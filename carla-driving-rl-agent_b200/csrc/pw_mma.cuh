@@ -191,7 +191,7 @@ CDRA_KERNEL __launch_bounds__(256, TN == 64 ? 3 : 2) pw_fwd_mma_kernel(PwMmaFwdA
     if (!a.do_stats) return;           // inference (block-uniform)
     __syncthreads();
     if (tid < ncols) {
-        double2* dst = a.tb.fst + (size_t)t * a.ldo + colmap_c(a.cm, col0 + tid);
+        double2* dst = stat_slot(a.tb.fst, a.ldo, stat_copy(), t, colmap_c(a.cm, col0 + tid));
         atomicAdd(&dst->x, (double)s_sum[tid]);
         atomicAdd(&dst->y, (double)s_sq[tid]);
     }
@@ -399,23 +399,39 @@ CDRA_KERNEL __launch_bounds__(256, 3) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
             for (int e = 0; e < 4; ++e) red[kg][nb * 4 + e][lane] = acc[nb][e];
     }
     __syncthreads();
+    // partial 64x64 tile of this CTA -> scratch (plain stores); pw_wgrad_reduce_kernel sums the row splits.
+    // (atomics from ~1000 CTAs onto the same 4096 addresses cost ~150 us per launch, and are not deterministic)
     if (mh == 0) {
+        float* part = a.partials + (((size_t)blockIdx.z * gridDim.x + blockIdx.x) * gridDim.y + blockIdx.y) * (kWgKT * kWgNT);
         const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float v = acc[nb][e] + red[kg][nb * 4 + e][lane];
-                const int k = k0t + kg * 16 + g + (e >> 1) * 8, j = j0t + nb * 8 + 2 * tg + (e & 1);
-                if (k <= K && j < N) {
-                    const int wc = colmap_w(a.cm, j);
-                    if (k < K) atomicAdd(a.dw + (size_t)k * N + wc, v);
-                    else atomicAdd(a.db + wc, v);
-                }
-            }
+            const int jl = nb * 8 + 2 * tg;
+            const float2 lo = make_float2(acc[nb][0] + red[kg][nb * 4 + 0][lane], acc[nb][1] + red[kg][nb * 4 + 1][lane]);
+            const float2 hi = make_float2(acc[nb][2] + red[kg][nb * 4 + 2][lane], acc[nb][3] + red[kg][nb * 4 + 3][lane]);
+            *reinterpret_cast<float2*>(part + (kg * 16 + g) * kWgNT + jl) = lo;
+            *reinterpret_cast<float2*>(part + (kg * 16 + g + 8) * kWgNT + jl) = hi;
         }
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {       // BN parameter gradients
+}
+
+// sums the per-CTA partial tiles (fixed order -> deterministic), writes dW / db / dgamma / dbeta
+struct PwWgReduceArgs { PwBwdArgs<bf16> a; int kt, nt, nz; };
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_wgrad_reduce_kernel(PwWgReduceArgs ra) {
+    const PwBwdArgs<bf16>& a = ra.a;
+    const int tid = threadIdx.x, N = a.cm.n, K = a.K;
+    const int k0t = blockIdx.x * kWgKT, j0t = blockIdx.y * kWgNT;
+    const size_t tile = (size_t)kWgKT * kWgNT, zstride = (size_t)ra.kt * ra.nt * tile;
+    const float* base = a.partials + ((size_t)blockIdx.x * ra.nt + blockIdx.y) * tile;
+    for (int e = tid; e < kWgKT * kWgNT; e += 256) {
+        const int k = k0t + e / kWgNT, j = j0t + e % kWgNT;
+        if (k > K || j >= N) continue;
+        float s = 0.f;
+        for (int z = 0; z < ra.nz; ++z) s += base[(size_t)z * zstride + e];
+        const int wc = colmap_w(a.cm, j);
+        if (k < K) a.dw[(size_t)k * N + wc] = s; else a.db[wc] = s;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {                           // BN parameter gradients
         for (int j = tid; j < N; j += 256) {
             const int c = colmap_c(a.cm, j), wc = colmap_w(a.cm, j);
             double gs = 0.0, bs = 0.0;

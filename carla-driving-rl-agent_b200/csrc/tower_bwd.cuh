@@ -37,6 +37,7 @@ struct BstatArgs {
     const T* R;           // raw tensor
     int ld, coff, C, Rt, clamp, rows_per_block;
     BnTables tb;
+    unsigned* counter;    // last-block ticket (folding of the replicated sums)
 };
 constexpr int kBstatMaxC = 768;
 
@@ -73,9 +74,17 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) bstat_kernel(BstatArgs<T> a) {
     }
     __syncthreads();
     for (int i = tid; i < a.C; i += 256) {
-        double2* d = a.tb.bst + (size_t)t * a.ld + a.coff + i;
+        double2* d = stat_slot(a.tb.bst, a.ld, stat_copy(), t, a.coff + i);
         atomicAdd(&d->x, (double)s1[i]);
         atomicAdd(&d->y, (double)s2[i]);
+    }
+    // the last block folds the replicas into replica 0, which is what the backward kernels read
+    if (last_block_ticket(a.counter, gridDim.x * gridDim.y)) {
+        for (int i = tid; i < kT * a.C; i += 256) {
+            const int tt = i / a.C, c = a.coff + (i - tt * a.C);
+            const double2 s = stat_fold(a.tb.bst, a.ld, tt, c);
+            *stat_slot(a.tb.bst, a.ld, 0, tt, c) = s;
+        }
     }
 }
 
@@ -90,6 +99,7 @@ struct PwBwdArgs {
     T* dx; int ldx, coffx, accumulate;      // dgrad destination (may differ in ld/coff from `in`)
     float* dw; float* db; float* dgamma; float* dbeta;   // wgrad destinations
     int row_splits;
+    float* partials;      // tensor-core path: per-CTA partial dW tiles (workspace scratch)
 };
 
 constexpr int kPwMaxN = 768;

@@ -94,7 +94,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(128) stem_fwd_kernel(StemArgs<T, TIn> a) {
     }
     __syncthreads();
     if (tid < kStemC) {
-        double2* dst = a.tb.fst + (size_t)t * kStemC + tid;
+        double2* dst = stat_slot(a.tb.fst, kStemC, stat_copy(), t, tid);
         atomicAdd(&dst->x, (double)s_sum[tid]);
         atomicAdd(&dst->y, (double)s_sq[tid]);
     }
@@ -240,7 +240,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_kernel(PwArgs<T> a) {
     if (!a.do_stats) return;
     __syncthreads();
     if (tid < kPwTN && col0 + tid < N) {
-        double2* dst = a.tb.fst + (size_t)t * a.ldo + colmap_c(a.cm, col0 + tid);
+        double2* dst = stat_slot(a.tb.fst, a.ldo, stat_copy(), t, colmap_c(a.cm, col0 + tid));
         atomicAdd(&dst->x, (double)s_sum[tid]);
         atomicAdd(&dst->y, (double)s_sq[tid]);
     }
@@ -326,7 +326,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_kernel(DwArgs<T> a) {
     if (!a.bn.training) return;        // inference (block-uniform)
     __syncthreads();
     for (int i = tid; i < a.C; i += 256) {
-        double2* dst = a.tb.fst + (size_t)t * a.C + i;
+        double2* dst = stat_slot(a.tb.fst, a.C, stat_copy(), t, i);
         atomicAdd(&dst->x, (double)s_sum[i]);
         atomicAdd(&dst->y, (double)s_sq[i]);
     }

@@ -74,18 +74,27 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pool_bwd2_kernel(PoolBwd2Args<T> a) {
 // loaded per output pixel (3 loads for stride 1 instead of 9), no per-pixel index divisions.
 template <int S, typename LoadF, typename EmitF>
 CDRA_DEV void dw_row_sweep(int Wo, int pad_l, LoadF ld, EmitF emit) {
-    float2 win[3][3];
+    float2 win[3][3], nxt[3][S];          // nxt: the S new columns of the next step, loaded one step ahead
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
         for (int kx = S; kx < 3; ++kx) win[ky][kx] = ld(ky, -S - pad_l + kx);
+#pragma unroll
+        for (int j = 0; j < S; ++j) nxt[ky][j] = ld(ky, -pad_l + 3 - S + j);
+    }
     for (int ox = 0; ox < Wo; ++ox) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
             for (int kx = 0; kx < 3 - S; ++kx) win[ky][kx] = win[ky][kx + S];
 #pragma unroll
-            for (int kx = 3 - S; kx < 3; ++kx) win[ky][kx] = ld(ky, ox * S - pad_l + kx);
+            for (int j = 0; j < S; ++j) win[ky][3 - S + j] = nxt[ky][j];
+        }
+        if (ox + 1 < Wo) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int j = 0; j < S; ++j) nxt[ky][j] = ld(ky, (ox + 1) * S - pad_l + 3 - S + j);
         }
         emit(ox, win);
     }
@@ -145,7 +154,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_row_kernel(DwArgs<T> a) {
     if (!a.bn.training) return;        // inference (block-uniform)
     __syncthreads();
     for (int i = tid; i < a.C; i += 256) {
-        double2* dst = a.tb.fst + (size_t)t * a.C + i;
+        double2* dst = stat_slot(a.tb.fst, a.C, stat_copy(), t, i);
         atomicAdd(&dst->x, (double)s_sum[i]);
         atomicAdd(&dst->y, (double)s_sq[i]);
     }
@@ -196,13 +205,20 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_wgrad_row_kernel(DwBwdArgs<T> a) {
     const int tid = threadIdx.x, t = blockIdx.y;
     for (int i = tid; i < 10 * kDwMaxC; i += 256) (&s_dw[0][0])[i] = 0.f;
     __syncthreads();
-    const DwRow R = dw_row_of(a.C, a.Ho, a.B * a.Ho, tid, blockIdx.x);
-    if (R.active) {
-        const int c = R.c;
+    // persistent over row blocks (grid.x may be smaller than the number of row blocks): the 20 per-thread sums
+    // are flushed once per CTA, which keeps the same-address atomic traffic low
+    const DwLanes L = dw_lanes(a.C, tid);
+    if (L.cl < (a.C >> 1) && L.rl < L.lanes_r) {
+        const int c = L.cl * 2, nrows = a.B * a.Ho;
         const double inv_n = 1.0 / ((double)a.B * a.Ho * a.Wo);
         const BnCol b0 = load_bncol(a.tb, a.C, t, c, inv_n), b1 = load_bncol(a.tb, a.C, t, c + 1, inv_n);
         float2 f0 = make_float2(1.f, 0.f), f1 = make_float2(1.f, 0.f);
         if (a.in.aff) { f0 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c]; f1 = a.in.aff[(size_t)t * a.in.ld + a.in.coff + c + 1]; }
+        float g0[10], g1[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { g0[k] = 0.f; g1[k] = 0.f; }
+      for (int row = blockIdx.x * L.lanes_r + L.rl; row < nrows; row += gridDim.x * L.lanes_r) {
+        DwRow R; R.b = row / a.Ho; R.y = row - R.b * a.Ho;
         const T* img = (const T*)a.in.data + ((size_t)(t * a.B + R.b) * a.Hi * a.Wi) * a.in.ld + a.in.coff + c;
         const int iy0 = R.y * S - a.pad_t;
         const int clampf = a.in.clamp, Wi = a.Wi, Hi = a.Hi, ld = a.in.ld, C = a.C;
@@ -215,9 +231,6 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_wgrad_row_kernel(DwBwdArgs<T> a) {
             return v;
         };
         const size_t orow = (((size_t)(t * a.B + R.b) * a.Ho + R.y) * a.Wo) * a.C + c;
-        float g0[10], g1[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) { g0[k] = 0.f; g1[k] = 0.f; }
         dw_row_sweep<S>(a.Wo, a.pad_l, load, [&](int ox, float2 (&win)[3][3]) {
             const size_t o = orow + (size_t)ox * C;
             const float2 dv = ld2(a.dout + o), rv = ld2(a.out + o);
@@ -226,6 +239,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_wgrad_row_kernel(DwBwdArgs<T> a) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) { g0[k] = fmaf(win[k / 3][k % 3].x, d0, g0[k]); g1[k] = fmaf(win[k / 3][k % 3].y, d1, g1[k]); }
         });
+      }
 #pragma unroll
         for (int k = 0; k < 10; ++k) { atomicAdd(&s_dw[k][c], g0[k]); atomicAdd(&s_dw[k][c + 1], g1[k]); }
     }
