@@ -172,7 +172,7 @@ template <typename T>
 static void launch_bstat(const RunCtx& c, const WsTensor& t, int coff, int C, bool clamp) {
     BstatArgs<T> a;
     a.dA = (const T*)(c.ws + t.grad); a.R = (const T*)(c.ws + t.data); a.ld = t.C; a.coff = coff; a.C = C; a.Rt = t.Rt;
-    a.clamp = clamp ? 1 : 0; a.tb = tables_of(c, t); a.counter = counter_ptr(c, t.bcounter);
+    a.clamp = clamp ? 1 : 0; a.tb = tables_of(c, t); a.counter = nullptr;    // sums go straight to replica 0 (no fold, no ticket)
     int rows = 16384 / C; if (rows < 64) rows = 64;
     a.rows_per_block = rows;
     prof_bytes(4.0 * t.Rt * C * 2 * sizeof(T));                // read dA and R once
@@ -210,7 +210,7 @@ static void launch_pw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
         prof_bytes(4.0 * Rt * (2.0 * cm.n + l.K) * sizeof(T));
         CDRA_LAUNCH(pw_wgrad_mma_kernel, dim3(kt, nt, kT * sp), dim3(256), 0, c.stream, a);
         PwWgReduceArgs ra{a, kt, nt, kT * sp};
-        CDRA_LAUNCH(pw_wgrad_reduce_kernel, dim3(kt, nt), dim3(256), 0, c.stream, ra);
+        CDRA_LAUNCH(pw_wgrad_reduce_kernel, dim3(kt, nt, kWgKT * kWgNT / 32), dim3(256), 0, c.stream, ra);
         return;
     }
 #endif

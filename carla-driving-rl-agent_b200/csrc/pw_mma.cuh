@@ -167,26 +167,29 @@ CDRA_KERNEL __launch_bounds__(256, TN == 64 ? 3 : 2) pw_fwd_mma_kernel(PwMmaFwdA
     }
     __syncthreads();
     const int rows = min(kMmTM, a.Rt - row0);
-    if (a.do_stats) {   // statistics over the stored (rounded) values: 256/TN threads per column
-        constexpr int kPer = 256 / TN;
-        const int j = tid % TN, part = tid / TN;
+    {   // one pass over the staged tile: thread <-> fixed column pair (destination channels resolved once), row lanes
+        // stride the rows; column statistics (over the stored, rounded values) accumulate in registers on the way out
+        constexpr int kPairs = TN / 2, kRowLanes = 256 / kPairs;
+        const int pj = tid % kPairs, rl = tid / kPairs, j = pj * 2;
         if (j < ncols) {
-            float s = 0.f, q = 0.f;
-            for (int r = part; r < rows; r += kPer) { const float v = __bfloat162float(Cs[r * kCLd + j]); s += v; q = fmaf(v, v, q); }
-            atomicAdd(&s_sum[j], s); atomicAdd(&s_sq[j], q);
+            const bool two = j + 1 < ncols;
+            const int c0 = colmap_c(a.cm, col0 + j), c1 = two ? colmap_c(a.cm, col0 + j + 1) : 0;
+            const bool vec = two && c1 == c0 + 1 && !(c0 & 1);
+            bf16* orow = a.out + ((size_t)t * a.Rt + row0) * a.ldo;
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+            for (int r = rl; r < rows; r += kRowLanes) {
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(Cs + r * kCLd + j);
+                const float2 v = unpack_bf16(u);
+                bf16* row = orow + (size_t)r * a.ldo;
+                if (vec) *reinterpret_cast<uint32_t*>(row + c0) = u;
+                else { row[c0] = Cs[r * kCLd + j]; if (two) row[c1] = Cs[r * kCLd + j + 1]; }
+                s0 += v.x; q0 = fmaf(v.x, v.x, q0); s1 += v.y; q1 = fmaf(v.y, v.y, q1);
+            }
+            if (a.do_stats) {
+                atomicAdd(&s_sum[j], s0); atomicAdd(&s_sq[j], q0);
+                if (two) { atomicAdd(&s_sum[j + 1], s1); atomicAdd(&s_sq[j + 1], q1); }
+            }
         }
-    }
-    // store: 2-column (4-byte) accesses whenever the destination pair is adjacent and aligned
-    const int npair = (ncols + 1) >> 1;
-    for (int i = tid; i < rows * npair; i += 256) {
-        const int r = i / npair, j = (i - r * npair) * 2;
-        bf16* row = a.out + ((size_t)t * a.Rt + row0 + r) * a.ldo;
-        const int c0 = colmap_c(a.cm, col0 + j);
-        if (j + 1 < ncols) {
-            const int c1 = colmap_c(a.cm, col0 + j + 1);
-            if (c1 == c0 + 1 && !(c0 & 1)) *reinterpret_cast<uint32_t*>(row + c0) = *reinterpret_cast<const uint32_t*>(Cs + r * kCLd + j);
-            else { row[c0] = Cs[r * kCLd + j]; row[c1] = Cs[r * kCLd + j + 1]; }
-        } else row[c0] = Cs[r * kCLd + j];
     }
     if (!a.do_stats) return;           // inference (block-uniform)
     __syncthreads();
@@ -196,7 +199,7 @@ CDRA_KERNEL __launch_bounds__(256, TN == 64 ? 3 : 2) pw_fwd_mma_kernel(PwMmaFwdA
         atomicAdd(&dst->y, (double)s_sq[tid]);
     }
     const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    if (last_block_ticket(a.bn.counter, total))
+    if (a.bn.counter != nullptr && last_block_ticket(a.bn.counter, total))
         bn_finalize(a.cm, a.tb, a.ldo, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)a.Rt,
                     a.bn.unbiased, a.bn.training, 256, tid);
 }
@@ -303,13 +306,21 @@ CDRA_KERNEL __launch_bounds__(256, TK == 64 ? 3 : 2) pw_dgrad_mma_kernel(PwMmaBw
     }
     __syncthreads();
     const int rows = min(kMmTM, a.Rt - row0);
-    const int npair = kcols >> 1;                       // K is even for every layer of the tower
-    for (int i = tid; i < rows * npair; i += 256) {
-        const int r = i / npair, k = (i - r * npair) * 2;
-        bf16* d = a.dx + ((size_t)t * a.Rt + row0 + r) * a.ldx + a.coffx + k0t + k;
-        float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(Cs + r * kCLd + k));
-        if (a.accumulate) { const float2 o = unpack_bf16(*reinterpret_cast<const uint32_t*>(d)); v.x += o.x; v.y += o.y; }
-        *reinterpret_cast<uint32_t*>(d) = pack_bf16(v.x, v.y);
+    {   // thread <-> fixed column pair, row lanes stride the rows (K is even for every layer of the tower)
+        constexpr int kPairs = TK / 2, kRowLanes = 256 / kPairs;
+        const int k = (tid % kPairs) * 2, rl = tid / kPairs;
+        if (k < kcols) {
+            bf16* dcol = a.dx + ((size_t)t * a.Rt + row0) * a.ldx + a.coffx + k0t + k;
+            for (int r = rl; r < rows; r += kRowLanes) {
+                bf16* d = dcol + (size_t)r * a.ldx;
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(Cs + r * kCLd + k);
+                if (a.accumulate) {
+                    float2 v = unpack_bf16(u);
+                    const float2 o = unpack_bf16(*reinterpret_cast<const uint32_t*>(d));
+                    *reinterpret_cast<uint32_t*>(d) = pack_bf16(v.x + o.x, v.y + o.y);
+                } else *reinterpret_cast<uint32_t*>(d) = u;
+            }
+        }
     }
 }
 
@@ -419,19 +430,28 @@ CDRA_KERNEL __launch_bounds__(256, 3) pw_wgrad_mma_kernel(PwBwdArgs<bf16> a) {
 struct PwWgReduceArgs { PwBwdArgs<bf16> a; int kt, nt, nz; };
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_wgrad_reduce_kernel(PwWgReduceArgs ra) {
     const PwBwdArgs<bf16>& a = ra.a;
-    const int tid = threadIdx.x, N = a.cm.n, K = a.K;
+    // grid = (kt, nt, 128): each CTA owns 32 elements of one tile; its 8 warps split the row-split partials
+    __shared__ float red[8][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, N = a.cm.n, K = a.K;
     const int k0t = blockIdx.x * kWgKT, j0t = blockIdx.y * kWgNT;
     const size_t tile = (size_t)kWgKT * kWgNT, zstride = (size_t)ra.kt * ra.nt * tile;
     const float* base = a.partials + ((size_t)blockIdx.x * ra.nt + blockIdx.y) * tile;
-    for (int e = tid; e < kWgKT * kWgNT; e += 256) {
+    const int e = blockIdx.z * 32 + lane;
+    float s = 0.f;
+    for (int z = warp; z < ra.nz; z += 8) s += base[(size_t)z * zstride + e];
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][lane];
         const int k = k0t + e / kWgNT, j = j0t + e % kWgNT;
-        if (k > K || j >= N) continue;
-        float s = 0.f;
-        for (int z = 0; z < ra.nz; ++z) s += base[(size_t)z * zstride + e];
-        const int wc = colmap_w(a.cm, j);
-        if (k < K) a.dw[(size_t)k * N + wc] = s; else a.db[wc] = s;
+        if (k <= K && j < N) {
+            const int wc = colmap_w(a.cm, j);
+            if (k < K) a.dw[(size_t)k * N + wc] = s; else a.db[wc] = s;
+        }
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0) {                           // BN parameter gradients
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {       // BN parameter gradients
         for (int j = tid; j < N; j += 256) {
             const int c = colmap_c(a.cm, j), wc = colmap_w(a.cm, j);
             double gs = 0.0, bs = 0.0;

@@ -74,12 +74,13 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) bstat_kernel(BstatArgs<T> a) {
     }
     __syncthreads();
     for (int i = tid; i < a.C; i += 256) {
-        double2* d = stat_slot(a.tb.bst, a.ld, stat_copy(), t, a.coff + i);
+        double2* d = stat_slot(a.tb.bst, a.ld, a.counter ? stat_copy() : 0, t, a.coff + i);
         atomicAdd(&d->x, (double)s1[i]);
         atomicAdd(&d->y, (double)s2[i]);
     }
-    // the last block folds the replicas into replica 0, which is what the backward kernels read
-    if (last_block_ticket(a.counter, gridDim.x * gridDim.y)) {
+    // replicated mode (counter != null): the last block folds the replicas into replica 0, which is what the
+    // backward kernels read; with counter == null everything accumulates in replica 0 directly
+    if (a.counter != nullptr && last_block_ticket(a.counter, gridDim.x * gridDim.y)) {
         for (int i = tid; i < kT * a.C; i += 256) {
             const int tt = i / a.C, c = a.coff + (i - tt * a.C);
             const double2 s = stat_fold(a.tb.bst, a.ld, tt, c);

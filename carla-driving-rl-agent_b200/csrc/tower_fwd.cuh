@@ -99,7 +99,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(128) stem_fwd_kernel(StemArgs<T, TIn> a) {
         atomicAdd(&dst->y, (double)s_sq[tid]);
     }
     const unsigned total = gridDim.x * gridDim.y;
-    if (last_block_ticket(a.bn.counter, total)) {
+    if (a.bn.counter != nullptr && last_block_ticket(a.bn.counter, total)) {
         ColMap cm{kStemC, 0, 0, 0};
         bn_finalize(cm, a.tb, kStemC, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)Rt,
                     a.bn.unbiased, a.bn.training, 128, tid);
@@ -245,7 +245,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) pw_fwd_kernel(PwArgs<T> a) {
         atomicAdd(&dst->y, (double)s_sq[tid]);
     }
     const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    if (last_block_ticket(a.bn.counter, total))
+    if (a.bn.counter != nullptr && last_block_ticket(a.bn.counter, total))
         bn_finalize(a.cm, a.tb, a.ldo, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)a.Rt,
                     a.bn.unbiased, a.bn.training, 256, tid);
 }
@@ -331,7 +331,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_kernel(DwArgs<T> a) {
         atomicAdd(&dst->y, (double)s_sq[i]);
     }
     const unsigned total_blocks = gridDim.x * gridDim.y;
-    if (last_block_ticket(a.bn.counter, total_blocks)) {
+    if (a.bn.counter != nullptr && last_block_ticket(a.bn.counter, total_blocks)) {
         ColMap cm{a.C, 0, 0, 0};
         bn_finalize(cm, a.tb, a.C, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)npix,
                     a.bn.unbiased, a.bn.training, 256, tid);

@@ -159,7 +159,7 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_fwd_row_kernel(DwArgs<T> a) {
         atomicAdd(&dst->y, (double)s_sq[i]);
     }
     const unsigned total_blocks = gridDim.x * gridDim.y;
-    if (last_block_ticket(a.bn.counter, total_blocks)) {
+    if (a.bn.counter != nullptr && last_block_ticket(a.bn.counter, total_blocks)) {
         ColMap cm{a.C, 0, 0, 0};
         bn_finalize(cm, a.tb, a.C, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, (double)a.B * a.Ho * a.Wo,
                     a.bn.unbiased, a.bn.training, 256, tid);
@@ -256,6 +256,16 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dw_wgrad_row_kernel(DwBwdArgs<T> a) {
             a.dgamma[c] = (float)g; a.dbeta[c] = (float)b;
         }
     }
+}
+
+// --------------------------------------------------------------------------- BatchNorm finalisation as its own launch
+// Folds the replicated fp64 sums of one layer into (scale, shift) / (mean, inv_std) and applies the 4 sequential
+// moving-average updates.  Running it as a separate 1-3 CTA kernel keeps device-wide fences ("last block" tickets)
+// out of every producer CTA, which ncu showed as a membar stall in all of them.
+struct BnFinArgs { ColMap cm; BnTables tb; int ld; BnLayer bn; double n; };
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) bn_finalize_kernel(BnFinArgs a) {
+    bn_finalize(a.cm, a.tb, a.ld, a.bn.gamma, a.bn.beta, a.bn.mov_mean, a.bn.mov_var, a.n, a.bn.unbiased, a.bn.training,
+                256 * gridDim.x, blockIdx.x * 256 + threadIdx.x);
 }
 
 // --------------------------------------------------------------------------- inference-mode BatchNorm affine

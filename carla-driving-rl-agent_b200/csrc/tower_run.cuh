@@ -35,8 +35,20 @@ inline BnLayer bn_of(const RunCtx& c, const BnConv& l, int unbiased = 1) {
     BnLayer b;
     b.gamma = c.params + l.g; b.beta = c.params + l.be;
     b.mov_mean = c.state ? c.state + l.mm : nullptr; b.mov_var = c.state ? c.state + l.mv : nullptr;
-    b.counter = counter_ptr(c, l.counter); b.training = c.training; b.unbiased = unbiased;
+    b.counter = nullptr;          // BN finalisation runs as its own launch (launch_bn_finalize), no in-kernel ticket
+    b.training = c.training; b.unbiased = unbiased;
     return b;
+}
+inline void launch_bn_finalize(const RunCtx& c, const BnConv& l, const WsTensor& dst, const ColMap& cm, double n) {
+    if (!c.training) return;
+    BnFinArgs a;
+    a.cm = cm; a.ld = dst.C; a.n = n;
+    a.tb.fst = (double2*)(c.ws + dst.fst); a.tb.bst = (double2*)(c.ws + dst.bst);
+    a.tb.aff = (float2*)(c.ws + dst.aff); a.tb.bnp = (float2*)(c.ws + dst.bnp);
+    a.bn.gamma = c.params + l.g; a.bn.beta = c.params + l.be;
+    a.bn.mov_mean = c.state ? c.state + l.mm : nullptr; a.bn.mov_var = c.state ? c.state + l.mv : nullptr;
+    a.bn.counter = nullptr; a.bn.training = c.training; a.bn.unbiased = 1;
+    CDRA_LAUNCH(bn_finalize_kernel, dim3((cm.n + 255) / 256), dim3(256), 0, c.stream, a);
 }
 inline ActView view_of(const RunCtx& c, const WsTensor& t, int coff, bool clamp) {
     ActView v; v.data = c.ws + t.data; v.ld = t.C; v.coff = coff;
@@ -60,12 +72,14 @@ void launch_pw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, int Rt, 
         static bool carve = (cudaFuncSetAttribute(k64, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
         (void)carve;
         CDRA_LAUNCH(k64, dim3(cdiv(Rt, kMmTM), kT, cdiv(cm.n, 64)), dim3(256), 0, c.stream, pa);
+        launch_bn_finalize(c, l, dst, cm, (double)Rt);
         return;
     }
 #endif
     dim3 grid(cdiv(Rt, kPwTM), kT, cdiv(cm.n, kPwTN));
     auto k = pw_fwd_kernel<T>;
     CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
+    launch_bn_finalize(c, l, dst, cm, (double)Rt);
 }
 
 #ifndef CDRA_EMU
@@ -95,6 +109,7 @@ void launch_dw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, const Un
     dim3 grid(cdiv((long long)a.B * u.Ho, 256 / lanes_c), kT);      // row-sweep kernels: one output row per thread
     if (u.stride == 1) { auto k = dw_fwd_row_kernel<T, 1>; CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a); }
     else { auto k = dw_fwd_row_kernel<T, 2>; CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a); }
+    launch_bn_finalize(c, l, dst, ColMap{C, 0, 0, 0}, (double)a.B * u.Ho * u.Wo);
 }
 
 template <typename T, typename TIn>
@@ -114,6 +129,7 @@ void tower_forward(const RunCtx& c, const TIn* image) {
         prof_bytes(4.0 * B * ((double)p.H * p.W * 3 * sizeof(TIn) + (double)p.Hs * p.Ws * kStemC * sizeof(T)));
         auto k = stem_fwd_kernel<T, TIn>;
         CDRA_LAUNCH(k, grid, dim3(128), 0, c.stream, a);
+        launch_bn_finalize(c, p.stem, ts, ColMap{kStemC, 0, 0, 0}, (double)ts.Rt);
     }
     {   // BN + ReLU6 on load, maxpool 3x3 s2 SAME                      :160-161
         const WsTensor& ts = p.tensors[p.t_stem];
