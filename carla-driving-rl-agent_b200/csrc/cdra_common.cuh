@@ -90,7 +90,7 @@ struct BnTables {
 // The fp64 sums are the one place where thousands of CTAs hit the same addresses; they are spread over
 // kStatCopies replicas (chosen by block index) and folded by the last block, which cuts the same-address
 // atomic contention that otherwise puts a ~150 us floor under every kernel.
-constexpr int kStatCopies = 16;
+constexpr int kStatCopies = 4;
 CDRA_DEV int stat_copy() { return (int)((blockIdx.x + 5u * blockIdx.z) & (kStatCopies - 1)); }
 CDRA_DEV double2* stat_slot(double2* table, int ld, int copy, int t, int c) {
     return table + ((size_t)copy * kT + t) * ld + c;

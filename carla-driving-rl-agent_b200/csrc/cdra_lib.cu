@@ -178,6 +178,11 @@ static void launch_bstat(const RunCtx& c, const WsTensor& t, int coff, int C, bo
     prof_bytes(4.0 * t.Rt * C * 2 * sizeof(T));                // read dA and R once
     auto k = bstat_kernel<T>;
     CDRA_LAUNCH(k, dim3(cdiv(t.Rt, rows), kT), dim3(256), 0, c.stream, a);
+    // gradient wrt the activated value -> gradient wrt the raw conv output, in place (BN + ReLU6 backward);
+    // every conv-backward kernel downstream consumes dR as a plain matrix
+    prof_bytes(4.0 * t.Rt * C * 3 * sizeof(T));
+    auto k2 = dr_kernel<T>;
+    CDRA_LAUNCH(k2, dim3(cdiv(t.Rt, rows), kT), dim3(256), 0, c.stream, a);
 }
 
 template <typename T>
@@ -272,6 +277,13 @@ static void tower_backward(const RunCtx& c, const TIn* image) {
         const bool in_clamp = tin.tables;
         const int sc = u.stride == 2 ? u.cin : u.cin / 2;
         T* dxin = (T*)(c.ws + tin.grad);
+        if (u.stride == 1) {
+            // the shortcut half first: the in-place dA -> dR pass below also rewrites the pass-through channels of
+            // the unit-output gradient (harmless once they have been copied out)
+            PassBwdArgs<T> a{(const T*)(c.ws + out.grad), out.C, dxin, tin.C, u.half, out.Rt};
+            auto k = pass_bwd_kernel<T>;
+            CDRA_LAUNCH(k, dim3(cdiv((long long)out.Rt * (u.half / 2), 256), kT), dim3(256), 0, c.stream, a);
+        }
         launch_bstat<T>(c, out, 0, out.C, true);
         // branch
         launch_pw_bwd<T>(c, u.pw2, out, ColMap{u.c - sc, 1, sc / 2, u.half}, view_of(c, r2, 0, false), r2.Rt,
@@ -288,10 +300,6 @@ static void tower_backward(const RunCtx& c, const TIn* image) {
                              (T*)(c.ws + rs.grad), rs.C, 0, false, true);
             launch_bstat<T>(c, rs, 0, rs.C, false);
             launch_dw_bwd<T>(c, u.scdw, rs, view_of(c, tin, 0, in_clamp), u, sc, dxin, tin.C, 0, true);
-        } else {
-            PassBwdArgs<T> a{(const T*)(c.ws + out.grad), out.C, dxin, tin.C, u.half, out.Rt};
-            auto k = pass_bwd_kernel<T>;
-            CDRA_LAUNCH(k, dim3(cdiv((long long)out.Rt * (u.half / 2), 256), kT), dim3(256), 0, c.stream, a);
         }
     }
     {   // maxpool + stem

@@ -128,7 +128,7 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
     // ---- workspace map
     size_t off = 0;
     auto alloc = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t kCopies = 16;        // == cdra::kStatCopies (cdra_common.cuh): replicated fp64 sums
+    const size_t kCopies = 4;       // == cdra::kStatCopies (cdra_common.cuh): replicated fp64 sums
     for (auto& t : p.tensors) if (t.tables) { t.fst = alloc(kCopies * 4 * t.C * 16); t.bst = alloc(kCopies * 4 * t.C * 16); }
     p.zero_bytes = off;
     p.counters_off = alloc((size_t)(p.n_counters + 16) * 4);

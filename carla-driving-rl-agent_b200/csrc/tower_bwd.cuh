@@ -23,12 +23,17 @@ CDRA_DEV BnCol load_bncol(const BnTables& tb, int ld, int t, int c, double inv_n
     r.k1 = (float)(s.x * inv_n); r.k2 = (float)(s.y * inv_n);
     return r;
 }
-CDRA_DEV float make_dr(float dA, float R, const BnCol& b, int clamp) {
+// gradient wrt the raw (pre-BN) conv output from the gradient wrt the activated value
+CDRA_DEV float bn_backward_elem(float dA, float R, const BnCol& b, int clamp) {
     const float z = fmaf(R, b.scale, b.shift);
     const float dz = (!clamp || (z > 0.f && z < 6.f)) ? dA : 0.f;
     const float xhat = (R - b.mean) * b.inv;
     return b.scale * (dz - b.k1 - xhat * b.k2);
 }
+// `dr_kernel` applies bn_backward_elem IN PLACE to every gradient tensor right after its `bstat` launch, so the
+// conv-backward kernels below read dR directly: for them the transform is the identity (the compiler drops the
+// then-unused loads of R and of the BN coefficients).  Keeping the call sites documents where dR is consumed.
+CDRA_DEV float make_dr(float dR, float /*R*/, const BnCol& /*b*/, int /*clamp*/) { return dR; }
 
 // --------------------------------------------------------------------------- S1/S2 sums
 template <typename T>
@@ -85,6 +90,29 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) bstat_kernel(BstatArgs<T> a) {
             const int tt = i / a.C, c = a.coff + (i - tt * a.C);
             const double2 s = stat_fold(a.tb.bst, a.ld, tt, c);
             *stat_slot(a.tb.bst, a.ld, 0, tt, c) = s;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- dA -> dR in place (BatchNorm + ReLU6 backward)
+template <typename T>
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) dr_kernel(BstatArgs<T> a) {
+    const int tid = threadIdx.x, t = blockIdx.y;
+    const int r0 = blockIdx.x * a.rows_per_block;
+    const int r1 = min(a.Rt, r0 + a.rows_per_block);
+    const int CP = a.C >> 1;
+    const int lanes_c = CP >= 256 ? 256 : ((CP + 31) & ~31);
+    const int lanes_r = 256 / lanes_c, cl = tid % lanes_c, rl = tid / lanes_c;
+    if (rl >= lanes_r) return;
+    const double inv_n = 1.0 / (double)a.Rt;
+    T* dA = const_cast<T*>(a.dA);
+    for (int cp = cl; cp < CP; cp += lanes_c) {
+        const int c = a.coff + cp * 2;
+        const BnCol b0 = load_bncol(a.tb, a.ld, t, c, inv_n), b1 = load_bncol(a.tb, a.ld, t, c + 1, inv_n);
+        for (int r = r0 + rl; r < r1; r += lanes_r) {
+            const size_t o = ((size_t)t * a.Rt + r) * a.ld + c;
+            const float2 d = ld2(dA + o), x = ld2(a.R + o);
+            st2(dA + o, make_float2(bn_backward_elem(d.x, x.x, b0, a.clamp), bn_backward_elem(d.y, x.y, b1, a.clamp)));
         }
     }
 }
