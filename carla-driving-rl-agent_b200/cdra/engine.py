@@ -109,6 +109,13 @@ class Engine:
     def tensor(self, name):
         """View of a named intermediate tensor inside the workspace (parity taps)."""
         off, dims, es = C.c_int64(), (C.c_int32 * 4)(), C.c_int32()
+        if self.dtype == 'bf16' and not self.emulated:
+            # perf mode stores padded, shuffled channel planes: ask the library for the logical layout (fp32 copy)
+            if self.lib.cdra_debug_export(self.plan, name.encode(), None, None, dims, None) == 0:
+                out = torch.empty([d for d in dims], dtype=torch.float32, device=self.device)
+                _lib.check(self.lib, self.lib.cdra_debug_export(self.plan, name.encode(), _lib.ptr(self.ws), _lib.ptr(out),
+                                                                dims, self._stream()), 'debug_export')
+                return out
         _lib.check(self.lib, self.lib.cdra_plan_tensor(self.plan, name.encode(), C.byref(off), dims, C.byref(es)), 'plan_tensor')
         shape = [d for d in dims]
         while len(shape) > 1 and shape[-1] == 1:

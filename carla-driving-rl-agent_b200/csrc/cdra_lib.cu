@@ -5,6 +5,7 @@
 #include "plan.h"
 #include "tower_run.cuh"
 #include "tower_opt.cuh"
+#include "v2_run.cuh"
 #include "tail.cuh"
 #include "ppo.cuh"
 
@@ -40,6 +41,7 @@ std::map<const void*, ProfEntry> g_entries;
 #ifndef CDRA_EMU
 cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 const void* g_cur = nullptr;
+const void* g_cur_dbg = nullptr;
 #endif
 }
 namespace cdra {
@@ -47,12 +49,23 @@ void prof_bytes(double b) { g_pending_bytes = b; }
 #ifndef CDRA_EMU
 void prof_pre(const void* func, cudaStream_t stream) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_cur_dbg = func;
     if (!g_prof) return;
     if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
     g_cur = func;
     cudaEventRecord(g_ev0, stream);
 }
 void prof_post(cudaStream_t stream) {
+    static const bool dbg = getenv("CDRA_DEBUG_SYNC") != nullptr;      // debugging aid: fail at the offending launch
+    if (dbg) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            const char* name = nullptr;
+            if (g_cur_dbg) cudaFuncGetName(&name, g_cur_dbg);
+            fprintf(stderr, "libcdra: launch %lld (%s) failed: %s\n", (long long)g_launches.load(), name ? name : "?", cudaGetErrorString(e));
+        }
+    }
     if (!g_prof) { g_pending_bytes = 0.0; return; }
     cudaEventRecord(g_ev1, stream);
     cudaEventSynchronize(g_ev1);
@@ -502,6 +515,15 @@ int cdra_plan_tensor(const cdra_plan_t* plan, const char* name, int64_t* byte_of
     return CDRA_OK;
 }
 
+int cdra_debug_export(cdra_plan_t* plan, const char* name, void* workspace, float* out, int32_t dims[4], void* stream) {
+    if (!plan || !name) return fail(CDRA_ERR_BADARG, "null argument");
+#ifndef CDRA_EMU
+    if (plan->p->v2.on && v2::export_tensor(*plan->p, name, (char*)workspace, out, dims, (cudaStream_t)stream))
+        return check_launch("debug_export");
+#endif
+    return fail(CDRA_ERR_BADARG, std::string("no exportable tensor ") + name);
+}
+
 int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, const void* image, const float* road,
                           const float* vehicle, const float* navigation, int training, float* out512, void* workspace,
                           void* stream) {
@@ -513,6 +535,13 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     if (training) zero_async(c.ws, p.zero_bytes, c.stream);
     else eval_affine(c);                 // BN affine from the moving statistics (CARLANetwork.dynamics_predict)
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
+#ifndef CDRA_EMU
+    if (p.v2.on) {               // bf16 perf mode: legacy stem + pool, then the v2 tower (padded planes, TMA tiles)
+        if (u8) tower_forward<bf16, uint8_t>(c, (const uint8_t*)image, true);
+        else tower_forward<bf16, float>(c, (const float*)image, true);
+        v2::tower_forward(c);
+    } else
+#endif
     if (bf && u8) tower_forward<bf16, uint8_t>(c, (const uint8_t*)image);
     else if (bf) tower_forward<bf16, float>(c, (const float*)image);
     else if (u8) tower_forward<float, uint8_t>(c, (const uint8_t*)image);

@@ -125,19 +125,73 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
     build_head(p.policy, true);
     build_head(p.value, false);
 
+    // ---- v2 tower tensors (bf16 perf mode): padded planes, see v2_common.cuh
+    p.v2.on = (p.elem == 2);
+    if (p.v2.on) {
+        V2Plan& v = p.v2;
+        auto r8 = [](int x) { return (x + 7) / 8 * 8; };
+        auto r16 = [](int x) { return (x + 15) / 16 * 16; };
+        auto addT = [&](const std::string& name, int H, int W, int n0, int n0p, int n1, bool has_bn) {
+            V2Tensor t; t.name = name; t.H = H; t.W = W; t.Rt = p.B * H * W; t.n0 = n0; t.n0p = n0p; t.n1 = n1;
+            t.cp = r8(n0p + n1); t.has_bn = has_bn;
+            v.index[name] = (int)v.t.size(); v.t.push_back(t);
+            return (int)v.t.size() - 1;
+        };
+        auto plain = [&](const std::string& name, int H, int W, int C, bool bn = true) { return addT(name, H, W, C, r8(C), 0, bn); };
+        auto like = [&](const std::string& name, int H, int W, int src) {
+            const V2Tensor s = v.t[src]; return addT(name, H, W, s.n0, s.n0p, s.n1, true);
+        };
+        auto pw = [&](V2Pw& g, int ksum, int nplanes, int gwp) {
+            g.KP = r16(ksum); g.nplanes = nplanes; g.gwp = gwp; g.NPall = nplanes * gwp;
+            g.counter = p.n_counters++; g.bcounter = p.n_counters++;
+        };
+        v.p0 = plain("tower.pool", p.Hp, p.Wp, kStemC, false);
+        int inA = v.p0, inB = -1;
+        for (const Unit& un : p.units) {
+            V2Unit u;
+            u.inA = inA; u.inB = inB;
+            u.r1 = plain(un.name + ".pw1", un.Hi, un.Wi, un.half);
+            u.r2 = plain(un.name + ".dw", un.Ho, un.Wo, un.half);
+            u.c_dw = p.n_counters++; u.cb_dw = p.n_counters++;
+            int n0, n0p, n1;
+            if (un.stride == 2) {
+                u.rsA = like(un.name + ".scdwA", un.Ho, un.Wo, inA);
+                u.c_scA = p.n_counters++; u.cb_scA = p.n_counters++;
+                if (inB >= 0) { u.rsB = like(un.name + ".scdwB", un.Ho, un.Wo, inB); u.c_scB = p.n_counters++; u.cb_scB = p.n_counters++; }
+                n0 = (un.c - un.cin) / 2; n0p = (n0 + 1) / 2 * 2; n1 = un.cin / 2;
+                pw(u.pw1, v.t[inA].cp + (inB >= 0 ? v.t[inB].cp : 0), 1, v.t[u.r1].cp);
+            } else {
+                n0 = un.half / 2; n0p = (n0 + 1) / 2 * 2; n1 = un.half / 2;
+                pw(u.pw1, v.t[inB].cp, 1, v.t[u.r1].cp);
+            }
+            u.outA = addT(un.name + ".outA", un.Ho, un.Wo, n0, n0p, n1, true);
+            u.outB = addT(un.name + ".outB", un.Ho, un.Wo, n0, n0p, n1, true);
+            if (un.stride == 2) pw(u.tail, v.t[u.r2].cp + v.t[u.rsA].cp + (u.rsB >= 0 ? v.t[u.rsB].cp : 0), 2, v.t[u.outA].cp);
+            else pw(u.tail, v.t[u.r2].cp, 2, r8(n0p));
+            v.u.push_back(u);
+            inA = u.outA; inB = u.outB;
+        }
+        v.head = plain("tower.head", v.t[inA].H, v.t[inA].W, kLastC);
+        pw(v.head_pw, v.t[inA].cp + v.t[inB].cp, 1, v.t[v.head].cp);
+        v.c_gap = p.n_counters++;
+    }
+
     // ---- workspace map
     size_t off = 0;
     auto alloc = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t kCopies = 4;       // == cdra::kStatCopies (cdra_common.cuh): replicated fp64 sums
-    for (auto& t : p.tensors) if (t.tables) { t.fst = alloc(kCopies * 4 * t.C * 16); t.bst = alloc(kCopies * 4 * t.C * 16); }
+    auto legacy = [&](const WsTensor& t) { return !p.v2.on || t.name == "tower.stem" || t.name == "tower.pool"; };
+    for (auto& t : p.tensors) if (t.tables && legacy(t)) { t.fst = alloc(kCopies * 4 * t.C * 16); t.bst = alloc(kCopies * 4 * t.C * 16); }
+    for (auto& t : p.v2.t) { t.fsum = alloc((size_t)4 * t.cp * 16); t.bsum = alloc((size_t)4 * t.cp * 16); }
     p.zero_bytes = off;
     p.counters_off = alloc((size_t)(p.n_counters + 16) * 4);
-    for (auto& t : p.tensors) if (t.tables) { t.aff = alloc((size_t)4 * t.C * 8); t.bnp = alloc((size_t)4 * t.C * 8); }
+    for (auto& t : p.tensors) if (t.tables && legacy(t)) { t.aff = alloc((size_t)4 * t.C * 8); t.bnp = alloc((size_t)4 * t.C * 8); }
+    for (auto& t : p.v2.t) { t.aff = alloc((size_t)4 * t.cp * 8); t.bnp = alloc((size_t)4 * t.cp * 8); }
     {   // bf16 weight copies for the tensor-core pointwise kernels
         auto pw = [&](BnConv& l, int split) {
             l.is_pw = true; l.split = split;
             l.Kp = (l.K + 31) / 32 * 32; l.Np = (l.N + 31) / 32 * 32;
-            if (p.elem == 2) {
+            if (p.elem == 2 && !p.v2.on) {
                 l.wt = alloc((size_t)((l.N + 7) / 8 * 8) * l.Kp * 2);
                 l.wn = alloc((size_t)((l.K + 7) / 8 * 8) * l.Np * 2);
             }
@@ -145,8 +199,24 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
         for (auto& u : p.units) { pw(u.pw1, 0); pw(u.pw2, 1); if (u.stride == 2) pw(u.scpw, 1); }
         pw(p.head, 0);
     }
-    for (auto& t : p.tensors) { t.data = alloc(t.bytes()); }
-    for (auto& t : p.tensors) { t.grad = t.has_grad ? alloc(t.bytes()) : 0; }
+    for (auto& t : p.tensors) if (legacy(t)) { t.data = alloc(t.bytes()); }
+    for (auto& t : p.tensors) if (legacy(t)) { t.grad = t.has_grad ? alloc(t.bytes()) : 0; }
+    if (p.v2.on) {
+        V2Plan& v = p.v2;
+        for (auto& t : v.t) {
+            if (t.name == "tower.pool") { t.data = p.tensors[p.t_pool].data; t.grad = p.tensors[p.t_pool].grad; continue; }
+            t.data = alloc(t.bytes() + 256);          // +256: TMA tiles / vector tails never leave the allocation
+        }
+        for (auto& t : v.t) if (t.name != "tower.pool") t.grad = alloc(t.bytes() + 256);
+        auto pwalloc = [&](V2Pw& g) {
+            g.wf = alloc((size_t)g.NPall * g.KP * 2); g.wb = alloc((size_t)g.NPall * g.KP * 2); g.bias = alloc((size_t)g.NPall * 4);
+        };
+        for (auto& u : v.u) { pwalloc(u.pw1); pwalloc(u.tail); }
+        pwalloc(v.head_pw);
+        v.desc_off = alloc(64 * 1024);
+        v.host_descs_buf.resize(64 * 1024);
+        v.host_descs = v.host_descs_buf.data();
+    }
     auto f32 = [&](const std::string& name, std::vector<int> dims) {
         size_t n = 1; for (int d : dims) n *= d;
         size_t o = alloc(n * 4);

@@ -84,8 +84,47 @@ struct HeadSpec {       // policy or value head
     int64_t bn1_mm, bn1_mv, bn2_mm, bn2_mv;
 };
 
+// ---- v2 tower (bf16 perf mode): padded plane layout, see v2_common.cuh
+struct V2Tensor {
+    std::string name;
+    int Rt = 0, H = 0, W = 0;
+    int cp = 0;                  // slots per row (multiple of 8)
+    int n0 = 0, n0p = 0, n1 = 0; // slot map: [part0 n0 valid of n0p | part1 n1 | pad]
+    size_t data = 0, grad = 0;   // bf16 [4*Rt][cp]
+    size_t fsum = 0, bsum = 0;   // double2 [4][cp] (inside the re-zeroed region)
+    size_t aff = 0, bnp = 0;     // float2 [4][cp]
+    bool has_bn = true;
+    int C() const { return n0 + n1; }
+    size_t bytes() const { return (size_t)4 * Rt * cp * 2; }
+};
+struct V2Pw {                    // one GEMM launch (pw1 / unit tail / head conv)
+    int KP = 0, NPall = 0, nplanes = 1, gwp = 0;
+    size_t wf = 0, wb = 0, bias = 0;    // workspace byte offsets of the prepared bf16 operands
+    int counter = -1, bcounter = -1;
+};
+struct V2Unit {
+    int inA = -1, inB = -1;      // input tensor(s): previous unit's planes, or (inA only) the pool output
+    int r1 = -1, r2 = -1, rsA = -1, rsB = -1, outA = -1, outB = -1;
+    V2Pw pw1, tail;
+    int c_dw = -1, c_scA = -1, c_scB = -1;          // forward ticket counters of the depthwise launches
+    int cb_dw = -1, cb_scA = -1, cb_scB = -1;       // backward
+};
+struct V2Plan {
+    bool on = false;
+    std::vector<V2Tensor> t;
+    std::map<std::string, int> index;
+    std::vector<V2Unit> u;
+    int p0 = -1, head = -1;      // pool output (plain, already activated), head conv output
+    V2Pw head_pw;
+    int c_gap = -1;
+    size_t desc_off = 0;         // device copies of the GEMM descriptors (uploaded at the start of every pass)
+    mutable std::vector<char> host_descs_buf;
+    void* host_descs = nullptr;
+};
+
 struct Plan {
     cdra_config cfg;
+    V2Plan v2;
     int B, H, W, elem;
     Arena dyn_params, dyn_state;
     HeadSpec policy, value;

@@ -113,11 +113,11 @@ void launch_dw_fwd(const RunCtx& c, const BnConv& l, const ActView& in, const Un
 }
 
 template <typename T, typename TIn>
-void tower_forward(const RunCtx& c, const TIn* image) {
+void tower_forward(const RunCtx& c, const TIn* image, bool stem_only = false) {
     const Plan& p = *c.p;
     const int B = p.B;
 #ifndef CDRA_EMU
-    if constexpr (std::is_same<T, bf16>::value) launch_wprep(c);
+    if constexpr (std::is_same<T, bf16>::value) if (!stem_only) launch_wprep(c);
 #endif
     {   // stem conv (+BN statistics)                                  core/architectures.py:159-160
         const WsTensor& ts = p.tensors[p.t_stem];
@@ -141,6 +141,7 @@ void tower_forward(const RunCtx& c, const TIn* image) {
         auto k = pool_fwd_kernel<T>;
         CDRA_LAUNCH(k, grid, dim3(256), 0, c.stream, a);
     }
+    if (stem_only) return;           // v2 tower (bf16): the units / head run through v2_run.cuh
     for (const Unit& u : p.units) {                                     // :120-151
         const WsTensor& tin = p.tensors[u.t_in];
         const WsTensor& r1 = p.tensors[u.t_r1];

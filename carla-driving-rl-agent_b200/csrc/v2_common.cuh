@@ -1,0 +1,178 @@
+// "v2" image tower (bf16 perf mode): shared device helpers.
+//
+// Layout: every tower activation is a bf16 matrix [4*Rt rows][cp slots], rows ordered
+// [slice t][sample b][y][x], cp a multiple of 8 so that rows are 16-byte aligned and whole row tiles are
+// CONTIGUOUS in HBM (one TMA bulk copy per tile).  A unit output (core/architectures.py:120-145) is stored as
+// two such matrices ("planes"): plane g holds the logical channels out[g*C/2 + i] = concat[2i + g]
+// (channel_shuffle, :109-118).  Inside a plane the physical slot order is
+//     [ part0: branch (pw2) outputs, n0 valid of n0p | part1: shortcut / pass-through, n1 valid | zero pad ]
+// while the plane's LOGICAL channel order (what the next layer's weights are indexed by) is [part1 | part0].
+// Plain tensors (pw1 / dw outputs, pool output, head conv) are the special case n1 = 0.
+#pragma once
+#ifndef CDRA_EMU
+#include "cdra_common.cuh"
+
+namespace cdra {
+namespace v2 {
+
+struct SlotMap { int n0, n0p, n1; };
+CDRA_DEV int slot_logical(const SlotMap& m, int s) {        // logical channel of slot s, -1 = padding
+    if (s < m.n0p) return s < m.n0 ? m.n1 + s : -1;
+    s -= m.n0p;
+    return s < m.n1 ? s : -1;
+}
+CDRA_DEV int logical_slot(const SlotMap& m, int l) { return l < m.n1 ? m.n0p + l : l - m.n1; }
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+CDRA_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CDRA_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+CDRA_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+CDRA_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+CDRA_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (contiguous bytes; 16-byte aligned, size multiple of 16); completion on `bar`
+CDRA_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+CDRA_DEV uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+CDRA_DEV float2 unpack2(uint32_t u) {
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+CDRA_DEV void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+CDRA_DEV void ldsm4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+CDRA_DEV void ldsm4t(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+CDRA_DEV uint4 ldg_cg16(const void* p) {        // L2-only 16-byte load (data written by other CTAs / streams of tiles)
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// relu6(scale * x + shift) on 8 packed bf16 (fp32 math, one rounding)
+CDRA_DEV uint4 affine8(uint4 v, const float2 (&c)[8], bool clamp) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = unpack2(w[i]);
+        f.x = fmaf(f.x, c[2 * i].x, c[2 * i].y);
+        f.y = fmaf(f.y, c[2 * i + 1].x, c[2 * i + 1].y);
+        if (clamp) { f.x = relu6f(f.x); f.y = relu6f(f.y); }
+        w[i] = pack2(f.x, f.y);
+    }
+    return v;
+}
+
+// "last CTA done" ticket with a single fencing thread (release: bar.sync orders the CTA's atomics before the fence)
+CDRA_DEV bool last_cta(unsigned* counter, unsigned total) {
+    __shared__ unsigned s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(counter, 1u);
+        s_last = (t == total - 1) ? 1u : 0u;
+        if (t == total - 1) *counter = 0;
+        __threadfence();
+    }
+    __syncthreads();
+    return s_last != 0;
+}
+CDRA_DEV double2 ld_sum(const double2* p) {      // sums written by atomics of other CTAs: read through L2
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// BatchNorm tables of one stored tensor (all [kT][cp])
+struct Tables {
+    double2* fsum;      // forward sums (sum x, sum x^2) over the stored (rounded) raw values
+    double2* bsum;      // backward sums (sum dz, sum dz*xhat)
+    float2* aff;        // (scale, shift)
+    float2* bnp;        // (mean, inv_std)
+};
+
+// One BatchNorm-ed conv layer (parameter / state arena offsets resolved to pointers)
+struct LayerP {
+    const float* w; const float* b; const float* g; const float* be;   // trainable
+    float* mm; float* mv;                                               // moving statistics (may be null)
+    float* dw; float* db; float* dg; float* dbe;                        // gradients (backward only)
+    int K, N;
+};
+
+// scale/shift/mean/inv for one (slice, channel) from batch sums or (inference) moving statistics, plus the
+// kT sequential Keras moving-average updates (core/architectures.py:44-57 applies the same layer object to every
+// time slice; FusedBatchNorm feeds the unbiased variance to the moving average).
+struct BnFin { float scale, shift, mean, inv; };
+CDRA_DEV BnFin bn_from_sums(double sx, double sxx, double n, float g, float b) {
+    const double mean = sx / n;
+    double var = sxx / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    BnFin r;
+    r.inv = (float)(1.0 / sqrt(var + (double)kBnEps));
+    r.mean = (float)mean;
+    r.scale = g * r.inv;
+    r.shift = b - r.mean * r.scale;
+    return r;
+}
+CDRA_DEV BnFin bn_from_moving(float mm, float mv, float g, float b) {
+    BnFin r;
+    r.inv = 1.0f / sqrtf(mv + kBnEps);
+    r.mean = mm;
+    r.scale = g * r.inv;
+    r.shift = b - mm * r.scale;
+    return r;
+}
+// finalise one output channel: tables for the 4 slices + moving statistics
+CDRA_DEV void bn_finalize_channel(const Tables& tb, int cp, int slot, const LayerP& L, int n_logical, double n, int training) {
+    const float g = L.g[n_logical], b = L.be[n_logical];
+    float mm = L.mm ? L.mm[n_logical] : 0.f, mv = L.mv ? L.mv[n_logical] : 1.f;
+    const float mm0 = mm, mv0 = mv;
+    for (int t = 0; t < kT; ++t) {
+        BnFin f;
+        if (training) {
+            const double2 s = ld_sum(tb.fsum + (size_t)t * cp + slot);
+            f = bn_from_sums(s.x, s.y, n, g, b);
+            const double mean = s.x / n;
+            double var = s.y / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double vm = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
+            mm -= (mm - (float)mean) * (1.f - kBnMomentum);
+            mv -= (mv - (float)vm) * (1.f - kBnMomentum);
+        } else {
+            f = bn_from_moving(mm0, mv0, g, b);
+        }
+        tb.aff[(size_t)t * cp + slot] = make_float2(f.scale, f.shift);
+        tb.bnp[(size_t)t * cp + slot] = make_float2(f.mean, f.inv);
+    }
+    if (training && L.mm) { L.mm[n_logical] = mm; L.mv[n_logical] = mv; }
+}
+
+}  // namespace v2
+}  // namespace cdra
+#endif

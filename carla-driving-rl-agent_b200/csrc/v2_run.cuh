@@ -1,0 +1,273 @@
+// v2 tower: host-side launch sequences (forward, backward) and the logical-layout export used by the parity taps.
+#pragma once
+#ifndef CDRA_EMU
+#include "plan.h"
+#include "tower_run.cuh"
+#include "v2_pw.cuh"
+#include "v2_dw.cuh"
+#include "v2_bwd.cuh"
+
+namespace cdra {
+namespace v2 {
+
+inline Tables tables_of(const RunCtx& c, const V2Tensor& t) {
+    Tables tb;
+    tb.fsum = (double2*)(c.ws + t.fsum); tb.bsum = (double2*)(c.ws + t.bsum);
+    tb.aff = (float2*)(c.ws + t.aff); tb.bnp = (float2*)(c.ws + t.bnp);
+    return tb;
+}
+inline LayerP layer_of(const RunCtx& c, const BnConv& l) {
+    LayerP L;
+    L.w = c.params + l.w; L.b = c.params + l.b; L.g = c.params + l.g; L.be = c.params + l.be;
+    L.mm = c.state ? c.state + l.mm : nullptr; L.mv = c.state ? c.state + l.mv : nullptr;
+    if (c.grads) { L.dw = c.grads + l.w; L.db = c.grads + l.b; L.dg = c.grads + l.g; L.dbe = c.grads + l.be; }
+    else { L.dw = L.db = L.dg = L.dbe = nullptr; }
+    L.K = l.K; L.N = l.N;
+    return L;
+}
+inline PwSrc src_of(const RunCtx& c, const V2Tensor& t, bool clamp, int kbase, int layer) {
+    PwSrc s;
+    s.data = (const bf16*)(c.ws + t.data); s.grad = (bf16*)(c.ws + t.grad);
+    s.aff = t.has_bn ? (const float2*)(c.ws + t.aff) : nullptr;
+    s.bnp = t.has_bn ? (const float2*)(c.ws + t.bnp) : nullptr;
+    s.bsum = (double2*)(c.ws + t.bsum);
+    s.cp = t.cp; s.clamp = clamp ? 1 : 0; s.map = SlotMap{t.n0, t.n0p, t.n1}; s.kbase = kbase; s.layer = layer;
+    s.sum_lo = 0; s.sum_hi = t.has_bn ? t.cp : 0; s.accumulate = 0;
+    return s;
+}
+
+// ---- GEMM descriptors of every pointwise launch (same objects drive weight prep, forward and backward)
+struct UnitDescs { PwDesc pw1, tail; };
+
+inline void fill_pw(PwDesc& d, const RunCtx& c, const V2Pw& g) {
+    d.KP = g.KP; d.NPall = g.NPall;
+    d.wf = (bf16*)(c.ws + g.wf); d.wb = (bf16*)(c.ws + g.wb); d.bias = (float*)(c.ws + g.bias);
+    d.cols.nplanes = g.nplanes; d.cols.gwp = g.gwp;
+}
+inline PwDesc desc_pw1(const RunCtx& c, int ui) {
+    const Plan& p = *c.p; const V2Plan& v = p.v2; const V2Unit& u = v.u[ui]; const Unit& un = p.units[ui];
+    PwDesc d; memset(&d, 0, sizeof d);
+    fill_pw(d, c, u.pw1);
+    const bool in_clamp = u.inB >= 0;            // unit outputs are BN+ReLU6 outputs; the pool output is already activated
+    if (un.stride == 2) {
+        d.nsrc = 0;
+        d.src[d.nsrc++] = src_of(c, v.t[u.inA], in_clamp, 0, 0);
+        if (u.inB >= 0) d.src[d.nsrc++] = src_of(c, v.t[u.inB], in_clamp, v.t[u.inA].C(), 0);
+    } else {
+        d.nsrc = 1; d.src[0] = src_of(c, v.t[u.inB], true, 0, 0);
+    }
+    d.layer[0] = layer_of(c, un.pw1); d.layer[1] = d.layer[0];
+    d.cols.seg0p = u.pw1.gwp; d.cols.seg0n = un.half; d.cols.seg1n = 0; d.cols.interleave = 0;
+    return d;
+}
+inline PwDesc desc_tail(const RunCtx& c, int ui) {
+    const Plan& p = *c.p; const V2Plan& v = p.v2; const V2Unit& u = v.u[ui]; const Unit& un = p.units[ui];
+    PwDesc d; memset(&d, 0, sizeof d);
+    fill_pw(d, c, u.tail);
+    const V2Tensor& o = v.t[u.outA];
+    d.nsrc = 0;
+    d.src[d.nsrc++] = src_of(c, v.t[u.r2], false, 0, 0);
+    d.layer[0] = layer_of(c, un.pw2); d.layer[1] = d.layer[0];
+    d.cols.interleave = 1;
+    d.cols.seg0p = o.n0p; d.cols.seg0n = o.n0; d.cols.seg1n = 0;
+    if (un.stride == 2) {
+        d.src[d.nsrc++] = src_of(c, v.t[u.rsA], false, 0, 1);
+        if (u.rsB >= 0) d.src[d.nsrc++] = src_of(c, v.t[u.rsB], false, v.t[u.rsA].C(), 1);
+        d.layer[1] = layer_of(c, un.scpw);
+        d.cols.seg1n = o.n1;
+    }
+    return d;
+}
+inline PwDesc desc_head(const RunCtx& c) {
+    const Plan& p = *c.p; const V2Plan& v = p.v2; const V2Unit& u = v.u.back();
+    PwDesc d; memset(&d, 0, sizeof d);
+    fill_pw(d, c, v.head_pw);
+    d.nsrc = 2;
+    d.src[0] = src_of(c, v.t[u.outA], true, 0, 0);
+    d.src[1] = src_of(c, v.t[u.outB], true, v.t[u.outA].C(), 0);
+    d.layer[0] = layer_of(c, p.head); d.layer[1] = d.layer[0];
+    d.cols.seg0p = v.head_pw.gwp; d.cols.seg0n = p.head.N; d.cols.seg1n = 0; d.cols.interleave = 0;
+    return d;
+}
+
+inline size_t desc_slot(const Plan& p, int i) { return p.v2.desc_off + (size_t)i * sizeof(PwDesc); }
+// launch index: 2*ui = pw1, 2*ui+1 = tail, 2*nunits = head
+inline const PwDesc* desc_dev(const RunCtx& c, int i) { return (const PwDesc*)(c.ws + desc_slot(*c.p, i)); }
+
+inline void upload_descs(const RunCtx& c) {
+    const Plan& p = *c.p; const int nu = (int)p.v2.u.size(), n = 2 * nu + 1;
+    PwDesc* host = (PwDesc*)p.v2.host_descs;
+    for (int ui = 0; ui < nu; ++ui) { host[2 * ui] = desc_pw1(c, ui); host[2 * ui + 1] = desc_tail(c, ui); }
+    host[2 * nu] = desc_head(c);
+    cudaMemcpyAsync(c.ws + p.v2.desc_off, host, (size_t)n * sizeof(PwDesc), cudaMemcpyHostToDevice, c.stream);
+}
+
+constexpr int kMaxDynSmem = 226 * 1024;      // 227 KB opt-in limit minus the kernels' few static bytes
+inline int num_sms() {
+    static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+    return n;
+}
+
+// ---- forward GEMM launch: picks the tile configuration by column count / shared-memory footprint
+template <int R, int WM, int WN, int MT, int NBW>
+inline bool try_pw_fwd(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd, int colmode, int min_ctas_per_sm) {
+    constexpr int NT = WN * NBW * 8;
+    int src_row_bytes = 0;
+    for (int i = 0; i < hd.nsrc; ++i) src_row_bytes += hd.src[i].cp * 2;
+    if (a.x1) src_row_bytes += a.x1cp * 2;
+    int gy = 1, splanes = hd.cols.nplanes, swidth = a.cpo;
+    a.colmode = colmode;
+    if (colmode == 0) { if (hd.NPall > NT) return false; a.ntiles_n = 1; }
+    else {                                   // N-tiled inside planes (no pass-through copy)
+        a.ntiles_n = (hd.cols.gwp + NT - 1) / NT; gy = hd.cols.nplanes * a.ntiles_n; splanes = 1; swidth = NT;
+    }
+    const PwFwdSmem L = pw_fwd_smem(R, NT, hd.KP, src_row_bytes, splanes, swidth);
+    if (L.total > kMaxDynSmem) return false;
+    if (min_ctas_per_sm > 1 && (L.total + 1024) * min_ctas_per_sm > 227 * 1024) return false;
+    auto k = pw_fwd_kernel<R, WM, WN, MT, NBW>;
+    static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
+    const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
+    int gx = std::max(1, num_sms() * per_sm / gy);
+    if (gx > ntile) gx = ntile;
+    a.tiles_per_cta = (ntile + gx - 1) / gx;
+    gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    CDRA_LAUNCH(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
+    return true;
+}
+
+inline void launch_pw_fwd(const RunCtx& c, int di, const PwDesc& hd, PwFwdArgs& a, bool allow_full_cols) {
+    a.d = desc_dev(c, di);
+    a.training = c.training;
+    double bytes = 0;
+    for (int i = 0; i < hd.nsrc; ++i) bytes += 4.0 * a.Rt * hd.src[i].map.n0 * 2 + 4.0 * a.Rt * hd.src[i].map.n1 * 2;
+    for (int pl = 0; pl < hd.cols.nplanes; ++pl) bytes += 4.0 * a.Rt * (hd.cols.seg0n + hd.cols.seg1n + a.ncopy) * 2;
+    if (a.x1) bytes += 4.0 * a.Rt * 2 * a.ncopy * 2;
+    prof_bytes(bytes);
+    bool ok = false;
+    if (allow_full_cols) {
+        if (hd.NPall <= 64) ok = try_pw_fwd<128, 8, 1, 1, 8>(c, a, hd, 0, 2) || try_pw_fwd<64, 4, 2, 1, 4>(c, a, hd, 0, 1);
+        else if (hd.NPall <= 128) ok = try_pw_fwd<64, 4, 2, 1, 8>(c, a, hd, 0, 2) || try_pw_fwd<32, 2, 4, 1, 4>(c, a, hd, 0, 1);
+        else if (hd.NPall <= 256) ok = try_pw_fwd<16, 1, 8, 1, 4>(c, a, hd, 0, 1);
+    }
+    if (!ok && !a.x1) ok = try_pw_fwd<32, 2, 4, 1, 4>(c, a, hd, 1, 1) || try_pw_fwd<32, 2, 4, 1, 2>(c, a, hd, 1, 1);
+    if (!ok) fprintf(stderr, "libcdra: no pw_fwd configuration fits (KP=%d NPall=%d)\n", hd.KP, hd.NPall);
+}
+
+inline void launch_dw_fwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, bool clamp, int kbase, const V2Tensor& out,
+                          const Unit& u, int counter) {
+    DwArgs a; memset(&a, 0, sizeof a);
+    a.in = (const bf16*)(c.ws + in.data); a.aff = in.has_bn ? (const float2*)(c.ws + in.aff) : nullptr; a.clamp = clamp ? 1 : 0;
+    a.cp = in.cp; a.map = SlotMap{in.n0, in.n0p, in.n1}; a.kbase = kbase;
+    a.B = c.p->B; a.Hi = u.Hi; a.Wi = u.Wi; a.Ho = u.Ho; a.Wo = u.Wo; a.stride = u.stride; a.pad_t = u.pad_t; a.pad_l = u.pad_l;
+    a.L = layer_of(c, l);
+    a.out = (bf16*)(c.ws + out.data); a.tb = tables_of(c, out);
+    a.training = c.training; a.counter = counter_ptr(c, counter);
+    const int frame_bytes = u.Hi * u.Wi * in.cp * 2, buf = (frame_bytes + 127) & ~127;
+    const int smem = ((64 + in.cp * 8 + 127) & ~127) + 2 * buf;
+    static bool attr = (cudaFuncSetAttribute(dw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr;
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem + 1024)));
+    const int nframes = kT * a.B;
+    int gx = std::min(nframes, num_sms() * per_sm);
+    a.frames_per_cta = (nframes + gx - 1) / gx;
+    gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
+    prof_bytes(4.0 * a.B * ((double)u.Hi * u.Wi + (double)u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
+    CDRA_LAUNCH(dw_fwd_kernel, dim3(gx), dim3(kDwThreads), smem, c.stream, a);
+}
+
+inline void tower_forward(const RunCtx& c) {
+    const Plan& p = *c.p; const V2Plan& v = p.v2;
+    const int nu = (int)v.u.size();
+    upload_descs(c);
+    const PwDesc* host = (const PwDesc*)v.host_descs;
+    CDRA_LAUNCH(pw_prep_kernel, dim3(2 * nu + 1, 8), dim3(256), 0, c.stream, desc_dev(c, 0));
+    for (int ui = 0; ui < nu; ++ui) {
+        const V2Unit& u = v.u[ui]; const Unit& un = p.units[ui];
+        const V2Tensor& r1 = v.t[u.r1]; const V2Tensor& r2 = v.t[u.r2];
+        const V2Tensor& oA = v.t[u.outA]; const V2Tensor& oB = v.t[u.outB];
+        {   // pw1 -> r1
+            PwFwdArgs a; memset(&a, 0, sizeof a);
+            a.Rt = r1.Rt; a.out[0] = (bf16*)(c.ws + r1.data); a.out[1] = a.out[0]; a.cpo = r1.cp;
+            a.tb[0] = tables_of(c, r1); a.tb[1] = a.tb[0]; a.gwv = r1.cp;
+            a.counter = counter_ptr(c, u.pw1.counter);
+            launch_pw_fwd(c, 2 * ui, host[2 * ui], a, true);
+        }
+        launch_dw_fwd(c, un.dw, r1, true, 0, r2, un, u.c_dw);
+        if (un.stride == 2) {
+            const bool in_clamp = u.inB >= 0;
+            launch_dw_fwd(c, un.scdw, v.t[u.inA], in_clamp, 0, v.t[u.rsA], un, u.c_scA);
+            if (u.inB >= 0) launch_dw_fwd(c, un.scdw, v.t[u.inB], in_clamp, v.t[u.inA].C(), v.t[u.rsB], un, u.c_scB);
+        }
+        {   // tail: pw2 (+ shortcut pw | pass-through) + shuffle -> planes A, B
+            PwFwdArgs a; memset(&a, 0, sizeof a);
+            a.Rt = oA.Rt; a.out[0] = (bf16*)(c.ws + oA.data); a.out[1] = (bf16*)(c.ws + oB.data); a.cpo = oA.cp;
+            a.tb[0] = tables_of(c, oA); a.tb[1] = tables_of(c, oB);
+            a.counter = counter_ptr(c, u.tail.counter);
+            if (un.stride == 2) a.gwv = oA.cp;
+            else {
+                const V2Tensor& x1 = v.t[u.inA];
+                a.gwv = oA.n0p;
+                a.x1 = (const bf16*)(c.ws + x1.data); a.x1cp = x1.cp; a.x1map = SlotMap{x1.n0, x1.n0p, x1.n1};
+                a.x1aff = (const float2*)(c.ws + x1.aff); a.x1bnp = (const float2*)(c.ws + x1.bnp);
+                a.ncopy = oA.n1; a.copy_dst0 = oA.n0p;
+            }
+            launch_pw_fwd(c, 2 * ui + 1, host[2 * ui + 1], a, true);
+        }
+    }
+    {   // head conv + global average pool
+        const V2Tensor& th = v.t[v.head];
+        PwFwdArgs a; memset(&a, 0, sizeof a);
+        a.Rt = th.Rt; a.out[0] = (bf16*)(c.ws + th.data); a.out[1] = a.out[0]; a.cpo = th.cp;
+        a.tb[0] = tables_of(c, th); a.tb[1] = a.tb[0]; a.gwv = th.cp;
+        a.counter = counter_ptr(c, v.head_pw.counter);
+        launch_pw_fwd(c, 2 * nu, host[2 * nu], a, false);
+        GapArgs g; memset(&g, 0, sizeof g);
+        g.in = (const bf16*)(c.ws + th.data); g.aff = (const float2*)(c.ws + th.aff); g.cp = th.cp; g.C = th.n0; g.HW = th.H * th.W;
+        g.F = kT * p.B; g.B = p.B; g.out = (float*)(c.ws + p.gap);
+        prof_bytes((double)g.F * g.HW * g.C * 2);
+        CDRA_LAUNCH(gap_fwd_kernel, dim3(cdiv((long long)g.F * (th.cp / 8), 256)), dim3(256), 0, c.stream, g);
+    }
+}
+
+// ---- logical-layout export of a tower tensor (or its gradient) for the parity taps: out [4B][H][W][C] fp32.
+// Unit outputs ("...out") are assembled from both planes in the reference's channel order.
+struct ExportArgs { const bf16* a; const bf16* b; int cp; SlotMap map; long long rows; int C; float* out; };
+__global__ void __launch_bounds__(256) export_kernel(const ExportArgs e) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= e.rows * e.C) return;
+    const long long r = i / e.C; int ch = (int)(i - r * e.C);
+    const bf16* src = e.a;
+    const int half = e.map.n0 + e.map.n1;
+    if (e.b && ch >= half) { src = e.b; ch -= half; }
+    e.out[i] = __bfloat162float(src[r * e.cp + logical_slot(e.map, ch)]);
+}
+inline bool export_tensor(const Plan& p, const char* name_c, char* ws, float* out, int32_t dims[4], cudaStream_t st) {
+    const V2Plan& v = p.v2;
+    std::string n(name_c);
+    bool grad = false;
+    if (n.rfind("grad:", 0) == 0) { grad = true; n = n.substr(5); }
+    int ia = -1, ib = -1;
+    auto it = v.index.find(n);
+    if (it != v.index.end()) ia = it->second;
+    else if (n.size() > 4 && n.substr(n.size() - 4) == ".out") {
+        auto a = v.index.find(n + "A"), b = v.index.find(n + "B");
+        if (a != v.index.end() && b != v.index.end()) { ia = a->second; ib = b->second; }
+    } else if (n.size() > 5 && n.substr(n.size() - 5) == ".scdw") {
+        auto a = v.index.find(n + "A"), b = v.index.find(n + "B");
+        if (a != v.index.end()) { ia = a->second; if (b != v.index.end()) ib = b->second; }
+    }
+    if (ia < 0) return false;
+    const V2Tensor& ta = v.t[ia];
+    ExportArgs e;
+    e.a = (const bf16*)(ws + (grad ? ta.grad : ta.data)); e.b = ib >= 0 ? (const bf16*)(ws + (grad ? v.t[ib].grad : v.t[ib].data)) : nullptr;
+    e.cp = ta.cp; e.map = SlotMap{ta.n0, ta.n0p, ta.n1}; e.rows = (long long)4 * ta.Rt; e.C = ta.C() * (ib >= 0 ? 2 : 1); e.out = out;
+    if (dims) { dims[0] = 4 * p.B; dims[1] = ta.H; dims[2] = ta.W; dims[3] = e.C; }
+    if (out) { CDRA_LAUNCH(export_kernel, dim3(cdiv(e.rows * e.C, 256)), dim3(256), 0, st, e); }
+    return true;
+}
+
+}  // namespace v2
+}  // namespace cdra
+#endif

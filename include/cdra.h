@@ -65,6 +65,11 @@ int cdra_arena_tensor(const cdra_plan_t* plan, int arena, int index, char* name,
 int cdra_plan_tensor(const cdra_plan_t* plan, const char* name, int64_t* byte_offset, int32_t dims[4],
                      int32_t* elem_size);
 
+/* Parity taps in bf16 perf mode: the tower stores padded, shuffled channel planes; this writes
+ * the named tensor ("tower.s2.u3.pw1", "tower.s1.u2.out", "grad:<name>" ...) in the reference's logical layout
+ * [4B][H][W][C] as fp32 into `out` (may be NULL to query dims only).  Test infrastructure, not on the hot path. */
+int cdra_debug_export(cdra_plan_t* plan, const char* name, void* workspace, float* out, int32_t dims[4], void* stream);
+
 /* CARLANetwork.dynamics_predict_train / dynamics_predict (core/networks.py:206-212) on
  * dynamics_layers (core/networks.py:37-56).  image [B,4,H,W,3] (u8 or f32), road [B,4,9],
  * vehicle [B,4,4], navigation [B,4,5] f32; out512 [B,512] f32.  training!=0 uses batch statistics and
