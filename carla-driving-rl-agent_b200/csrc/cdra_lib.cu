@@ -269,10 +269,10 @@ static void launch_dw_bwd(const RunCtx& c, const BnConv& l, const WsTensor& out,
 }
 
 template <typename T, typename TIn>
-static void tower_backward(const RunCtx& c, const TIn* image) {
+static void tower_backward(const RunCtx& c, const TIn* image, bool stem_only = false) {
     const Plan& p = *c.p; const int B = p.B;
     const WsTensor& th = p.tensors[p.t_head];
-    {   // GAP backward, head conv backward
+    if (!stem_only) {   // GAP backward, head conv backward
         GapBwdArgs<T> a{F(c.ws, p.dgap), (T*)(c.ws + th.grad), B, th.H * th.W, th.C};
         auto k = gap_bwd_kernel<T>;
         CDRA_LAUNCH(k, dim3(cdiv((long long)B * th.H * th.W * th.C, 256), kT), dim3(256), 0, c.stream, a);
@@ -281,7 +281,7 @@ static void tower_backward(const RunCtx& c, const TIn* image) {
         launch_pw_bwd<T>(c, p.head, th, ColMap{p.head.N, 0, 0, 0}, view_of(c, tin, 0, true), tin.Rt,
                          (T*)(c.ws + tin.grad), tin.C, 0, false, true);
     }
-    for (int ui = (int)p.units.size() - 1; ui >= 0; --ui) {
+    for (int ui = (int)p.units.size() - 1; ui >= 0 && !stem_only; --ui) {
         const Unit& u = p.units[ui];
         const WsTensor& tin = p.tensors[u.t_in];
         const WsTensor& r1 = p.tensors[u.t_r1];
@@ -561,6 +561,13 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
     zero_async(c.ws, p.zero_bytes, c.stream);      // BN-backward sums (the forward sums are already folded into aff/bnp)
     tail_backward(c, road, vehicle, navigation, d_out512);
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
+#ifndef CDRA_EMU
+    if (p.v2.on) {
+        v2::tower_backward(c);
+        if (u8) tower_backward<bf16, uint8_t>(c, (const uint8_t*)image, true);
+        else tower_backward<bf16, float>(c, (const float*)image, true);
+    } else
+#endif
     if (bf && u8) tower_backward<bf16, uint8_t>(c, (const uint8_t*)image);
     else if (bf) tower_backward<bf16, float>(c, (const float*)image);
     else if (u8) tower_backward<float, uint8_t>(c, (const uint8_t*)image);

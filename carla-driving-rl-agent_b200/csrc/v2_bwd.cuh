@@ -1,7 +1,790 @@
-// v2 tower: backward kernels (placeholder while the forward path is validated)
+// v2 tower: backward kernels -- what tape.gradient(loss, dynamics.trainable_variables) (core/carla_agent.py:361-365,
+// 440-444) computes through the pointwise / depthwise layers, the channel shuffle and the global average pool.
+//
+// Gradient tensors hold d loss / d (activated value) in the layout of the forward tensor.  A layer's own BatchNorm
+// (+ReLU6) backward is applied when its output gradient is loaded:
+//     dR = scale * (dz - S1/n - xhat * S2/n),   dz = dA * [0 < z < 6],   xhat = (R - mean) * inv_std
+// where S1 = sum dz, S2 = sum dz * xhat over the slice.  Those sums are produced by whichever kernel WRITES the final
+// gradient of a tensor (it has the raw tensor in shared memory anyway), so no separate statistics pass exists.
+// Biases that feed a training-mode BatchNorm have an analytically zero gradient: it is written as 0.
 #pragma once
 #ifndef CDRA_EMU
 #include "v2_pw.cuh"
 #include "v2_dw.cuh"
-namespace cdra { namespace v2 { } }
+
+namespace cdra {
+namespace v2 {
+
+// per-column constants of the BatchNorm(+ReLU6) backward:  dR = fma(dz, x, fma(raw, w, z)),  mask from fma(raw, x, y)
+CDRA_DEV float4 bnbwd_consts(float2 aff, float2 bnp, double2 bsum, double inv_n) {
+    const float k1 = (float)(bsum.x * inv_n), k2 = (float)(bsum.y * inv_n);
+    float4 c;
+    c.x = aff.x;                                   // scale
+    c.y = aff.y;                                   // shift
+    c.z = aff.x * (k2 * bnp.x * bnp.y - k1);       // A0 = scale * (k2 * mean * inv - k1)
+    c.w = -aff.x * k2 * bnp.y;                     // B1 = -scale * k2 * inv
+    return c;
+}
+CDRA_DEV float bnbwd_apply(float dA, float raw, const float4& c, bool clamp) {
+    const float z = fmaf(raw, c.x, c.y);
+    const float dz = (!clamp || (z > 0.f && z < 6.f)) ? dA : 0.f;
+    return fmaf(dz, c.x, fmaf(raw, c.w, c.z));
+}
+// per-slot constants for the sums of a freshly written gradient: (scale, shift, inv, -mean*inv)
+CDRA_DEV float4 sum_consts(const float2* aff, const float2* bnp, size_t idx) {
+    if (!aff) return make_float4(1.f, 0.f, 0.f, 0.f);
+    const float2 a = aff[idx], b = bnp[idx];
+    return make_float4(a.x, a.y, b.y, -b.x * b.y);
+}
+CDRA_DEV void sum_accum(float dA, float raw, const float4& c, bool clamp, float& s1, float& s2) {
+    const float z = fmaf(raw, c.x, c.y);
+    const float dz = (!clamp || (z > 0.f && z < 6.f)) ? dA : 0.f;
+    s1 += dz;
+    s2 = fmaf(dz, fmaf(raw, c.z, c.w), s2);
+}
+
+struct PwBwdArgs {
+    const PwDesc* d;
+    int Rt;
+    const bf16* out[2]; const bf16* dout[2]; int cpo; Tables tb[2];   // the layer's output plane(s): raw, gradient, tables
+    int out_clamp;
+    // pass-through half of a stride-1 unit: d x1[slot(2i+p)] = d out_p[copy_dst0 + i]
+    const bf16* x1; bf16* dx1; int x1cp; SlotMap x1map; const float2* x1aff; const float2* x1bnp; double2* x1bsum;
+    int x1clamp, ncopy, copy_dst0;
+    int tiles_per_cta, nbuf;
+    int direct;                 // 1: d out / out are read straight from HBM by the transform (very wide layers), not TMA-staged
+    int ntiles_k[kMaxSrc];      // dgrad: K tiles per source
+    // wgrad tiling
+    int kt_tiles, nt_tiles;
+    unsigned* counter;
+};
+
+struct PwDgradSmem { int colc, srcc, x1c, stat, w, raw, dr, st, st2, total, raw_stride, ldr, ldw, lds, lds2; };
+inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, int nplanes, int cpo, int src_cp, int x1cp, int nbuf, int direct) {
+    PwDgradSmem s;
+    s.ldr = NPall + 8; s.ldw = NPall + 8; s.lds = KT + 8; s.lds2 = x1cp + 8;
+    int off = 64;
+    s.colc = off; off += NPall * 16;
+    s.srcc = off; off += KT * 16;
+    s.x1c = off; off += x1cp * 16;
+    s.stat = off; off += (KT + x1cp) * 8;
+    off = (off + 127) & ~127;
+    s.w = off; off += KT * s.ldw * 2;
+    off = (off + 127) & ~127;
+    s.raw_stride = (R * ((direct ? 0 : 2 * nplanes * cpo) + src_cp + x1cp) * 2 + 127) & ~127;
+    s.raw = off; off += nbuf * s.raw_stride;
+    s.dr = off; off += R * s.ldr * 2;
+    off = (off + 127) & ~127;
+    s.st = off; off += R * s.lds * 2;
+    off = (off + 127) & ~127;
+    s.st2 = off; off += x1cp ? R * s.lds2 * 2 : 0;
+    s.total = off;
+    return s;
+}
+
+// ======================================================================================== data gradient
+// d src[r][kk] = sum_j dR[r][j] * W[kk][j]  for the K tile (source, k0..k0+kw) of this CTA; epilogue: store (or add to)
+// the source's gradient tensor and accumulate its BatchNorm-backward sums.
+template <int R, int WM, int WN, int MT, int NBW>
+__global__ void __launch_bounds__(256) pw_dgrad_kernel(const PwBwdArgs a) {
+    constexpr int KT = WN * NBW * 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PwDesc& d = *a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = d.NPall, gwp = d.cols.gwp, nplanes = d.cols.nplanes;
+    // ---- this CTA's K tile
+    int si = 0, ky = blockIdx.y, koff = 0;
+    while (ky >= a.ntiles_k[si]) { ky -= a.ntiles_k[si]; koff += d.src[si].cp; ++si; }
+    const PwSrc& S = d.src[si];
+    const int k0 = ky * KT, kw = min(KT, S.cp - k0);
+    const bool do_x1 = a.x1 != nullptr && blockIdx.y == 0;
+    const int x1cp = do_x1 ? a.x1cp : 0;
+    const PwDgradSmem L = pw_dgrad_smem(R, KT, NP, nplanes, a.cpo, S.cp, a.x1 ? a.x1cp : 0, a.nbuf, a.direct);
+    const int NP16 = (NP + 15) & ~15;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
+    float4* s_srcc = reinterpret_cast<float4*>(smem + L.srcc);
+    float4* s_x1c = reinterpret_cast<float4*>(smem + L.x1c);
+    float* s_stat = reinterpret_cast<float*>(smem + L.stat);
+    bf16* Ws = reinterpret_cast<bf16*>(smem + L.w);
+    unsigned char* raw = smem + L.raw;
+    bf16* Dr = reinterpret_cast<bf16*>(smem + L.dr);
+    bf16* St = reinterpret_cast<bf16*>(smem + L.st);
+    bf16* St2 = reinterpret_cast<bf16*>(smem + L.st2);
+    const int ldr = L.ldr, ldw = L.ldw, lds = L.lds, lds2 = L.lds2;
+    // raw buffer layout (rows R each): [dout p0][dout p1][out p0][out p1][src][x1]
+    const int plane_bytes = a.cpo * 2;
+    const int o_dout = 0, o_out = nplanes * plane_bytes, o_src = a.direct ? 0 : 2 * nplanes * plane_bytes, o_x1 = o_src + S.cp * 2;
+
+    const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
+    const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    for (int i = tid; i < KT * (ldw / 8); i += 256) {
+        const int k = i / (ldw / 8), c = i - k * (ldw / 8);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (k < kw && c < NP / 8) v = *reinterpret_cast<const uint4*>(d.wb + (size_t)(koff + k0 + k) * NP + c * 8);
+        *reinterpret_cast<uint4*>(Ws + (size_t)k * ldw + c * 8) = v;
+    }
+    for (int i = tid; i < R * ldr / 2; i += 256) reinterpret_cast<uint32_t*>(Dr)[i] = 0u;
+    for (int i = tid; i < R * lds / 2; i += 256) reinterpret_cast<uint32_t*>(St)[i] = 0u;
+    if (do_x1) for (int i = tid; i < R * lds2 / 2; i += 256) reinterpret_cast<uint32_t*>(St2)[i] = 0u;
+    for (int i = tid; i < (KT + x1cp) * 2; i += 256) s_stat[i] = 0.f;
+    __syncthreads();
+
+    auto issue = [&](int tile, int buf) {
+        const int t = tile / tps, r0 = (tile - t * tps) * R, rows = min(R, a.Rt - r0);
+        unsigned char* dst = raw + (size_t)buf * L.raw_stride;
+        const size_t row = (size_t)t * a.Rt + r0;
+        uint32_t bytes = rows * ((a.direct ? 0 : 2 * nplanes * plane_bytes) + S.cp * 2 + x1cp * 2);
+        mbar_expect_tx(&full[buf], bytes);
+        if (!a.direct) for (int p = 0; p < nplanes; ++p) {
+            bulk_g2s(dst + (size_t)R * (o_dout + p * plane_bytes), a.dout[p] + row * a.cpo, rows * plane_bytes, &full[buf]);
+            bulk_g2s(dst + (size_t)R * (o_out + p * plane_bytes), a.out[p] + row * a.cpo, rows * plane_bytes, &full[buf]);
+        }
+        bulk_g2s(dst + (size_t)R * o_src, S.data + row * S.cp, rows * S.cp * 2, &full[buf]);
+        if (do_x1) bulk_g2s(dst + (size_t)R * o_x1, a.x1 + row * a.x1cp, rows * x1cp * 2, &full[buf]);
+    };
+    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (tile_lo + b < tile_hi) issue(tile_lo + b, b);
+
+    const int wm = warp % WM, wn = warp / WM, g = lane >> 2, tg = lane & 3;
+    // roles
+    const int nq = nplanes * (gwp >> 3), tq = tid % nq, trl = tid / nq, tnrl = 256 / nq;            // dR transform
+    const int tp = tq / (gwp >> 3), tc = (tq - tp * (gwp >> 3)) * 8;
+    const int nv = kw >> 3, vq = tid % nv, vrl = tid / nv, vnrl = 256 / nv;                          // store pass
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    const int nx = do_x1 ? (x1cp >> 3) : 1, xq = tid % nx, xrl = tid / nx, xnrl = 256 / nx;          // pass-through store pass
+    float x1s1[8], x1s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x1s1[i] = 0.f; x1s2[i] = 0.f; }
+    int cs_src = -1, cs_rl = 0, cs_nrl = 1, cs_slot = 0;                                            // pass-through gather
+    if (do_x1) {
+        cs_nrl = 256 / x1cp; cs_rl = tid / x1cp; cs_slot = tid % x1cp;
+        if (cs_rl < cs_nrl) {
+            const int l = slot_logical(a.x1map, cs_slot);
+            if (l >= 0 && (l >> 1) < a.ncopy) cs_src = (l & 1) * plane_bytes / 2 * R + a.copy_dst0 + (l >> 1);   // element offset inside the dout region
+            else cs_src = -2;                                                                      // padding -> zero gradient
+        }
+    }
+    const bool sclamp = S.clamp != 0, oclamp = a.out_clamp != 0, xclamp = a.x1clamp != 0;
+    const double inv_n = 1.0 / (double)a.Rt;
+
+    auto flush = [&](int t) {
+        if (vrl < vnrl) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                atomicAdd(&s_stat[(vq * 8 + i) * 2], s1[i]); atomicAdd(&s_stat[(vq * 8 + i) * 2 + 1], s2[i]);
+                s1[i] = 0.f; s2[i] = 0.f;
+            }
+        }
+        if (do_x1 && xrl < xnrl) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                atomicAdd(&s_stat[(KT + xq * 8 + i) * 2], x1s1[i]); atomicAdd(&s_stat[(KT + xq * 8 + i) * 2 + 1], x1s2[i]);
+                x1s1[i] = 0.f; x1s2[i] = 0.f;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < kw; i += 256) {
+            const int s = k0 + i;
+            if (s >= S.sum_lo && s < S.sum_hi) {
+                double2* dst = S.bsum + (size_t)t * S.cp + s;
+                atomicAdd(&dst->x, (double)s_stat[2 * i]); atomicAdd(&dst->y, (double)s_stat[2 * i + 1]);
+            }
+            s_stat[2 * i] = 0.f; s_stat[2 * i + 1] = 0.f;
+        }
+        if (do_x1) for (int i = tid; i < x1cp; i += 256) {
+            double2* dst = a.x1bsum + (size_t)t * x1cp + i;
+            atomicAdd(&dst->x, (double)s_stat[(KT + i) * 2]); atomicAdd(&dst->y, (double)s_stat[(KT + i) * 2 + 1]);
+            s_stat[(KT + i) * 2] = 0.f; s_stat[(KT + i) * 2 + 1] = 0.f;
+        }
+        __syncthreads();
+    };
+
+    int cur_t = -1;
+    for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it) {
+        const int buf = it % a.nbuf;
+        const int t = tile / tps, r0 = (tile - t * tps) * R, rows = min(R, a.Rt - r0);
+        if (t != cur_t) {
+            if (cur_t >= 0) flush(cur_t);
+            __syncthreads();
+            for (int j = tid; j < NP; j += 256) {
+                int p, s, l, n;
+                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pw_col(d, j, p, s, l, n)) {
+                    const size_t idx = (size_t)t * a.cpo + s;
+                    c = bnbwd_consts(a.tb[p].aff[idx], a.tb[p].bnp[idx], a.tb[p].bsum[idx], inv_n);
+                }
+                s_colc[j] = c;
+            }
+            for (int i = tid; i < kw; i += 256) s_srcc[i] = sum_consts(S.aff, S.bnp, (size_t)t * S.cp + k0 + i);
+            if (do_x1) for (int i = tid; i < x1cp; i += 256) s_x1c[i] = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + i);
+            cur_t = t;
+            __syncthreads();
+        }
+        mbar_wait(&full[buf], (it / a.nbuf) & 1);
+        const unsigned char* rb = raw + (size_t)buf * L.raw_stride;
+        // ---- dR tile from (d out, out): BatchNorm + ReLU6 backward on load
+        if (trl < tnrl) {
+            float4 c8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_colc[tp * gwp + tc + q];
+            const uint4* dv = reinterpret_cast<const uint4*>(rb + (size_t)R * (o_dout + tp * plane_bytes));
+            const uint4* ov = reinterpret_cast<const uint4*>(rb + (size_t)R * (o_out + tp * plane_bytes));
+            if (a.direct) {
+                dv = reinterpret_cast<const uint4*>(a.dout[tp] + ((size_t)t * a.Rt + r0) * a.cpo);
+                ov = reinterpret_cast<const uint4*>(a.out[tp] + ((size_t)t * a.Rt + r0) * a.cpo);
+            }
+            const int nch = a.cpo >> 3, ch = tc >> 3;
+            for (int r = trl; r < rows; r += tnrl) {
+                uint4 dvv = dv[r * nch + ch]; const uint4 ovv = ov[r * nch + ch];
+                uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
+                    dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], oclamp), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], oclamp));
+                }
+                *reinterpret_cast<uint4*>(Dr + (size_t)r * ldr + tp * gwp + tc) = dvv;
+            }
+        }
+        // rows beyond `rows` of a partial tile keep stale (finite) values: their products are never stored
+        __syncthreads();
+        // ---- MMA: d src tile [R x KT] = dR [R x NP] * Wb^T
+        float acc[MT][NBW][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb) { acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.f; }
+        {
+            const int arow = wm * MT * 16 + (lane & 15), acol = (lane >> 4) * 8;
+            const int mi = lane >> 3;
+            const int brow = wn * NBW * 8 + (mi >> 1) * 8 + (lane & 7), bcol = (mi & 1) * 8;
+            for (int ks = 0; ks < NP16; ks += 16) {
+                uint32_t af[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) ldsm4(af[mt], Dr + (size_t)(arow + mt * 16) * ldr + ks + acol);
+#pragma unroll
+                for (int nb2 = 0; nb2 < NBW / 2; ++nb2) {
+                    uint32_t bfr[4];
+                    ldsm4(bfr, Ws + (size_t)(brow + nb2 * 16) * ldw + ks + bcol);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma16816(acc[mt][2 * nb2], af[mt], bfr[0], bfr[1]);
+                        mma16816(acc[mt][2 * nb2 + 1], af[mt], bfr[2], bfr[3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int nb = 0; nb < NBW; ++nb) {
+            const int jl = wn * NBW * 8 + nb * 8 + 2 * tg;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = wm * MT * 16 + mt * 16 + g;
+                *reinterpret_cast<uint32_t*>(St + (size_t)r * lds + jl) = pack2(acc[mt][nb][0], acc[mt][nb][1]);
+                *reinterpret_cast<uint32_t*>(St + (size_t)(r + 8) * lds + jl) = pack2(acc[mt][nb][2], acc[mt][nb][3]);
+            }
+        }
+        // ---- pass-through half: gather d x1 from the output planes' gradient (bit-exact)
+        if (cs_src != -1) {
+            const bf16* dreg = reinterpret_cast<const bf16*>(rb + (size_t)R * o_dout);
+            if (cs_src >= 0) {
+                const int pl = cs_src / (plane_bytes / 2 * R), col = cs_src - pl * (plane_bytes / 2 * R);
+                const bf16* srcp = dreg + (size_t)pl * R * a.cpo + col;
+                for (int r = cs_rl; r < rows; r += cs_nrl) St2[(size_t)r * lds2 + cs_slot] = srcp[(size_t)r * a.cpo];
+            }
+        }
+        __syncthreads();
+        // ---- store d src (+ existing partial gradient), accumulate its BatchNorm-backward sums
+        if (vrl < vnrl) {
+            float4 c8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_srcc[vq * 8 + q];
+            bf16* grow = S.grad + ((size_t)t * a.Rt + r0) * S.cp + k0 + vq * 8;
+            const uint4* rv = reinterpret_cast<const uint4*>(rb + (size_t)R * o_src);
+            const int nch = S.cp >> 3, ch = (k0 >> 3) + vq;
+            for (int r = vrl; r < rows; r += vnrl) {
+                uint4 v = *reinterpret_cast<const uint4*>(St + (size_t)r * lds + vq * 8);
+                uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+                if (S.accumulate) {
+                    const uint4 e = *reinterpret_cast<const uint4*>(grow + (size_t)r * S.cp);
+                    const uint32_t* ew = reinterpret_cast<const uint32_t*>(&e);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float2 x = unpack2(w[i]), y = unpack2(ew[i]); w[i] = pack2(x.x + y.x, x.y + y.y); }
+                }
+                *reinterpret_cast<uint4*>(grow + (size_t)r * S.cp) = v;
+                const uint4 rw = rv[r * nch + ch];
+                const uint32_t* rww = reinterpret_cast<const uint32_t*>(&rw);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 x = unpack2(w[i]), y = unpack2(rww[i]);
+                    sum_accum(x.x, y.x, c8[2 * i], sclamp, s1[2 * i], s2[2 * i]);
+                    sum_accum(x.y, y.y, c8[2 * i + 1], sclamp, s1[2 * i + 1], s2[2 * i + 1]);
+                }
+            }
+        }
+        if (do_x1 && xrl < xnrl) {
+            float4 c8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_x1c[xq * 8 + q];
+            bf16* grow = a.dx1 + ((size_t)t * a.Rt + r0) * x1cp + xq * 8;
+            const uint4* rv = reinterpret_cast<const uint4*>(rb + (size_t)R * o_x1);
+            const int nch = x1cp >> 3;
+            for (int r = xrl; r < rows; r += xnrl) {
+                const uint4 v = *reinterpret_cast<const uint4*>(St2 + (size_t)r * lds2 + xq * 8);
+                *reinterpret_cast<uint4*>(grow + (size_t)r * x1cp) = v;
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+                const uint4 rw = rv[r * nch + xq];
+                const uint32_t* rww = reinterpret_cast<const uint32_t*>(&rw);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 x = unpack2(w[i]), y = unpack2(rww[i]);
+                    sum_accum(x.x, y.x, c8[2 * i], xclamp, x1s1[2 * i], x1s2[2 * i]);
+                    sum_accum(x.y, y.y, c8[2 * i + 1], xclamp, x1s1[2 * i + 1], x1s2[2 * i + 1]);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && tile + a.nbuf < tile_hi) issue(tile + a.nbuf, buf);
+    }
+    if (cur_t >= 0) flush(cur_t);
+}
+
+// ======================================================================================== weight gradient
+// dW[kk][j] += sum_r act(src)[r][kk] * dR[r][j] over this CTA's rows, for its (K tile, N tile); fp32 atomics into the
+// (pre-zeroed) gradient arena in the reference's logical layout.  BN gamma/beta gradients come from the final sums.
+constexpr int kWgK = 64, kWgR = 64;
+struct PwWgradSmem { int colc, aff, raw, xs, rs, total, raw_stride, ldx, ldr; };
+inline __host__ __device__ PwWgradSmem pw_wgrad_smem(int NTW, int cpo, int src_cp, int nbuf, int direct) {
+    PwWgradSmem s;
+    s.ldx = kWgK + 8; s.ldr = NTW + 8;
+    int off = 64;
+    s.colc = off; off += NTW * 16;
+    s.aff = off; off += kWgK * 8;
+    off = (off + 127) & ~127;
+    s.raw_stride = (kWgR * ((direct ? 0 : 2 * cpo) + src_cp) * 2 + 127) & ~127;
+    s.raw = off; off += nbuf * s.raw_stride;
+    s.xs = off; off += kWgR * s.ldx * 2;
+    off = (off + 127) & ~127;
+    s.rs = off; off += kWgR * s.ldr * 2;
+    s.total = off;
+    return s;
+}
+
+template <int NBW>          // n-blocks per warp: N tile = 2 * NBW * 8 columns
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const PwBwdArgs a) {
+    constexpr int NTW = 2 * NBW * 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PwDesc& d = *a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = d.NPall, gwp = d.cols.gwp;
+    // ---- tile: K tile (source si, k0) x N tile (plane pn, slot n0)
+    const int kti = blockIdx.y / a.nt_tiles, nti = blockIdx.y - kti * a.nt_tiles;
+    int si = 0, ky = kti, koff = 0;
+    while (ky >= a.ntiles_k[si]) { ky -= a.ntiles_k[si]; koff += d.src[si].cp; ++si; }
+    const PwSrc& S = d.src[si];
+    const int k0 = ky * kWgK, kw = min(kWgK, S.cp - k0);
+    const int ntp = (gwp + NTW - 1) / NTW;                 // N tiles per plane
+    const int pn = nti / ntp, n0 = (nti - pn * ntp) * NTW, nw = min(NTW, gwp - n0);
+    const PwWgradSmem L = pw_wgrad_smem(NTW, a.cpo, S.cp, a.nbuf, a.direct);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
+    float2* s_aff = reinterpret_cast<float2*>(smem + L.aff);
+    unsigned char* raw = smem + L.raw;
+    bf16* Xs = reinterpret_cast<bf16*>(smem + L.xs);
+    bf16* Rs = reinterpret_cast<bf16*>(smem + L.rs);
+    const int ldx = L.ldx, ldr = L.ldr;
+    const int plane_bytes = a.cpo * 2;
+    const int o_dout = 0, o_out = plane_bytes, o_src = a.direct ? 0 : 2 * plane_bytes;
+
+    const int tps = (a.Rt + kWgR - 1) / kWgR, ntile = kT * tps;
+    const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    for (int i = tid; i < kWgR * ldx / 2; i += 256) reinterpret_cast<uint32_t*>(Xs)[i] = 0u;
+    for (int i = tid; i < kWgR * ldr / 2; i += 256) reinterpret_cast<uint32_t*>(Rs)[i] = 0u;
+    __syncthreads();
+    auto issue = [&](int tile, int buf) {
+        const int t = tile / tps, r0 = (tile - t * tps) * kWgR, rows = min(kWgR, a.Rt - r0);
+        unsigned char* dst = raw + (size_t)buf * L.raw_stride;
+        const size_t row = (size_t)t * a.Rt + r0;
+        mbar_expect_tx(&full[buf], rows * ((a.direct ? 0 : 2 * plane_bytes) + S.cp * 2));
+        if (!a.direct) {
+            bulk_g2s(dst + (size_t)kWgR * o_dout, a.dout[pn] + row * a.cpo, rows * plane_bytes, &full[buf]);
+            bulk_g2s(dst + (size_t)kWgR * o_out, a.out[pn] + row * a.cpo, rows * plane_bytes, &full[buf]);
+        }
+        bulk_g2s(dst + (size_t)kWgR * o_src, S.data + row * S.cp, rows * S.cp * 2, &full[buf]);
+    };
+    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (tile_lo + b < tile_hi) issue(tile_lo + b, b);
+
+    const int kg = warp & 3, nh = warp >> 2;               // warp: k rows kg*16.., n columns nh*NBW*8..
+    float acc[NBW][4];
+#pragma unroll
+    for (int nb = 0; nb < NBW; ++nb) { acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f; }
+    const int nqr = nw >> 3, rq = tid % nqr, rrl = tid / nqr, rnrl = 256 / nqr;          // dR transform role
+    const int nqx = kw >> 3, xq = tid % nqx, xrl = tid / nqx, xnrl = 256 / nqx;          // act(src) transform role
+    const bool sclamp = S.clamp != 0, oclamp = a.out_clamp != 0;
+    const double inv_n = 1.0 / (double)a.Rt;
+
+    int cur_t = -1;
+    for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it) {
+        const int buf = it % a.nbuf;
+        const int t = tile / tps, r0 = (tile - t * tps) * kWgR, rows = min(kWgR, a.Rt - r0);
+        if (t != cur_t) {
+            __syncthreads();
+            for (int j = tid; j < nw; j += 256) {
+                int p, s, l, n;
+                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pw_col(d, pn * gwp + n0 + j, p, s, l, n)) {
+                    const size_t idx = (size_t)t * a.cpo + s;
+                    c = bnbwd_consts(a.tb[p].aff[idx], a.tb[p].bnp[idx], a.tb[p].bsum[idx], inv_n);
+                }
+                s_colc[j] = c;
+            }
+            for (int i = tid; i < kw; i += 256) s_aff[i] = S.aff ? S.aff[(size_t)t * S.cp + k0 + i] : make_float2(1.f, 0.f);
+            cur_t = t;
+            __syncthreads();
+        }
+        mbar_wait(&full[buf], (it / a.nbuf) & 1);
+        const unsigned char* rb = raw + (size_t)buf * L.raw_stride;
+        if (rrl < rnrl) {
+            float4 c8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_colc[rq * 8 + q];
+            const uint4* dv = reinterpret_cast<const uint4*>(rb + (size_t)kWgR * o_dout);
+            const uint4* ov = reinterpret_cast<const uint4*>(rb + (size_t)kWgR * o_out);
+            if (a.direct) {
+                dv = reinterpret_cast<const uint4*>(a.dout[pn] + ((size_t)t * a.Rt + r0) * a.cpo);
+                ov = reinterpret_cast<const uint4*>(a.out[pn] + ((size_t)t * a.Rt + r0) * a.cpo);
+            }
+            const int nch = a.cpo >> 3, ch = (n0 >> 3) + rq;
+            for (int r = rrl; r < kWgR; r += rnrl) {
+                uint4 dvv = make_uint4(0, 0, 0, 0);
+                if (r < rows) {
+                    dvv = dv[r * nch + ch]; const uint4 ovv = ov[r * nch + ch];
+                    uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
+                        dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], oclamp), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], oclamp));
+                    }
+                }
+                *reinterpret_cast<uint4*>(Rs + (size_t)r * ldr + rq * 8) = dvv;       // rows past the slice end contribute zero
+            }
+        }
+        if (xrl < xnrl) {
+            float2 c8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_aff[xq * 8 + q];
+            const uint4* sv = reinterpret_cast<const uint4*>(rb + (size_t)kWgR * o_src);
+            const int nch = S.cp >> 3, ch = (k0 >> 3) + xq;
+            for (int r = xrl; r < kWgR; r += xnrl) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (r < rows) v = affine8(sv[r * nch + ch], c8, sclamp);
+                *reinterpret_cast<uint4*>(Xs + (size_t)r * ldx + xq * 8) = v;
+            }
+        }
+        __syncthreads();
+        {
+            const int mi = lane >> 3;
+#pragma unroll
+            for (int ks = 0; ks < kWgR; ks += 16) {
+                uint32_t af[4];
+                ldsm4t(af, Xs + (size_t)(ks + (mi >> 1) * 8 + (lane & 7)) * ldx + kg * 16 + (mi & 1) * 8);
+#pragma unroll
+                for (int nb2 = 0; nb2 < NBW / 2; ++nb2) {
+                    uint32_t bfr[4];
+                    ldsm4t(bfr, Rs + (size_t)(ks + (mi & 1) * 8 + (lane & 7)) * ldr + nh * NBW * 8 + nb2 * 16 + (mi >> 1) * 8);
+                    mma16816(acc[2 * nb2], af, bfr[0], bfr[1]);
+                    mma16816(acc[2 * nb2 + 1], af, bfr[2], bfr[3]);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && tile + a.nbuf < tile_hi) issue(tile + a.nbuf, buf);
+    }
+    // ---- accumulate this CTA's partial tile into the gradient arena (logical layout)
+    {
+        const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+        for (int nb = 0; nb < NBW; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int kk = koff + k0 + kg * 16 + g + (e >> 1) * 8;
+                const int j = pn * gwp + n0 + nh * NBW * 8 + nb * 8 + 2 * tg + (e & 1);
+                int lk, k, p, s, lj, n;
+                if (kg * 16 + g + (e >> 1) * 8 < kw && nh * NBW * 8 + nb * 8 + 2 * tg + (e & 1) < nw &&
+                    pw_row(d, kk, lk, k) && pw_col(d, j, p, s, lj, n) && lk == lj)
+                    atomicAdd(d.layer[lk].dw + (size_t)k * d.layer[lk].N + n, acc[nb][e]);
+            }
+        }
+    }
+    // ---- BatchNorm parameter gradients (one CTA): dgamma = sum_t S2, dbeta = sum_t S1
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int j = tid; j < NP; j += 256) {
+            int p, s, l, n;
+            if (!pw_col(d, j, p, s, l, n)) continue;
+            double gs = 0.0, bs = 0.0;
+            for (int t = 0; t < kT; ++t) { const double2 v = a.tb[p].bsum[(size_t)t * a.cpo + s]; bs += v.x; gs += v.y; }
+            d.layer[l].dg[n] = (float)gs; d.layer[l].dbe[n] = (float)bs;
+        }
+    }
+}
+
+// ======================================================================================== depthwise backward
+// One CTA per frame at a time: d out frame + raw out frame + raw in frame by TMA; dR (BatchNorm backward) and act(in)
+// are built in place; thread <-> (channel pair, column) runs the transposed stencil (data gradient, with the input
+// tensor's BatchNorm-backward sums) and the 9-tap weight gradient (registers, reduced once per CTA).
+struct DwBwdSmem { int stat, wred, colc, dr, outr, inr, ina, total; };
+inline __host__ __device__ DwBwdSmem dw_bwd_smem(int cp, int in_px, int out_px) {
+    DwBwdSmem s;
+    int off = 64;
+    s.stat = off; off += cp * 8;
+    s.wred = off; off += cp * 9 * 4;
+    s.colc = off; off += cp * 16;
+    off = (off + 127) & ~127;
+    s.dr = off; off += (out_px * cp * 2 + 127) & ~127;
+    s.outr = off; off += (out_px * cp * 2 + 127) & ~127;
+    s.inr = off; off += (in_px * cp * 2 + 127) & ~127;
+    s.ina = off; off += (in_px * cp * 2 + 127) & ~127;
+    s.total = off;
+    return s;
+}
+
+__global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int cp = a.cp, npair = cp >> 1;
+    const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo;
+    const DwBwdSmem L = dw_bwd_smem(cp, in_px, out_px);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    float* s_stat = reinterpret_cast<float*>(smem + L.stat);
+    float* s_wred = reinterpret_cast<float*>(smem + L.wred);
+    float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
+    bf16* Dr = reinterpret_cast<bf16*>(smem + L.dr);
+    const bf16* Or = reinterpret_cast<const bf16*>(smem + L.outr);
+    const bf16* Ir = reinterpret_cast<const bf16*>(smem + L.inr);
+    bf16* Ia = reinterpret_cast<bf16*>(smem + L.ina);
+    const uint32_t out_bytes = (uint32_t)out_px * cp * 2, in_bytes = (uint32_t)in_px * cp * 2;
+    const int nframes = kT * a.B;
+    const int f_lo = blockIdx.x * a.frames_per_cta, f_hi = min(nframes, f_lo + a.frames_per_cta);
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_fence_init(); }
+    for (int i = tid; i < cp * 2; i += kDwThreads) s_stat[i] = 0.f;
+    for (int i = tid; i < cp * 9; i += kDwThreads) s_wred[i] = 0.f;
+    __syncthreads();
+    auto issue = [&](int f) {
+        mbar_expect_tx(&full[0], 2 * out_bytes + in_bytes);
+        bulk_g2s(Dr, a.dout + (size_t)f * out_px * cp, out_bytes, &full[0]);
+        bulk_g2s(smem + L.outr, a.out + (size_t)f * out_px * cp, out_bytes, &full[0]);
+        bulk_g2s(smem + L.inr, a.in + (size_t)f * in_px * cp, in_bytes, &full[0]);
+    };
+    if (tid == 0 && f_lo < f_hi) issue(f_lo);
+
+    const int nch = cp >> 3, tch = tid % nch, tpl = tid / nch, tnpl = kDwThreads / nch;
+    const int pr = tid % npair, xl = tid / npair, nxl = kDwThreads / npair;
+    const bool active = xl < nxl;
+    float w0[9], w1[9], g0[9], g1[9];
+    {
+        const int l0 = slot_logical(a.map, 2 * pr), l1 = slot_logical(a.map, 2 * pr + 1);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            w0[k] = l0 >= 0 ? a.L.w[k * a.L.N + a.kbase + l0] : 0.f;
+            w1[k] = l1 >= 0 ? a.L.w[k * a.L.N + a.kbase + l1] : 0.f;
+            g0[k] = 0.f; g1[k] = 0.f;
+        }
+    }
+    float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+    float4 ic0 = make_float4(1.f, 0.f, 0.f, 0.f), ic1 = ic0;      // sums constants of this thread's input channels
+    float2 ac8[8];
+    const bool iclamp = a.clamp != 0;
+    const double inv_n = 1.0 / ((double)a.B * out_px);
+    auto flush = [&](int t) {
+        if (active) {
+            atomicAdd(&s_stat[4 * pr], s1a); atomicAdd(&s_stat[4 * pr + 1], s2a);
+            atomicAdd(&s_stat[4 * pr + 2], s1b); atomicAdd(&s_stat[4 * pr + 3], s2b);
+        }
+        s1a = s2a = s1b = s2b = 0.f;
+        __syncthreads();
+        for (int c = tid; c < cp; c += kDwThreads) {
+            if (a.in_bsum && c >= a.in_sum_lo && c < a.in_sum_hi) {
+                double2* dst = a.in_bsum + (size_t)t * cp + c;
+                atomicAdd(&dst->x, (double)s_stat[2 * c]); atomicAdd(&dst->y, (double)s_stat[2 * c + 1]);
+            }
+            s_stat[2 * c] = 0.f; s_stat[2 * c + 1] = 0.f;
+        }
+        __syncthreads();
+    };
+
+    int cur_t = -1;
+    for (int f = f_lo, it = 0; f < f_hi; ++f, ++it) {
+        const int t = f / a.B;
+        if (t != cur_t) {
+            if (cur_t >= 0) flush(cur_t);
+            __syncthreads();
+            for (int s = tid; s < cp; s += kDwThreads) {
+                const int l = slot_logical(a.map, s);
+                const size_t idx = (size_t)t * cp + s;
+                s_colc[s] = l >= 0 ? bnbwd_consts(a.tb.aff[idx], a.tb.bnp[idx], a.tb.bsum[idx], inv_n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (tpl < tnpl) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ac8[q] = a.aff ? a.aff[(size_t)t * cp + tch * 8 + q] : make_float2(1.f, 0.f);
+            }
+            ic0 = sum_consts(a.aff, a.bnp, (size_t)t * cp + 2 * pr);
+            ic1 = sum_consts(a.aff, a.bnp, (size_t)t * cp + 2 * pr + 1);
+            cur_t = t;
+            __syncthreads();
+        }
+        mbar_wait(&full[0], it & 1);
+        if (tpl < tnpl) {
+            float4 c8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_colc[tch * 8 + q];
+            uint4* dv = reinterpret_cast<uint4*>(Dr);
+            const uint4* ov = reinterpret_cast<const uint4*>(Or);
+            for (int px = tpl; px < out_px; px += tnpl) {
+                uint4 dvv = dv[px * nch + tch]; const uint4 ovv = ov[px * nch + tch];
+                uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
+                    dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], false), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], false));
+                }
+                dv[px * nch + tch] = dvv;
+            }
+            const uint4* iv = reinterpret_cast<const uint4*>(Ir);
+            uint4* av = reinterpret_cast<uint4*>(Ia);
+            for (int px = tpl; px < in_px; px += tnpl) av[px * nch + tch] = affine8(iv[px * nch + tch], ac8, iclamp);
+        }
+        __syncthreads();
+        if (active) {
+            // weight gradient: dw[ky][kx] += act(in)[oy*s - pt + ky][ox*s - pl + kx] * dR[oy][ox]
+            for (int ox = xl; ox < a.Wo; ox += nxl) {
+                const int ix0 = ox * a.stride - a.pad_l;
+                for (int oy = 0; oy < a.Ho; ++oy) {
+                    const int iy0 = oy * a.stride - a.pad_t;
+                    const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(Dr + ((size_t)oy * a.Wo + ox) * cp + 2 * pr));
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int iy = iy0 + ky;
+                        if (iy < 0 || iy >= a.Hi) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int ix = ix0 + kx;
+                            if (ix < 0 || ix >= a.Wi) continue;
+                            const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(Ia + ((size_t)iy * a.Wi + ix) * cp + 2 * pr));
+                            g0[ky * 3 + kx] = fmaf(v.x, dr.x, g0[ky * 3 + kx]);
+                            g1[ky * 3 + kx] = fmaf(v.y, dr.y, g1[ky * 3 + kx]);
+                        }
+                    }
+                }
+            }
+            // data gradient: d in[iy][ix] = sum_{ky,kx} w[ky][kx] * dR[(iy + pt - ky)/s][(ix + pl - kx)/s]
+            for (int ix = xl; ix < a.Wi; ix += nxl) {
+                bf16* gcol = a.din + ((size_t)f * in_px + ix) * cp + 2 * pr;
+                for (int iy = 0; iy < a.Hi; ++iy) {
+                    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int ny = iy + a.pad_t - ky;
+                        if (ny < 0 || (a.stride == 2 && (ny & 1))) continue;
+                        const int oy = a.stride == 2 ? ny >> 1 : ny;
+                        if (oy >= a.Ho) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int nx = ix + a.pad_l - kx;
+                            if (nx < 0 || (a.stride == 2 && (nx & 1))) continue;
+                            const int ox = a.stride == 2 ? nx >> 1 : nx;
+                            if (ox >= a.Wo) continue;
+                            const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(Dr + ((size_t)oy * a.Wo + ox) * cp + 2 * pr));
+                            acc0 = fmaf(dr.x, w0[ky * 3 + kx], acc0);
+                            acc1 = fmaf(dr.y, w1[ky * 3 + kx], acc1);
+                        }
+                    }
+                    bf16* gp = gcol + (size_t)iy * a.Wi * cp;
+                    if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
+                    const uint32_t pk = pack2(acc0, acc1);
+                    *reinterpret_cast<uint32_t*>(gp) = pk;
+                    const float2 gr = unpack2(pk);
+                    const float2 rw = unpack2(*reinterpret_cast<const uint32_t*>(Ir + ((size_t)iy * a.Wi + ix) * cp + 2 * pr));
+                    sum_accum(gr.x, rw.x, ic0, iclamp, s1a, s2a);
+                    sum_accum(gr.y, rw.y, ic1, iclamp, s1b, s2b);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && f + 1 < f_hi) issue(f + 1);
+    }
+    if (cur_t >= 0) flush(cur_t);
+    // ---- weight gradients of this CTA
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { atomicAdd(&s_wred[(2 * pr) * 9 + k], g0[k]); atomicAdd(&s_wred[(2 * pr + 1) * 9 + k], g1[k]); }
+    }
+    __syncthreads();
+    for (int i = tid; i < cp * 9; i += kDwThreads) {
+        const int s = i / 9, k = i - s * 9, l = slot_logical(a.map, s);
+        if (l >= 0) atomicAdd(a.L.dw + (size_t)k * a.L.N + a.kbase + l, s_wred[i]);
+    }
+    if (blockIdx.x == 0) {
+        for (int s = tid; s < cp; s += kDwThreads) {
+            const int l = slot_logical(a.map, s);
+            if (l < 0) continue;
+            double gs = 0.0, bs = 0.0;
+            for (int t = 0; t < kT; ++t) { const double2 v = a.tb.bsum[(size_t)t * cp + s]; bs += v.x; gs += v.y; }
+            a.L.dg[a.kbase + l] = (float)gs; a.L.dbe[a.kbase + l] = (float)bs;
+        }
+    }
+}
+
+// ======================================================================================== global average pool backward
+// d head[f][p][c] = d gap[f][c] / HW (gradient wrt the activated head output) + its BatchNorm-backward sums
+__global__ void __launch_bounds__(256) gap_bwd_kernel(const GapArgs a, int frames_per_block) {
+    extern __shared__ float s_acc[];              // [cp][2]
+    const int t = blockIdx.y, nch = a.cp >> 3, tid = threadIdx.x;
+    for (int i = tid; i < a.cp * 2; i += 256) s_acc[i] = 0.f;
+    __syncthreads();
+    const int b_lo = blockIdx.x * frames_per_block, b_hi = min(a.B, b_lo + frames_per_block);
+    const float inv = 1.0f / (float)a.HW;
+    for (int item = tid; item < (b_hi - b_lo) * nch; item += 256) {
+        const int b = b_lo + item / nch, ch = item % nch, f = t * a.B + b;
+        float4 c8[8];
+        float gv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            c8[q] = sum_consts(a.aff, a.bnp, (size_t)t * a.cp + ch * 8 + q);
+            gv[q] = ch * 8 + q < a.C ? a.dgap[(size_t)f * a.C + ch * 8 + q] * inv : 0.f;
+        }
+        uint4 gvec;
+        uint32_t* gw = reinterpret_cast<uint32_t*>(&gvec);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gw[i] = pack2(gv[2 * i], gv[2 * i + 1]);
+        float s1[8], s2[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { s1[q] = 0.f; s2[q] = 0.f; }
+        const uint4* src = reinterpret_cast<const uint4*>(a.in + (size_t)f * a.HW * a.cp) + ch;
+        uint4* dst = reinterpret_cast<uint4*>(a.dout + (size_t)f * a.HW * a.cp) + ch;
+        for (int p = 0; p < a.HW; ++p) {
+            const uint4 rv = src[(size_t)p * nch];
+            dst[(size_t)p * nch] = gvec;
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 x = unpack2(gw[i]), y = unpack2(rw[i]);
+                sum_accum(x.x, y.x, c8[2 * i], true, s1[2 * i], s2[2 * i]);
+                sum_accum(x.y, y.y, c8[2 * i + 1], true, s1[2 * i + 1], s2[2 * i + 1]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { atomicAdd(&s_acc[(ch * 8 + q) * 2], s1[q]); atomicAdd(&s_acc[(ch * 8 + q) * 2 + 1], s2[q]); }
+    }
+    __syncthreads();
+    for (int c = tid; c < a.cp; c += 256) {
+        double2* d = a.bsum + (size_t)t * a.cp + c;
+        atomicAdd(&d->x, (double)s_acc[2 * c]); atomicAdd(&d->y, (double)s_acc[2 * c + 1]);
+    }
+}
+
+}  // namespace v2
+}  // namespace cdra
 #endif

@@ -53,6 +53,7 @@ inline PwDesc desc_pw1(const RunCtx& c, int ui) {
         d.nsrc = 0;
         d.src[d.nsrc++] = src_of(c, v.t[u.inA], in_clamp, 0, 0);
         if (u.inB >= 0) d.src[d.nsrc++] = src_of(c, v.t[u.inB], in_clamp, v.t[u.inA].C(), 0);
+        for (int i = 0; i < d.nsrc; ++i) d.src[i].accumulate = 1;     // backward: the shortcut depthwise wrote its share first
     } else {
         d.nsrc = 1; d.src[0] = src_of(c, v.t[u.inB], true, 0, 0);
     }
@@ -228,6 +229,165 @@ inline void tower_forward(const RunCtx& c) {
         g.F = kT * p.B; g.B = p.B; g.out = (float*)(c.ws + p.gap);
         prof_bytes((double)g.F * g.HW * g.C * 2);
         CDRA_LAUNCH(gap_fwd_kernel, dim3(cdiv((long long)g.F * (th.cp / 8), 256)), dim3(256), 0, c.stream, g);
+    }
+}
+
+// ================================================================================================ backward
+template <int R, int WM, int WN, int MT, int NBW>
+inline bool try_pw_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nbuf, int direct, int min_ctas_per_sm) {
+    constexpr int KT = WN * NBW * 8;
+    int max_cp = 0, gy = 0;
+    for (int i = 0; i < kMaxSrc; ++i) a.ntiles_k[i] = 0;
+    for (int i = 0; i < hd.nsrc; ++i) { max_cp = std::max(max_cp, hd.src[i].cp); a.ntiles_k[i] = (hd.src[i].cp + KT - 1) / KT; gy += a.ntiles_k[i]; }
+    if (direct && a.x1) return false;
+    const PwDgradSmem L = pw_dgrad_smem(R, KT, hd.NPall, hd.cols.nplanes, a.cpo, max_cp, a.x1 ? a.x1cp : 0, nbuf, direct);
+    if (L.total > kMaxDynSmem) return false;
+    if (min_ctas_per_sm > 1 && (L.total + 1024) * min_ctas_per_sm > 227 * 1024) return false;
+    auto k = pw_dgrad_kernel<R, WM, WN, MT, NBW>;
+    static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nbuf; a.direct = direct;
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
+    const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
+    int gx = std::max(1, num_sms() * per_sm / gy);
+    if (gx > ntile) gx = ntile;
+    a.tiles_per_cta = (ntile + gx - 1) / gx;
+    gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    CDRA_LAUNCH(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
+    return true;
+}
+
+template <int NBW>
+inline bool try_pw_wgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nbuf, int direct) {
+    constexpr int NTW = 2 * NBW * 8;
+    int max_cp = 0;
+    a.kt_tiles = 0;
+    for (int i = 0; i < kMaxSrc; ++i) a.ntiles_k[i] = 0;
+    for (int i = 0; i < hd.nsrc; ++i) { max_cp = std::max(max_cp, hd.src[i].cp); a.ntiles_k[i] = (hd.src[i].cp + kWgK - 1) / kWgK; a.kt_tiles += a.ntiles_k[i]; }
+    a.nt_tiles = hd.cols.nplanes * ((hd.cols.gwp + NTW - 1) / NTW);
+    const PwWgradSmem L = pw_wgrad_smem(NTW, a.cpo, max_cp, nbuf, direct);
+    if (L.total > kMaxDynSmem) return false;
+    auto k = pw_wgrad_kernel<NBW>;
+    static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nbuf; a.direct = direct;
+    const int gy = a.kt_tiles * a.nt_tiles;
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
+    const int tps = (a.Rt + kWgR - 1) / kWgR, ntile = kT * tps;
+    int gx = std::max(1, num_sms() * per_sm / gy);
+    if (gx > ntile) gx = ntile;
+    a.tiles_per_cta = (ntile + gx - 1) / gx;
+    gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    CDRA_LAUNCH(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
+    return true;
+}
+
+// data gradient (+ pass-through, + BN-backward sums of the inputs) and weight gradient of one GEMM launch
+inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a) {
+    a.d = desc_dev(c, di);
+    a.out_clamp = 1;
+    int max_cp = 0;
+    for (int i = 0; i < hd.nsrc; ++i) max_cp = std::max(max_cp, hd.src[i].cp);
+    double bytes = 0;
+    for (int i = 0; i < hd.nsrc; ++i) bytes += 4.0 * a.Rt * (hd.src[i].map.n0 + hd.src[i].map.n1) * 2 * 2;          // raw src read, d src written
+    bytes += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n + a.ncopy) * 2 * 2;                      // d out, out read
+    if (a.x1) bytes += 4.0 * a.Rt * 2 * a.ncopy * 2 * 2;
+    prof_bytes(bytes);
+    bool ok;
+    if (max_cp <= 64)
+        ok = try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 2, 0, 2) || try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 1, 0, 2) ||
+             try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 2, 0, 1) || try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 1, 0, 1) ||
+             try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 0, 1) || try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 1, 1);
+    else
+        ok = try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 2, 0, 2) || try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 1, 0, 2) ||
+             try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 2, 0, 1) || try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 1, 0, 1) ||
+             try_pw_dgrad<32, 2, 4, 1, 4>(c, a, hd, 1, 0, 1) || try_pw_dgrad<32, 2, 4, 1, 4>(c, a, hd, 1, 1, 1) ||
+             try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 1, 1);
+    if (!ok) fprintf(stderr, "libcdra: no pw_dgrad configuration fits (KP=%d NPall=%d)\n", hd.KP, hd.NPall);
+    bytes = 0;
+    for (int i = 0; i < hd.nsrc; ++i) bytes += 4.0 * a.Rt * (hd.src[i].map.n0 + hd.src[i].map.n1) * 2;
+    bytes += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n) * 2 * 2;
+    prof_bytes(bytes);
+    if (hd.cols.gwp <= 64)
+        ok = try_pw_wgrad<4>(c, a, hd, 2, 0) || try_pw_wgrad<4>(c, a, hd, 1, 0) || try_pw_wgrad<4>(c, a, hd, 1, 1);
+    else
+        ok = try_pw_wgrad<8>(c, a, hd, 2, 0) || try_pw_wgrad<8>(c, a, hd, 1, 0) || try_pw_wgrad<8>(c, a, hd, 1, 1);
+    if (!ok) fprintf(stderr, "libcdra: no pw_wgrad configuration fits (KP=%d NPall=%d)\n", hd.KP, hd.NPall);
+}
+
+inline void launch_dw_bwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, bool clamp, int kbase, const V2Tensor& out,
+                          const Unit& u, bool accumulate, bool final_grad) {
+    DwArgs a; memset(&a, 0, sizeof a);
+    a.in = (const bf16*)(c.ws + in.data); a.aff = in.has_bn ? (const float2*)(c.ws + in.aff) : nullptr;
+    a.bnp = in.has_bn ? (const float2*)(c.ws + in.bnp) : nullptr; a.clamp = clamp ? 1 : 0;
+    a.din = (bf16*)(c.ws + in.grad); a.accumulate = accumulate ? 1 : 0;
+    a.in_bsum = (final_grad && in.has_bn) ? (double2*)(c.ws + in.bsum) : nullptr; a.in_sum_lo = 0; a.in_sum_hi = in.cp;
+    a.cp = in.cp; a.map = SlotMap{in.n0, in.n0p, in.n1}; a.kbase = kbase;
+    a.B = c.p->B; a.Hi = u.Hi; a.Wi = u.Wi; a.Ho = u.Ho; a.Wo = u.Wo; a.stride = u.stride; a.pad_t = u.pad_t; a.pad_l = u.pad_l;
+    a.L = layer_of(c, l);
+    a.out = (bf16*)(c.ws + out.data); a.dout = (const bf16*)(c.ws + out.grad); a.tb = tables_of(c, out);
+    a.training = 1;
+    const DwBwdSmem L = dw_bwd_smem(in.cp, u.Hi * u.Wi, u.Ho * u.Wo);
+    static bool attr = (cudaFuncSetAttribute(dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr;
+    if (L.total > kMaxDynSmem) { fprintf(stderr, "libcdra: dw_bwd frame does not fit in shared memory (%d bytes)\n", L.total); return; }
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
+    const int nframes = kT * a.B;
+    int gx = std::min(nframes, num_sms() * per_sm);
+    a.frames_per_cta = (nframes + gx - 1) / gx;
+    gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
+    prof_bytes(4.0 * a.B * (2.0 * u.Hi * u.Wi + 2.0 * u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
+    CDRA_LAUNCH(dw_bwd_kernel, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
+}
+
+inline void tower_backward(const RunCtx& c) {
+    const Plan& p = *c.p; const V2Plan& v = p.v2;
+    const int nu = (int)v.u.size();
+    upload_descs(c);
+    const PwDesc* host = (const PwDesc*)v.host_descs;
+    {   // global average pool + head conv
+        const V2Tensor& th = v.t[v.head];
+        GapArgs g; memset(&g, 0, sizeof g);
+        g.in = (const bf16*)(c.ws + th.data); g.aff = (const float2*)(c.ws + th.aff); g.bnp = (const float2*)(c.ws + th.bnp);
+        g.cp = th.cp; g.C = th.n0; g.HW = th.H * th.W; g.F = kT * p.B; g.B = p.B;
+        g.dgap = (const float*)(c.ws + p.dgap); g.dout = (bf16*)(c.ws + th.grad); g.bsum = (double2*)(c.ws + th.bsum);
+        const int fpb = 4;
+        prof_bytes((double)g.F * g.HW * g.C * 2 * 2);
+        CDRA_LAUNCH(gap_bwd_kernel, dim3(cdiv(p.B, fpb), kT), dim3(256), th.cp * 8, c.stream, g, fpb);
+        PwBwdArgs a; memset(&a, 0, sizeof a);
+        a.Rt = th.Rt; a.out[0] = a.out[1] = (const bf16*)(c.ws + th.data); a.dout[0] = a.dout[1] = (const bf16*)(c.ws + th.grad);
+        a.cpo = th.cp; a.tb[0] = a.tb[1] = tables_of(c, th);
+        launch_pw_bwd(c, 2 * nu, host[2 * nu], a);
+    }
+    for (int ui = nu - 1; ui >= 0; --ui) {
+        const V2Unit& u = v.u[ui]; const Unit& un = p.units[ui];
+        const V2Tensor& r1 = v.t[u.r1]; const V2Tensor& r2 = v.t[u.r2];
+        const V2Tensor& oA = v.t[u.outA]; const V2Tensor& oB = v.t[u.outB];
+        {   // tail: pw2 (+ shortcut pw | pass-through)
+            PwBwdArgs a; memset(&a, 0, sizeof a);
+            a.Rt = oA.Rt; a.out[0] = (const bf16*)(c.ws + oA.data); a.out[1] = (const bf16*)(c.ws + oB.data);
+            a.dout[0] = (const bf16*)(c.ws + oA.grad); a.dout[1] = (const bf16*)(c.ws + oB.grad);
+            a.cpo = oA.cp; a.tb[0] = tables_of(c, oA); a.tb[1] = tables_of(c, oB);
+            if (un.stride == 1) {
+                const V2Tensor& x1 = v.t[u.inA];
+                a.x1 = (const bf16*)(c.ws + x1.data); a.dx1 = (bf16*)(c.ws + x1.grad); a.x1cp = x1.cp; a.x1map = SlotMap{x1.n0, x1.n0p, x1.n1};
+                a.x1aff = (const float2*)(c.ws + x1.aff); a.x1bnp = (const float2*)(c.ws + x1.bnp); a.x1bsum = (double2*)(c.ws + x1.bsum);
+                a.x1clamp = 1; a.ncopy = oA.n1; a.copy_dst0 = oA.n0p;
+            }
+            launch_pw_bwd(c, 2 * ui + 1, host[2 * ui + 1], a);
+        }
+        launch_dw_bwd(c, un.dw, r1, true, 0, r2, un, false, true);
+        if (un.stride == 2) {   // shortcut depthwise first (plain write), pw1 then adds its share and finalises the sums
+            const bool in_clamp = u.inB >= 0;
+            launch_dw_bwd(c, un.scdw, v.t[u.inA], in_clamp, 0, v.t[u.rsA], un, false, false);
+            if (u.inB >= 0) launch_dw_bwd(c, un.scdw, v.t[u.inB], in_clamp, v.t[u.inA].C(), v.t[u.rsB], un, false, false);
+        }
+        {   // pw1
+            PwBwdArgs a; memset(&a, 0, sizeof a);
+            a.Rt = r1.Rt; a.out[0] = a.out[1] = (const bf16*)(c.ws + r1.data); a.dout[0] = a.dout[1] = (const bf16*)(c.ws + r1.grad);
+            a.cpo = r1.cp; a.tb[0] = a.tb[1] = tables_of(c, r1);
+            launch_pw_bwd(c, 2 * ui, host[2 * ui], a);
+        }
     }
 }
 
