@@ -73,7 +73,7 @@ inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, i
     off = (off + 127) & ~127;
     s.raw_stride = (R * ((direct ? 0 : 2 * nplanes * cpo) + src_cp + x1cp) * 2 + 127) & ~127;
     s.raw = off; off += nbuf * s.raw_stride;
-    s.dr = off; off += R * s.ldr * 2;
+    { const int dr_bytes = R * s.ldr * 2; s.dr = off; off += dr_bytes > 32768 ? dr_bytes : 32768; }     // doubles as the flush scratch
     off = (off + 127) & ~127;
     s.st = off; off += R * s.lds * 2;
     off = (off + 127) & ~127;
@@ -86,7 +86,7 @@ inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, i
 // d src[r][kk] = sum_j dR[r][j] * W[kk][j]  for the K tile (source, k0..k0+kw) of this CTA; epilogue: store (or add to)
 // the source's gradient tensor and accumulate its BatchNorm-backward sums.
 template <int R, int WM, int WN, int MT, int NBW>
-__global__ void __launch_bounds__(256) pw_dgrad_kernel(const PwBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
     constexpr int KT = WN * NBW * 8;
     extern __shared__ __align__(128) unsigned char smem[];
     const PwDesc& d = *a.d;
@@ -170,35 +170,37 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const PwBwdArgs a) {
     const bool sclamp = S.clamp != 0, oclamp = a.out_clamp != 0, xclamp = a.x1clamp != 0;
     const double inv_n = 1.0 / (double)a.Rt;
 
+    // sums: registers -> scratch (the idle dR tile) -> one thread per column -> fp64 atomics (no shared-memory float atomics)
     auto flush = [&](int t) {
+        __syncthreads();
+        float2* scr = reinterpret_cast<float2*>(Dr);              // [vnrl][kw] then [xnrl][x1cp]; <= 2 * 2048 entries
         if (vrl < vnrl) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                atomicAdd(&s_stat[(vq * 8 + i) * 2], s1[i]); atomicAdd(&s_stat[(vq * 8 + i) * 2 + 1], s2[i]);
-                s1[i] = 0.f; s2[i] = 0.f;
-            }
+            for (int i = 0; i < 8; ++i) { scr[vrl * kw + vq * 8 + i] = make_float2(s1[i], s2[i]); s1[i] = 0.f; s2[i] = 0.f; }
         }
+        float2* scr2 = scr + 2048;
         if (do_x1 && xrl < xnrl) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                atomicAdd(&s_stat[(KT + xq * 8 + i) * 2], x1s1[i]); atomicAdd(&s_stat[(KT + xq * 8 + i) * 2 + 1], x1s2[i]);
-                x1s1[i] = 0.f; x1s2[i] = 0.f;
-            }
+            for (int i = 0; i < 8; ++i) { scr2[xrl * x1cp + xq * 8 + i] = make_float2(x1s1[i], x1s2[i]); x1s1[i] = 0.f; x1s2[i] = 0.f; }
         }
         __syncthreads();
         for (int i = tid; i < kw; i += 256) {
             const int s = k0 + i;
             if (s >= S.sum_lo && s < S.sum_hi) {
+                float a1 = 0.f, a2 = 0.f;
+                for (int l = 0; l < vnrl; ++l) { const float2 v = scr[l * kw + i]; a1 += v.x; a2 += v.y; }
                 double2* dst = S.bsum + (size_t)t * S.cp + s;
-                atomicAdd(&dst->x, (double)s_stat[2 * i]); atomicAdd(&dst->y, (double)s_stat[2 * i + 1]);
+                atomicAdd(&dst->x, (double)a1); atomicAdd(&dst->y, (double)a2);
             }
-            s_stat[2 * i] = 0.f; s_stat[2 * i + 1] = 0.f;
         }
         if (do_x1) for (int i = tid; i < x1cp; i += 256) {
+            float a1 = 0.f, a2 = 0.f;
+            for (int l = 0; l < xnrl; ++l) { const float2 v = scr2[l * x1cp + i]; a1 += v.x; a2 += v.y; }
             double2* dst = a.x1bsum + (size_t)t * x1cp + i;
-            atomicAdd(&dst->x, (double)s_stat[(KT + i) * 2]); atomicAdd(&dst->y, (double)s_stat[(KT + i) * 2 + 1]);
-            s_stat[(KT + i) * 2] = 0.f; s_stat[(KT + i) * 2 + 1] = 0.f;
+            atomicAdd(&dst->x, (double)a1); atomicAdd(&dst->y, (double)a2);
         }
+        __syncthreads();
+        for (int i = tid; i < R * ldr / 2; i += 256) reinterpret_cast<uint32_t*>(Dr)[i] = 0u;      // K padding columns back to zero
         __syncthreads();
     };
 
@@ -216,10 +218,10 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const PwBwdArgs a) {
                     const size_t idx = (size_t)t * a.cpo + s;
                     c = bnbwd_consts(a.tb[p].aff[idx], a.tb[p].bnp[idx], a.tb[p].bsum[idx], inv_n);
                 }
-                s_colc[j] = c;
+                s_colc[tcol(j, NP >> 3)] = c;
             }
-            for (int i = tid; i < kw; i += 256) s_srcc[i] = sum_consts(S.aff, S.bnp, (size_t)t * S.cp + k0 + i);
-            if (do_x1) for (int i = tid; i < x1cp; i += 256) s_x1c[i] = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + i);
+            for (int i = tid; i < kw; i += 256) s_srcc[tcol(i, KT >> 3)] = sum_consts(S.aff, S.bnp, (size_t)t * S.cp + k0 + i);
+            if (do_x1) for (int i = tid; i < x1cp; i += 256) s_x1c[tcol(i, x1cp >> 3)] = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + i);
             cur_t = t;
             __syncthreads();
         }
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const PwBwdArgs a) {
         if (trl < tnrl) {
             float4 c8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = s_colc[tp * gwp + tc + q];
+            for (int q = 0; q < 8; ++q) c8[q] = s_colc[q * (NP >> 3) + ((tp * gwp + tc) >> 3)];
             const uint4* dv = reinterpret_cast<const uint4*>(rb + (size_t)R * (o_dout + tp * plane_bytes));
             const uint4* ov = reinterpret_cast<const uint4*>(rb + (size_t)R * (o_out + tp * plane_bytes));
             if (a.direct) {
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const PwBwdArgs a) {
         if (vrl < vnrl) {
             float4 c8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = s_srcc[vq * 8 + q];
+            for (int q = 0; q < 8; ++q) c8[q] = s_srcc[q * (KT >> 3) + vq];
             bf16* grow = S.grad + ((size_t)t * a.Rt + r0) * S.cp + k0 + vq * 8;
             const uint4* rv = reinterpret_cast<const uint4*>(rb + (size_t)R * o_src);
             const int nch = S.cp >> 3, ch = (k0 >> 3) + vq;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const PwBwdArgs a) {
         if (do_x1 && xrl < xnrl) {
             float4 c8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = s_x1c[xq * 8 + q];
+            for (int q = 0; q < 8; ++q) c8[q] = s_x1c[q * (x1cp >> 3) + xq];
             bf16* grow = a.dx1 + ((size_t)t * a.Rt + r0) * x1cp + xq * 8;
             const uint4* rv = reinterpret_cast<const uint4*>(rb + (size_t)R * o_x1);
             const int nch = x1cp >> 3;
@@ -373,7 +375,7 @@ inline __host__ __device__ PwWgradSmem pw_wgrad_smem(int NTW, int cpo, int src_c
 }
 
 template <int NBW>          // n-blocks per warp: N tile = 2 * NBW * 8 columns
-__global__ void __launch_bounds__(256) pw_wgrad_kernel(const PwBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
     constexpr int NTW = 2 * NBW * 8;
     extern __shared__ __align__(128) unsigned char smem[];
     const PwDesc& d = *a.d;
@@ -439,9 +441,9 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const PwBwdArgs a) {
                     const size_t idx = (size_t)t * a.cpo + s;
                     c = bnbwd_consts(a.tb[p].aff[idx], a.tb[p].bnp[idx], a.tb[p].bsum[idx], inv_n);
                 }
-                s_colc[j] = c;
+                s_colc[tcol(j, NTW >> 3)] = c;
             }
-            for (int i = tid; i < kw; i += 256) s_aff[i] = S.aff ? S.aff[(size_t)t * S.cp + k0 + i] : make_float2(1.f, 0.f);
+            for (int i = tid; i < kw; i += 256) s_aff[tcol(i, kWgK >> 3)] = S.aff ? S.aff[(size_t)t * S.cp + k0 + i] : make_float2(1.f, 0.f);
             cur_t = t;
             __syncthreads();
         }
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const PwBwdArgs a) {
         if (rrl < rnrl) {
             float4 c8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = s_colc[rq * 8 + q];
+            for (int q = 0; q < 8; ++q) c8[q] = s_colc[q * (NTW >> 3) + rq];
             const uint4* dv = reinterpret_cast<const uint4*>(rb + (size_t)kWgR * o_dout);
             const uint4* ov = reinterpret_cast<const uint4*>(rb + (size_t)kWgR * o_out);
             if (a.direct) {
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const PwBwdArgs a) {
         if (xrl < xnrl) {
             float2 c8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = s_aff[xq * 8 + q];
+            for (int q = 0; q < 8; ++q) c8[q] = s_aff[q * (kWgK >> 3) + xq];
             const uint4* sv = reinterpret_cast<const uint4*>(rb + (size_t)kWgR * o_src);
             const int nch = S.cp >> 3, ch = (k0 >> 3) + xq;
             for (int r = xrl; r < kWgR; r += xnrl) {
@@ -532,57 +534,45 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const PwBwdArgs a) {
 }
 
 // ======================================================================================== depthwise backward
-// One CTA per frame at a time: d out frame + raw out frame + raw in frame by TMA; dR (BatchNorm backward) and act(in)
-// are built in place; thread <-> (channel pair, column) runs the transposed stencil (data gradient, with the input
-// tensor's BatchNorm-backward sums) and the 9-tap weight gradient (registers, reduced once per CTA).
-struct DwBwdSmem { int stat, wred, colc, dr, outr, inr, ina, total; };
-inline __host__ __device__ DwBwdSmem dw_bwd_smem(int cp, int in_px, int out_px) {
-    DwBwdSmem s;
-    int off = 64;
-    s.stat = off; off += cp * 8;
-    s.wred = off; off += cp * 9 * 4;
-    s.colc = off; off += cp * 16;
-    off = (off + 127) & ~127;
-    s.dr = off; off += (out_px * cp * 2 + 127) & ~127;
-    s.outr = off; off += (out_px * cp * 2 + 127) & ~127;
-    s.inr = off; off += (in_px * cp * 2 + 127) & ~127;
-    s.ina = off; off += (in_px * cp * 2 + 127) & ~127;
-    s.total = off;
-    return s;
-}
-
+// One frame at a time per CTA: d out + raw out frames by TMA (dense), input frame rows by TMA into the halo-padded
+// tile (activated in place); dR (BatchNorm backward of the depthwise output) goes into a second halo-padded tile.
+// thread <-> (channel pair, column) runs the 9-tap weight gradient (registers, reduced once per CTA) and the
+// transposed stencil (data gradient + the BatchNorm-backward sums of the input tensor).  The sums are taken from the
+// ACTIVATED input a = relu6(scale*raw + shift) held in shared memory: mask = 0 < a < 6, xhat = (a - beta) / gamma.
+template <int CP, int S>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NPAIR = CP / 2, NCH = CP / 8, NXL = kDwThreads / NPAIR, TNPL = kDwThreads / NCH;
     const int tid = threadIdx.x;
-    const int cp = a.cp, npair = cp >> 1;
-    const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo;
-    const DwBwdSmem L = dw_bwd_smem(cp, in_px, out_px);
+    const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo, PW = a.Wi + 2, QW = a.Wo + 2;
+    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, true);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     float* s_stat = reinterpret_cast<float*>(smem + L.stat);
     float* s_wred = reinterpret_cast<float*>(smem + L.wred);
     float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
-    bf16* Dr = reinterpret_cast<bf16*>(smem + L.dr);
-    const bf16* Or = reinterpret_cast<const bf16*>(smem + L.outr);
-    const bf16* Ir = reinterpret_cast<const bf16*>(smem + L.inr);
-    bf16* Ia = reinterpret_cast<bf16*>(smem + L.ina);
-    const uint32_t out_bytes = (uint32_t)out_px * cp * 2, in_bytes = (uint32_t)in_px * cp * 2;
+    bf16* Pdr = reinterpret_cast<bf16*>(smem + L.pdr);
+    const uint32_t out_bytes = (uint32_t)out_px * CP * 2, row_bytes = (uint32_t)a.Wi * CP * 2;
     const int nframes = kT * a.B;
     const int f_lo = blockIdx.x * a.frames_per_cta, f_hi = min(nframes, f_lo + a.frames_per_cta);
-    if (tid == 0) { mbar_init(&full[0], 1); mbar_fence_init(); }
-    for (int i = tid; i < cp * 2; i += kDwThreads) s_stat[i] = 0.f;
-    for (int i = tid; i < cp * 9; i += kDwThreads) s_wred[i] = 0.f;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    for (int i = tid; i < CP * 2; i += kDwThreads) s_stat[i] = 0.f;
+    for (int i = tid; i < CP * 9; i += kDwThreads) s_wred[i] = 0.f;
+    for (int i = tid; i < a.nbuf * L.pin_stride / 4; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + L.pin)[i] = 0u;
+    for (int i = tid; i < (a.Ho + 2) * QW * (CP / 2); i += kDwThreads) reinterpret_cast<uint32_t*>(Pdr)[i] = 0u;
     __syncthreads();
-    auto issue = [&](int f) {
-        mbar_expect_tx(&full[0], 2 * out_bytes + in_bytes);
-        bulk_g2s(Dr, a.dout + (size_t)f * out_px * cp, out_bytes, &full[0]);
-        bulk_g2s(smem + L.outr, a.out + (size_t)f * out_px * cp, out_bytes, &full[0]);
-        bulk_g2s(smem + L.inr, a.in + (size_t)f * in_px * cp, in_bytes, &full[0]);
+    auto issue = [&](int f, int buf) {
+        mbar_expect_tx(&full[buf], 2 * out_bytes + row_bytes * a.Hi);
+        bulk_g2s(smem + L.raw_dout + (size_t)buf * L.out_stride, a.dout + (size_t)f * out_px * CP, out_bytes, &full[buf]);
+        bulk_g2s(smem + L.raw_out + (size_t)buf * L.out_stride, a.out + (size_t)f * out_px * CP, out_bytes, &full[buf]);
+        unsigned char* dst = smem + L.pin + (size_t)buf * L.pin_stride + (PW + 1) * CP * 2;
+        const bf16* src = a.in + (size_t)f * in_px * CP;
+        for (int y = 0; y < a.Hi; ++y) bulk_g2s(dst + (size_t)y * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
     };
-    if (tid == 0 && f_lo < f_hi) issue(f_lo);
+    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (f_lo + b < f_hi) issue(f_lo + b, b);
 
-    const int nch = cp >> 3, tch = tid % nch, tpl = tid / nch, tnpl = kDwThreads / nch;
-    const int pr = tid % npair, xl = tid / npair, nxl = kDwThreads / npair;
-    const bool active = xl < nxl;
+    const int tch = tid % NCH, tpl = tid / NCH;
+    const int pr = tid % NPAIR, xl = tid / NPAIR;
+    const bool active = xl < NXL;
     float w0[9], w1[9], g0[9], g1[9];
     {
         const int l0 = slot_logical(a.map, 2 * pr), l1 = slot_logical(a.map, 2 * pr + 1);
@@ -594,9 +584,9 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
         }
     }
     float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-    float4 ic0 = make_float4(1.f, 0.f, 0.f, 0.f), ic1 = ic0;      // sums constants of this thread's input channels
+    float2 xc0 = make_float2(0.f, 0.f), xc1 = xc0;              // xhat = a * x + y  for this thread's two input channels
     float2 ac8[8];
-    const bool iclamp = a.clamp != 0;
+    const bool iclamp = a.clamp != 0, xform = a.aff != nullptr || iclamp, want_sums = a.in_bsum != nullptr;
     const double inv_n = 1.0 / ((double)a.B * out_px);
     auto flush = [&](int t) {
         if (active) {
@@ -605,115 +595,138 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
         }
         s1a = s2a = s1b = s2b = 0.f;
         __syncthreads();
-        for (int c = tid; c < cp; c += kDwThreads) {
-            if (a.in_bsum && c >= a.in_sum_lo && c < a.in_sum_hi) {
-                double2* dst = a.in_bsum + (size_t)t * cp + c;
+        for (int c = tid; c < CP; c += kDwThreads) {
+            if (want_sums && c >= a.in_sum_lo && c < a.in_sum_hi) {
+                double2* dst = a.in_bsum + (size_t)t * CP + c;
                 atomicAdd(&dst->x, (double)s_stat[2 * c]); atomicAdd(&dst->y, (double)s_stat[2 * c + 1]);
             }
             s_stat[2 * c] = 0.f; s_stat[2 * c + 1] = 0.f;
         }
         __syncthreads();
     };
-
+    auto xhat_consts = [&](int t, int slot) {
+        if (!a.aff) return make_float2(0.f, 0.f);
+        const float2 af = a.aff[(size_t)t * CP + slot], bp = a.bnp[(size_t)t * CP + slot];
+        if (af.x == 0.f) return make_float2(0.f, 0.f);
+        const float r = bp.y / af.x;                              // inv_std / scale = 1 / gamma
+        return make_float2(r, -af.y * r - bp.x * bp.y);
+    };
+    const int row_step = S * PW * CP;
     int cur_t = -1;
     for (int f = f_lo, it = 0; f < f_hi; ++f, ++it) {
-        const int t = f / a.B;
+        const int buf = it % a.nbuf, t = f / a.B;
         if (t != cur_t) {
             if (cur_t >= 0) flush(cur_t);
             __syncthreads();
-            for (int s = tid; s < cp; s += kDwThreads) {
+            for (int s = tid; s < CP; s += kDwThreads) {
                 const int l = slot_logical(a.map, s);
-                const size_t idx = (size_t)t * cp + s;
+                const size_t idx = (size_t)t * CP + s;
                 s_colc[s] = l >= 0 ? bnbwd_consts(a.tb.aff[idx], a.tb.bnp[idx], a.tb.bsum[idx], inv_n) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (tpl < tnpl) {
+            if (tpl < TNPL) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) ac8[q] = a.aff ? a.aff[(size_t)t * cp + tch * 8 + q] : make_float2(1.f, 0.f);
+                for (int q = 0; q < 8; ++q) ac8[q] = a.aff ? a.aff[(size_t)t * CP + tch * 8 + q] : make_float2(1.f, 0.f);
             }
-            ic0 = sum_consts(a.aff, a.bnp, (size_t)t * cp + 2 * pr);
-            ic1 = sum_consts(a.aff, a.bnp, (size_t)t * cp + 2 * pr + 1);
+            xc0 = xhat_consts(t, 2 * pr); xc1 = xhat_consts(t, 2 * pr + 1);
             cur_t = t;
             __syncthreads();
         }
-        mbar_wait(&full[0], it & 1);
-        if (tpl < tnpl) {
+        mbar_wait(&full[buf], (it / a.nbuf) & 1);
+        bf16* Pin = reinterpret_cast<bf16*>(smem + L.pin + (size_t)buf * L.pin_stride);
+        if (tpl < TNPL) {
             float4 c8[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) c8[q] = s_colc[tch * 8 + q];
-            uint4* dv = reinterpret_cast<uint4*>(Dr);
-            const uint4* ov = reinterpret_cast<const uint4*>(Or);
-            for (int px = tpl; px < out_px; px += tnpl) {
-                uint4 dvv = dv[px * nch + tch]; const uint4 ovv = ov[px * nch + tch];
+            const uint4* dv = reinterpret_cast<const uint4*>(smem + L.raw_dout + (size_t)buf * L.out_stride) + tch;
+            const uint4* ov = reinterpret_cast<const uint4*>(smem + L.raw_out + (size_t)buf * L.out_stride) + tch;
+            uint4* qv = reinterpret_cast<uint4*>(Pdr) + tch;
+            PxWalk wo(tpl, TNPL, a.Wo);
+            for (int px = tpl; px < out_px; px += TNPL, wo.next()) {
+                uint4 dvv = dv[px * NCH]; const uint4 ovv = ov[px * NCH];
                 uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
                     dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], false), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], false));
                 }
-                dv[px * nch + tch] = dvv;
+                qv[((wo.y + 1) * QW + wo.x + 1) * NCH] = dvv;
             }
-            const uint4* iv = reinterpret_cast<const uint4*>(Ir);
-            uint4* av = reinterpret_cast<uint4*>(Ia);
-            for (int px = tpl; px < in_px; px += tnpl) av[px * nch + tch] = affine8(iv[px * nch + tch], ac8, iclamp);
+            if (xform) {
+                uint4* pv = reinterpret_cast<uint4*>(Pin) + tch;
+                PxWalk wi(tpl, TNPL, a.Wi);
+                for (int px = tpl; px < in_px; px += TNPL, wi.next()) {
+                    uint4* q = pv + ((wi.y + 1) * PW + wi.x + 1) * NCH;
+                    *q = affine8(*q, ac8, iclamp);
+                }
+            }
         }
         __syncthreads();
         if (active) {
-            // weight gradient: dw[ky][kx] += act(in)[oy*s - pt + ky][ox*s - pl + kx] * dR[oy][ox]
-            for (int ox = xl; ox < a.Wo; ox += nxl) {
-                const int ix0 = ox * a.stride - a.pad_l;
+            // weight gradient: dw[ky][kx] += act(in)(oy*S - pt + ky, ox*S - pl + kx) * dR(oy, ox)
+            for (int ox = xl; ox < a.Wo; ox += NXL) {
+                const bf16* win = Pin + ((1 - a.pad_t) * PW + ox * S + 1 - a.pad_l) * CP + 2 * pr;
+                const bf16* dp = Pdr + (QW + ox + 1) * CP + 2 * pr;
                 for (int oy = 0; oy < a.Ho; ++oy) {
-                    const int iy0 = oy * a.stride - a.pad_t;
-                    const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(Dr + ((size_t)oy * a.Wo + ox) * cp + 2 * pr));
+                    const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(dp));
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int iy = iy0 + ky;
-                        if (iy < 0 || iy >= a.Hi) continue;
+                    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            const int ix = ix0 + kx;
-                            if (ix < 0 || ix >= a.Wi) continue;
-                            const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(Ia + ((size_t)iy * a.Wi + ix) * cp + 2 * pr));
+                            const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(win + ky * PW * CP + kx * CP));
                             g0[ky * 3 + kx] = fmaf(v.x, dr.x, g0[ky * 3 + kx]);
                             g1[ky * 3 + kx] = fmaf(v.y, dr.y, g1[ky * 3 + kx]);
                         }
-                    }
+                    win += row_step; dp += QW * CP;
                 }
             }
-            // data gradient: d in[iy][ix] = sum_{ky,kx} w[ky][kx] * dR[(iy + pt - ky)/s][(ix + pl - kx)/s]
-            for (int ix = xl; ix < a.Wi; ix += nxl) {
-                bf16* gcol = a.din + ((size_t)f * in_px + ix) * cp + 2 * pr;
+            // data gradient: d in(iy, ix) = sum_{ky,kx} w[ky][kx] * dR((iy + pt - ky)/S, (ix + pl - kx)/S)
+            for (int ix = xl; ix < a.Wi; ix += NXL) {
+                bf16* gp = a.din + ((size_t)f * in_px + ix) * CP + 2 * pr;
+                const bf16* ap = Pin + (PW + ix + 1) * CP + 2 * pr;
                 for (int iy = 0; iy < a.Hi; ++iy) {
                     float acc0 = 0.f, acc1 = 0.f;
+                    if (S == 1) {
+                        const bf16* dwin = Pdr + ((iy + 2) * QW + ix + 2) * CP + 2 * pr;      // (iy + 1 - ky) + 1, (ix + 1 - kx) + 1
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int ny = iy + a.pad_t - ky;
-                        if (ny < 0 || (a.stride == 2 && (ny & 1))) continue;
-                        const int oy = a.stride == 2 ? ny >> 1 : ny;
-                        if (oy >= a.Ho) continue;
+                        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const int nx = ix + a.pad_l - kx;
-                            if (nx < 0 || (a.stride == 2 && (nx & 1))) continue;
-                            const int ox = a.stride == 2 ? nx >> 1 : nx;
-                            if (ox >= a.Wo) continue;
-                            const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(Dr + ((size_t)oy * a.Wo + ox) * cp + 2 * pr));
-                            acc0 = fmaf(dr.x, w0[ky * 3 + kx], acc0);
-                            acc1 = fmaf(dr.y, w1[ky * 3 + kx], acc1);
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(dwin - ky * QW * CP - kx * CP));
+                                acc0 = fmaf(dr.x, w0[ky * 3 + kx], acc0);
+                                acc1 = fmaf(dr.y, w1[ky * 3 + kx], acc1);
+                            }
+                    } else {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int ny = iy + a.pad_t - ky;
+                            if (ny & 1) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int nx = ix + a.pad_l - kx;
+                                if (nx & 1) continue;
+                                const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(Pdr + (((ny >> 1) + 1) * QW + (nx >> 1) + 1) * CP + 2 * pr));
+                                acc0 = fmaf(dr.x, w0[ky * 3 + kx], acc0);
+                                acc1 = fmaf(dr.y, w1[ky * 3 + kx], acc1);
+                            }
                         }
                     }
-                    bf16* gp = gcol + (size_t)iy * a.Wi * cp;
                     if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
                     const uint32_t pk = pack2(acc0, acc1);
                     *reinterpret_cast<uint32_t*>(gp) = pk;
-                    const float2 gr = unpack2(pk);
-                    const float2 rw = unpack2(*reinterpret_cast<const uint32_t*>(Ir + ((size_t)iy * a.Wi + ix) * cp + 2 * pr));
-                    sum_accum(gr.x, rw.x, ic0, iclamp, s1a, s2a);
-                    sum_accum(gr.y, rw.y, ic1, iclamp, s1b, s2b);
+                    if (want_sums) {
+                        const float2 gr = unpack2(pk);
+                        const float2 av = unpack2(*reinterpret_cast<const uint32_t*>(ap));
+                        const float d0 = (!iclamp || (av.x > 0.f && av.x < 6.f)) ? gr.x : 0.f;
+                        const float d1 = (!iclamp || (av.y > 0.f && av.y < 6.f)) ? gr.y : 0.f;
+                        s1a += d0; s2a = fmaf(d0, fmaf(av.x, xc0.x, xc0.y), s2a);
+                        s1b += d1; s2b = fmaf(d1, fmaf(av.y, xc1.x, xc1.y), s2b);
+                    }
+                    gp += a.Wi * CP; ap += PW * CP;
                 }
             }
         }
         __syncthreads();
-        if (tid == 0 && f + 1 < f_hi) issue(f + 1);
+        if (tid == 0 && f + a.nbuf < f_hi) issue(f + a.nbuf, buf);
     }
     if (cur_t >= 0) flush(cur_t);
     // ---- weight gradients of this CTA
@@ -722,16 +735,16 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
         for (int k = 0; k < 9; ++k) { atomicAdd(&s_wred[(2 * pr) * 9 + k], g0[k]); atomicAdd(&s_wred[(2 * pr + 1) * 9 + k], g1[k]); }
     }
     __syncthreads();
-    for (int i = tid; i < cp * 9; i += kDwThreads) {
+    for (int i = tid; i < CP * 9; i += kDwThreads) {
         const int s = i / 9, k = i - s * 9, l = slot_logical(a.map, s);
         if (l >= 0) atomicAdd(a.L.dw + (size_t)k * a.L.N + a.kbase + l, s_wred[i]);
     }
     if (blockIdx.x == 0) {
-        for (int s = tid; s < cp; s += kDwThreads) {
+        for (int s = tid; s < CP; s += kDwThreads) {
             const int l = slot_logical(a.map, s);
             if (l < 0) continue;
             double gs = 0.0, bs = 0.0;
-            for (int t = 0; t < kT; ++t) { const double2 v = a.tb.bsum[(size_t)t * cp + s]; bs += v.x; gs += v.y; }
+            for (int t = 0; t < kT; ++t) { const double2 v = a.tb.bsum[(size_t)t * CP + s]; bs += v.x; gs += v.y; }
             a.L.dg[a.kbase + l] = (float)gs; a.L.dbe[a.kbase + l] = (float)bs;
         }
     }

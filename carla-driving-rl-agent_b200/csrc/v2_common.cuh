@@ -75,19 +75,28 @@ CDRA_DEV uint4 ldg_cg16(const void* p) {        // L2-only 16-byte load (data wr
     return v;
 }
 
-// relu6(scale * x + shift) on 8 packed bf16 (fp32 math, one rounding)
+// relu6(scale * x + shift) on 8 packed bf16: fp32 FMA, one rounding, then the clamp on the packed pair (0 and 6 are
+// exact in bf16 and rounding is monotonic, so clamping after the rounding gives the same bits as clamping before)
+CDRA_DEV uint32_t relu6_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    v = __hmin2(__hmax2(v, __float2bfloat162_rn(0.f)), __float2bfloat162_rn(6.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 CDRA_DEV uint4 affine8(uint4 v, const float2 (&c)[8], bool clamp) {
     uint32_t* w = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 f = unpack2(w[i]);
-        f.x = fmaf(f.x, c[2 * i].x, c[2 * i].y);
-        f.y = fmaf(f.y, c[2 * i + 1].x, c[2 * i + 1].y);
-        if (clamp) { f.x = relu6f(f.x); f.y = relu6f(f.y); }
-        w[i] = pack2(f.x, f.y);
+        const float2 f = unpack2(w[i]);
+        w[i] = pack2(fmaf(f.x, c[2 * i].x, c[2 * i].y), fmaf(f.y, c[2 * i + 1].x, c[2 * i + 1].y));
+        if (clamp) w[i] = relu6_bf16x2(w[i]);
     }
     return v;
 }
+
+// Per-column constant tables in shared memory are stored "chunk-transposed": column c of a table with nch 8-column
+// chunks lives at (c & 7) * nch + (c >> 3), so that the q-th constants of the chunks a warp works on are contiguous
+// (one wavefront per load instead of an 8-way bank conflict).
+CDRA_DEV int tcol(int c, int nch) { return (c & 7) * nch + (c >> 3); }
 
 // "last CTA done" ticket with a single fencing thread (release: bar.sync orders the CTA's atomics before the fence)
 CDRA_DEV bool last_cta(unsigned* counter, unsigned total) {

@@ -22,38 +22,65 @@ struct DwArgs {
     bf16* out; const bf16* dout; Tables tb;                              // output tensor [4*B*Ho*Wo][cp] (raw) + tables
     int training;
     unsigned* counter;
-    int frames_per_cta;
+    int frames_per_cta, nbuf;
 };
 
+// shared-memory carve-up of the depthwise kernels (host + device).  The input frame lives in a halo-padded tile
+// [(Hi+2)][(Wi+2)][cp] (zero border = TF SAME padding): TMA row copies land in its interior and the producer's
+// BatchNorm affine (+ReLU6) is applied in place, so the stencils need no bounds checks.
+struct DwSmem { int stat, wred, colc, pin, raw_out, raw_dout, pdr, total, pin_stride, out_stride; };
+inline __host__ __device__ DwSmem dw_smem(int cp, int Hi, int Wi, int Ho, int Wo, int nbuf, bool backward) {
+    DwSmem s;
+    int off = 64;
+    s.stat = off; off += cp * 8;
+    s.wred = off; off += backward ? cp * 9 * 4 : 0;
+    s.colc = off; off += backward ? cp * 16 : 0;
+    off = (off + 127) & ~127;
+    s.pin_stride = ((Hi + 2) * (Wi + 2) * cp * 2 + 127) & ~127;
+    s.out_stride = (Ho * Wo * cp * 2 + 127) & ~127;
+    s.pin = off; off += nbuf * s.pin_stride;
+    s.raw_out = off; off += backward ? nbuf * s.out_stride : 0;
+    s.raw_dout = off; off += backward ? nbuf * s.out_stride : 0;
+    s.pdr = off; off += backward ? (((Ho + 2) * (Wo + 2) * cp * 2 + 127) & ~127) : 0;   // dR with a zero halo
+    s.total = off;
+    return s;
+}
+
+// per-thread (y, x) walker over the pixels px = lane, lane + step, ... of a W-wide frame without divisions in the loop
+struct PxWalk {
+    int y, x, dy, dx, W;
+    __device__ PxWalk(int lane, int step, int W_) : W(W_) { y = lane / W_; x = lane - y * W_; dy = step / W_; dx = step - dy * W_; }
+    __device__ void next() { y += dy; x += dx; if (x >= W) { x -= W; ++y; } }
+};
+
+// forward: out(oy, ox) = b + sum_{ky,kx} w[ky][kx] * act(in)(oy*S - pt + ky, ox*S - pl + kx)   (zero outside the frame)
+template <int CP, int S>
 __global__ void __launch_bounds__(kDwThreads) dw_fwd_kernel(const DwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NPAIR = CP / 2, NCH = CP / 8, NXL = kDwThreads / NPAIR, TNPL = kDwThreads / NCH;
     const int tid = threadIdx.x;
-    const int cp = a.cp, npair = cp >> 1;
-    const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo;
-    const uint32_t frame_bytes = (uint32_t)in_px * cp * 2;
-    const int buf_stride = (frame_bytes + 127) & ~127;
+    const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo, PW = a.Wi + 2;
+    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, false);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    float* s_stat = reinterpret_cast<float*>(smem + 64);                 // [cp][2]
-    unsigned char* fb = smem + ((64 + cp * 8 + 127) & ~127);
+    float* s_stat = reinterpret_cast<float*>(smem + L.stat);
+    const uint32_t row_bytes = (uint32_t)a.Wi * CP * 2;
     const int nframes = kT * a.B;
     const int f_lo = blockIdx.x * a.frames_per_cta, f_hi = min(nframes, f_lo + a.frames_per_cta);
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
-    for (int i = tid; i < cp * 2; i += kDwThreads) s_stat[i] = 0.f;
+    for (int i = tid; i < CP * 2; i += kDwThreads) s_stat[i] = 0.f;
+    for (int i = tid; i < a.nbuf * L.pin_stride / 4; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + L.pin)[i] = 0u;
     __syncthreads();
     auto issue = [&](int f, int buf) {
-        mbar_expect_tx(&full[buf], frame_bytes);
-        bulk_g2s(fb + (size_t)buf * buf_stride, a.in + (size_t)f * in_px * cp, frame_bytes, &full[buf]);
+        mbar_expect_tx(&full[buf], row_bytes * a.Hi);
+        unsigned char* dst = smem + L.pin + (size_t)buf * L.pin_stride + (PW + 1) * CP * 2;
+        const bf16* src = a.in + (size_t)f * in_px * CP;
+        for (int y = 0; y < a.Hi; ++y) bulk_g2s(dst + (size_t)y * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
     };
-    if (tid == 0) {
-        if (f_lo < f_hi) issue(f_lo, 0);
-        if (f_lo + 1 < f_hi) issue(f_lo + 1, 1);
-    }
-    // transform role: fixed 8-slot chunk, pixel lanes
-    const int nch = cp >> 3, tch = tid % nch, tpl = tid / nch, tnpl = kDwThreads / nch;
-    float2 c8[8];
-    // stencil role: fixed channel pair, column lanes
-    const int pr = tid % npair, xl = tid / npair, nxl = kDwThreads / npair;
-    const bool active = xl < nxl;
+    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (f_lo + b < f_hi) issue(f_lo + b, b);
+
+    const int tch = tid % NCH, tpl = tid / NCH;                       // transform role
+    const int pr = tid % NPAIR, xl = tid / NPAIR;                     // stencil role
+    const bool active = xl < NXL;
     float w0[9], w1[9], b0 = 0.f, b1 = 0.f;
     {
         const int l0 = slot_logical(a.map, 2 * pr), l1 = slot_logical(a.map, 2 * pr + 1);
@@ -65,80 +92,81 @@ __global__ void __launch_bounds__(kDwThreads) dw_fwd_kernel(const DwArgs a) {
         if (l0 >= 0) b0 = a.L.b[a.kbase + l0];
         if (l1 >= 0) b1 = a.L.b[a.kbase + l1];
     }
+    float2 c8[8];
     float ssum0 = 0.f, ssum1 = 0.f, ssq0 = 0.f, ssq1 = 0.f;
-    auto flush = [&](int t) {                         // CTA-uniform
+    auto flush = [&](int t) {
         if (active) {
             atomicAdd(&s_stat[4 * pr], ssum0); atomicAdd(&s_stat[4 * pr + 1], ssq0);
             atomicAdd(&s_stat[4 * pr + 2], ssum1); atomicAdd(&s_stat[4 * pr + 3], ssq1);
         }
         ssum0 = ssum1 = ssq0 = ssq1 = 0.f;
         __syncthreads();
-        for (int c = tid; c < cp; c += kDwThreads) {
-            double2* dst = a.tb.fsum + (size_t)t * cp + c;
+        for (int c = tid; c < CP; c += kDwThreads) {
+            double2* dst = a.tb.fsum + (size_t)t * CP + c;
             atomicAdd(&dst->x, (double)s_stat[2 * c]); atomicAdd(&dst->y, (double)s_stat[2 * c + 1]);
             s_stat[2 * c] = 0.f; s_stat[2 * c + 1] = 0.f;
         }
         __syncthreads();
     };
-
+    const bool clamp = a.clamp != 0, xform = a.aff != nullptr || clamp;
+    const int row_step = S * PW * CP, ostep = a.Wo * CP;
     int cur_t = -1;
     for (int f = f_lo, it = 0; f < f_hi; ++f, ++it) {
-        const int buf = it & 1, t = f / a.B;
+        const int buf = it % a.nbuf, t = f / a.B;
         if (t != cur_t) {
             if (cur_t >= 0 && a.training) flush(cur_t);
-            if (tpl < tnpl) {
+            if (tpl < TNPL) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) c8[q] = a.aff ? a.aff[(size_t)t * cp + tch * 8 + q] : make_float2(1.f, 0.f);
+                for (int q = 0; q < 8; ++q) c8[q] = a.aff ? a.aff[(size_t)t * CP + tch * 8 + q] : make_float2(1.f, 0.f);
             }
             cur_t = t;
         }
-        mbar_wait(&full[buf], (it >> 1) & 1);
-        bf16* fr = reinterpret_cast<bf16*>(fb + (size_t)buf * buf_stride);
-        if (a.aff != nullptr || a.clamp) {            // producer's BatchNorm affine (+ReLU6), in place
-            if (tpl < tnpl) {
-                uint4* v = reinterpret_cast<uint4*>(fr);
-                for (int px = tpl; px < in_px; px += tnpl) v[px * nch + tch] = affine8(v[px * nch + tch], c8, a.clamp != 0);
+        mbar_wait(&full[buf], (it / a.nbuf) & 1);
+        bf16* Pin = reinterpret_cast<bf16*>(smem + L.pin + (size_t)buf * L.pin_stride);
+        if (xform) {                                                  // producer's BatchNorm affine (+ReLU6), in place
+            if (tpl < TNPL) {
+                uint4* pv = reinterpret_cast<uint4*>(Pin) + tch;
+                PxWalk w(tpl, TNPL, a.Wi);
+                for (int px = tpl; px < in_px; px += TNPL, w.next()) {
+                    uint4* q = pv + ((w.y + 1) * PW + w.x + 1) * NCH;
+                    *q = affine8(*q, c8, clamp);
+                }
             }
             __syncthreads();
         }
         if (active) {
-            for (int ox = xl; ox < a.Wo; ox += nxl) {
-                const int ix0 = ox * a.stride - a.pad_l;
-                bf16* ocol = a.out + ((size_t)f * out_px + ox) * cp + 2 * pr;
+            for (int ox = xl; ox < a.Wo; ox += NXL) {
+                const bf16* win = Pin + ((1 - a.pad_t) * PW + ox * S + 1 - a.pad_l) * CP + 2 * pr;
+                bf16* optr = a.out + ((size_t)f * out_px + ox) * CP + 2 * pr;
                 for (int oy = 0; oy < a.Ho; ++oy) {
-                    const int iy0 = oy * a.stride - a.pad_t;
                     float acc0 = b0, acc1 = b1;
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int iy = iy0 + ky;
-                        if (iy < 0 || iy >= a.Hi) continue;
+                    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            const int ix = ix0 + kx;
-                            if (ix < 0 || ix >= a.Wi) continue;
-                            const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(fr + ((size_t)iy * a.Wi + ix) * cp + 2 * pr));
+                            const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(win + ky * PW * CP + kx * CP));
                             acc0 = fmaf(v.x, w0[ky * 3 + kx], acc0);
                             acc1 = fmaf(v.y, w1[ky * 3 + kx], acc1);
                         }
-                    }
                     const uint32_t pk = pack2(acc0, acc1);
-                    *reinterpret_cast<uint32_t*>(ocol + (size_t)oy * a.Wo * cp) = pk;
+                    *reinterpret_cast<uint32_t*>(optr) = pk;
                     const float2 r = unpack2(pk);
                     ssum0 += r.x; ssq0 = fmaf(r.x, r.x, ssq0);
                     ssum1 += r.y; ssq1 = fmaf(r.y, r.y, ssq1);
+                    win += row_step; optr += ostep;
                 }
             }
         }
         __syncthreads();
-        if (tid == 0 && f + 2 < f_hi) issue(f + 2, buf);
+        if (tid == 0 && f + a.nbuf < f_hi) issue(f + a.nbuf, buf);
     }
     if (cur_t >= 0 && a.training) flush(cur_t);
     if (a.counter == nullptr) return;
     if (!last_cta(a.counter, gridDim.x)) return;
-    for (int s = tid; s < cp; s += kDwThreads) {
+    for (int s = tid; s < CP; s += kDwThreads) {
         const int l = slot_logical(a.map, s);
-        if (l >= 0) bn_finalize_channel(a.tb, cp, s, a.L, a.kbase + l, (double)a.B * out_px, a.training);
-        else for (int t = 0; t < kT; ++t) { a.tb.aff[(size_t)t * cp + s] = make_float2(0.f, 0.f); a.tb.bnp[(size_t)t * cp + s] = make_float2(0.f, 1.f); }
+        if (l >= 0) bn_finalize_channel(a.tb, CP, s, a.L, a.kbase + l, (double)a.B * out_px, a.training);
+        else for (int t = 0; t < kT; ++t) { a.tb.aff[(size_t)t * CP + s] = make_float2(0.f, 0.f); a.tb.bnp[(size_t)t * CP + s] = make_float2(0.f, 1.f); }
     }
 }
 

@@ -142,13 +142,13 @@ inline __host__ __device__ PwFwdSmem pw_fwd_smem(int R, int NT, int KP, int src_
     s.raw = off; off += 2 * s.raw_stride;
     s.a = off; off += R * s.lda * 2;
     off = (off + 127) & ~127;
-    s.st = off; off += splanes * R * s.lds * 2;
+    { const int st_bytes = splanes * R * s.lds * 2; s.st = off; off += st_bytes > 16384 ? st_bytes : 16384; }   // doubles as the 16 KB flush scratch
     s.total = off;
     return s;
 }
 
 template <int R, int WM, int WN, int MT, int NBW>
-__global__ void __launch_bounds__(256) pw_fwd_kernel(const PwFwdArgs a) {
+__global__ void __launch_bounds__(256, 2) pw_fwd_kernel(const PwFwdArgs a) {
     constexpr int NT = WN * NBW * 8;
     extern __shared__ __align__(128) unsigned char smem[];
     const PwDesc& d = *a.d;
@@ -213,17 +213,32 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(const PwFwdArgs a) {
         if (tile_lo + 1 < tile_hi) issue(tile_lo + 1, 1);
     }
 
-    // ---- per-thread constant roles
+    // ---- per-thread constant roles (everything that needs a division is computed once, outside the tile loop)
     const int wm = warp % WM, wn = warp / WM;
     const int g = lane >> 2, tg = lane & 3;
     int dsto[NBW];                                    // staging offset of this thread's column pair per n-block, -1 = not stored
+    float bias0[NBW], bias1[NBW];
 #pragma unroll
     for (int nb = 0; nb < NBW; ++nb) {
         const int jl = wn * NBW * 8 + nb * 8 + 2 * tg;
         dsto[nb] = -1;
+        bias0[nb] = s_bias[jl]; bias1[nb] = s_bias[jl + 1];
         if (jl < ncols) {
             const int j = jt0 + jl, p = j / gwp, c = j - p * gwp;
-            if (c < a.gwv) dsto[nb] = (p - p0) * R * lds + (c - scol0);
+            if (c < a.gwv) dsto[nb] = (p - p0) * R * lds + (c - scol0) + (wm * MT * 16 + g) * lds;
+        }
+    }
+    // transform roles: per source, thread <-> one 8-slot chunk, row lanes stride the rows
+    int x_off[kMaxSrc], x_offb[kMaxSrc], x_nch[kMaxSrc], x_ch[kMaxSrc], x_rl[kMaxSrc], x_nrl[kMaxSrc];
+    {
+        int off = 0, offb = 0;
+        for (int i = 0; i < kMaxSrc; ++i) {
+            x_off[i] = off; x_offb[i] = offb; x_nch[i] = 1; x_ch[i] = 0; x_rl[i] = 1; x_nrl[i] = 0;
+            if (i < d.nsrc) {
+                const int cp = d.src[i].cp;
+                x_nch[i] = cp >> 3; x_ch[i] = tid % x_nch[i]; x_rl[i] = tid / x_nch[i]; x_nrl[i] = 256 / x_nch[i];
+                off += cp; offb += cp * 2;
+            }
         }
     }
     // vector pass: thread <-> one 8-slot chunk of one covered plane, row lanes stride the rows
@@ -232,125 +247,142 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(const PwFwdArgs a) {
     float ssum[8], ssq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
-    // pass-through copy: thread <-> one destination slot (plane, i), row lanes stride the rows
-    int cp_src = -1, cp_dst = 0, cp_rl = 0, cp_nrl = 1;
+    // pass-through copy: thread <-> one destination slot PAIR (plane, 2q, 2q+1), row lanes stride the rows
+    int cp_s0 = -1, cp_s1 = -1, cp_dst = 0, cp_rl = 0, cp_nrl = 1;
     if (a.x1) {
-        const int nitem = 2 * a.ncopy;
+        const int npairs = (a.ncopy + 1) >> 1, nitem = 2 * npairs;
         cp_nrl = 256 / nitem; cp_rl = tid / nitem;
-        const int it = tid % nitem, p = it / a.ncopy, i = it - p * a.ncopy;
-        if (cp_rl < cp_nrl) { cp_src = logical_slot(a.x1map, 2 * i + p); cp_dst = p * R * lds + a.copy_dst0 + i; }
+        const int it = tid % nitem, p = it / npairs, q = it - p * npairs;
+        if (cp_rl < cp_nrl) {
+            cp_s0 = logical_slot(a.x1map, 2 * (2 * q) + p);
+            cp_s1 = (2 * q + 1 < a.ncopy) ? logical_slot(a.x1map, 2 * (2 * q + 1) + p) : -1;
+            cp_dst = p * R * lds + a.copy_dst0 + 2 * q;
+        }
     }
 
-    auto flush_stats = [&](int t) {                   // CTA-uniform
+    // per-(slice, channel) sums: registers -> scratch rows in the (idle) staging tile -> one thread per column -> fp64 atomics
+    auto flush_stats = [&](int t) {                   // CTA-uniform; the staging tile is free here
+        __syncthreads();
+        float* scr = reinterpret_cast<float*>(St);    // [vnrl][splanes*swidth][2]
+        const int ncolt = splanes * swidth;
         if (vrl < vnrl) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                atomicAdd(&s_stat[(vp * swidth + vc + i) * 2], ssum[i]);
-                atomicAdd(&s_stat[(vp * swidth + vc + i) * 2 + 1], ssq[i]);
+                reinterpret_cast<float2*>(scr)[vrl * ncolt + vp * swidth + vc + i] = make_float2(ssum[i], ssq[i]);
                 ssum[i] = 0.f; ssq[i] = 0.f;
             }
         }
         __syncthreads();
-        for (int i = tid; i < splanes * swidth; i += 256) {
+        for (int i = tid; i < ncolt; i += 256) {
+            float sx = 0.f, sq = 0.f;
+            for (int l = 0; l < vnrl; ++l) { const float2 v = reinterpret_cast<const float2*>(scr)[l * ncolt + i]; sx += v.x; sq += v.y; }
             const int p = i / swidth, c = i - p * swidth;
             double2* dst = a.tb[p0 + p].fsum + (size_t)t * a.cpo + scol0 + c;
-            atomicAdd(&dst->x, (double)s_stat[2 * i]);
-            atomicAdd(&dst->y, (double)s_stat[2 * i + 1]);
-            s_stat[2 * i] = 0.f; s_stat[2 * i + 1] = 0.f;
+            atomicAdd(&dst->x, (double)sx);
+            atomicAdd(&dst->y, (double)sq);
         }
+        __syncthreads();
+        for (int i = tid; i < splanes * R * lds / 2; i += 256) reinterpret_cast<uint32_t*>(St)[i] = 0u;   // pad slots back to zero
         __syncthreads();
     };
 
     int cur_t = -1;
-    for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it) {
+    int t = tile_lo / tps, r0 = (tile_lo - t * tps) * R;
+    for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it, r0 += R) {
         const int buf = it & 1;
-        const int t = tile / tps, r0 = (tile - t * tps) * R, rows = min(R, a.Rt - r0);
+        if (r0 >= a.Rt) { r0 = 0; ++t; }
+        const int rows = min(R, a.Rt - r0);
         if (t != cur_t) {
             if (cur_t >= 0 && a.training) flush_stats(cur_t);
             __syncthreads();
             int off = 0;
             for (int i = 0; i < d.nsrc; ++i) {
                 for (int k = tid; k < d.src[i].cp; k += 256)
-                    s_aff[off + k] = d.src[i].aff ? d.src[i].aff[(size_t)t * d.src[i].cp + k] : make_float2(1.f, 0.f);
+                    s_aff[tcol(off + k, KP >> 3)] = d.src[i].aff ? d.src[i].aff[(size_t)t * d.src[i].cp + k] : make_float2(1.f, 0.f);
                 off += d.src[i].cp;
             }
             cur_t = t;
             __syncthreads();
         }
         mbar_wait(&full[buf], (it >> 1) & 1);
+        const unsigned char* rb = raw + (size_t)buf * L.raw_stride;
         // ---- transform: raw rows -> BN affine (+ReLU6) -> padded MMA tile
-        {
-            const unsigned char* rb = raw + (size_t)buf * L.raw_stride;
-            int off = 0, offb = 0;
-            for (int i = 0; i < d.nsrc; ++i) {
-                const int cp = d.src[i].cp, nch = cp >> 3, ch = tid % nch, rl = tid / nch, nrl = 256 / nch;
-                if (rl < nrl) {
-                    float2 c8[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) c8[q] = s_aff[off + ch * 8 + q];
-                    const bool clamp = d.src[i].clamp != 0;
-                    const uint4* srcv = reinterpret_cast<const uint4*>(rb + (size_t)R * offb);
-                    for (int r = rl; r < rows; r += nrl) {
-                        const uint4 v = affine8(srcv[r * nch + ch], c8, clamp);
-                        *reinterpret_cast<uint4*>(As + (size_t)r * lda + off + ch * 8) = v;
-                    }
+        for (int i = 0; i < kMaxSrc; ++i) {
+            if (i < d.nsrc && x_rl[i] < x_nrl[i]) {
+                float2 c8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) c8[q] = s_aff[q * (KP >> 3) + (x_off[i] >> 3) + x_ch[i]];
+                const bool clamp = d.src[i].clamp != 0;
+                const uint4* srcv = reinterpret_cast<const uint4*>(rb + (size_t)R * x_offb[i]) + x_rl[i] * x_nch[i] + x_ch[i];
+                bf16* dstp = As + x_rl[i] * lda + x_off[i] + x_ch[i] * 8;
+                const int sstep = x_nrl[i] * x_nch[i], dstep = x_nrl[i] * lda;
+                for (int r = x_rl[i]; r < rows; r += x_nrl[i]) {
+                    *reinterpret_cast<uint4*>(dstp) = affine8(*srcv, c8, clamp);
+                    srcv += sstep; dstp += dstep;
                 }
-                off += cp; offb += cp * 2;
             }
         }
         __syncthreads();
-        // ---- MMA: warp (wm, wn) -> rows wm*MT*16.., columns wn*NBW*8..
+        // ---- MMA: warp (wm, wn) -> rows wm*MT*16.., columns wn*NBW*8..   (accumulators start at the bias)
         float acc[MT][NBW][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int nb = 0; nb < NBW; ++nb) { acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.f; }
-        const int arow = wm * MT * 16 + (lane & 15), acol = (lane >> 4) * 8;
-        const int mi = lane >> 3;
-        const int brow = wn * NBW * 8 + (mi >> 1) * 8 + (lane & 7), bcol = (mi & 1) * 8;
-        for (int ks = 0; ks < KP; ks += 16) {
-            uint32_t af[MT][4];
+            for (int nb = 0; nb < NBW; ++nb) { acc[mt][nb][0] = acc[mt][nb][2] = bias0[nb]; acc[mt][nb][1] = acc[mt][nb][3] = bias1[nb]; }
+        {
+            const int mi = lane >> 3;
+            const bf16* ap = As + (wm * MT * 16 + (lane & 15)) * lda + (lane >> 4) * 8;
+            const bf16* bp = Ws + (wn * NBW * 8 + (mi >> 1) * 8 + (lane & 7)) * ldw + (mi & 1) * 8;
+            for (int ks = 0; ks < KP; ks += 16) {
+                uint32_t af[MT][4];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) ldsm4(af[mt], As + (size_t)(arow + mt * 16) * lda + ks + acol);
+                for (int mt = 0; mt < MT; ++mt) ldsm4(af[mt], ap + mt * 16 * lda + ks);
 #pragma unroll
-            for (int nb2 = 0; nb2 < NBW / 2; ++nb2) {
-                uint32_t bfr[4];
-                ldsm4(bfr, Ws + (size_t)(brow + nb2 * 16) * ldw + ks + bcol);
+                for (int nb2 = 0; nb2 < NBW / 2; ++nb2) {
+                    uint32_t bfr[4];
+                    ldsm4(bfr, bp + nb2 * 16 * ldw + ks);
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    mma16816(acc[mt][2 * nb2], af[mt], bfr[0], bfr[1]);
-                    mma16816(acc[mt][2 * nb2 + 1], af[mt], bfr[2], bfr[3]);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma16816(acc[mt][2 * nb2], af[mt], bfr[0], bfr[1]);
+                        mma16816(acc[mt][2 * nb2 + 1], af[mt], bfr[2], bfr[3]);
+                    }
                 }
             }
         }
-        // ---- epilogue: bias, bf16, into the staging rows at the final slot positions
+        // ---- epilogue: bf16, into the staging rows at the final slot positions
 #pragma unroll
         for (int nb = 0; nb < NBW; ++nb) {
             if (dsto[nb] >= 0) {
-                const int jl = wn * NBW * 8 + nb * 8 + 2 * tg;
-                const float b0 = s_bias[jl], b1 = s_bias[jl + 1];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    const int r = wm * MT * 16 + mt * 16 + g;
-                    *reinterpret_cast<uint32_t*>(St + dsto[nb] + (size_t)r * lds) = pack2(acc[mt][nb][0] + b0, acc[mt][nb][1] + b1);
-                    *reinterpret_cast<uint32_t*>(St + dsto[nb] + (size_t)(r + 8) * lds) = pack2(acc[mt][nb][2] + b0, acc[mt][nb][3] + b1);
+                    bf16* sp = St + dsto[nb] + mt * 16 * lds;
+                    *reinterpret_cast<uint32_t*>(sp) = pack2(acc[mt][nb][0], acc[mt][nb][1]);
+                    *reinterpret_cast<uint32_t*>(sp + 8 * lds) = pack2(acc[mt][nb][2], acc[mt][nb][3]);
                 }
             }
         }
-        // ---- pass-through half: bit-exact gather of the raw x1 values into the shuffled slots
-        if (cp_src >= 0) {
-            const bf16* xr = reinterpret_cast<const bf16*>(raw + (size_t)buf * L.raw_stride + (size_t)R * x1_off_rows);
-            for (int r = cp_rl; r < rows; r += cp_nrl) St[cp_dst + (size_t)r * lds] = xr[(size_t)r * a.x1cp + cp_src];
+        // ---- pass-through half: bit-exact gather of the raw x1 values into the shuffled slots (two slots per store)
+        if (cp_s0 >= 0) {
+            const unsigned short* xr = reinterpret_cast<const unsigned short*>(rb + (size_t)R * x1_off_rows) + cp_rl * a.x1cp;
+            bf16* dp = St + cp_dst + cp_rl * lds;
+            const int xstep = cp_nrl * a.x1cp, dstep = cp_nrl * lds;
+            for (int r = cp_rl; r < rows; r += cp_nrl) {
+                const uint32_t lo = xr[cp_s0], hi = cp_s1 >= 0 ? xr[cp_s1] : 0u;
+                *reinterpret_cast<uint32_t*>(dp) = lo | (hi << 16);
+                xr += xstep; dp += dstep;
+            }
         }
         __syncthreads();
         if (tid == 0 && tile + 2 < tile_hi) issue(tile + 2, buf);
         // ---- store + statistics
         if (vrl < vnrl) {
-            bf16* orow = a.out[p0 + vp] + ((size_t)t * a.Rt + r0) * a.cpo + scol0 + vc;
-            const bf16* srow = St + (size_t)vp * R * lds + vc;
+            bf16* orow = a.out[p0 + vp] + ((size_t)t * a.Rt + r0 + vrl) * a.cpo + scol0 + vc;
+            const bf16* srow = St + vp * R * lds + vc + vrl * lds;
+            const int ostep = vnrl * a.cpo, sstep = vnrl * lds;
             for (int r = vrl; r < rows; r += vnrl) {
-                const uint4 v = *reinterpret_cast<const uint4*>(srow + (size_t)r * lds);
-                *reinterpret_cast<uint4*>(orow + (size_t)r * a.cpo) = v;
+                const uint4 v = *reinterpret_cast<const uint4*>(srow);
+                *reinterpret_cast<uint4*>(orow) = v;
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -358,6 +390,7 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(const PwFwdArgs a) {
                     ssum[2 * i] += f.x; ssq[2 * i] = fmaf(f.x, f.x, ssq[2 * i]);
                     ssum[2 * i + 1] += f.y; ssq[2 * i + 1] = fmaf(f.y, f.y, ssq[2 * i + 1]);
                 }
+                orow += ostep; srow += sstep;
             }
         }
     }

@@ -165,17 +165,26 @@ inline void launch_dw_fwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
     a.L = layer_of(c, l);
     a.out = (bf16*)(c.ws + out.data); a.tb = tables_of(c, out);
     a.training = c.training; a.counter = counter_ptr(c, counter);
-    const int frame_bytes = u.Hi * u.Wi * in.cp * 2, buf = (frame_bytes + 127) & ~127;
-    const int smem = ((64 + in.cp * 8 + 127) & ~127) + 2 * buf;
-    static bool attr = (cudaFuncSetAttribute(dw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
-    (void)attr;
-    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem + 1024)));
+    typedef void (*KernelT)(const DwArgs);
+    KernelT k = nullptr;
+    switch (in.cp * 10 + u.stride) {
+        case 641: k = dw_fwd_kernel<64, 1>; break;    case 1201: k = dw_fwd_kernel<120, 1>; break;  case 2321: k = dw_fwd_kernel<232, 1>; break;
+        case 242: k = dw_fwd_kernel<24, 2>; break;    case 642: k = dw_fwd_kernel<64, 2>; break;
+        case 1202: k = dw_fwd_kernel<120, 2>; break;  case 2322: k = dw_fwd_kernel<232, 2>; break;
+    }
+    if (!k) { fprintf(stderr, "libcdra: no depthwise kernel for cp=%d stride=%d\n", in.cp, u.stride); return; }
+    a.nbuf = 2;
+    DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, false);
+    if (L.total > kMaxDynSmem) { a.nbuf = 1; L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, 1, false); }
+    if (L.total > kMaxDynSmem) { fprintf(stderr, "libcdra: depthwise frame does not fit in shared memory (%d bytes)\n", L.total); return; }
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
     const int nframes = kT * a.B;
     int gx = std::min(nframes, num_sms() * per_sm);
     a.frames_per_cta = (nframes + gx - 1) / gx;
     gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
     prof_bytes(4.0 * a.B * ((double)u.Hi * u.Wi + (double)u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
-    CDRA_LAUNCH(dw_fwd_kernel, dim3(gx), dim3(kDwThreads), smem, c.stream, a);
+    CDRA_LAUNCH(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
 }
 
 inline void tower_forward(const RunCtx& c) {
@@ -327,17 +336,26 @@ inline void launch_dw_bwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
     a.L = layer_of(c, l);
     a.out = (bf16*)(c.ws + out.data); a.dout = (const bf16*)(c.ws + out.grad); a.tb = tables_of(c, out);
     a.training = 1;
-    const DwBwdSmem L = dw_bwd_smem(in.cp, u.Hi * u.Wi, u.Ho * u.Wo);
-    static bool attr = (cudaFuncSetAttribute(dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
-    (void)attr;
+    typedef void (*KernelT)(const DwArgs);
+    KernelT k = nullptr;
+    switch (in.cp * 10 + u.stride) {
+        case 641: k = dw_bwd_kernel<64, 1>; break;    case 1201: k = dw_bwd_kernel<120, 1>; break;  case 2321: k = dw_bwd_kernel<232, 1>; break;
+        case 242: k = dw_bwd_kernel<24, 2>; break;    case 642: k = dw_bwd_kernel<64, 2>; break;
+        case 1202: k = dw_bwd_kernel<120, 2>; break;  case 2322: k = dw_bwd_kernel<232, 2>; break;
+    }
+    if (!k) { fprintf(stderr, "libcdra: no depthwise kernel for cp=%d stride=%d\n", in.cp, u.stride); return; }
+    a.nbuf = 2;
+    DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true);
+    if (L.total > kMaxDynSmem) { a.nbuf = 1; L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, 1, true); }
     if (L.total > kMaxDynSmem) { fprintf(stderr, "libcdra: dw_bwd frame does not fit in shared memory (%d bytes)\n", L.total); return; }
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
     const int nframes = kT * a.B;
     int gx = std::min(nframes, num_sms() * per_sm);
     a.frames_per_cta = (nframes + gx - 1) / gx;
     gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
     prof_bytes(4.0 * a.B * (2.0 * u.Hi * u.Wi + 2.0 * u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
-    CDRA_LAUNCH(dw_bwd_kernel, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
+    CDRA_LAUNCH(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
 }
 
 inline void tower_backward(const RunCtx& c) {
