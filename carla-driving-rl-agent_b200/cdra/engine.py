@@ -154,6 +154,14 @@ class Engine:
             p(obs['state_navigation']), p(d_out), p(self.g_dyn), p(self.ws), self._stream()), 'dynamics_backward')
         return self.g_dyn
 
+    def debug_stem_backward(self, obs, legacy):
+        """stem gradients only, from the workspace a training step left behind (parity aid) -> fresh gradient arena"""
+        g = torch.zeros_like(self.g_dyn)
+        _lib.check(self.lib, self.lib.cdra_debug_stem_backward(
+            self.plan, _lib.ptr(self.dyn.flat), _lib.ptr(obs['state_image']), _lib.ptr(g), _lib.ptr(self.ws),
+            1 if legacy else 0, self._stream()), 'debug_stem_backward')
+        return g
+
     def policy_head(self, x512, actions_eval, logp_old, adv, true_speed, true_sim, clip_ratio=0.2, ent_coef=1.0,
                     training=True, grad_scale=1.0, backward=True, update_moving=True):
         p = _lib.ptr

@@ -537,7 +537,8 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
 #ifndef CDRA_EMU
     if (p.v2.on) {               // bf16 perf mode: legacy stem + pool, then the v2 tower (padded planes, TMA tiles)
-        if (u8) tower_forward<bf16, uint8_t>(c, (const uint8_t*)image, true);
+        if (p.v2.stem_on) v2::stem_forward(c, (const uint8_t*)image);
+        else if (u8) tower_forward<bf16, uint8_t>(c, (const uint8_t*)image, true);
         else tower_forward<bf16, float>(c, (const float*)image, true);
         v2::tower_forward(c);
     } else
@@ -564,7 +565,8 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
 #ifndef CDRA_EMU
     if (p.v2.on) {
         v2::tower_backward(c);
-        if (u8) tower_backward<bf16, uint8_t>(c, (const uint8_t*)image, true);
+        if (p.v2.stem_on) v2::stem_backward(c, (const uint8_t*)image);
+        else if (u8) tower_backward<bf16, uint8_t>(c, (const uint8_t*)image, true);
         else tower_backward<bf16, float>(c, (const float*)image, true);
     } else
 #endif
@@ -573,6 +575,28 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
     else if (u8) tower_backward<float, uint8_t>(c, (const uint8_t*)image);
     else tower_backward<float, float>(c, (const float*)image);
     return check_launch("dynamics_backward");
+}
+
+int cdra_debug_stem_backward(cdra_plan_t* plan, const float* params, const void* image, float* grads, void* workspace,
+                             int legacy, void* stream) {
+    if (!plan || !params || !image || !grads || !workspace) return fail(CDRA_ERR_BADARG, "null argument");
+    const Plan& p = *plan->p;
+    RunCtx c{&p, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, 1};
+    zero_async(grads, (size_t)p.dyn_params.size * 4, c.stream);
+    zero_async(c.ws, p.zero_bytes, c.stream);
+    const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
+#ifndef CDRA_EMU
+    if (!legacy) {
+        if (!p.v2.stem_on) return fail(CDRA_ERR_BADARG, "tensor-core stem not active for this plan");
+        v2::stem_backward(c, (const uint8_t*)image);
+        return check_launch("debug_stem_backward");
+    }
+#endif
+    if (bf && u8) tower_backward<bf16, uint8_t>(c, (const uint8_t*)image, true);
+    else if (bf) tower_backward<bf16, float>(c, (const float*)image, true);
+    else if (u8) tower_backward<float, uint8_t>(c, (const uint8_t*)image, true);
+    else tower_backward<float, float>(c, (const float*)image, true);
+    return check_launch("debug_stem_backward");
 }
 
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,

@@ -1,5 +1,6 @@
 // Plan construction (host only).  See plan.h.
 #include "plan.h"
+#include <cstdlib>
 #include <cstdio>
 
 namespace cdra {
@@ -183,6 +184,7 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
     auto legacy = [&](const WsTensor& t) { return !p.v2.on || t.name == "tower.stem" || t.name == "tower.pool"; };
     for (auto& t : p.tensors) if (t.tables && legacy(t)) { t.fst = alloc(kCopies * 4 * t.C * 16); t.bst = alloc(kCopies * 4 * t.C * 16); }
     for (auto& t : p.v2.t) { t.fsum = alloc((size_t)4 * t.cp * 16); t.bsum = alloc((size_t)4 * t.cp * 16); }
+    if (p.v2.on) p.v2.stem_gacc = alloc((size_t)4 * 2048 * 8);      // >= 4 * v2::kGaccN doubles
     p.zero_bytes = off;
     p.counters_off = alloc((size_t)(p.n_counters + 16) * 4);
     for (auto& t : p.tensors) if (t.tables && legacy(t)) { t.aff = alloc((size_t)4 * t.C * 8); t.bnp = alloc((size_t)4 * t.C * 8); }
@@ -213,6 +215,9 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
         };
         for (auto& u : v.u) { pwalloc(u.pw1); pwalloc(u.tail); }
         pwalloc(v.head_pw);
+        v.stem_idx = alloc((size_t)4 * p.B * p.Hp * p.Wp * kStemC + 256);
+        // the tensor-core stem needs 16-byte aligned TMA rows of the uint8 frames and 8-bit pixel coordinates
+        v.stem_on = cfg.image_u8 != 0 && p.W % 8 == 0 && ((size_t)p.H * p.W * 3) % 16 == 0 && p.Ws < 256 && getenv("CDRA_LEGACY_STEM") == nullptr;
         v.desc_off = alloc(64 * 1024);
         v.host_descs_buf.resize(64 * 1024);
         v.host_descs = v.host_descs_buf.data();

@@ -118,6 +118,10 @@ struct V2Plan {
     V2Pw head_pw;
     int c_gap = -1;
     size_t desc_off = 0;         // device copies of the GEMM descriptors (uploaded at the start of every pass)
+    // tensor-core stem for uint8 frames (v2_stem.cuh): winner positions of the max pool, per-slice fp64 sums of the backward
+    bool stem_on = false;
+    size_t stem_idx = 0, stem_gacc = 0;
+    int stem_fwd_hb = 0, stem_bwd_hb = 0, pool_pb = 0;
     mutable std::vector<char> host_descs_buf;
     void* host_descs = nullptr;
 };

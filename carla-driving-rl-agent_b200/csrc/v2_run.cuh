@@ -6,6 +6,7 @@
 #include "v2_pw.cuh"
 #include "v2_dw.cuh"
 #include "v2_bwd.cuh"
+#include "v2_stem.cuh"
 
 namespace cdra {
 namespace v2 {
@@ -407,6 +408,77 @@ inline void tower_backward(const RunCtx& c) {
             launch_pw_bwd(c, 2 * ui, host[2 * ui], a);
         }
     }
+}
+
+
+// ================================================================================================ stem (uint8 frames)
+inline StemGeom stem_geom(const Plan& p) {
+    StemGeom g; g.B = p.B; g.H = p.H; g.W = p.W; g.W3 = 3 * p.W; g.Hs = p.Hs; g.Ws = p.Ws; g.Hp = p.Hp; g.Wp = p.Wp;
+    g.pad_t = p.pool_pad_t; g.pad_l = p.pool_pad_l;
+    return g;
+}
+// rows per band: the largest count whose shared-memory footprint stays under `limit`, evened out over the bands
+template <typename F>
+inline int band_rows(int rows, int limit, F smem_of) {
+    int hb = 1;
+    while (hb < rows && smem_of(hb + 1) <= limit) ++hb;
+    const int nb = (rows + hb - 1) / hb;
+    return (rows + nb - 1) / nb;
+}
+inline void persistent_grid(int nunits, int ctas_per_sm, int& gx, int& per_cta) {
+    gx = std::min(nunits, num_sms() * ctas_per_sm);
+    per_cta = (nunits + gx - 1) / gx;
+    gx = (nunits + per_cta - 1) / per_cta;
+}
+
+inline void stem_forward(const RunCtx& c, const uint8_t* image) {
+    const Plan& p = *c.p; const StemGeom g = stem_geom(p);
+    const WsTensor& ts = p.tensors[p.t_stem]; const WsTensor& tp = p.tensors[p.t_pool];
+    const int limit = 108 * 1024;
+    {   // conv 3x3 s2 (+ sums of the stored values)                         core/architectures.py:159
+        StemFwdArgs a; memset(&a, 0, sizeof a);
+        a.img = image; a.g = g; a.w = c.params + p.stem.w; a.bias = c.params + p.stem.b;
+        a.out = (bf16*)(c.ws + ts.data); a.fst = (double2*)(c.ws + ts.fst); a.training = c.training;
+        a.HB = band_rows(g.Hs, limit, [&](int hb) { return 2 * hb * g.W3 + 6 * g.Ws >= 65536 ? (1 << 30) : stem_fwd_smem(hb, g.Ws, g.W3).total; });
+        a.nbands = (g.Hs + a.HB - 1) / a.HB;
+        int gx; persistent_grid(kT * g.B * a.nbands, 2, gx, a.units_per_cta);
+        const int smem = stem_fwd_smem(a.HB, g.Ws, g.W3).total;
+        static bool attr = (cudaFuncSetAttribute(stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true); (void)attr;
+        prof_bytes(4.0 * g.B * ((double)g.H * g.W3 + (double)g.Hs * g.Ws * kSC * 2));
+        CDRA_LAUNCH(stem_fwd_kernel, dim3(gx), dim3(kStemThreads), smem, c.stream, a);
+        launch_bn_finalize(c, p.stem, ts, ColMap{kSC, 0, 0, 0}, (double)ts.Rt);
+    }
+    {   // BN + ReLU6, max pool 3x3 s2 SAME (+ winner positions)              :160-161
+        PoolFwdArgs a; memset(&a, 0, sizeof a);
+        a.stem = (const bf16*)(c.ws + ts.data); a.aff = (const float2*)(c.ws + ts.aff); a.g = g;
+        a.pool = (bf16*)(c.ws + tp.data); a.idx = (uint8_t*)(c.ws + p.v2.stem_idx);
+        a.PB = band_rows(g.Hp, 44 * 1024, [&](int pb) { return pool_fwd_smem(pb, g.Ws).total; });
+        a.nbands = (g.Hp + a.PB - 1) / a.PB;
+        int gx; persistent_grid(kT * g.B * a.nbands, 4, gx, a.units_per_cta);
+        const int smem = pool_fwd_smem(a.PB, g.Ws).total;
+        static bool attr = (cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true); (void)attr;
+        prof_bytes(4.0 * g.B * ((double)g.Hs * g.Ws + (double)g.Hp * g.Wp) * kSC * 2);
+        CDRA_LAUNCH(pool_fwd_kernel, dim3(gx), dim3(kStemThreads), smem, c.stream, a);
+    }
+}
+
+inline void stem_backward(const RunCtx& c, const uint8_t* image) {
+    const Plan& p = *c.p; const StemGeom g = stem_geom(p);
+    const WsTensor& ts = p.tensors[p.t_stem]; const WsTensor& tp = p.tensors[p.t_pool];
+    StemBwdArgs a; memset(&a, 0, sizeof a);
+    a.img = image; a.g = g; a.stem = (const bf16*)(c.ws + ts.data); a.dpool = (const bf16*)(c.ws + tp.grad);
+    a.idx = (const uint8_t*)(c.ws + p.v2.stem_idx); a.aff = (const float2*)(c.ws + ts.aff); a.bnp = (const float2*)(c.ws + ts.bnp);
+    a.gacc = (double*)(c.ws + p.v2.stem_gacc);
+    a.HB = band_rows(g.Hs, 108 * 1024, [&](int hb) { return 2 * hb * g.W3 + 6 * g.Ws >= 65536 ? (1 << 30) : stem_bwd_smem(hb, g.Ws, g.Wp, g.W3).total; });
+    a.nbands = (g.Hs + a.HB - 1) / a.HB;
+    int gx; persistent_grid(kT * g.B * a.nbands, 2, gx, a.units_per_cta);
+    const int smem = stem_bwd_smem(a.HB, g.Ws, g.Wp, g.W3).total;
+    static bool attr = (cudaFuncSetAttribute(stem_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true); (void)attr;
+    prof_bytes(4.0 * g.B * ((double)g.H * g.W3 + (double)g.Hs * g.Ws * kSC * 2 + (double)g.Hp * g.Wp * kSC * 2));
+    CDRA_LAUNCH(stem_bwd_kernel, dim3(gx), dim3(kStemThreads), smem, c.stream, a);
+    StemFinArgs f; f.gacc = a.gacc; f.aff = a.aff; f.dw = c.grads + p.stem.w; f.dgamma = c.grads + p.stem.g; f.dbeta = c.grads + p.stem.be;
+    f.n = (double)ts.Rt;
+    CDRA_LAUNCH(stem_bwd_finish_kernel, dim3(1), dim3(kStemThreads), 0, c.stream, f);
 }
 
 // ---- logical-layout export of a tower tensor (or its gradient) for the parity taps: out [4B][H][W][C] fp32.

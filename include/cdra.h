@@ -70,6 +70,14 @@ int cdra_plan_tensor(const cdra_plan_t* plan, const char* name, int64_t* byte_of
  * [4B][H][W][C] as fp32 into `out` (may be NULL to query dims only).  Test infrastructure, not on the hot path. */
 int cdra_debug_export(cdra_plan_t* plan, const char* name, void* workspace, float* out, int32_t dims[4], void* stream);
 
+/* Parity aid for the stem backward (max-pool backward + BatchNorm backward + weight gradient of the 3x3 s2 conv,
+ * core/architectures.py:159-161): re-runs ONLY that part on the workspace left by a training forward + backward (stem
+ * output, pool winners and the pool-output gradient are still there) and writes the stem's gradients into `grads`
+ * (dynamics arena layout, zeroed first).  legacy != 0 selects the CUDA-core kernels, 0 the tensor-core band kernel
+ * (uint8 frames, bf16 mode), so tests can compare both on identical inputs.  Test infrastructure. */
+int cdra_debug_stem_backward(cdra_plan_t* plan, const float* params, const void* image, float* grads, void* workspace,
+                             int legacy, void* stream);
+
 /* CARLANetwork.dynamics_predict_train / dynamics_predict (core/networks.py:206-212) on
  * dynamics_layers (core/networks.py:37-56).  image [B,4,H,W,3] (u8 or f32), road [B,4,9],
  * vehicle [B,4,4], navigation [B,4,5] f32; out512 [B,512] f32.  training!=0 uses batch statistics and

@@ -236,3 +236,21 @@ def test_full_size_properties_bf16(built_libs, params):
         losses.append(s[0].item())
         eng.clip_adam('dyn', 3e-4); eng.clip_adam('val', 3e-4, clip_norm=1.0)
     assert losses[-1] < losses[0]
+
+
+def test_stem_backward_tensor_core_vs_cuda_core(built_libs, params):
+    """the one-pass tensor-core stem backward (max-pool backward + BN backward folded into the weight gradient by
+    linearity, v2_stem.cuh) against the CUDA-core kernels that materialise every intermediate, on identical inputs"""
+    B = 8
+    dyn, pol, val = params
+    eng = _engine(B, 'bf16')
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = _dev(C.synthetic_obs(B, H, W, seed=61)), _dev(C.synthetic_batch(B, seed=62))
+    C.policy_step_engine(eng, obs, bt)
+    g_step = eng.dyn.to_dict(eng.g_dyn.clone())
+    g_new = eng.dyn.to_dict(eng.debug_stem_backward(obs, False))
+    g_old = eng.dyn.to_dict(eng.debug_stem_backward(obs, True))
+    for k in ('tower.stem.w', 'tower.stem.g', 'tower.stem.be'):
+        assert C.rel_l2(g_new[k], g_step[k]) < 5e-3, k      # replay == the step (up to the order of the bf16 / fp64 atomics)
+        assert C.rel_l2(g_new[k], g_old[k]) < 2e-2, (k, C.rel_l2(g_new[k], g_old[k]))           # bf16 storage of d stem in the legacy path
+    assert g_new['tower.stem.b'].abs().max().item() == 0.0                                      # bias before a training-mode BN
