@@ -77,10 +77,21 @@ void prof_post(cudaStream_t stream) {
 }
 
 // ----------------------------------------------------------------------------------------------- small launch helpers
+static thread_local bool t_gemm_tf32 = false;     // set by every ABI entry: bf16 perf mode runs the dense GEMMs on tensor cores
 static void gemm(cudaStream_t st, bool ta, bool tb, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                  const float* bias, int M, int N, int K, bool accumulate) {
     GemmArgs g{A, lda, B, ldb, C, ldc, bias, M, N, K, accumulate ? 1 : 0};
     dim3 grid(cdiv(M, kGT), cdiv(N, kGT));
+#ifndef CDRA_EMU
+    if (t_gemm_tf32) {
+        TGemmArgs t{g, (((uintptr_t)A & 15) == 0 && lda % 4 == 0) ? 1 : 0, (((uintptr_t)B & 15) == 0 && ldb % 4 == 0) ? 1 : 0};
+        if (!ta && !tb) { auto k = tgemm_kernel<false, false>; CDRA_LAUNCH(k, grid, dim3(256), 0, st, t); }
+        else if (!ta && tb) { auto k = tgemm_kernel<false, true>; CDRA_LAUNCH(k, grid, dim3(256), 0, st, t); }
+        else if (ta && !tb) { auto k = tgemm_kernel<true, false>; CDRA_LAUNCH(k, grid, dim3(256), 0, st, t); }
+        else { auto k = tgemm_kernel<true, true>; CDRA_LAUNCH(k, grid, dim3(256), 0, st, t); }
+        return;
+    }
+#endif
     if (!ta && !tb) { auto k = sgemm_kernel<false, false>; CDRA_LAUNCH(k, grid, dim3(256), 0, st, g); }
     else if (!ta && tb) { auto k = sgemm_kernel<false, true>; CDRA_LAUNCH(k, grid, dim3(256), 0, st, g); }
     else if (ta && !tb) { auto k = sgemm_kernel<true, false>; CDRA_LAUNCH(k, grid, dim3(256), 0, st, g); }
@@ -390,6 +401,7 @@ static int run_head(bool policy, cdra_plan_t* plan, const float* params, float* 
                     const float* true_speed, const float* true_sim, float clip, float ent_coef, int training,
                     float grad_scale, float* scalars, float* head_out, float* d_x512, float* grads, char* ws, cudaStream_t st) {
     const Plan& p = *plan->p; const HeadSpec& h = policy ? p.policy : p.value; const int B = p.B;
+    t_gemm_tf32 = p.cfg.dtype == CDRA_DTYPE_BF16 && getenv("CDRA_NO_TF32") == nullptr;
     float* n1 = F(ws, named_off(p, "head.n1")); float* pre1 = F(ws, named_off(p, "head.pre1")); float* a1 = F(ws, named_off(p, "head.a1"));
     float* n2 = F(ws, named_off(p, "head.n2")); float* pre2 = F(ws, named_off(p, "head.pre2")); float* a2 = F(ws, named_off(p, "head.a2"));
     float2* st1 = (float2*)(ws + named_off(p, "head.st1")); float2* st2 = (float2*)(ws + named_off(p, "head.st2"));
@@ -532,6 +544,7 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     if (!training && !state) return fail(CDRA_ERR_BADARG, "inference needs the moving statistics");
     const Plan& p = *plan->p;
     RunCtx c{&p, (char*)workspace, params, state, nullptr, (cudaStream_t)stream, training ? 1 : 0};
+    t_gemm_tf32 = p.cfg.dtype == CDRA_DTYPE_BF16 && getenv("CDRA_NO_TF32") == nullptr;
     if (training) zero_async(c.ws, p.zero_bytes, c.stream);
     else eval_affine(c);                 // BN affine from the moving statistics (CARLANetwork.dynamics_predict)
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
@@ -558,6 +571,7 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
         return fail(CDRA_ERR_BADARG, "null argument");
     const Plan& p = *plan->p;
     RunCtx c{&p, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, 1};
+    t_gemm_tf32 = p.cfg.dtype == CDRA_DTYPE_BF16 && getenv("CDRA_NO_TF32") == nullptr;
     zero_async(grads, (size_t)p.dyn_params.size * 4, c.stream);
     zero_async(c.ws, p.zero_bytes, c.stream);      // BN-backward sums (the forward sums are already folded into aff/bnp)
     tail_backward(c, road, vehicle, navigation, d_out512);
@@ -575,6 +589,14 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
     else if (u8) tower_backward<float, uint8_t>(c, (const uint8_t*)image);
     else tower_backward<float, float>(c, (const float*)image);
     return check_launch("dynamics_backward");
+}
+
+int cdra_debug_gemm(int ta, int tb, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                    int M, int N, int K, int accumulate, int tensor_core, void* stream) {
+    if (!A || !B || !C || M < 1 || N < 1 || K < 1) return fail(CDRA_ERR_BADARG, "bad gemm argument");
+    t_gemm_tf32 = tensor_core != 0;
+    gemm((cudaStream_t)stream, ta != 0, tb != 0, A, lda, B, ldb, C, ldc, bias, M, N, K, accumulate != 0);
+    return check_launch("debug_gemm");
 }
 
 int cdra_debug_stem_backward(cdra_plan_t* plan, const float* params, const void* image, float* grads, void* workspace,

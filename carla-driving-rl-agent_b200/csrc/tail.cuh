@@ -89,6 +89,108 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) sgemm_kernel(GemmArgs a) {
     }
 }
 
+#ifndef CDRA_EMU
+// --------------------------------------------------------------------------- the same GEMM on tensor cores (perf mode)
+// TF32 mma.sync m16n8k8, fp32 accumulate: operands are fp32 in HBM and are rounded to TF32 (10-bit mantissa) when they
+// are staged; used by the bf16 "perf mode" for the GRU projections, the trunk and the control branches (the fp32 parity
+// mode keeps sgemm_kernel).  64x64x32 tiles, register-prefetched double buffer; each operand keeps its HBM orientation
+// in shared memory (coalesced, conflict-free staging) and the fragment indexing follows the orientation.
+constexpr int kTgK = 32;
+CDRA_DEV uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+CDRA_DEV void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// stage a [rows x cols] block of a row-major matrix (row stride ld) starting at (r0, c0) into registers: 8 values / thread
+template <int ROWS, int COLS>
+CDRA_DEV void tg_load(float (&v)[8], const float* M, int ld, int r0, int c0, int nrows, int ncols, bool vec) {
+    // ROWS x COLS = 2048 values, 256 threads, 2 float4 per thread: thread covers rows (tid / (COLS/4)) + {0, ROWS/2}
+    const int cq = (threadIdx.x % (COLS / 4)) * 4, rr = threadIdx.x / (COLS / 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = r0 + rr + h * (ROWS / 2), c = c0 + cq;
+        if (r < nrows && c + 3 < ncols && vec) {
+            const float4 t = *reinterpret_cast<const float4*>(M + (size_t)r * ld + c);
+            v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[4 * h + q] = (r < nrows && c + q < ncols) ? M[(size_t)r * ld + c + q] : 0.f;
+        }
+    }
+}
+template <int ROWS, int COLS, int LD>
+CDRA_DEV void tg_store(uint32_t* S, const float (&v)[8]) {
+    const int cq = (threadIdx.x % (COLS / 4)) * 4, rr = threadIdx.x / (COLS / 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        *reinterpret_cast<uint4*>(S + (rr + h * (ROWS / 2)) * LD + cq) =
+            make_uint4(to_tf32(v[4 * h]), to_tf32(v[4 * h + 1]), to_tf32(v[4 * h + 2]), to_tf32(v[4 * h + 3]));
+}
+
+struct TGemmArgs { GemmArgs g; int vecA, vecB; };
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) tgemm_kernel(const TGemmArgs ta) {
+    const GemmArgs& a = ta.g;
+    // A: !TA -> [64 m][32 k + 4] ; TA -> [32 k][64 m + 8].   B: !TB -> [32 k][64 n + 8] ; TB -> [64 n][32 k + 4]   (2304 words each)
+    __shared__ __align__(16) uint32_t As[2][2304];
+    __shared__ __align__(16) uint32_t Bs[2][2304];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;             // warp tile: rows wm*16.., columns wn*32..
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    float ra[8], rb[8];
+    auto load = [&](int k0) {
+        if (!TA) tg_load<64, 32>(ra, a.A, a.lda, m0, k0, a.M, a.K, ta.vecA != 0);
+        else tg_load<32, 64>(ra, a.A, a.lda, k0, m0, a.K, a.M, ta.vecA != 0);
+        if (!TB) tg_load<32, 64>(rb, a.B, a.ldb, k0, n0, a.K, a.N, ta.vecB != 0);
+        else tg_load<64, 32>(rb, a.B, a.ldb, n0, k0, a.N, a.K, ta.vecB != 0);
+    };
+    auto store = [&](int buf) {
+        if (!TA) tg_store<64, 32, 36>(As[buf], ra); else tg_store<32, 64, 72>(As[buf], ra);
+        if (!TB) tg_store<32, 64, 72>(Bs[buf], rb); else tg_store<64, 32, 36>(Bs[buf], rb);
+    };
+    const int nk = (a.K + kTgK - 1) / kTgK;
+    load(0); store(0);
+    __syncthreads();
+    for (int kb = 0; kb < nk; ++kb) {
+        const int buf = kb & 1;
+        if (kb + 1 < nk) load((kb + 1) * kTgK);
+        const uint32_t* A_ = As[buf]; const uint32_t* B_ = Bs[buf];
+#pragma unroll
+        for (int ks = 0; ks < kTgK; ks += 8) {
+            uint32_t af[4];
+            const int r = wm * 16 + g;
+            if (!TA) { af[0] = A_[r * 36 + ks + tg]; af[1] = A_[(r + 8) * 36 + ks + tg]; af[2] = A_[r * 36 + ks + tg + 4]; af[3] = A_[(r + 8) * 36 + ks + tg + 4]; }
+            else { af[0] = A_[(ks + tg) * 72 + r]; af[1] = A_[(ks + tg) * 72 + r + 8]; af[2] = A_[(ks + tg + 4) * 72 + r]; af[3] = A_[(ks + tg + 4) * 72 + r + 8]; }
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const int n = wn * 32 + nb * 8 + g;
+                uint32_t b0, b1;
+                if (!TB) { b0 = B_[(ks + tg) * 72 + n]; b1 = B_[(ks + tg + 4) * 72 + n]; }
+                else { b0 = B_[n * 36 + ks + tg]; b1 = B_[n * 36 + ks + tg + 4]; }
+                mma_tf32(acc[nb], af, b0, b1);
+            }
+        }
+        if (kb + 1 < nk) store(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int m = m0 + wm * 16 + g + (e >> 1) * 8, n = n0 + wn * 32 + nb * 8 + 2 * tg + (e & 1);
+            if (m < a.M && n < a.N) {
+                const float v = acc[nb][e] + (a.bias ? a.bias[n] : 0.f);
+                float* c = a.C + (size_t)m * a.ldc + n;
+                *c = a.accumulate ? *c + v : v;
+            }
+        }
+}
+#endif
+
 // out[n] (=|+=) sum_m X[m][n]
 struct ColsumArgs { const float* X; int ldx, M, N; float* out; int accumulate; };
 CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) colsum_kernel(ColsumArgs a) {

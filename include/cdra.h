@@ -100,6 +100,13 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
  * 2 loss_entropy(=coef*H), 3 loss_speed, 4 loss_similarity, 5 ratio mean, 6 log_prob mean, 7 entropy,
  * 8 speed mean, 9 similarity mean.  d_x512 [B,512]; grads = policy gradient arena (overwritten).
  * grad_scale multiplies every gradient (1/world_size under data parallelism). */
+/* The dense GEMM behind the GRU projections, the trunk and the control branches (Keras Dense / GRU kernels,
+ * core/networks.py:24-66): C[M][N] (=|+=) opA(A) opB(B) (+ bias[n]) on fp32 row-major device matrices; ta: A is stored
+ * [K][M]; tb: B is stored [N][K].  tensor_core = 0: fp32 CUDA-core kernel (parity mode); 1: TF32 mma.sync kernel (bf16
+ * perf mode).  Exposed for the parity tests. */
+int cdra_debug_gemm(int ta, int tb, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                    int M, int N, int K, int accumulate, int tensor_core, void* stream);
+
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
                                   const float* actions_eval, const float* logp_old, const float* adv,
                                   const float* true_speed, const float* true_sim, float clip_ratio,

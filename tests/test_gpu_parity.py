@@ -254,3 +254,29 @@ def test_stem_backward_tensor_core_vs_cuda_core(built_libs, params):
         assert C.rel_l2(g_new[k], g_step[k]) < 5e-3, k      # replay == the step (up to the order of the bf16 / fp64 atomics)
         assert C.rel_l2(g_new[k], g_old[k]) < 2e-2, (k, C.rel_l2(g_new[k], g_old[k]))           # bf16 storage of d stem in the legacy path
     assert g_new['tower.stem.b'].abs().max().item() == 0.0                                      # bias before a training-mode BN
+
+
+@pytest.mark.parametrize('tensor_core', [0, 1])
+def test_dense_gemm_matches_torch(built_libs, tensor_core):
+    """the GEMM under the GRUs / trunk / control branches, all four operand orientations, ragged sizes, unaligned bases"""
+    from cdra import _lib
+    lib = _lib.load()
+    g = torch.Generator(device='cuda').manual_seed(5)
+    tol = 2e-3 if tensor_core else 1e-5          # TF32 operands (10-bit mantissa) vs fp32
+    for (M, N, K) in ((2048, 768, 768), (512, 512, 352), (8, 96, 16), (70, 130, 33), (352, 512, 512)):
+        for ta in (0, 1):
+            for tb in (0, 1):
+                for off in (0, 1):               # off = 1: operands start at an odd float (no 16-byte alignment)
+                    A = torch.randn((K, M) if ta else (M, K), generator=g, device='cuda')
+                    Bm = torch.randn((N, K) if tb else (K, N), generator=g, device='cuda')
+                    bias = torch.randn(N, generator=g, device='cuda')
+                    bufA, bufB = torch.zeros(A.numel() + 1, device='cuda'), torch.zeros(Bm.numel() + 1, device='cuda')
+                    bufA[off:off + A.numel()] = A.flatten(); bufB[off:off + Bm.numel()] = Bm.flatten()
+                    Cm = torch.ones(M, N, device='cuda')
+                    ref = (A.double().t() if ta else A.double()) @ (Bm.double().t() if tb else Bm.double()) + bias.double() + 1.0
+                    pa, pb = bufA.data_ptr() + 4 * off, bufB.data_ptr() + 4 * off
+                    rc = lib.cdra_debug_gemm(ta, tb, pa, A.shape[1], pb, Bm.shape[1], _lib.ptr(Cm), N, _lib.ptr(bias), M, N, K, 1, tensor_core, None)
+                    assert rc == 0
+                    torch.cuda.synchronize()
+                    err = ((Cm.double() - ref).abs().max() / ref.abs().max()).item()
+                    assert err < tol, (M, N, K, ta, tb, off, err)
