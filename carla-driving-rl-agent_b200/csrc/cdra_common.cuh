@@ -32,6 +32,29 @@ void prof_post(cudaStream_t stream);
         kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);           \
         cdra::prof_post(stream);                                      \
     } while (0)
+// Programmatic dependent launch: the kernel may start while its predecessor in the stream is still draining; it runs
+// its private prologue (shared-memory setup, weights that were final long before), then pdl_wait() blocks until the
+// predecessor grid has completed and its memory is visible.  Kernels launched this way must not read upstream-produced
+// data or write global memory before pdl_wait().  CDRA_NO_PDL=1 falls back to plain stream order.
+namespace cdra {
+bool pdl_enabled();
+template <typename K, typename... Args>
+inline void launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+}
+#define CDRA_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                    \
+    do {                                                                            \
+        cdra::prof_pre((const void*)(kernel), stream);                              \
+        cdra::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__);           \
+        cdra::prof_post(stream);                                                    \
+    } while (0)
 #define CDRA_DYN_SMEM(name) extern __shared__ __align__(1024) char name[]
 #define CDRA_RESTRICT __restrict__
 #endif

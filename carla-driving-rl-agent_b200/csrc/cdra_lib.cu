@@ -76,6 +76,10 @@ void prof_post(cudaStream_t stream) {
 #endif
 }
 
+#ifndef CDRA_EMU
+bool cdra::pdl_enabled() { static const bool v = getenv("CDRA_NO_PDL") == nullptr; return v; }
+#endif
+
 // ----------------------------------------------------------------------------------------------- small launch helpers
 static thread_local bool t_gemm_tf32 = false;     // set by every ABI entry: bf16 perf mode runs the dense GEMMs on tensor cores
 static void gemm(cudaStream_t st, bool ta, bool tb, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
@@ -550,6 +554,7 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
 #ifndef CDRA_EMU
     if (p.v2.on) {               // bf16 perf mode: legacy stem + pool, then the v2 tower (padded planes, TMA tiles)
+        v2::tower_prepare(c);
         if (p.v2.stem_on) v2::stem_forward(c, (const uint8_t*)image);
         else if (u8) tower_forward<bf16, uint8_t>(c, (const uint8_t*)image, true);
         else tower_forward<bf16, float>(c, (const float*)image, true);
@@ -597,6 +602,20 @@ int cdra_debug_gemm(int ta, int tb, const float* A, int lda, const float* B, int
     t_gemm_tf32 = tensor_core != 0;
     gemm((cudaStream_t)stream, ta != 0, tb != 0, A, lda, B, ldb, C, ldc, bias, M, N, K, accumulate != 0);
     return check_launch("debug_gemm");
+}
+
+int cdra_debug_umma_selftest(const void* X, const void* Y, float* C, int rows, int Mw, int Nw, void* stream) {
+    if (!X || !Y || !C || rows < 64 || rows % 64 || (Mw != 128 && Mw != 256) || Nw < 16 || Nw % 16 || Nw > 256 || (Mw / 128) * Nw > 512)
+        return fail(CDRA_ERR_BADARG, "bad umma selftest shape");
+#ifndef CDRA_EMU
+    v2::UmmaTestArgs a{(const bf16*)X, (const bf16*)Y, C, rows, Mw, Nw};
+    const int smem = (Mw / 64 + (Nw + 63) / 64) * 64 * 128 + 1024;
+    cudaFuncSetAttribute(v2::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    CDRA_LAUNCH(v2::umma_selftest_kernel, dim3(1), dim3(256), smem, (cudaStream_t)stream, a);
+    return check_launch("debug_umma_selftest");
+#else
+    return fail(CDRA_ERR_BADARG, "no tensor cores in the CPU logic-check build");
+#endif
 }
 
 int cdra_debug_stem_backward(cdra_plan_t* plan, const float* params, const void* image, float* grads, void* workspace,

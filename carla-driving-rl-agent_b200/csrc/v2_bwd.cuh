@@ -62,7 +62,7 @@ struct PwBwdArgs {
 struct PwDgradSmem { int colc, srcc, x1c, stat, w, raw, dr, st, st2, total, raw_stride, ldr, ldw, lds, lds2; };
 inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, int nplanes, int cpo, int src_cp, int x1cp, int nbuf, int direct) {
     PwDgradSmem s;
-    s.ldr = NPall + 8; s.ldw = NPall + 8; s.lds = KT + 8; s.lds2 = x1cp + 8;
+    s.ldr = pad_ld(NPall); s.ldw = pad_ld(NPall); s.lds = pad_ld(KT); s.lds2 = pad_ld(x1cp);
     int off = 64;
     s.colc = off; off += NPall * 16;
     s.srcc = off; off += KT * 16;
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const PwDesc& d = *a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
     const int NP = d.NPall, gwp = d.cols.gwp, nplanes = d.cols.nplanes;
     // ---- this CTA's K tile
     int si = 0, ky = blockIdx.y, koff = 0;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
         bulk_g2s(dst + (size_t)R * o_src, S.data + row * S.cp, rows * S.cp * 2, &full[buf]);
         if (do_x1) bulk_g2s(dst + (size_t)R * o_x1, a.x1 + row * a.x1cp, rows * x1cp * 2, &full[buf]);
     };
+    pdl_wait();
     if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (tile_lo + b < tile_hi) issue(tile_lo + b, b);
 
     const int wm = warp % WM, wn = warp / WM, g = lane >> 2, tg = lane & 3;
@@ -360,7 +362,7 @@ constexpr int kWgK = 64, kWgR = 64;
 struct PwWgradSmem { int colc, aff, raw, xs, rs, total, raw_stride, ldx, ldr; };
 inline __host__ __device__ PwWgradSmem pw_wgrad_smem(int NTW, int cpo, int src_cp, int nbuf, int direct) {
     PwWgradSmem s;
-    s.ldx = kWgK + 8; s.ldr = NTW + 8;
+    s.ldx = pad_ld(kWgK); s.ldr = pad_ld(NTW);
     int off = 64;
     s.colc = off; off += NTW * 16;
     s.aff = off; off += kWgK * 8;
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const PwDesc& d = *a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
     const int NP = d.NPall, gwp = d.cols.gwp;
     // ---- tile: K tile (source si, k0) x N tile (plane pn, slot n0)
     const int kti = blockIdx.y / a.nt_tiles, nti = blockIdx.y - kti * a.nt_tiles;
@@ -417,6 +420,7 @@ __global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
         }
         bulk_g2s(dst + (size_t)kWgR * o_src, S.data + row * S.cp, rows * S.cp * 2, &full[buf]);
     };
+    pdl_wait();
     if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (tile_lo + b < tile_hi) issue(tile_lo + b, b);
 
     const int kg = warp & 3, nh = warp >> 2;               // warp: k rows kg*16.., n columns nh*NBW*8..
@@ -544,6 +548,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NPAIR = CP / 2, NCH = CP / 8, NXL = kDwThreads / NPAIR, TNPL = kDwThreads / NCH;
     const int tid = threadIdx.x;
+    pdl_trigger();
     const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo, PW = a.Wi + 2, QW = a.Wo + 2;
     const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, true);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
         const bf16* src = a.in + (size_t)f * in_px * CP;
         for (int y = 0; y < a.Hi; ++y) bulk_g2s(dst + (size_t)y * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
     };
+    pdl_wait();
     if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (f_lo + b < f_hi) issue(f_lo + b, b);
 
     const int tch = tid % NCH, tpl = tid / NCH;

@@ -23,6 +23,11 @@ CDRA_DEV int slot_logical(const SlotMap& m, int s) {        // logical channel o
 }
 CDRA_DEV int logical_slot(const SlotMap& m, int l) { return l < m.n1 ? m.n0p + l : l - m.n1; }
 
+// shared-memory row stride (elements) of a bf16 tile with n used columns: covers the 16-column MMA k steps and is an
+// ODD multiple of 16 bytes, so the 8 rows of an ldmatrix / of an accumulator store fall into 8 different bank groups
+// (n + 8 is not enough: 120 + 8 = 128 elements = 256 bytes puts every row on the same banks)
+inline __host__ __device__ int pad_ld(int n) { return ((n + 15) & ~15) + 8; }
+
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 CDRA_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 CDRA_DEV void mbar_init(uint64_t* bar, uint32_t count) {
@@ -48,6 +53,11 @@ CDRA_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// programmatic dependent launch (see CDRA_LAUNCH_PDL): let the next kernel in the stream start its prologue / block until
+// the previous kernel's results are complete and visible
+CDRA_DEV void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+CDRA_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 CDRA_DEV uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_fwd_kernel(const DwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NPAIR = CP / 2, NCH = CP / 8, NXL = kDwThreads / NPAIR, TNPL = kDwThreads / NCH;
     const int tid = threadIdx.x;
+    pdl_trigger();
     const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo, PW = a.Wi + 2;
     const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, false);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_fwd_kernel(const DwArgs a) {
         const bf16* src = a.in + (size_t)f * in_px * CP;
         for (int y = 0; y < a.Hi; ++y) bulk_g2s(dst + (size_t)y * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
     };
+    pdl_wait();
     if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (f_lo + b < f_hi) issue(f_lo + b, b);
 
     const int tch = tid % NCH, tpl = tid / NCH;                       // transform role
@@ -182,6 +184,8 @@ struct GapArgs {
 __global__ void __launch_bounds__(256) gap_fwd_kernel(const GapArgs a) {
     const int nch = a.cp >> 3;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (idx >= (long long)a.F * nch) return;
     const int f = (int)(idx / nch), ch = (int)(idx - (long long)f * nch), t = f / a.B;
     float2 c8[8];

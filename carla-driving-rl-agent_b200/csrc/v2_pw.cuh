@@ -130,7 +130,7 @@ struct PwFwdSmem {
 };
 inline __host__ __device__ PwFwdSmem pw_fwd_smem(int R, int NT, int KP, int src_row_bytes, int splanes, int swidth) {
     PwFwdSmem s;
-    s.lda = KP + 8; s.ldw = KP + 8; s.lds = swidth + 8;
+    s.lda = pad_ld(KP); s.ldw = pad_ld(KP); s.lds = pad_ld(swidth);
     int off = 64;                                     // mbarriers
     s.aff = off; off += KP * 8;
     s.bias = off; off += NT * 4;
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256, 2) pw_fwd_kernel(const PwFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const PwDesc& d = *a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
     const int KP = d.KP, gwp = d.cols.gwp;
     // ---- this CTA's column tile
     int jt0, ncols, p0, splanes, scol0, swidth;
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(256, 2) pw_fwd_kernel(const PwFwdArgs a) {
         }
         if (a.x1) bulk_g2s(dst + (size_t)R * x1_off_rows, a.x1 + ((size_t)t * a.Rt + r0) * a.x1cp, rows * a.x1cp * 2, &full[buf]);
     };
+    pdl_wait();                                       // everything above touched only this launch's descriptor / prepared weights
     if (tid == 0) {
         if (tile_lo < tile_hi) issue(tile_lo, 0);
         if (tile_lo + 1 < tile_hi) issue(tile_lo + 1, 1);

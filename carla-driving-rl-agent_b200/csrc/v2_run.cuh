@@ -7,6 +7,7 @@
 #include "v2_dw.cuh"
 #include "v2_bwd.cuh"
 #include "v2_stem.cuh"
+#include "v2_umma.cuh"
 
 namespace cdra {
 namespace v2 {
@@ -135,7 +136,7 @@ inline bool try_pw_fwd(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd, int colm
     if (gx > ntile) gx = ntile;
     a.tiles_per_cta = (ntile + gx - 1) / gx;
     gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    CDRA_LAUNCH(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
+    CDRA_LAUNCH_PDL(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
     return true;
 }
 
@@ -185,15 +186,21 @@ inline void launch_dw_fwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
     a.frames_per_cta = (nframes + gx - 1) / gx;
     gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
     prof_bytes(4.0 * a.B * ((double)u.Hi * u.Wi + (double)u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
-    CDRA_LAUNCH(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
+    CDRA_LAUNCH_PDL(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
+}
+
+// descriptors + bf16 operand matrices of every GEMM; runs BEFORE the stem so that the programmatically launched tower
+// kernels (whose prologues read them ahead of pdl_wait) are separated from it by fully ordered launches
+inline void tower_prepare(const RunCtx& c) {
+    const int nu = (int)c.p->v2.u.size();
+    upload_descs(c);
+    CDRA_LAUNCH(pw_prep_kernel, dim3(2 * nu + 1, 8), dim3(256), 0, c.stream, desc_dev(c, 0));
 }
 
 inline void tower_forward(const RunCtx& c) {
     const Plan& p = *c.p; const V2Plan& v = p.v2;
     const int nu = (int)v.u.size();
-    upload_descs(c);
     const PwDesc* host = (const PwDesc*)v.host_descs;
-    CDRA_LAUNCH(pw_prep_kernel, dim3(2 * nu + 1, 8), dim3(256), 0, c.stream, desc_dev(c, 0));
     for (int ui = 0; ui < nu; ++ui) {
         const V2Unit& u = v.u[ui]; const Unit& un = p.units[ui];
         const V2Tensor& r1 = v.t[u.r1]; const V2Tensor& r2 = v.t[u.r2];
@@ -238,7 +245,7 @@ inline void tower_forward(const RunCtx& c) {
         g.in = (const bf16*)(c.ws + th.data); g.aff = (const float2*)(c.ws + th.aff); g.cp = th.cp; g.C = th.n0; g.HW = th.H * th.W;
         g.F = kT * p.B; g.B = p.B; g.out = (float*)(c.ws + p.gap);
         prof_bytes((double)g.F * g.HW * g.C * 2);
-        CDRA_LAUNCH(gap_fwd_kernel, dim3(cdiv((long long)g.F * (th.cp / 8), 256)), dim3(256), 0, c.stream, g);
+        CDRA_LAUNCH_PDL(gap_fwd_kernel, dim3(cdiv((long long)g.F * (th.cp / 8), 256)), dim3(256), 0, c.stream, g);
     }
 }
 
@@ -263,7 +270,7 @@ inline bool try_pw_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nb
     if (gx > ntile) gx = ntile;
     a.tiles_per_cta = (ntile + gx - 1) / gx;
     gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    CDRA_LAUNCH(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
+    CDRA_LAUNCH_PDL(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
     return true;
 }
 
@@ -288,7 +295,7 @@ inline bool try_pw_wgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nb
     if (gx > ntile) gx = ntile;
     a.tiles_per_cta = (ntile + gx - 1) / gx;
     gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    CDRA_LAUNCH(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
+    CDRA_LAUNCH_PDL(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
     return true;
 }
 
@@ -356,7 +363,7 @@ inline void launch_dw_bwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
     a.frames_per_cta = (nframes + gx - 1) / gx;
     gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
     prof_bytes(4.0 * a.B * (2.0 * u.Hi * u.Wi + 2.0 * u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
-    CDRA_LAUNCH(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
+    CDRA_LAUNCH_PDL(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
 }
 
 inline void tower_backward(const RunCtx& c) {

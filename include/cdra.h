@@ -107,6 +107,12 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
 int cdra_debug_gemm(int ta, int tb, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
                     int M, int N, int K, int accumulate, int tensor_core, void* stream);
 
+/* Self test of the tcgen05 / TMEM path used by the tower's weight-gradient kernel: C[Mw][Nw] (fp32) = X^T Y for row-major
+ * bf16 device matrices X [rows][Mw], Y [rows][Nw]; both operands are staged MN-major in 128-byte-swizzled shared memory
+ * and accumulated over 64-row tiles in tensor memory.  Mw in {128, 256}, Nw % 16 == 0, Nw <= 256, (Mw / 128) * Nw <= 512,
+ * rows % 64 == 0.  Test infrastructure. */
+int cdra_debug_umma_selftest(const void* X, const void* Y, float* C, int rows, int Mw, int Nw, void* stream);
+
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
                                   const float* actions_eval, const float* logp_old, const float* adv,
                                   const float* true_speed, const float* true_sim, float clip_ratio,

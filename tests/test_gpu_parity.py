@@ -280,3 +280,19 @@ def test_dense_gemm_matches_torch(built_libs, tensor_core):
                     torch.cuda.synchronize()
                     err = ((Cm.double() - ref).abs().max() / ref.abs().max()).item()
                     assert err < tol, (M, N, K, ta, tb, off, err)
+
+
+@pytest.mark.parametrize('shape', [(128, 128, 64), (256, 128, 128), (128, 256, 240), (192, 256, 48)])
+def test_tcgen05_selftest(built_libs, shape):
+    """tcgen05.mma with MN-major 128B-swizzled operands and TMEM accumulators (the weight-gradient product X^T Y)"""
+    from cdra import _lib
+    lib = _lib.load()
+    rows, Mw, Nw = shape
+    g = torch.Generator(device='cuda').manual_seed(rows + Nw)
+    X = torch.randn(rows, Mw, generator=g, device='cuda').bfloat16()
+    Y = torch.randn(rows, Nw, generator=g, device='cuda').bfloat16()
+    Cm = torch.full((Mw, Nw), float('nan'), device='cuda')
+    assert lib.cdra_debug_umma_selftest(_lib.ptr(X), _lib.ptr(Y), _lib.ptr(Cm), rows, Mw, Nw, None) == 0
+    torch.cuda.synchronize()
+    ref = X.double().t() @ Y.double()
+    assert ((Cm.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
