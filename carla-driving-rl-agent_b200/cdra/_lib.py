@@ -39,6 +39,7 @@ _SIGNATURES = {
     'cdra_debug_export': (C.c_int, [_P, C.c_char_p, _P, _P, C.POINTER(C.c_int32), _P]),
     'cdra_debug_gemm': (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     'cdra_debug_umma_selftest': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    'cdra_debug_set': (C.c_int, [C.c_char_p, C.c_int]),
     'cdra_debug_stem_backward': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     'cdra_dynamics_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     'cdra_dynamics_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

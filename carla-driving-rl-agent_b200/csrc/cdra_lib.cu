@@ -618,6 +618,14 @@ int cdra_debug_umma_selftest(const void* X, const void* Y, float* C, int rows, i
 #endif
 }
 
+int cdra_debug_set(const char* key, int value) {
+    if (!key) return fail(CDRA_ERR_BADARG, "null key");
+#ifndef CDRA_EMU
+    if (std::string(key) == "tc") { v2::tc_override() = value; return CDRA_OK; }
+#endif
+    return fail(CDRA_ERR_BADARG, "unknown debug key");
+}
+
 int cdra_debug_stem_backward(cdra_plan_t* plan, const float* params, const void* image, float* grads, void* workspace,
                              int legacy, void* stream) {
     if (!plan || !params || !image || !grads || !workspace) return fail(CDRA_ERR_BADARG, "null argument");

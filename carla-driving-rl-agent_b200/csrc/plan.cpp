@@ -1,6 +1,7 @@
 // Plan construction (host only).  See plan.h.
 #include "plan.h"
 #include <cstdlib>
+#include <algorithm>
 #include <cstdio>
 
 namespace cdra {
@@ -218,6 +219,15 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
         v.stem_idx = alloc((size_t)4 * p.B * p.Hp * p.Wp * kStemC + 256);
         // the tensor-core stem needs 16-byte aligned TMA rows of the uint8 frames and 8-bit pixel coordinates
         v.stem_on = cfg.image_u8 != 0 && p.W % 8 == 0 && ((size_t)p.H * p.W * 3) % 16 == 0 && p.Ws < 256 && getenv("CDRA_LEGACY_STEM") == nullptr;
+        {   // largest [4*Rt][NPall] bf16 gradient matrix of any GEMM launch
+            size_t mx = 0;
+            for (auto& u : v.u) {
+                mx = std::max(mx, (size_t)4 * v.t[u.r1].Rt * u.pw1.NPall * 2);
+                mx = std::max(mx, (size_t)4 * v.t[u.outA].Rt * u.tail.NPall * 2);
+            }
+            mx = std::max(mx, (size_t)4 * v.t[v.head].Rt * v.head_pw.NPall * 2);
+            v.dr_scratch = alloc(mx + 256);
+        }
         v.desc_off = alloc(64 * 1024);
         v.host_descs_buf.resize(64 * 1024);
         v.host_descs = v.host_descs_buf.data();

@@ -121,6 +121,7 @@ struct V2Plan {
     // tensor-core stem for uint8 frames (v2_stem.cuh): winner positions of the max pool, per-slice fp64 sums of the backward
     bool stem_on = false;
     size_t stem_idx = 0, stem_gacc = 0;
+    size_t dr_scratch = 0;       // dR hand-off between the data-gradient and the tcgen05 weight-gradient kernel of one layer
     int stem_fwd_hb = 0, stem_bwd_hb = 0, pool_pb = 0;
     mutable std::vector<char> host_descs_buf;
     void* host_descs = nullptr;

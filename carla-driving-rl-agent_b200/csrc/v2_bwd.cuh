@@ -11,6 +11,7 @@
 #ifndef CDRA_EMU
 #include "v2_pw.cuh"
 #include "v2_dw.cuh"
+#include "v2_umma.cuh"
 
 namespace cdra {
 namespace v2 {
@@ -57,6 +58,9 @@ struct PwBwdArgs {
     // wgrad tiling
     int kt_tiles, nt_tiles;
     unsigned* counter;
+    // dR = BatchNorm(+ReLU6) backward of d out, [4*Rt][NPall] bf16: written once by the data-gradient kernel (it builds
+    // the tile anyway), consumed by the tcgen05 weight-gradient kernel, which then needs no transform of its own
+    bf16* dr;
 };
 
 struct PwDgradSmem { int colc, srcc, x1c, stat, w, raw, dr, st, st2, total, raw_stride, ldr, ldw, lds, lds2; };
@@ -254,6 +258,14 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
         }
         // rows beyond `rows` of a partial tile keep stale (finite) values: their products are never stored
         __syncthreads();
+        if (a.dr != nullptr && blockIdx.y == 0) {     // hand the finished dR tile to the weight-gradient kernel
+            const int nch = NP >> 3;
+            bf16* drow = a.dr + ((size_t)t * a.Rt + r0) * NP;
+            for (int i = tid; i < rows * nch; i += 256) {
+                const int r = i / nch, c = i - r * nch;
+                *reinterpret_cast<uint4*>(drow + (size_t)r * NP + c * 8) = *reinterpret_cast<const uint4*>(Dr + (size_t)r * ldr + c * 8);
+            }
+        }
         // ---- MMA: d src tile [R x KT] = dR [R x NP] * Wb^T
         float acc[MT][NBW][4];
 #pragma unroll
@@ -532,6 +544,195 @@ __global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
             if (!pw_col(d, j, p, s, l, n)) continue;
             double gs = 0.0, bs = 0.0;
             for (int t = 0; t < kT; ++t) { const double2 v = a.tb[p].bsum[(size_t)t * a.cpo + s]; bs += v.x; gs += v.y; }
+            d.layer[l].dg[n] = (float)gs; d.layer[l].dbe[n] = (float)bs;
+        }
+    }
+}
+
+// ======================================================================================== weight gradient on tcgen05
+// The same product on the 5th-generation tensor cores: dW[kk][j] = sum_r act(src)[r][kk] * dR[r][j] with BOTH operands
+// MN-major (the reduction runs over rows), staged by the transform passes straight into the 128-byte-swizzled layout,
+// and the WHOLE [KP x NPall] accumulator resident in tensor memory for the life of the CTA: every CTA covers all K and
+// N of its rows, so each row tile is loaded and transformed exactly once (the mma.sync kernel above re-reads it once per
+// (K tile, N tile)).  One elected thread issues tcgen05.mma (M = 128 per K block, N = NPall, K = 16 rows); staging is
+// double buffered against the tensor pipe through tcgen05.commit -> mbarrier.  Epilogue: TMEM -> registers -> shared
+// (transposed) -> coalesced fp32 atomics in the reference's logical layout.
+struct PwWgTcSmem { int colc, aff, rmap, cmap, raw, stg, total, raw_stride, stg_stride, xs_bytes, mb, np, nblk, tmem_cols; };
+inline __host__ __device__ PwWgTcSmem pw_wgrad_tc_smem(int R, int KP, int NPall, int nplanes, int cpo, int src_cp_sum, int nbuf) {
+    PwWgTcSmem s;
+    s.mb = (KP + 127) / 128; s.np = (NPall + 15) & ~15; s.nblk = (s.np + 63) / 64;
+    int cols = s.mb * s.np; s.tmem_cols = 32; while (s.tmem_cols < cols) s.tmem_cols *= 2;
+    int off = 128;                                     // mbarriers (8 TMA + 2 MMA) + TMEM slot
+    s.colc = off; off += s.np * 16;
+    s.aff = off; off += s.mb * 128 * 8;
+    s.rmap = off; off += s.mb * 128 * 4;
+    s.cmap = off; off += s.np * 4;
+    off = (off + 1023) & ~1023;
+    s.xs_bytes = s.mb * 2 * R * 128;
+    s.stg_stride = s.xs_bytes + s.nblk * R * 128;      // [Xs blocks | Rs blocks], multiple of 1024 for R >= 8
+    s.stg = off; off += 2 * s.stg_stride;
+    { const int scratch = 128 * 65 * 4; if (2 * s.stg_stride < scratch) off = s.stg + ((scratch + 1023) & ~1023); }   // epilogue transposition tile
+    (void)nplanes; (void)cpo;
+    s.raw_stride = (R * (NPall + src_cp_sum) * 2 + 127) & ~127;       // [dR rows | source rows]
+    s.raw = off; off += nbuf * s.raw_stride;
+    s.total = off + 1024;                              // slack for the manual 1024-byte alignment of the base
+    return s;
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) pw_wgrad_tc_kernel(const PwBwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const PwDesc& d = *a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    const int NP = d.NPall, gwp = d.cols.gwp, nplanes = d.cols.nplanes, KP = d.KP;
+    int src_cp_sum = 0;
+    for (int i = 0; i < d.nsrc; ++i) src_cp_sum += d.src[i].cp;
+    const PwWgTcSmem L = pw_wgrad_tc_smem(R, KP, NP, nplanes, a.cpo, src_cp_sum, a.nbuf);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [0..7] TMA ring, [8..9] MMA done
+    uint64_t* mma_done = full + 8;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 96);
+    float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
+    float2* s_aff = reinterpret_cast<float2*>(smem + L.aff);
+    int* s_rmap = reinterpret_cast<int*>(smem + L.rmap);
+    int* s_cmap = reinterpret_cast<int*>(smem + L.cmap);
+    unsigned char* raw = smem + L.raw;
+    const int o_src = NP * 2;                          // per-row byte offset of the source regions inside a raw buffer
+
+    const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
+    const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
+    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
+    if (tid == 0) { for (int b = 0; b < 10; ++b) mbar_init(&full[b], 1); mbar_fence_init(); }
+    // logical maps: GEMM row kk -> (layer << 24 | k), GEMM column j -> (layer << 24 | n); -1 = padding
+    for (int kk = tid; kk < L.mb * 128; kk += 256) { int l, k; s_rmap[kk] = (kk < KP && pw_row(d, kk, l, k)) ? ((l << 24) | k) : -1; }
+    for (int j = tid; j < L.np; j += 256) { int p, sl, l, n; s_cmap[j] = (j < NP && pw_col(d, j, p, sl, l, n)) ? ((l << 24) | n) : -1; }
+    for (int i = tid; i < 2 * L.stg_stride / 16; i += 256) reinterpret_cast<uint4*>(smem + L.stg)[i] = make_uint4(0, 0, 0, 0);   // padding rows / columns stay zero
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t idesc = umma_idesc(128, L.np, 1, 1);
+
+    auto issue = [&](int tile, int buf) {
+        const int t = tile / tps, r0 = (tile - t * tps) * R, rows = min(R, a.Rt - r0);
+        unsigned char* dst = raw + (size_t)buf * L.raw_stride;
+        const size_t row = (size_t)t * a.Rt + r0;
+        mbar_expect_tx(&full[buf], (uint32_t)rows * (NP + src_cp_sum) * 2);
+        bulk_g2s(dst, a.dr + row * NP, rows * NP * 2, &full[buf]);
+        int off = 0;
+        for (int i = 0; i < d.nsrc; ++i) {
+            bulk_g2s(dst + (size_t)R * (o_src + off), d.src[i].data + row * d.src[i].cp, rows * d.src[i].cp * 2, &full[buf]);
+            off += d.src[i].cp * 2;
+        }
+    };
+    pdl_wait();
+    if (tid == 32) for (int b = 0; b < a.nbuf; ++b) if (tile_lo + b < tile_hi) issue(tile_lo + b, b);     // deep ring: nbuf - 1 tiles in flight
+
+    // transform roles: thread <-> one 8-column chunk (fixed), row lanes stride the rows
+    const int nqr = NP >> 3, rq = tid % nqr, rrl = tid / nqr, rnrl = 256 / nqr;                    // dR chunks (plain copy)
+    const int nqx = src_cp_sum >> 3, xq = tid % nqx, xrl = tid / nqx, xnrl = 256 / nqx;            // act(src) chunks over all sources
+    int xsrc = 0, xch = xq, xoffb = 0;                                                              // source of this thread's chunk
+    while (xsrc < d.nsrc - 1 && xch >= (d.src[xsrc].cp >> 3)) { xch -= d.src[xsrc].cp >> 3; xoffb += d.src[xsrc].cp * 2; ++xsrc; }
+    const int xnch = d.src[xsrc].cp >> 3;
+    const bool sclamp = d.src[xsrc].clamp != 0;
+
+    int cur_t = -1;
+    int nissued[2] = {0, 0};                           // commits per staging set (thread 0 bookkeeping is CTA-uniform)
+    for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it) {
+        const int buf = it % a.nbuf, sb = it & 1;
+        const int t = tile / tps, r0 = (tile - t * tps) * R, rows = min(R, a.Rt - r0);
+        if (t != cur_t) {
+            __syncthreads();
+            {
+                int off = 0;
+                for (int i = 0; i < d.nsrc; ++i) {
+                    for (int k = tid; k < d.src[i].cp; k += 256) s_aff[off + k] = d.src[i].aff ? d.src[i].aff[(size_t)t * d.src[i].cp + k] : make_float2(1.f, 0.f);
+                    off += d.src[i].cp;
+                }
+            }
+            cur_t = t;
+            __syncthreads();
+        }
+        mbar_wait(&full[buf], (it / a.nbuf) & 1);
+        if (nissued[sb] > 0) { mbar_wait(&mma_done[sb], (nissued[sb] - 1) & 1); tc_fence_after(); }      // staging set free again
+        unsigned char* Xs = smem + L.stg + (size_t)sb * L.stg_stride;
+        unsigned char* Rs = Xs + L.xs_bytes;
+        const unsigned char* rb = raw + (size_t)buf * L.raw_stride;
+        if (rrl < rnrl) {                                  // dR rows -> swizzled MN-major tile (rows past the slice end contribute zero)
+            const uint4* dv = reinterpret_cast<const uint4*>(rb);
+#pragma unroll 4
+            for (int r = rrl; r < R; r += rnrl)
+                *reinterpret_cast<uint4*>(Rs + sw128_offset(r, rq * 8, R)) = r < rows ? dv[r * nqr + rq] : make_uint4(0, 0, 0, 0);
+        }
+        if (xrl < xnrl) {
+            float2 c8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_aff[xq * 8 + q];
+            const uint4* sv = reinterpret_cast<const uint4*>(rb + (size_t)R * (o_src + xoffb));
+#pragma unroll 2
+            for (int r = xrl; r < R; r += xnrl) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (r < rows) v = affine8(sv[r * xnch + xch], c8, sclamp);
+                *reinterpret_cast<uint4*>(Xs + sw128_offset(r, xq * 8, R)) = v;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 32 && tile + a.nbuf < tile_hi) issue(tile + a.nbuf, buf);
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t xa = smem_u32(Xs), ra = smem_u32(Rs);
+            for (int mb = 0; mb < L.mb; ++mb)
+#pragma unroll
+                for (int ks = 0; ks < R / 16; ++ks)
+                    umma_bf16(tmem + (uint32_t)(mb * L.np), umma_desc(xa + mb * 2 * R * 128 + ks * 2048, R * 128, 1024),
+                              umma_desc(ra + ks * 2048, R * 128, 1024), idesc, it > 0 || ks > 0);
+            umma_commit(&mma_done[sb]);
+        }
+        ++nissued[sb];
+    }
+    // ---- drain: the last commit of each staging set covers every MMA issued before it
+    for (int sb = 0; sb < 2; ++sb)
+        if (nissued[sb] > 0) mbar_wait(&mma_done[sb], (nissued[sb] - 1) & 1);
+    tc_fence_after();
+    __syncthreads();
+    // ---- epilogue: 64-column chunks through a transposition tile, then coalesced atomics (logical layout)
+    if (tile_lo < tile_hi) {
+        float* S = reinterpret_cast<float*>(smem + L.stg);          // [128][65]
+        for (int mb = 0; mb < L.mb; ++mb)
+            for (int c0 = 0; c0 < L.np; c0 += 64) {
+                const int ncol = min(64, L.np - c0);
+                if (warp < 4) {
+                    for (int c = 0; c < ncol; c += 8) {
+                        float v[8];
+                        tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mb * L.np + c0 + c), v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) S[(32 * warp + lane) * 65 + c + i] = v[i];
+                    }
+                }
+                __syncthreads();
+                for (int i = tid; i < 128 * ncol; i += 256) {
+                    const int row = i / ncol, col = i - row * ncol;
+                    const int rm = s_rmap[mb * 128 + row], cm = s_cmap[c0 + col];
+                    if (rm >= 0 && cm >= 0 && (rm >> 24) == (cm >> 24)) {
+                        const LayerP& Lp = d.layer[rm >> 24];
+                        atomicAdd(Lp.dw + (size_t)(rm & 0xffffff) * Lp.N + (cm & 0xffffff), S[row * 65 + col]);
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
+    // ---- BatchNorm parameter gradients (one CTA): dgamma = sum_t S2, dbeta = sum_t S1
+    if (blockIdx.x == 0) {
+        for (int j = tid; j < NP; j += 256) {
+            int p, sl, l, n;
+            if (!pw_col(d, j, p, sl, l, n)) continue;
+            double gs = 0.0, bs = 0.0;
+            for (int t = 0; t < kT; ++t) { const double2 v = a.tb[p].bsum[(size_t)t * a.cpo + sl]; bs += v.x; gs += v.y; }
             d.layer[l].dg[n] = (float)gs; d.layer[l].dbe[n] = (float)bs;
         }
     }

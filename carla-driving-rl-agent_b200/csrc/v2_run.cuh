@@ -299,10 +299,38 @@ inline bool try_pw_wgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nb
     return true;
 }
 
+// weight gradient on tcgen05 with the accumulator resident in TMEM (every layer whose [KP x NPall] tile fits 512 columns)
+inline int& tc_override() { static int v = -1; return v; }      // cdra_debug_set("tc", 0 | 1): A/B parity runs in one process
+inline bool use_tc() { static const bool env = getenv("CDRA_NO_TC") == nullptr; return tc_override() < 0 ? env : tc_override() != 0; }
+template <int R>
+inline bool try_pw_wgrad_tc(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int min_ring) {
+    int sum = 0;
+    for (int i = 0; i < hd.nsrc; ++i) sum += hd.src[i].cp;
+    const PwWgTcSmem L0 = pw_wgrad_tc_smem(R, hd.KP, hd.NPall, hd.cols.nplanes, a.cpo, sum, 0);
+    if (L0.np > 256 || L0.mb * L0.np > 512) return false;
+    // one CTA per SM; whatever shared memory the staging tiles leave goes to the TMA ring (bytes in flight hide the HBM latency)
+    const int nbuf = std::min(8, (kMaxDynSmem - L0.total) / L0.raw_stride);
+    if (nbuf < min_ring) return false;
+    const PwWgTcSmem L = pw_wgrad_tc_smem(R, hd.KP, hd.NPall, hd.cols.nplanes, a.cpo, sum, nbuf);
+    auto k = pw_wgrad_tc_kernel<R>;
+    static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nbuf; a.direct = 0;
+    const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
+    int gx = std::min(ntile, num_sms());
+    a.tiles_per_cta = (ntile + gx - 1) / gx;
+    gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    CDRA_LAUNCH_PDL(k, dim3(gx), dim3(256), L.total, c.stream, a);
+    return true;
+}
+
 // data gradient (+ pass-through, + BN-backward sums of the inputs) and weight gradient of one GEMM launch
 inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a) {
     a.d = desc_dev(c, di);
     a.out_clamp = 1;
+    const int tc_np = (hd.NPall + 15) & ~15, tc_mb = (hd.KP + 127) / 128;
+    const bool tc = use_tc() && tc_np <= 256 && tc_mb * tc_np <= 512;       // the [KP x NPall] accumulator fits the SM's TMEM
+    a.dr = tc ? (bf16*)(c.ws + c.p->v2.dr_scratch) : nullptr;
     int max_cp = 0;
     for (int i = 0; i < hd.nsrc; ++i) max_cp = std::max(max_cp, hd.src[i].cp);
     double bytes = 0;
@@ -325,6 +353,8 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
     for (int i = 0; i < hd.nsrc; ++i) bytes += 4.0 * a.Rt * (hd.src[i].map.n0 + hd.src[i].map.n1) * 2;
     bytes += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n) * 2 * 2;
     prof_bytes(bytes);
+    if (tc && (try_pw_wgrad_tc<64>(c, a, hd, 4) || try_pw_wgrad_tc<32>(c, a, hd, 4) || try_pw_wgrad_tc<16>(c, a, hd, 3) ||
+                     try_pw_wgrad_tc<32>(c, a, hd, 2) || try_pw_wgrad_tc<16>(c, a, hd, 2))) return;
     if (hd.cols.gwp <= 64)
         ok = try_pw_wgrad<4>(c, a, hd, 2, 0) || try_pw_wgrad<4>(c, a, hd, 1, 0) || try_pw_wgrad<4>(c, a, hd, 1, 1);
     else

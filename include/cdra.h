@@ -113,6 +113,11 @@ int cdra_debug_gemm(int ta, int tb, const float* A, int lda, const float* B, int
  * rows % 64 == 0.  Test infrastructure. */
 int cdra_debug_umma_selftest(const void* X, const void* Y, float* C, int rows, int Mw, int Nw, void* stream);
 
+/* Kernel-selection switches for A/B parity runs inside one process: key "tc" = 1 | 0 routes the tower's pointwise weight
+ * gradient through the tcgen05 / TMEM kernel or the mma.sync kernel (default: tcgen05 unless CDRA_NO_TC is set).
+ * Returns CDRA_ERR_BADARG for an unknown key.  Test infrastructure. */
+int cdra_debug_set(const char* key, int value);
+
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
                                   const float* actions_eval, const float* logp_old, const float* adv,
                                   const float* true_speed, const float* true_sim, float clip_ratio,
