@@ -172,6 +172,14 @@ def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    debug = os.environ.get('BENCH_DEBUG')
+    if debug:                                                       # where is a stuck rank?  (stderr, after BENCH_DEBUG seconds)
+        import faulthandler
+        faulthandler.dump_traceback_later(int(debug), exit=True)
+
+    def stage(msg):
+        if debug:
+            print(f'[bench rank {rank}] {msg}', file=sys.stderr, flush=True)
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
     torch.cuda.set_device(local)
@@ -179,6 +187,7 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
+        stage('process group up')
     bs, T, H, W = args.bs, args.T, args.height, args.width
     eng = Engine(bs, H, W, dtype=args.dtype, image_u8=True, device=dev)
     init_engine(eng, seed=42)                                       # Keras-default random init, same on every rank
@@ -265,8 +274,11 @@ def run_b200(args):
         return ms.item()
 
     launches0 = eng.lib.cdra_launch_count()
+    stage('rollout ready')
     for i in range(args.warmup):
         sgd_step(i)
+        if debug:
+            torch.cuda.synchronize(); stage(f'warm-up step {i} done')
     torch.cuda.synchronize()
     per_step_launches = (eng.lib.cdra_launch_count() - launches0) / max(1, args.warmup)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -275,6 +287,7 @@ def run_b200(args):
     l0 = eng.lib.cdra_launch_count()
     ms = timed(args.steps, args.warmup)
     launches = eng.lib.cdra_launch_count() - l0
+    stage('timed region done')
     clocks = sampler.finish() if sampler else None
     value = world * bs * args.steps / (ms / 1e3)
 
@@ -314,8 +327,11 @@ def run_b200(args):
         out['roofline_step'] = {'bound': 'hbm', 'achieved': value / world * bps / 1e9, 'peak': peak, 'unit': 'GB/s',
                                 'frac': value / world * bps / 1e9 / peak, 'bytes_per_sample': bps,
                                 'note': 'canonical algorithmic bytes of SURVEY 8(d) x samples/s/GPU; peak ' + peak_src}
-    if rank == 0 and not args.no_profile:
-        out['roofline'] = kernel_roofline(eng, sgd_step, args.warmup + args.steps, peak, peak_src)
+    if not args.no_profile:
+        # every rank runs the two profiled steps (they contain the gradient all-reduce); rank 0 reports
+        roof = kernel_roofline(eng, sgd_step, args.warmup + args.steps, peak, peak_src)
+        if rank == 0:
+            out['roofline'] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, sec, cores = cpu_reference_rate(2, 1, args.cpu_batch, H, W)
         out['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',

@@ -64,7 +64,7 @@ struct PwBwdArgs {
 };
 
 struct PwDgradSmem { int colc, srcc, x1c, stat, w, raw, dr, st, st2, total, raw_stride, ldr, ldw, lds, lds2; };
-inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, int nplanes, int cpo, int src_cp, int x1cp, int nbuf, int direct) {
+inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, int nplanes, int cpo, int src_cp, int x1cp, int nbuf, int direct, int nt = 256) {
     PwDgradSmem s;
     s.ldr = pad_ld(NPall); s.ldw = pad_ld(NPall); s.lds = pad_ld(KT); s.lds2 = pad_ld(x1cp);
     int off = 64;
@@ -77,7 +77,7 @@ inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, i
     off = (off + 127) & ~127;
     s.raw_stride = (R * ((direct ? 0 : 2 * nplanes * cpo) + src_cp + x1cp) * 2 + 127) & ~127;
     s.raw = off; off += nbuf * s.raw_stride;
-    { const int dr_bytes = R * s.ldr * 2; s.dr = off; off += dr_bytes > 32768 ? dr_bytes : 32768; }     // doubles as the flush scratch
+    { const int dr_bytes = R * s.ldr * 2, scr = nt * 128; s.dr = off; off += dr_bytes > scr ? dr_bytes : scr; }     // doubles as the flush scratch (2 x nt*8 float2)
     off = (off + 127) & ~127;
     s.st = off; off += R * s.lds * 2;
     off = (off + 127) & ~127;
@@ -90,8 +90,8 @@ inline __host__ __device__ PwDgradSmem pw_dgrad_smem(int R, int KT, int NPall, i
 // d src[r][kk] = sum_j dR[r][j] * W[kk][j]  for the K tile (source, k0..k0+kw) of this CTA; epilogue: store (or add to)
 // the source's gradient tensor and accumulate its BatchNorm-backward sums.
 template <int R, int WM, int WN, int MT, int NBW>
-__global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
-    constexpr int KT = WN * NBW * 8;
+__global__ void __launch_bounds__(WM * WN * 32, (WM * WN == 8 ? 2 : 1)) pw_dgrad_kernel(const PwBwdArgs a) {
+    constexpr int KT = WN * NBW * 8, NT = WM * WN * 32;     // 8 warps (two CTAs per SM) or 16 warps (one CTA per SM)
     extern __shared__ __align__(128) unsigned char smem[];
     const PwDesc& d = *a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
     const int k0 = ky * KT, kw = min(KT, S.cp - k0);
     const bool do_x1 = a.x1 != nullptr && blockIdx.y == 0;
     const int x1cp = do_x1 ? a.x1cp : 0;
-    const PwDgradSmem L = pw_dgrad_smem(R, KT, NP, nplanes, a.cpo, S.cp, a.x1 ? a.x1cp : 0, a.nbuf, a.direct);
+    const PwDgradSmem L = pw_dgrad_smem(R, KT, NP, nplanes, a.cpo, S.cp, a.x1 ? a.x1cp : 0, a.nbuf, a.direct, NT);
     const int NP16 = (NP + 15) & ~15;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
@@ -124,16 +124,16 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
     const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
     const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
-    for (int i = tid; i < KT * (ldw / 8); i += 256) {
+    for (int i = tid; i < KT * (ldw / 8); i += NT) {
         const int k = i / (ldw / 8), c = i - k * (ldw / 8);
         uint4 v = make_uint4(0, 0, 0, 0);
         if (k < kw && c < NP / 8) v = *reinterpret_cast<const uint4*>(d.wb + (size_t)(koff + k0 + k) * NP + c * 8);
         *reinterpret_cast<uint4*>(Ws + (size_t)k * ldw + c * 8) = v;
     }
-    for (int i = tid; i < R * ldr / 2; i += 256) reinterpret_cast<uint32_t*>(Dr)[i] = 0u;
-    for (int i = tid; i < R * lds / 2; i += 256) reinterpret_cast<uint32_t*>(St)[i] = 0u;
-    if (do_x1) for (int i = tid; i < R * lds2 / 2; i += 256) reinterpret_cast<uint32_t*>(St2)[i] = 0u;
-    for (int i = tid; i < (KT + x1cp) * 2; i += 256) s_stat[i] = 0.f;
+    for (int i = tid; i < R * ldr / 2; i += NT) reinterpret_cast<uint32_t*>(Dr)[i] = 0u;
+    for (int i = tid; i < R * lds / 2; i += NT) reinterpret_cast<uint32_t*>(St)[i] = 0u;
+    if (do_x1) for (int i = tid; i < R * lds2 / 2; i += NT) reinterpret_cast<uint32_t*>(St2)[i] = 0u;
+    for (int i = tid; i < (KT + x1cp) * 2; i += NT) s_stat[i] = 0.f;
     __syncthreads();
 
     auto issue = [&](int tile, int buf) {
@@ -154,19 +154,19 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
 
     const int wm = warp % WM, wn = warp / WM, g = lane >> 2, tg = lane & 3;
     // roles
-    const int nq = nplanes * (gwp >> 3), tq = tid % nq, trl = tid / nq, tnrl = 256 / nq;            // dR transform
+    const int nq = nplanes * (gwp >> 3), tq = tid % nq, trl = tid / nq, tnrl = NT / nq;            // dR transform
     const int tp = tq / (gwp >> 3), tc = (tq - tp * (gwp >> 3)) * 8;
-    const int nv = kw >> 3, vq = tid % nv, vrl = tid / nv, vnrl = 256 / nv;                          // store pass
+    const int nv = kw >> 3, vq = tid % nv, vrl = tid / nv, vnrl = NT / nv;                          // store pass
     float s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-    const int nx = do_x1 ? (x1cp >> 3) : 1, xq = tid % nx, xrl = tid / nx, xnrl = 256 / nx;          // pass-through store pass
+    const int nx = do_x1 ? (x1cp >> 3) : 1, xq = tid % nx, xrl = tid / nx, xnrl = NT / nx;          // pass-through store pass
     float x1s1[8], x1s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x1s1[i] = 0.f; x1s2[i] = 0.f; }
     int cs_src = -1, cs_rl = 0, cs_nrl = 1, cs_slot = 0;                                            // pass-through gather
     if (do_x1) {
-        cs_nrl = 256 / x1cp; cs_rl = tid / x1cp; cs_slot = tid % x1cp;
+        cs_nrl = NT / x1cp; cs_rl = tid / x1cp; cs_slot = tid % x1cp;
         if (cs_rl < cs_nrl) {
             const int l = slot_logical(a.x1map, cs_slot);
             if (l >= 0 && (l >> 1) < a.ncopy) cs_src = (l & 1) * plane_bytes / 2 * R + a.copy_dst0 + (l >> 1);   // element offset inside the dout region
@@ -179,18 +179,18 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
     // sums: registers -> scratch (the idle dR tile) -> one thread per column -> fp64 atomics (no shared-memory float atomics)
     auto flush = [&](int t) {
         __syncthreads();
-        float2* scr = reinterpret_cast<float2*>(Dr);              // [vnrl][kw] then [xnrl][x1cp]; <= 2 * 2048 entries
+        float2* scr = reinterpret_cast<float2*>(Dr);              // [vnrl][kw] then [xnrl][x1cp]; <= 2 * NT*8 entries
         if (vrl < vnrl) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { scr[vrl * kw + vq * 8 + i] = make_float2(s1[i], s2[i]); s1[i] = 0.f; s2[i] = 0.f; }
         }
-        float2* scr2 = scr + 2048;
+        float2* scr2 = scr + NT * 8;
         if (do_x1 && xrl < xnrl) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { scr2[xrl * x1cp + xq * 8 + i] = make_float2(x1s1[i], x1s2[i]); x1s1[i] = 0.f; x1s2[i] = 0.f; }
         }
         __syncthreads();
-        for (int i = tid; i < kw; i += 256) {
+        for (int i = tid; i < kw; i += NT) {
             const int s = k0 + i;
             if (s >= S.sum_lo && s < S.sum_hi) {
                 float a1 = 0.f, a2 = 0.f;
@@ -199,14 +199,14 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
                 atomicAdd(&dst->x, (double)a1); atomicAdd(&dst->y, (double)a2);
             }
         }
-        if (do_x1) for (int i = tid; i < x1cp; i += 256) {
+        if (do_x1) for (int i = tid; i < x1cp; i += NT) {
             float a1 = 0.f, a2 = 0.f;
             for (int l = 0; l < xnrl; ++l) { const float2 v = scr2[l * x1cp + i]; a1 += v.x; a2 += v.y; }
             double2* dst = a.x1bsum + (size_t)t * x1cp + i;
             atomicAdd(&dst->x, (double)a1); atomicAdd(&dst->y, (double)a2);
         }
         __syncthreads();
-        for (int i = tid; i < R * ldr / 2; i += 256) reinterpret_cast<uint32_t*>(Dr)[i] = 0u;      // K padding columns back to zero
+        for (int i = tid; i < R * ldr / 2; i += NT) reinterpret_cast<uint32_t*>(Dr)[i] = 0u;      // K padding columns back to zero
         __syncthreads();
     };
 
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
         if (t != cur_t) {
             if (cur_t >= 0) flush(cur_t);
             __syncthreads();
-            for (int j = tid; j < NP; j += 256) {
+            for (int j = tid; j < NP; j += NT) {
                 int p, s, l, n;
                 float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pw_col(d, j, p, s, l, n)) {
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
                 }
                 s_colc[tcol(j, NP >> 3)] = c;
             }
-            for (int i = tid; i < kw; i += 256) s_srcc[tcol(i, KT >> 3)] = sum_consts(S.aff, S.bnp, (size_t)t * S.cp + k0 + i);
-            if (do_x1) for (int i = tid; i < x1cp; i += 256) s_x1c[tcol(i, x1cp >> 3)] = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + i);
+            for (int i = tid; i < kw; i += NT) s_srcc[tcol(i, KT >> 3)] = sum_consts(S.aff, S.bnp, (size_t)t * S.cp + k0 + i);
+            if (do_x1) for (int i = tid; i < x1cp; i += NT) s_x1c[tcol(i, x1cp >> 3)] = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + i);
             cur_t = t;
             __syncthreads();
         }
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) pw_dgrad_kernel(const PwBwdArgs a) {
         if (a.dr != nullptr && blockIdx.y == 0) {     // hand the finished dR tile to the weight-gradient kernel
             const int nch = NP >> 3;
             bf16* drow = a.dr + ((size_t)t * a.Rt + r0) * NP;
-            for (int i = tid; i < rows * nch; i += 256) {
+            for (int i = tid; i < rows * nch; i += NT) {
                 const int r = i / nch, c = i - r * nch;
                 *reinterpret_cast<uint4*>(drow + (size_t)r * NP + c * 8) = *reinterpret_cast<const uint4*>(Dr + (size_t)r * ldr + c * 8);
             }
@@ -579,8 +579,8 @@ inline __host__ __device__ PwWgTcSmem pw_wgrad_tc_smem(int R, int KP, int NPall,
     return s;
 }
 
-template <int R>
-__global__ void __launch_bounds__(256) pw_wgrad_tc_kernel(const PwBwdArgs a) {
+template <int R, int NT>
+__global__ void __launch_bounds__(NT, 1) pw_wgrad_tc_kernel(const PwBwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const PwDesc& d = *a.d;
@@ -605,9 +605,9 @@ __global__ void __launch_bounds__(256) pw_wgrad_tc_kernel(const PwBwdArgs a) {
     if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
     if (tid == 0) { for (int b = 0; b < 10; ++b) mbar_init(&full[b], 1); mbar_fence_init(); }
     // logical maps: GEMM row kk -> (layer << 24 | k), GEMM column j -> (layer << 24 | n); -1 = padding
-    for (int kk = tid; kk < L.mb * 128; kk += 256) { int l, k; s_rmap[kk] = (kk < KP && pw_row(d, kk, l, k)) ? ((l << 24) | k) : -1; }
-    for (int j = tid; j < L.np; j += 256) { int p, sl, l, n; s_cmap[j] = (j < NP && pw_col(d, j, p, sl, l, n)) ? ((l << 24) | n) : -1; }
-    for (int i = tid; i < 2 * L.stg_stride / 16; i += 256) reinterpret_cast<uint4*>(smem + L.stg)[i] = make_uint4(0, 0, 0, 0);   // padding rows / columns stay zero
+    for (int kk = tid; kk < L.mb * 128; kk += NT) { int l, k; s_rmap[kk] = (kk < KP && pw_row(d, kk, l, k)) ? ((l << 24) | k) : -1; }
+    for (int j = tid; j < L.np; j += NT) { int p, sl, l, n; s_cmap[j] = (j < NP && pw_col(d, j, p, sl, l, n)) ? ((l << 24) | n) : -1; }
+    for (int i = tid; i < 2 * L.stg_stride / 16; i += NT) reinterpret_cast<uint4*>(smem + L.stg)[i] = make_uint4(0, 0, 0, 0);   // padding rows / columns stay zero
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(256) pw_wgrad_tc_kernel(const PwBwdArgs a) {
     if (tid == 32) for (int b = 0; b < a.nbuf; ++b) if (tile_lo + b < tile_hi) issue(tile_lo + b, b);     // deep ring: nbuf - 1 tiles in flight
 
     // transform roles: thread <-> one 8-column chunk (fixed), row lanes stride the rows
-    const int nqr = NP >> 3, rq = tid % nqr, rrl = tid / nqr, rnrl = 256 / nqr;                    // dR chunks (plain copy)
-    const int nqx = src_cp_sum >> 3, xq = tid % nqx, xrl = tid / nqx, xnrl = 256 / nqx;            // act(src) chunks over all sources
+    const int nqr = NP >> 3, rq = tid % nqr, rrl = tid / nqr, rnrl = NT / nqr;                    // dR chunks (plain copy)
+    const int nqx = src_cp_sum >> 3, xq = tid % nqx, xrl = tid / nqx, xnrl = NT / nqx;            // act(src) chunks over all sources
     int xsrc = 0, xch = xq, xoffb = 0;                                                              // source of this thread's chunk
     while (xsrc < d.nsrc - 1 && xch >= (d.src[xsrc].cp >> 3)) { xch -= d.src[xsrc].cp >> 3; xoffb += d.src[xsrc].cp * 2; ++xsrc; }
     const int xnch = d.src[xsrc].cp >> 3;
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_tc_kernel(const PwBwdArgs a) {
             {
                 int off = 0;
                 for (int i = 0; i < d.nsrc; ++i) {
-                    for (int k = tid; k < d.src[i].cp; k += 256) s_aff[off + k] = d.src[i].aff ? d.src[i].aff[(size_t)t * d.src[i].cp + k] : make_float2(1.f, 0.f);
+                    for (int k = tid; k < d.src[i].cp; k += NT) s_aff[off + k] = d.src[i].aff ? d.src[i].aff[(size_t)t * d.src[i].cp + k] : make_float2(1.f, 0.f);
                     off += d.src[i].cp;
                 }
             }
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_tc_kernel(const PwBwdArgs a) {
                     }
                 }
                 __syncthreads();
-                for (int i = tid; i < 128 * ncol; i += 256) {
+                for (int i = tid; i < 128 * ncol; i += NT) {
                     const int row = i / ncol, col = i - row * ncol;
                     const int rm = s_rmap[mb * 128 + row], cm = s_cmap[c0 + col];
                     if (rm >= 0 && cm >= 0 && (rm >> 24) == (cm >> 24)) {
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_tc_kernel(const PwBwdArgs a) {
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
     // ---- BatchNorm parameter gradients (one CTA): dgamma = sum_t S2, dbeta = sum_t S1
     if (blockIdx.x == 0) {
-        for (int j = tid; j < NP; j += 256) {
+        for (int j = tid; j < NP; j += NT) {
             int p, sl, l, n;
             if (!pw_col(d, j, p, sl, l, n)) continue;
             double gs = 0.0, bs = 0.0;

@@ -194,7 +194,7 @@ inline void launch_dw_fwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
 inline void tower_prepare(const RunCtx& c) {
     const int nu = (int)c.p->v2.u.size();
     upload_descs(c);
-    CDRA_LAUNCH(pw_prep_kernel, dim3(2 * nu + 1, 8), dim3(256), 0, c.stream, desc_dev(c, 0));
+    CDRA_LAUNCH(pw_prep_kernel, dim3(2 * nu + 1, 32), dim3(256), 0, c.stream, desc_dev(c, 0));
 }
 
 inline void tower_forward(const RunCtx& c) {
@@ -252,25 +252,26 @@ inline void tower_forward(const RunCtx& c) {
 // ================================================================================================ backward
 template <int R, int WM, int WN, int MT, int NBW>
 inline bool try_pw_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nbuf, int direct, int min_ctas_per_sm) {
-    constexpr int KT = WN * NBW * 8;
+    constexpr int KT = WN * NBW * 8, NT = WM * WN * 32;
     int max_cp = 0, gy = 0;
     for (int i = 0; i < kMaxSrc; ++i) a.ntiles_k[i] = 0;
     for (int i = 0; i < hd.nsrc; ++i) { max_cp = std::max(max_cp, hd.src[i].cp); a.ntiles_k[i] = (hd.src[i].cp + KT - 1) / KT; gy += a.ntiles_k[i]; }
     if (direct && a.x1) return false;
-    const PwDgradSmem L = pw_dgrad_smem(R, KT, hd.NPall, hd.cols.nplanes, a.cpo, max_cp, a.x1 ? a.x1cp : 0, nbuf, direct);
+    const PwDgradSmem L = pw_dgrad_smem(R, KT, hd.NPall, hd.cols.nplanes, a.cpo, max_cp, a.x1 ? a.x1cp : 0, nbuf, direct, NT);
+    if (NT > 256 && min_ctas_per_sm > 1) return false;
     if (L.total > kMaxDynSmem) return false;
     if (min_ctas_per_sm > 1 && (L.total + 1024) * min_ctas_per_sm > 227 * 1024) return false;
     auto k = pw_dgrad_kernel<R, WM, WN, MT, NBW>;
     static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
     (void)attr_done;
     a.nbuf = nbuf; a.direct = direct;
-    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
+    const int per_sm = NT > 256 ? 1 : std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
     const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
     int gx = std::max(1, num_sms() * per_sm / gy);
     if (gx > ntile) gx = ntile;
     a.tiles_per_cta = (ntile + gx - 1) / gx;
     gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    CDRA_LAUNCH_PDL(k, dim3(gx, gy), dim3(256), L.total, c.stream, a);
+    CDRA_LAUNCH_PDL(k, dim3(gx, gy), dim3(NT), L.total, c.stream, a);
     return true;
 }
 
@@ -302,7 +303,7 @@ inline bool try_pw_wgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nb
 // weight gradient on tcgen05 with the accumulator resident in TMEM (every layer whose [KP x NPall] tile fits 512 columns)
 inline int& tc_override() { static int v = -1; return v; }      // cdra_debug_set("tc", 0 | 1): A/B parity runs in one process
 inline bool use_tc() { static const bool env = getenv("CDRA_NO_TC") == nullptr; return tc_override() < 0 ? env : tc_override() != 0; }
-template <int R>
+template <int R, int NT = 512>
 inline bool try_pw_wgrad_tc(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int min_ring) {
     int sum = 0;
     for (int i = 0; i < hd.nsrc; ++i) sum += hd.src[i].cp;
@@ -312,7 +313,7 @@ inline bool try_pw_wgrad_tc(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int
     const int nbuf = std::min(8, (kMaxDynSmem - L0.total) / L0.raw_stride);
     if (nbuf < min_ring) return false;
     const PwWgTcSmem L = pw_wgrad_tc_smem(R, hd.KP, hd.NPall, hd.cols.nplanes, a.cpo, sum, nbuf);
-    auto k = pw_wgrad_tc_kernel<R>;
+    auto k = pw_wgrad_tc_kernel<R, NT>;
     static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
     (void)attr_done;
     a.nbuf = nbuf; a.direct = 0;
@@ -320,7 +321,7 @@ inline bool try_pw_wgrad_tc(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int
     int gx = std::min(ntile, num_sms());
     a.tiles_per_cta = (ntile + gx - 1) / gx;
     gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    CDRA_LAUNCH_PDL(k, dim3(gx), dim3(256), L.total, c.stream, a);
+    CDRA_LAUNCH_PDL(k, dim3(gx), dim3(NT), L.total, c.stream, a);
     return true;
 }
 
@@ -345,7 +346,7 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
              try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 0, 1) || try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 1, 1);
     else
         ok = try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 2, 0, 2) || try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 1, 0, 2) ||
-             try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 2, 0, 1) || try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 1, 0, 1) ||
+             try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 2, 0, 1) || try_pw_dgrad<64, 4, 4, 1, 4>(c, a, hd, 2, 0, 1) || try_pw_dgrad<64, 4, 4, 1, 4>(c, a, hd, 1, 0, 1) ||      // 16 warps, one CTA per SM try_pw_dgrad<64, 4, 2, 1, 8>(c, a, hd, 1, 0, 1) ||
              try_pw_dgrad<32, 2, 4, 1, 4>(c, a, hd, 1, 0, 1) || try_pw_dgrad<32, 2, 4, 1, 4>(c, a, hd, 1, 1, 1) ||
              try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 1, 1);
     if (!ok) fprintf(stderr, "libcdra: no pw_dgrad configuration fits (KP=%d NPall=%d)\n", hd.KP, hd.NPall);
