@@ -372,14 +372,14 @@ __global__ void __launch_bounds__(WM * WN * 32, (WM * WN == 8 ? 2 : 1)) pw_dgrad
 // (pre-zeroed) gradient arena in the reference's logical layout.  BN gamma/beta gradients come from the final sums.
 constexpr int kWgK = 64, kWgR = 64;
 struct PwWgradSmem { int colc, aff, raw, xs, rs, total, raw_stride, ldx, ldr; };
-inline __host__ __device__ PwWgradSmem pw_wgrad_smem(int NTW, int cpo, int src_cp, int nbuf, int direct) {
+inline __host__ __device__ PwWgradSmem pw_wgrad_smem(int NTW, int cpo, int src_cp, int nbuf, int direct, int dr_cols = 0) {
     PwWgradSmem s;
     s.ldx = pad_ld(kWgK); s.ldr = pad_ld(NTW);
     int off = 64;
     s.colc = off; off += NTW * 16;
     s.aff = off; off += kWgK * 8;
     off = (off + 127) & ~127;
-    s.raw_stride = (kWgR * ((direct ? 0 : 2 * cpo) + src_cp) * 2 + 127) & ~127;
+    s.raw_stride = (kWgR * ((dr_cols ? dr_cols : (direct ? 0 : 2 * cpo)) + src_cp) * 2 + 127) & ~127;    // dr_cols: finished dR rows instead of (d out, out)
     s.raw = off; off += nbuf * s.raw_stride;
     s.xs = off; off += kWgR * s.ldx * 2;
     off = (off + 127) & ~127;
@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
     const int k0 = ky * kWgK, kw = min(kWgK, S.cp - k0);
     const int ntp = (gwp + NTW - 1) / NTW;                 // N tiles per plane
     const int pn = nti / ntp, n0 = (nti - pn * ntp) * NTW, nw = min(NTW, gwp - n0);
-    const PwWgradSmem L = pw_wgrad_smem(NTW, a.cpo, S.cp, a.nbuf, a.direct);
+    const bool have_dr = a.dr != nullptr;              // the data-gradient kernel left the finished dR matrix [4*Rt][NP]
+    const PwWgradSmem L = pw_wgrad_smem(NTW, a.cpo, S.cp, a.nbuf, a.direct, have_dr ? NP : 0);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
     float2* s_aff = reinterpret_cast<float2*>(smem + L.aff);
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
     bf16* Rs = reinterpret_cast<bf16*>(smem + L.rs);
     const int ldx = L.ldx, ldr = L.ldr;
     const int plane_bytes = a.cpo * 2;
-    const int o_dout = 0, o_out = plane_bytes, o_src = a.direct ? 0 : 2 * plane_bytes;
+    const int o_dout = 0, o_out = plane_bytes, o_src = have_dr ? NP * 2 : (a.direct ? 0 : 2 * plane_bytes);
 
     const int tps = (a.Rt + kWgR - 1) / kWgR, ntile = kT * tps;
     const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
@@ -425,8 +426,9 @@ __global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
         const int t = tile / tps, r0 = (tile - t * tps) * kWgR, rows = min(kWgR, a.Rt - r0);
         unsigned char* dst = raw + (size_t)buf * L.raw_stride;
         const size_t row = (size_t)t * a.Rt + r0;
-        mbar_expect_tx(&full[buf], rows * ((a.direct ? 0 : 2 * plane_bytes) + S.cp * 2));
-        if (!a.direct) {
+        mbar_expect_tx(&full[buf], rows * ((have_dr ? NP * 2 : (a.direct ? 0 : 2 * plane_bytes)) + S.cp * 2));
+        if (have_dr) bulk_g2s(dst, a.dr + row * NP, rows * NP * 2, &full[buf]);
+        else if (!a.direct) {
             bulk_g2s(dst + (size_t)kWgR * o_dout, a.dout[pn] + row * a.cpo, rows * plane_bytes, &full[buf]);
             bulk_g2s(dst + (size_t)kWgR * o_out, a.out[pn] + row * a.cpo, rows * plane_bytes, &full[buf]);
         }
@@ -465,7 +467,14 @@ __global__ void __launch_bounds__(256, 2) pw_wgrad_kernel(const PwBwdArgs a) {
         }
         mbar_wait(&full[buf], (it / a.nbuf) & 1);
         const unsigned char* rb = raw + (size_t)buf * L.raw_stride;
-        if (rrl < rnrl) {
+        if (have_dr) {
+            if (rrl < rnrl) {                            // plain copy of this CTA's dR columns
+                const uint4* dv = reinterpret_cast<const uint4*>(rb);
+                const int nch = NP >> 3, ch = ((pn * gwp + n0) >> 3) + rq;
+                for (int r = rrl; r < kWgR; r += rnrl)
+                    *reinterpret_cast<uint4*>(Rs + (size_t)r * ldr + rq * 8) = r < rows ? dv[r * nch + ch] : make_uint4(0, 0, 0, 0);
+            }
+        } else if (rrl < rnrl) {
             float4 c8[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) c8[q] = s_colc[q * (NTW >> 3) + rq];
@@ -869,40 +878,75 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
         }
         __syncthreads();
         if (active) {
-            // weight gradient: dw[ky][kx] += act(in)(oy*S - pt + ky, ox*S - pl + kx) * dR(oy, ox)
+            // weight gradient: dw[ky][kx] += act(in)(oy*S - pt + ky, ox*S - pl + kx) * dR(oy, ox)   (rows shared between
+            // consecutive outputs stay in registers)
             for (int ox = xl; ox < a.Wo; ox += NXL) {
                 const bf16* win = Pin + ((1 - a.pad_t) * PW + ox * S + 1 - a.pad_l) * CP + 2 * pr;
                 const bf16* dp = Pdr + (QW + ox + 1) * CP + 2 * pr;
-                for (int oy = 0; oy < a.Ho; ++oy) {
+                auto emit = [&](const float2 (&A)[3], const float2 (&B)[3], const float2 (&C)[3]) {
                     const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(dp));
+                    dw_grad_row(A, dr, g0, g1); dw_grad_row(B, dr, g0 + 3, g1 + 3); dw_grad_row(C, dr, g0 + 6, g1 + 6);
+                    dp += QW * CP;
+                };
+                float2 A[3], B[3], C[3];
+                if (S == 1) {
+                    dw_ldrow<CP>(win, A); dw_ldrow<CP>(win + PW * CP, B);
+                    const bf16* nxt = win + 2 * PW * CP;
+                    for (int oy = 0; oy < a.Ho; oy += 3) {
+                        dw_ldrow<CP>(nxt, C); emit(A, B, C); nxt += PW * CP;
+                        if (oy + 1 < a.Ho) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += PW * CP; }
+                        if (oy + 2 < a.Ho) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += PW * CP; }
+                    }
+                } else {
+                    dw_ldrow<CP>(win, A);
+                    for (int oy = 0; oy < a.Ho; ++oy) {
+                        dw_ldrow<CP>(win + PW * CP, B); dw_ldrow<CP>(win + 2 * PW * CP, C);
+                        emit(A, B, C);
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(win + ky * PW * CP + kx * CP));
-                            g0[ky * 3 + kx] = fmaf(v.x, dr.x, g0[ky * 3 + kx]);
-                            g1[ky * 3 + kx] = fmaf(v.y, dr.y, g1[ky * 3 + kx]);
-                        }
-                    win += row_step; dp += QW * CP;
+                        for (int j = 0; j < 3; ++j) A[j] = C[j];
+                        win += row_step;
+                    }
                 }
             }
             // data gradient: d in(iy, ix) = sum_{ky,kx} w[ky][kx] * dR((iy + pt - ky)/S, (ix + pl - kx)/S)
             for (int ix = xl; ix < a.Wi; ix += NXL) {
                 bf16* gp = a.din + ((size_t)f * in_px + ix) * CP + 2 * pr;
                 const bf16* ap = Pin + (PW + ix + 1) * CP + 2 * pr;
-                for (int iy = 0; iy < a.Hi; ++iy) {
-                    float acc0 = 0.f, acc1 = 0.f;
-                    if (S == 1) {
-                        const bf16* dwin = Pdr + ((iy + 2) * QW + ix + 2) * CP + 2 * pr;      // (iy + 1 - ky) + 1, (ix + 1 - kx) + 1
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(dwin - ky * QW * CP - kx * CP));
-                                acc0 = fmaf(dr.x, w0[ky * 3 + kx], acc0);
-                                acc1 = fmaf(dr.y, w1[ky * 3 + kx], acc1);
-                            }
-                    } else {
+                auto finish = [&](float acc0, float acc1) {       // (+ existing share), store, BatchNorm-backward sums of the input
+                    if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
+                    const uint32_t pk = pack2(acc0, acc1);
+                    *reinterpret_cast<uint32_t*>(gp) = pk;
+                    if (want_sums) {
+                        const float2 gr = unpack2(pk);
+                        const float2 av = unpack2(*reinterpret_cast<const uint32_t*>(ap));
+                        const float d0 = (!iclamp || (av.x > 0.f && av.x < 6.f)) ? gr.x : 0.f;
+                        const float d1 = (!iclamp || (av.y > 0.f && av.y < 6.f)) ? gr.y : 0.f;
+                        s1a += d0; s2a = fmaf(d0, fmaf(av.x, xc0.x, xc0.y), s2a);
+                        s1b += d1; s2b = fmaf(d1, fmaf(av.y, xc1.x, xc1.y), s2b);
+                    }
+                    gp += a.Wi * CP; ap += PW * CP;
+                };
+                if (S == 1) {
+                    // d in(iy, ix) = sum w[ky][kx] * dR tile(iy + 2 - ky, ix + 2 - kx): tile rows iy, iy+1, iy+2 <-> ky = 2, 1, 0
+                    auto emit = [&](const float2 (&A)[3], const float2 (&B)[3], const float2 (&C)[3]) {
+                        float acc0 = 0.f, acc1 = 0.f;
+                        dw_mac_row<true>(A, w0 + 6, w1 + 6, acc0, acc1);
+                        dw_mac_row<true>(B, w0 + 3, w1 + 3, acc0, acc1);
+                        dw_mac_row<true>(C, w0, w1, acc0, acc1);
+                        finish(acc0, acc1);
+                    };
+                    const bf16* dwin = Pdr + ix * CP + 2 * pr;
+                    float2 A[3], B[3], C[3];
+                    dw_ldrow<CP>(dwin, A); dw_ldrow<CP>(dwin + QW * CP, B);
+                    const bf16* nxt = dwin + 2 * QW * CP;
+                    for (int iy = 0; iy < a.Hi; iy += 3) {
+                        dw_ldrow<CP>(nxt, C); emit(A, B, C); nxt += QW * CP;
+                        if (iy + 1 < a.Hi) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += QW * CP; }
+                        if (iy + 2 < a.Hi) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += QW * CP; }
+                    }
+                } else {
+                    for (int iy = 0; iy < a.Hi; ++iy) {
+                        float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
                             const int ny = iy + a.pad_t - ky;
@@ -916,19 +960,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                                 acc1 = fmaf(dr.y, w1[ky * 3 + kx], acc1);
                             }
                         }
+                        finish(acc0, acc1);
                     }
-                    if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
-                    const uint32_t pk = pack2(acc0, acc1);
-                    *reinterpret_cast<uint32_t*>(gp) = pk;
-                    if (want_sums) {
-                        const float2 gr = unpack2(pk);
-                        const float2 av = unpack2(*reinterpret_cast<const uint32_t*>(ap));
-                        const float d0 = (!iclamp || (av.x > 0.f && av.x < 6.f)) ? gr.x : 0.f;
-                        const float d1 = (!iclamp || (av.y > 0.f && av.y < 6.f)) ? gr.y : 0.f;
-                        s1a += d0; s2a = fmaf(d0, fmaf(av.x, xc0.x, xc0.y), s2a);
-                        s1b += d1; s2b = fmaf(d1, fmaf(av.y, xc1.x, xc1.y), s2b);
-                    }
-                    gp += a.Wi * CP; ap += PW * CP;
                 }
             }
         }

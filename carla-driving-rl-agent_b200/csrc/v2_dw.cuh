@@ -53,6 +53,28 @@ struct PxWalk {
     __device__ void next() { y += dy; x += dx; if (x >= W) { x -= W; ++y; } }
 };
 
+// three horizontally adjacent taps (one channel pair each) of a tile row; the stencils slide DOWN a column and keep the rows
+// they share between consecutive outputs in registers (stride 1: one new row per output instead of three)
+template <int CP>
+CDRA_DEV void dw_ldrow(const bf16* p, float2 (&r)[3]) {
+    r[0] = unpack2(*reinterpret_cast<const uint32_t*>(p));
+    r[1] = unpack2(*reinterpret_cast<const uint32_t*>(p + CP));
+    r[2] = unpack2(*reinterpret_cast<const uint32_t*>(p + 2 * CP));
+}
+// acc += sum_j r[j] * w[j]   (REV: taps mirrored, w[2 - j])
+template <bool REV>
+CDRA_DEV void dw_mac_row(const float2 (&r)[3], const float* w0, const float* w1, float& a0, float& a1) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        a0 = fmaf(r[j].x, w0[REV ? 2 - j : j], a0);
+        a1 = fmaf(r[j].y, w1[REV ? 2 - j : j], a1);
+    }
+}
+CDRA_DEV void dw_grad_row(const float2 (&r)[3], float2 dr, float* g0, float* g1) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { g0[j] = fmaf(r[j].x, dr.x, g0[j]); g1[j] = fmaf(r[j].y, dr.y, g1[j]); }
+}
+
 // forward: out(oy, ox) = b + sum_{ky,kx} w[ky][kx] * act(in)(oy*S - pt + ky, ox*S - pl + kx)   (zero outside the frame)
 template <int CP, int S>
 __global__ void __launch_bounds__(kDwThreads) dw_fwd_kernel(const DwArgs a) {
@@ -140,22 +162,36 @@ __global__ void __launch_bounds__(kDwThreads) dw_fwd_kernel(const DwArgs a) {
             for (int ox = xl; ox < a.Wo; ox += NXL) {
                 const bf16* win = Pin + ((1 - a.pad_t) * PW + ox * S + 1 - a.pad_l) * CP + 2 * pr;
                 bf16* optr = a.out + ((size_t)f * out_px + ox) * CP + 2 * pr;
-                for (int oy = 0; oy < a.Ho; ++oy) {
+                auto emit = [&](const float2 (&A)[3], const float2 (&B)[3], const float2 (&C)[3]) {
                     float acc0 = b0, acc1 = b1;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(win + ky * PW * CP + kx * CP));
-                            acc0 = fmaf(v.x, w0[ky * 3 + kx], acc0);
-                            acc1 = fmaf(v.y, w1[ky * 3 + kx], acc1);
-                        }
+                    dw_mac_row<false>(A, w0, w1, acc0, acc1);
+                    dw_mac_row<false>(B, w0 + 3, w1 + 3, acc0, acc1);
+                    dw_mac_row<false>(C, w0 + 6, w1 + 6, acc0, acc1);
                     const uint32_t pk = pack2(acc0, acc1);
                     *reinterpret_cast<uint32_t*>(optr) = pk;
                     const float2 r = unpack2(pk);
                     ssum0 += r.x; ssq0 = fmaf(r.x, r.x, ssq0);
                     ssum1 += r.y; ssq1 = fmaf(r.y, r.y, ssq1);
-                    win += row_step; optr += ostep;
+                    optr += ostep;
+                };
+                float2 A[3], B[3], C[3];
+                if (S == 1) {
+                    dw_ldrow<CP>(win, A); dw_ldrow<CP>(win + PW * CP, B);
+                    const bf16* nxt = win + 2 * PW * CP;
+                    for (int oy = 0; oy < a.Ho; oy += 3) {
+                        dw_ldrow<CP>(nxt, C); emit(A, B, C); nxt += PW * CP;
+                        if (oy + 1 < a.Ho) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += PW * CP; }
+                        if (oy + 2 < a.Ho) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += PW * CP; }
+                    }
+                } else {
+                    dw_ldrow<CP>(win, A);
+                    for (int oy = 0; oy < a.Ho; ++oy) {
+                        dw_ldrow<CP>(win + PW * CP, B); dw_ldrow<CP>(win + 2 * PW * CP, C);
+                        emit(A, B, C);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) A[j] = C[j];
+                        win += row_step;
+                    }
                 }
             }
         }

@@ -283,7 +283,7 @@ inline bool try_pw_wgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nb
     for (int i = 0; i < kMaxSrc; ++i) a.ntiles_k[i] = 0;
     for (int i = 0; i < hd.nsrc; ++i) { max_cp = std::max(max_cp, hd.src[i].cp); a.ntiles_k[i] = (hd.src[i].cp + kWgK - 1) / kWgK; a.kt_tiles += a.ntiles_k[i]; }
     a.nt_tiles = hd.cols.nplanes * ((hd.cols.gwp + NTW - 1) / NTW);
-    const PwWgradSmem L = pw_wgrad_smem(NTW, a.cpo, max_cp, nbuf, direct);
+    const PwWgradSmem L = pw_wgrad_smem(NTW, a.cpo, max_cp, nbuf, direct, a.dr ? hd.NPall : 0);
     if (L.total > kMaxDynSmem) return false;
     auto k = pw_wgrad_kernel<NBW>;
     static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
@@ -331,7 +331,7 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
     a.out_clamp = 1;
     const int tc_np = (hd.NPall + 15) & ~15, tc_mb = (hd.KP + 127) / 128;
     const bool tc = use_tc() && tc_np <= 256 && tc_mb * tc_np <= 512;       // the [KP x NPall] accumulator fits the SM's TMEM
-    a.dr = tc ? (bf16*)(c.ws + c.p->v2.dr_scratch) : nullptr;
+    a.dr = use_tc() ? (bf16*)(c.ws + c.p->v2.dr_scratch) : nullptr;     // every layer hands dR over; the mma.sync weight gradient takes it too
     int max_cp = 0;
     for (int i = 0; i < hd.nsrc; ++i) max_cp = std::max(max_cp, hd.src[i].cp);
     double bytes = 0;
