@@ -219,53 +219,94 @@ def run_b200(args):
             for t in ts:
                 dist.all_reduce(t)
 
-    def sgd_step(i, host=None):
-        if i % T == 0:
-            gae()                                                     # once per update (PPOAgent.end_episode)
-        lo = (i % T) * bs
-        if host is None:
-            gather(perm_p[lo:lo + bs], 'policy')
-        else:
-            for k in host[0]:
-                mb[k].copy_(host[0][k], non_blocking=True)
-        # ---- policy pass (rl/agents/ppo.py:199-210, core/carla_agent.py:351-388)
-        x = eng.dynamics_forward(mb)
-        eng.policy_head(x, mb['actions'], mb['logp_old'], mb['adv'], mb['true_speed'], mb['true_sim'], 0.2, 1.0)
-        eng.dynamics_backward(mb, eng.d_x512)
+    def policy_pass(m):
+        # rl/agents/ppo.py:199-210, core/carla_agent.py:351-388
+        x = eng.dynamics_forward(m)
+        eng.policy_head(x, m['actions'], m['logp_old'], m['adv'], m['true_speed'], m['true_sim'], 0.2, 1.0)
+        eng.dynamics_backward(m, eng.d_x512)
         allreduce(eng.g_dyn, eng.g_pol)
         eng.clip_adam('dyn', 3e-4, None, gscale)
         old_pol.copy_(eng.pol.flat)                                   # update_old_policy before the Adam step (ppo.py:249)
         eng.clip_adam('pol', 3e-4, 1.0, gscale)
-        loss_p = eng.scalars[0].clone()
-        # ---- value pass (rl/agents/ppo.py:213-224, core/carla_agent.py:430-463)
-        if host is None:
-            gather(perm_v[lo:lo + bs], 'value')
-        else:
-            for k in host[1]:
-                mb[k].copy_(host[1][k], non_blocking=True)
-        x = eng.dynamics_forward(mb)
-        eng.value_head(x, mb['returns'], mb['true_speed'], mb['true_sim'])
-        eng.dynamics_backward(mb, eng.d_x512)
+        return eng.scalars[0].clone()
+
+    def value_pass(m):
+        # rl/agents/ppo.py:213-224, core/carla_agent.py:430-463
+        x = eng.dynamics_forward(m)
+        eng.value_head(x, m['returns'], m['true_speed'], m['true_sim'])
+        eng.dynamics_backward(m, eng.d_x512)
         allreduce(eng.g_dyn, eng.g_val)
         eng.clip_adam('dyn', 3e-4, None, gscale)
         eng.clip_adam('val', 3e-4, 1.0, gscale)
-        return loss_p, eng.scalars[0]
+        return eng.scalars[0]
+
+    def sgd_step(i, feeder=None, nxt=None):
+        """one SGD minibatch index through both passes.  feeder = None: minibatches gathered from the HBM-resident rollout;
+        else: minibatches arrive from pinned HOST memory through the feeder's copy stream (end-to-end leg), and `nxt` =
+        (policy, value) host minibatches of the following step, prefetched while this step computes"""
+        if i % T == 0:
+            gae()                                                     # once per update (PPOAgent.end_episode)
+        lo = (i % T) * bs
+        if feeder is None:
+            gather(perm_p[lo:lo + bs], 'policy')
+            loss_p = policy_pass(mb)
+            gather(perm_v[lo:lo + bs], 'value')
+            return loss_p, value_pass(mb)
+        loss_p = policy_pass(feeder.acquire('p'))
+        feeder.release('p')
+        if nxt is not None:
+            feeder.prefetch('p', nxt[0])
+        loss_v = value_pass(feeder.acquire('v')).clone()
+        feeder.release('v')
+        if nxt is not None:
+            feeder.prefetch('v', nxt[1])
+        return loss_p, loss_v
+
+    class HostFeeder:
+        """double-buffered H2D staging of the two per-step minibatches on a copy stream (pinned host -> device), so the
+        copy of the next pass overlaps the kernels of the current one; events order buffer reuse both ways"""
+        def __init__(self, like_p, like_v):
+            self.cs = torch.cuda.Stream(device=dev)
+            self.bufs = {'p': {k: torch.empty_like(v, device=dev) for k, v in like_p.items()},
+                         'v': {k: torch.empty_like(v, device=dev) for k, v in like_v.items()}}
+            self.ready = {w: torch.cuda.Event() for w in 'pv'}
+            self.free = {w: torch.cuda.Event() for w in 'pv'}
+            for w in 'pv':
+                self.free[w].record(torch.cuda.current_stream())
+
+        def prefetch(self, which, host):
+            with torch.cuda.stream(self.cs):
+                self.cs.wait_event(self.free[which])
+                for k, v in host.items():
+                    self.bufs[which][k].copy_(v, non_blocking=True)
+                self.ready[which].record(self.cs)
+
+        def acquire(self, which):
+            torch.cuda.current_stream().wait_event(self.ready[which])
+            return self.bufs[which]
+
+        def release(self, which):
+            self.free[which].record(torch.cuda.current_stream())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, first, host_bufs=None):
+    def timed(nsteps, first, host_bufs=None, feeder=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if host_bufs is not None:                                     # first step's inputs: H2D inside the clock as well
+            feeder.prefetch('p', host_bufs[0][0]); feeder.prefetch('v', host_bufs[0][1])
         for i in range(nsteps):
             if host_bufs is None:
                 sgd_step(first + i)
             else:
-                lp, lv = sgd_step(first + i, host_bufs[i % len(host_bufs)])
-                host_loss[0].copy_(lp, non_blocking=False); host_loss[1].copy_(lv, non_blocking=False)   # D2H read of the step's result
+                nxt = host_bufs[(i + 1) % len(host_bufs)] if i + 1 < nsteps else None
+                lp, lv = sgd_step(first + i, feeder, nxt)
+                hl = host_loss[i % len(host_loss)]                    # D2H read of the step's result (pinned, asynchronous)
+                hl[0].copy_(lp, non_blocking=True); hl[1].copy_(lv, non_blocking=True)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -301,11 +342,13 @@ def run_b200(args):
         gather(perm_v[j * bs:(j + 1) * bs], 'value')
         hv = {k: mb[k].cpu().pin_memory() for k in keys + ('returns',)}
         host_bufs.append((hp, hv))
-    host_loss = [torch.empty((), pin_memory=True), torch.empty((), pin_memory=True)]
+    host_loss = [[torch.empty((), pin_memory=True), torch.empty((), pin_memory=True)] for _ in range(4)]
     h2d = sum(t.numel() * t.element_size() for h in host_bufs[0] for t in h.values())
+    feeder = HostFeeder(host_bufs[0][0], host_bufs[0][1])
     e2e_steps = max(2, args.steps // 2)
-    timed(1, 1, host_bufs)
-    ms_e2e = timed(e2e_steps, 1, host_bufs)
+    timed(1, 1, host_bufs, feeder)
+    ms_e2e = timed(e2e_steps, 1, host_bufs, feeder)
+    assert all(torch.isfinite(h[0]) and torch.isfinite(h[1]) for h in host_loss[:min(4, e2e_steps)])
     e2e_value = world * bs * e2e_steps / (ms_e2e / 1e3)
 
     out = {
@@ -318,7 +361,8 @@ def run_b200(args):
                    'l2': f'inputs ({roll["state_image"].numel() / 1e9:.1f} GB rollout) and activations exceed L2; no flush needed',
                    'parallelism': f'dp{world}', 'optimizer': 'Keras-style Adam x3, per-tensor clip 1.0 on heads'},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
-                'ms_per_step': ms_e2e / e2e_steps},
+                'ms_per_step': ms_e2e / e2e_steps,
+                'note': 'pinned host minibatches -> device on a copy stream (double-buffered, overlapped with the previous pass), losses read back every step'},
         'gpu_launches': int(launches), 'launches_per_step': per_step_launches, 'clocks': clocks,
     }
     peak, peak_src = measured_peaks()
@@ -372,7 +416,15 @@ def kernel_roofline(eng, sgd_step, first, peak, peak_src):
     top = sorted(agg.items(), key=lambda kv: -kv[1][1])
     name, (cnt, ms, by) = top[0]
     ach = by / (ms / 1e3) / 1e9 if ms > 0 else 0.0
-    return {'bound': 'hbm', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+    traffic = None                                   # DRAM bytes per launch of that kernel from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+        if tj.get('kernel') == name:
+            traffic = tj['dram_bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        pass
+    return {'bound': 'hbm', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic,
+            'algorithmic_bytes_per_launch': by / max(cnt, 1),
             'launches': cnt, 'avg_ms': ms / max(cnt, 1), 'share_of_step': ms / total if total else None, 'peak_source': peak_src,
             'by_kernel': {k: {'launches': v[0], 'ms': round(v[1], 3), 'share': round(v[1] / total, 4),
                               'GBps': round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None} for k, v in top[:14]}}
