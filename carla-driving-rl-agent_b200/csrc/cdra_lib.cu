@@ -130,16 +130,58 @@ static void feat_args(const Plan& p, char* ws, const float* params, float* state
     }
 }
 
-static void tail_forward(const RunCtx& c, const float* road, const float* vehicle, const float* nav, float* out512) {
-    const Plan& p = *c.p; const int B = p.B; cudaStream_t st = c.stream;
-    {   // feature MLPs                                                   core/networks.py:41-43
+// ---- side stream: tower-independent work runs next to the image tower; fork = "side may start after everything
+// enqueued on the caller's stream so far", join = "the caller's stream continues after the side work"
+#ifndef CDRA_EMU
+static cudaStream_t side_stream(const RunCtx& c) {
+    static const bool off = getenv("CDRA_NO_SIDE") != nullptr;
+    if (off || g_prof) return c.stream;
+    const Plan& p = *c.p;
+    if (!p.side_stream) {
+        cudaStream_t s; cudaEvent_t e0, e1;
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&e0, cudaEventDisableTiming); cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
+        p.side_stream = s; p.ev_fork = e0; p.ev_join = e1;
+    }
+    return (cudaStream_t)p.side_stream;
+}
+static void side_fork(const RunCtx& c, cudaStream_t sd) {
+    if (sd == c.stream) return;
+    cudaEventRecord((cudaEvent_t)c.p->ev_fork, c.stream);
+    cudaStreamWaitEvent(sd, (cudaEvent_t)c.p->ev_fork, 0);
+}
+static void side_join(const RunCtx& c, cudaStream_t sd) {
+    if (sd == c.stream) return;
+    cudaEventRecord((cudaEvent_t)c.p->ev_join, sd);
+    cudaStreamWaitEvent(c.stream, (cudaEvent_t)c.p->ev_join, 0);
+}
+static void side_destroy(Plan* p) {
+    if (p->side_stream) {
+        cudaStreamDestroy((cudaStream_t)p->side_stream);
+        cudaEventDestroy((cudaEvent_t)p->ev_fork); cudaEventDestroy((cudaEvent_t)p->ev_join);
+        p->side_stream = p->ev_fork = p->ev_join = nullptr;
+    }
+}
+#else
+static cudaStream_t side_stream(const RunCtx& c) { return c.stream; }
+static void side_fork(const RunCtx&, cudaStream_t) {}
+static void side_join(const RunCtx&, cudaStream_t) {}
+static void side_destroy(Plan*) {}
+#endif
+
+// which = 1: feature MLPs + their three GRUs (independent of the image tower);  2: image GRU + trunk;  3: both
+static void tail_forward(const RunCtx& c, const float* road, const float* vehicle, const float* nav, float* out512,
+                         cudaStream_t st, int which) {
+    const Plan& p = *c.p; const int B = p.B;
+    if (which & 1) {   // feature MLPs                                    core/networks.py:41-43
         FeatArgs3 aa; const float* x[3] = {road, vehicle, nav};
         feat_args(p, c.ws, c.params, c.state, nullptr, x, c.training, aa);
         CDRA_LAUNCH(featnet_fwd_kernel, dim3(3), dim3(kFeatThreads), 0, st, aa);
     }
-    int col = 0;
+    int col = 0, gi = 0;
     for (const GruSpec& g : p.grus) {                                    // core/networks.py:46-50
         const int u = g.units, u3 = 3 * u;
+        if (!(which & (gi++ == 0 ? 2 : 1))) { col += u; continue; }
         const float* K = c.params + g.k; const float* R = c.params + g.r; const float* b = c.params + g.b;
         gemm(st, false, false, F(c.ws, g.x_in), g.din, K, u3, F(c.ws, g.xp), u3, b, 4 * B, u3, g.din, false);
         for (int t = 0; t < kT; ++t) {
@@ -156,7 +198,7 @@ static void tail_forward(const RunCtx& c, const float* road, const float* vehicl
         }
         col += u;
     }
-    {   // linear_combination: BN(352) -> Dense 512                      core/networks.py:24-30,53-55
+    if (which & 2) {   // linear_combination: BN(352) -> Dense 512       core/networks.py:24-30,53-55
         Bn1dArgs a; memset(&a, 0, sizeof a);
         a.x = F(c.ws, p.dyn_in); a.ldx = 352; a.y = F(c.ws, p.trunk_n); a.ldy = 352;
         a.stat = (float2*)(c.ws + p.trunk_stat); a.gamma = c.params + p.trunk_g; a.beta = c.params + p.trunk_be;
@@ -366,6 +408,7 @@ static void tail_backward(const RunCtx& c, const float* road, const float* vehic
         a.dgamma = c.grads + p.trunk_g; a.dbeta = c.grads + p.trunk_be; a.B = B; a.C = 352;
         CDRA_LAUNCH(bn1d_bwd_kernel, dim3(cdiv(352, 32)), dim3(256), 0, st, a);
     }
+    cudaStream_t sd = side_stream(c);    // leaf parameter gradients + feature-MLP backward: nothing downstream reads them
     int col = 0;
     for (const GruSpec& g : p.grus) {
         const int u = g.units, u3 = 3 * u;
@@ -384,18 +427,20 @@ static void tail_backward(const RunCtx& c, const float* road, const float* vehic
             if (t > 0)      // dh_{t-1} += dhp_t R^T
                 gemm(st, false, true, a.dhp, u3, R, u3, a.dhprev, u, nullptr, B, u, u3, true);
         }
-        // parameter gradients
-        gemm(st, true, false, F(c.ws, g.hs), u, F(c.ws, g.dhp) + (size_t)B * u3, u3, c.grads + g.r, u3, nullptr, u, u3, 3 * B, false);
-        colsum(st, F(c.ws, g.dxp), u3, 4 * B, u3, c.grads + g.b, false);
-        colsum(st, F(c.ws, g.dhp), u3, 4 * B, u3, c.grads + g.b + u3, false);
-        gemm(st, true, false, F(c.ws, g.x_in), g.din, F(c.ws, g.dxp), u3, c.grads + g.k, u3, nullptr, g.din, u3, 4 * B, false);
+        // parameter gradients (side stream)
+        side_fork(c, sd);
+        gemm(sd, true, false, F(c.ws, g.hs), u, F(c.ws, g.dhp) + (size_t)B * u3, u3, c.grads + g.r, u3, nullptr, u, u3, 3 * B, false);
+        colsum(sd, F(c.ws, g.dxp), u3, 4 * B, u3, c.grads + g.b, false);
+        colsum(sd, F(c.ws, g.dhp), u3, 4 * B, u3, c.grads + g.b + u3, false);
+        gemm(sd, true, false, F(c.ws, g.x_in), g.din, F(c.ws, g.dxp), u3, c.grads + g.k, u3, nullptr, g.din, u3, 4 * B, false);
         gemm(st, false, true, F(c.ws, g.dxp), u3, K, u3, F(c.ws, g.dx_in), g.din, nullptr, 4 * B, g.din, u3, false);
         col += u;
     }
     {
+        side_fork(c, sd);
         FeatArgs3 aa; const float* x[3] = {road, vehicle, nav};
         feat_args(p, c.ws, c.params, nullptr, c.grads, x, 1, aa);
-        CDRA_LAUNCH(featnet_bwd_kernel, dim3(3), dim3(kFeatThreads), 0, st, aa);
+        CDRA_LAUNCH(featnet_bwd_kernel, dim3(3), dim3(kFeatThreads), 0, sd, aa);
     }
 }
 
@@ -480,7 +525,7 @@ int cdra_plan_create(const cdra_config* cfg, cdra_plan_t** out) {
     *out = new cdra_plan{p};
     return CDRA_OK;
 }
-void cdra_plan_destroy(cdra_plan_t* plan) { if (plan) { delete plan->p; delete plan; } }
+void cdra_plan_destroy(cdra_plan_t* plan) { if (plan) { side_destroy(plan->p); delete plan->p; delete plan; } }
 size_t cdra_plan_workspace_bytes(const cdra_plan_t* plan) { return plan ? plan->p->ws_bytes : 0; }
 
 static const Arena* arena_of(const cdra_plan_t* plan, int which) {
@@ -552,6 +597,9 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     if (training) zero_async(c.ws, p.zero_bytes, c.stream);
     else eval_affine(c);                 // BN affine from the moving statistics (CARLANetwork.dynamics_predict)
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
+    cudaStream_t sd = side_stream(c);
+    side_fork(c, sd);
+    tail_forward(c, road, vehicle, navigation, out512, sd, 1);       // feature MLPs + their GRUs, next to the image tower
 #ifndef CDRA_EMU
     if (p.v2.on) {               // bf16 perf mode: legacy stem + pool, then the v2 tower (padded planes, TMA tiles)
         v2::tower_prepare(c);
@@ -565,7 +613,8 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     else if (bf) tower_forward<bf16, float>(c, (const float*)image);
     else if (u8) tower_forward<float, uint8_t>(c, (const uint8_t*)image);
     else tower_forward<float, float>(c, (const float*)image);
-    tail_forward(c, road, vehicle, navigation, out512);
+    side_join(c, sd);
+    tail_forward(c, road, vehicle, navigation, out512, c.stream, 2);
     return check_launch("dynamics_forward");
 }
 
@@ -593,6 +642,7 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
     else if (bf) tower_backward<bf16, float>(c, (const float*)image);
     else if (u8) tower_backward<float, uint8_t>(c, (const uint8_t*)image);
     else tower_backward<float, float>(c, (const float*)image);
+    side_join(c, side_stream(c));
     return check_launch("dynamics_backward");
 }
 

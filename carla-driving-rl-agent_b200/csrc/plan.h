@@ -154,6 +154,12 @@ struct Plan {
     size_t head_buf;             // scratch for the policy/value head (see heads.cuh)
     size_t scratch;              // generic scratch
     std::map<std::string, std::pair<size_t, std::vector<int>>> named;   // extra fp32 buffers for taps
+    // side stream (+ fork / join events) for work that is independent of the image tower: the feature MLPs and their
+    // GRUs in the forward, the leaf parameter gradients of the GRUs and the feature-MLP backward in the backward.
+    // Created on first use (cudaStream_t / cudaEvent_t as void*), destroyed with the plan.
+    mutable void* side_stream = nullptr;
+    mutable void* ev_fork = nullptr;
+    mutable void* ev_join = nullptr;
 };
 
 Plan* build_plan(const cdra_config& cfg, std::string& err);

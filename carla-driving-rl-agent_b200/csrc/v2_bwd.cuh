@@ -591,7 +591,9 @@ inline __host__ __device__ PwWgTcSmem pw_wgrad_tc_smem(int R, int KP, int NPall,
 template <int R, int NT>
 __global__ void __launch_bounds__(NT, 1) pw_wgrad_tc_kernel(const PwBwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the swizzled tiles by OFFSET (an integer round trip of the pointer would drop the shared
+    // address space and turn every tile access into a generic load)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const PwDesc& d = *a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();

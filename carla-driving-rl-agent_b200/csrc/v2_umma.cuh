@@ -81,7 +81,7 @@ CDRA_DEV void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 struct UmmaTestArgs { const bf16* X; const bf16* Y; float* C; int rows, Mw, Nw; };
 __global__ void __launch_bounds__(256) umma_selftest_kernel(const UmmaTestArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t mma_done;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

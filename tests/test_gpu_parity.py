@@ -330,3 +330,20 @@ def test_pointwise_wgrad_tcgen05_vs_mma(built_libs):
         # the last unit sees identical inputs in both runs (same bf16 operands, fp32 accumulation in a different order);
         # further upstream the run-to-run order of the fp64 / bf16 atomics already moves the gradients by a few 1e-3
         assert e < (2e-3 if k.startswith('tower.s3.u3') else (0.15 if k.endswith('.w') else 0.5)), (k, e)
+
+
+def test_high_res_tower_bf16(built_libs, params):
+    """BASELINE config 4 geometry (180x240): stage-1 frames exceed shared memory, so the plan routes the bf16 tower through
+    the row-sweep kernels; perf mode must still track the fp32 parity mode of the same weights"""
+    B, h, w = 2, 180, 240
+    dyn, pol, val = C.trained_params(torch.float64)
+    obs, bt = _dev(C.synthetic_obs(B, h, w, seed=81)), _dev(C.synthetic_batch(B, seed=82))
+    outs = {}
+    for dt in ('f32', 'bf16'):
+        eng = _engine(B, dt, h, w)
+        C.load_engine(eng, dyn, pol, val)
+        sc = C.policy_step_engine(eng, obs, bt)
+        assert torch.isfinite(sc[:10]).all() and torch.isfinite(eng.g_dyn).all()
+        outs[dt] = (eng.x512.clone(), sc[0].item())
+    assert C.rel_l2(outs['bf16'][0], outs['f32'][0]) < 5e-2
+    assert abs(outs['bf16'][1] - outs['f32'][1]) < 0.05 * max(1.0, abs(outs['f32'][1]))
