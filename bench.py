@@ -146,8 +146,14 @@ def cpu_reference_rate(steps, warmup, batch, H, W, threads=None):
     return batch * steps / dt, dt / steps, torch.get_num_threads()
 
 
+def workload_text(H, W, bs, world, T):
+    return (f'PPO update (policy pass + value pass), obs {H}x{W}x3 x4-frame stack + road/vehicle/nav vectors, '
+            f'bs={bs}/GPU (global {bs * world}), T={T}, N=bs*T rollout resident in HBM')
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return
     rate, sec, cores = cpu_reference_rate(args.steps, max(1, min(args.warmup, 2)), args.cpu_batch, args.height, args.width)
@@ -156,10 +162,11 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'PPO update, {args.height}x{args.width}x3 x4-frame obs, bs={args.bs}/GPU, T={args.T}',
-                   'note': 'TF 2.3.1 is not installable here; the CPU arm is the oracle port of the reference path'},
+        'config': {'workload': workload_text(args.height, args.width, args.bs, world, args.T),
+                   'step': 'one SGD minibatch index through both passes; each timed step is a bounded sample of it (see cpu_baseline.sample)',
+                   'note': 'TF 2.3.1 is not installable here; the CPU arm is the oracle port of the reference path (host cores, rank 0 only)'},
         'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), file=_REAL_STDOUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU arm
@@ -355,8 +362,7 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
         'data': 'synthetic',
-        'config': {'workload': f'PPO update (policy pass + value pass), obs {H}x{W}x3 x4-frame stack + road/vehicle/nav vectors, '
-                               f'bs={bs}/GPU (global {bs * world}), T={T}, N=bs*T rollout resident in HBM',
+        'config': {'workload': workload_text(H, W, bs, world, T),
                    'step': 'one SGD minibatch index = bs samples/GPU through both passes; GAE once per T steps',
                    'l2': f'inputs ({roll["state_image"].numel() / 1e9:.1f} GB rollout) and activations exceed L2; no flush needed',
                    'parallelism': f'dp{world}', 'optimizer': 'Keras-style Adam x3, per-tensor clip 1.0 on heads'},
@@ -381,7 +387,7 @@ def run_b200(args):
         out['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                'sample': f'2 timed SGD steps of {args.cpu_batch} samples (both passes + clip + Adam), fp32 oracle on the host'}
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -430,8 +436,17 @@ def kernel_roofline(eng, sgd_step, first, peak, peak_src):
                               'GBps': round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None} for k, v in top[:14]}}
 
 
+def _quiet_stdout():
+    """stdout carries exactly ONE JSON line: library chatter written to fd 1 (e.g. NCCL's version banner) goes to stderr"""
+    real = os.fdopen(os.dup(1), 'w')
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == '__main__':
     a = parse()
+    _REAL_STDOUT = _quiet_stdout()
     if a.impl == 'reference':
         run_reference(a)
     else:
