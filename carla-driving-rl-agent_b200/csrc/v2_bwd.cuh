@@ -649,6 +649,7 @@ __global__ void __launch_bounds__(NT, 1) pw_wgrad_tc_kernel(const PwBwdArgs a) {
     const bool sclamp = d.src[xsrc].clamp != 0;
 
     int cur_t = -1;
+    float2 c8[8];
     int nissued[2] = {0, 0};                           // commits per staging set (thread 0 bookkeeping is CTA-uniform)
     for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it) {
         const int buf = it % a.nbuf, sb = it & 1;
@@ -664,6 +665,8 @@ __global__ void __launch_bounds__(NT, 1) pw_wgrad_tc_kernel(const PwBwdArgs a) {
             }
             cur_t = t;
             __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = s_aff[xq * 8 + q];     // this thread's chunk constants for the whole slice
         }
         mbar_wait(&full[buf], (it / a.nbuf) & 1);
         if (nissued[sb] > 0) { mbar_wait(&mma_done[sb], (nissued[sb] - 1) & 1); tc_fence_after(); }      // staging set free again
@@ -677,9 +680,6 @@ __global__ void __launch_bounds__(NT, 1) pw_wgrad_tc_kernel(const PwBwdArgs a) {
                 *reinterpret_cast<uint4*>(Rs + sw128_offset(r, rq * 8, R)) = r < rows ? dv[r * nqr + rq] : make_uint4(0, 0, 0, 0);
         }
         if (xrl < xnrl) {
-            float2 c8[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = s_aff[xq * 8 + q];
             const uint4* sv = reinterpret_cast<const uint4*>(rb + (size_t)R * (o_src + xoffb));
 #pragma unroll 2
             for (int r = xrl; r < R; r += xnrl) {

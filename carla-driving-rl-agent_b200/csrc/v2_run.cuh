@@ -354,7 +354,7 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
     for (int i = 0; i < hd.nsrc; ++i) bytes += 4.0 * a.Rt * (hd.src[i].map.n0 + hd.src[i].map.n1) * 2;
     bytes += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n) * 2 * 2;
     prof_bytes(bytes);
-    if (tc && (try_pw_wgrad_tc<64>(c, a, hd, 4) || try_pw_wgrad_tc<32>(c, a, hd, 4) || try_pw_wgrad_tc<16>(c, a, hd, 3) ||
+    if (tc && (try_pw_wgrad_tc<128>(c, a, hd, 3) || try_pw_wgrad_tc<64>(c, a, hd, 4) || try_pw_wgrad_tc<32>(c, a, hd, 4) || try_pw_wgrad_tc<16>(c, a, hd, 3) ||
                      try_pw_wgrad_tc<32>(c, a, hd, 2) || try_pw_wgrad_tc<16>(c, a, hd, 2))) return;
     if (hd.cols.gwp <= 64)
         ok = try_pw_wgrad<4>(c, a, hd, 2, 0) || try_pw_wgrad<4>(c, a, hd, 1, 0) || try_pw_wgrad<4>(c, a, hd, 1, 1);
