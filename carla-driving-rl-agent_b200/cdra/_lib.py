@@ -38,6 +38,7 @@ _SIGNATURES = {
     'cdra_plan_tensor': (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'cdra_debug_export': (C.c_int, [_P, C.c_char_p, _P, _P, C.POINTER(C.c_int32), _P]),
     'cdra_debug_gemm': (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    'cdra_debug_umma_selftest_k': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     'cdra_debug_umma_selftest': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     'cdra_debug_set': (C.c_int, [C.c_char_p, C.c_int]),
     'cdra_debug_stem_backward': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),

@@ -668,6 +668,20 @@ int cdra_debug_umma_selftest(const void* X, const void* Y, float* C, int rows, i
 #endif
 }
 
+int cdra_debug_umma_selftest_k(const void* A, const void* B, float* C, int Mw, int Nw, int Kw, void* stream) {
+    if (!A || !B || !C || (Mw != 128 && Mw != 256) || Nw < 16 || Nw % 16 || Nw > 256 || (Mw / 128) * Nw > 512 || Kw < 64 || Kw % 64 || Kw > 256)
+        return fail(CDRA_ERR_BADARG, "bad umma selftest shape");
+#ifndef CDRA_EMU
+    v2::UmmaTestKArgs a{(const bf16*)A, (const bf16*)B, C, Mw, Nw, Kw};
+    const int smem = (Mw + Nw) * (Kw / 64) * 128 + 1024;
+    cudaFuncSetAttribute(v2::umma_selftest_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    CDRA_LAUNCH(v2::umma_selftest_k_kernel, dim3(1), dim3(256), smem, (cudaStream_t)stream, a);
+    return check_launch("debug_umma_selftest_k");
+#else
+    return fail(CDRA_ERR_BADARG, "no tensor cores in the CPU logic-check build");
+#endif
+}
+
 int cdra_debug_set(const char* key, int value) {
     if (!key) return fail(CDRA_ERR_BADARG, "null key");
 #ifndef CDRA_EMU

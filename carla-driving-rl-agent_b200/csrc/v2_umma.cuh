@@ -138,6 +138,60 @@ __global__ void __launch_bounds__(256) umma_selftest_kernel(const UmmaTestArgs a
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// C[Mw][Nw] (fp32) = A B^T for row-major bf16 A [Mw][Kw], B [Nw][Kw]: both operands K-major (the forward / data-gradient
+// shape): per 64-column K block a [rows][128 B] swizzled tile; 16-element K steps advance the descriptor start by 32 bytes.
+struct UmmaTestKArgs { const bf16* A; const bf16* B; float* C; int Mw, Nw, Kw; };
+__global__ void __launch_bounds__(256) umma_selftest_k_kernel(const UmmaTestKArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t mma_done;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = a.Kw >> 6, nmb = a.Mw >> 7;
+    unsigned char* As = smem;                                          // [nmb][nkb] blocks of [128][128 B]
+    unsigned char* Bs = smem + (size_t)nmb * nkb * 128 * 128;           // [nkb] blocks of [Nw][128 B]
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    if (tid == 0) { mbar_init(&mma_done, 1); mbar_fence_init(); }
+    for (int i = tid; i < a.Mw * (a.Kw >> 3); i += 256) {
+        const int r = i / (a.Kw >> 3), c = i - r * (a.Kw >> 3), mb = r >> 7, kb = c >> 3;
+        *reinterpret_cast<uint4*>(As + (size_t)(mb * nkb + kb) * 128 * 128 + sw128_offset(r & 127, (c & 7) * 8, 128)) =
+            *reinterpret_cast<const uint4*>(a.A + (size_t)r * a.Kw + c * 8);
+    }
+    for (int i = tid; i < a.Nw * (a.Kw >> 3); i += 256) {
+        const int r = i / (a.Kw >> 3), c = i - r * (a.Kw >> 3), kb = c >> 3;
+        *reinterpret_cast<uint4*>(Bs + (size_t)kb * a.Nw * 128 + sw128_offset(r, (c & 7) * 8, a.Nw)) =
+            *reinterpret_cast<const uint4*>(a.B + (size_t)r * a.Kw + c * 8);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc(128, a.Nw, 0, 0);
+        for (int mb = 0; mb < nmb; ++mb)
+            for (int kb = 0; kb < nkb; ++kb)
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(tmem + mb * a.Nw, umma_desc(smem_u32(As) + (mb * nkb + kb) * 128 * 128 + ks * 32, 16, 1024),
+                              umma_desc(smem_u32(Bs) + kb * a.Nw * 128 + ks * 32, 16, 1024), idesc, kb > 0 || ks > 0);
+        umma_commit(&mma_done);
+    }
+    mbar_wait(&mma_done, 0);
+    tc_fence_after();
+    if (warp < 4)
+        for (int mb = 0; mb < nmb; ++mb)
+            for (int c0 = 0; c0 < a.Nw; c0 += 8) {
+                float v[8];
+                tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + mb * a.Nw + c0, v);
+                float* dst = a.C + (size_t)(mb * 128 + 32 * warp + lane) * a.Nw + c0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = v[i];
+            }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace v2
 }  // namespace cdra
 #endif

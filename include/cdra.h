@@ -112,6 +112,9 @@ int cdra_debug_gemm(int ta, int tb, const float* A, int lda, const float* B, int
  * and accumulated over 64-row tiles in tensor memory.  Mw in {128, 256}, Nw % 16 == 0, Nw <= 256, (Mw / 128) * Nw <= 512,
  * rows % 64 == 0.  Test infrastructure. */
 int cdra_debug_umma_selftest(const void* X, const void* Y, float* C, int rows, int Mw, int Nw, void* stream);
+/* Same for K-major operands (the forward / data-gradient product): C[Mw][Nw] = A B^T, A [Mw][Kw], B [Nw][Kw] row-major
+ * bf16; Mw in {128, 256}, Nw % 16 == 0, Nw <= 256, (Mw / 128) * Nw <= 512, Kw % 64 == 0, Kw <= 256. */
+int cdra_debug_umma_selftest_k(const void* A, const void* B, float* C, int Mw, int Nw, int Kw, void* stream);
 
 /* Kernel-selection switches for A/B parity runs inside one process: key "tc" = 1 | 0 routes the tower's pointwise weight
  * gradient through the tcgen05 / TMEM kernel or the mma.sync kernel (default: tcgen05 unless CDRA_NO_TC is set).

@@ -347,3 +347,19 @@ def test_high_res_tower_bf16(built_libs, params):
         outs[dt] = (eng.x512.clone(), sc[0].item())
     assert C.rel_l2(outs['bf16'][0], outs['f32'][0]) < 5e-2
     assert abs(outs['bf16'][1] - outs['f32'][1]) < 0.05 * max(1.0, abs(outs['f32'][1]))
+
+
+@pytest.mark.parametrize('shape', [(128, 64, 64), (128, 128, 128), (256, 240, 128), (128, 256, 192)])
+def test_tcgen05_selftest_k_major(built_libs, shape):
+    """tcgen05.mma with K-major 128B-swizzled operands (the forward / data-gradient product A B^T)"""
+    from cdra import _lib
+    lib = _lib.load()
+    Mw, Nw, Kw = shape
+    g = torch.Generator(device='cuda').manual_seed(Mw + Nw + Kw)
+    A = torch.randn(Mw, Kw, generator=g, device='cuda').bfloat16()
+    Bm = torch.randn(Nw, Kw, generator=g, device='cuda').bfloat16()
+    Cm = torch.full((Mw, Nw), float('nan'), device='cuda')
+    assert lib.cdra_debug_umma_selftest_k(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(Cm), Mw, Nw, Kw, None) == 0
+    torch.cuda.synchronize()
+    ref = A.double() @ Bm.double().t()
+    assert ((Cm.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
