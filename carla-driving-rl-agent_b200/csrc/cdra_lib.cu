@@ -686,6 +686,7 @@ int cdra_debug_set(const char* key, int value) {
     if (!key) return fail(CDRA_ERR_BADARG, "null key");
 #ifndef CDRA_EMU
     if (std::string(key) == "tc") { v2::tc_override() = value; return CDRA_OK; }
+    if (std::string(key) == "fwd_tc") { v2::fwd_tc_override() = value; return CDRA_OK; }
 #endif
     return fail(CDRA_ERR_BADARG, "unknown debug key");
 }

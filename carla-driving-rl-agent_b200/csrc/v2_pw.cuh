@@ -114,6 +114,7 @@ struct PwFwdArgs {
     int colmode;                // 0: every CTA covers all GEMM columns; 1: blockIdx.y = (plane, N tile)
     int ntiles_n;               // colmode 1: N tiles per plane
     int tiles_per_cta;
+    int nbuf;                   // tcgen05 kernel: depth of the TMA ring
 };
 
 template <int R, int WM, int WN, int MT, int NBW>

@@ -8,6 +8,7 @@
 #include "v2_bwd.cuh"
 #include "v2_stem.cuh"
 #include "v2_umma.cuh"
+#include "v2_pw_tc.cuh"
 
 namespace cdra {
 namespace v2 {
@@ -106,6 +107,10 @@ inline void upload_descs(const RunCtx& c) {
 }
 
 constexpr int kMaxDynSmem = 226 * 1024;      // 227 KB opt-in limit minus the kernels' few static bytes
+inline int& tc_override() { static int v = -1; return v; }      // cdra_debug_set("tc", 0 | 1): A/B parity runs in one process
+inline bool use_tc() { static const bool env = getenv("CDRA_NO_TC") == nullptr; return tc_override() < 0 ? env : tc_override() != 0; }
+inline int& fwd_tc_override() { static int v = -1; return v; }  // cdra_debug_set("fwd_tc", 0 | 1)
+inline bool use_fwd_tc() { static const bool env = getenv("CDRA_NO_FWD_TC") == nullptr; return fwd_tc_override() < 0 ? env : fwd_tc_override() != 0; }
 inline int num_sms() {
     static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
     return n;
@@ -140,6 +145,29 @@ inline bool try_pw_fwd(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd, int colm
     return true;
 }
 
+// plain-output layers (pw1 of every unit) on tcgen05: one CTA per SM, TMEM accumulator, weights resident in the swizzled layout
+inline bool try_pw_fwd_tc(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
+    constexpr int NT = 512;
+    if (hd.cols.nplanes != 1 || a.x1 || hd.cols.interleave || a.gwv != a.cpo) return false;
+    int sum = 0;
+    for (int i = 0; i < hd.nsrc; ++i) sum += hd.src[i].cp;
+    const PwFwdTcSmem L0 = pw_fwd_tc_smem(hd.KP, hd.NPall, a.cpo, sum, 0, NT);
+    if (L0.np > 256 || L0.nkb > 4 || (NT / (a.cpo >> 3)) < 1 || (NT / (sum >> 3)) < 1) return false;
+    const int nbuf = std::min(8, (kMaxDynSmem - L0.total) / L0.raw_stride);
+    if (nbuf < 2) return false;
+    const PwFwdTcSmem L = pw_fwd_tc_smem(hd.KP, hd.NPall, a.cpo, sum, nbuf, NT);
+    auto k = pw_fwd_tc_kernel<NT>;
+    static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nbuf; a.colmode = 0; a.ntiles_n = 1;
+    const int tps = (a.Rt + 127) / 128, ntile = kT * tps;
+    int gx = std::min(ntile, num_sms());
+    a.tiles_per_cta = (ntile + gx - 1) / gx;
+    gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    CDRA_LAUNCH_PDL(k, dim3(gx), dim3(NT), L.total, c.stream, a);
+    return true;
+}
+
 inline void launch_pw_fwd(const RunCtx& c, int di, const PwDesc& hd, PwFwdArgs& a, bool allow_full_cols) {
     a.d = desc_dev(c, di);
     a.training = c.training;
@@ -149,6 +177,7 @@ inline void launch_pw_fwd(const RunCtx& c, int di, const PwDesc& hd, PwFwdArgs& 
     if (a.x1) bytes += 4.0 * a.Rt * 2 * a.ncopy * 2;
     prof_bytes(bytes);
     bool ok = false;
+    if (allow_full_cols && use_tc() && use_fwd_tc() && try_pw_fwd_tc(c, a, hd)) return;
     if (allow_full_cols) {
         if (hd.NPall <= 64) ok = try_pw_fwd<128, 8, 1, 1, 8>(c, a, hd, 0, 2) || try_pw_fwd<64, 4, 2, 1, 4>(c, a, hd, 0, 1);
         else if (hd.NPall <= 128) ok = try_pw_fwd<64, 4, 2, 1, 8>(c, a, hd, 0, 2) || try_pw_fwd<32, 2, 4, 1, 4>(c, a, hd, 0, 1);
@@ -301,8 +330,6 @@ inline bool try_pw_wgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int nb
 }
 
 // weight gradient on tcgen05 with the accumulator resident in TMEM (every layer whose [KP x NPall] tile fits 512 columns)
-inline int& tc_override() { static int v = -1; return v; }      // cdra_debug_set("tc", 0 | 1): A/B parity runs in one process
-inline bool use_tc() { static const bool env = getenv("CDRA_NO_TC") == nullptr; return tc_override() < 0 ? env : tc_override() != 0; }
 template <int R, int NT = 512>
 inline bool try_pw_wgrad_tc(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int min_ring) {
     int sum = 0;

@@ -117,7 +117,8 @@ int cdra_debug_umma_selftest(const void* X, const void* Y, float* C, int rows, i
 int cdra_debug_umma_selftest_k(const void* A, const void* B, float* C, int Mw, int Nw, int Kw, void* stream);
 
 /* Kernel-selection switches for A/B parity runs inside one process: key "tc" = 1 | 0 routes the tower's pointwise weight
- * gradient through the tcgen05 / TMEM kernel or the mma.sync kernel (default: tcgen05 unless CDRA_NO_TC is set).
+ * gradient through the tcgen05 / TMEM kernel or the mma.sync kernel (default: tcgen05 unless CDRA_NO_TC is set); key
+ * "fwd_tc" does the same for the forward of the plain-output pointwise layers (pw1 of every unit).
  * Returns CDRA_ERR_BADARG for an unknown key.  Test infrastructure. */
 int cdra_debug_set(const char* key, int value);
 

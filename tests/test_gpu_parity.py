@@ -363,3 +363,30 @@ def test_tcgen05_selftest_k_major(built_libs, shape):
     torch.cuda.synchronize()
     ref = A.double() @ Bm.double().t()
     assert ((Cm.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_pointwise_forward_tcgen05_vs_mma(built_libs):
+    """the tcgen05 forward kernel of the plain-output pointwise layers (K-major swizzled operands, TMEM accumulator)
+    against the mma.sync kernel on identical inputs"""
+    from cdra import _lib
+    lib = _lib.load()
+    B = 8
+    dyn, pol, val = C.trained_params(torch.float64)
+    eng = _engine(B, 'bf16')
+    C.load_engine(eng, dyn, pol, val)
+    obs = _dev(C.synthetic_obs(B, H, W, seed=91))
+    names = ('tower.s1.u0.pw1', 'tower.s1.u2.pw1', 'tower.s2.u3.pw1', 'tower.s3.u1.pw1', 'tower.head')
+    res = {}
+    try:
+        for v in (0, 1):
+            assert lib.cdra_debug_set(b'fwd_tc', v) == 0
+            out = eng.dynamics_forward(obs).clone()
+            torch.cuda.synchronize()
+            res[v] = ({n: eng.tensor(n).float().clone() for n in names}, out)
+    finally:
+        lib.cdra_debug_set(b'fwd_tc', -1)
+    # first layer: same bf16 operands, only the fp32 accumulation order differs (a few results round the other way)
+    assert C.rel_l2(res[1][0]['tower.s1.u0.pw1'], res[0][0]['tower.s1.u0.pw1']) < 5e-4
+    for n in names[1:]:
+        assert C.rel_l2(res[1][0][n], res[0][0][n]) < 3e-2, n        # bf16 rounding differences carried through the layers
+    assert C.rel_l2(res[1][1], res[0][1]) < 1e-2
