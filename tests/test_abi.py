@@ -38,6 +38,23 @@ def test_cuda_library_exports_every_symbol(built_libs):
     assert l2.cdra_arena_size(plan, _lib.ARENA_POL_PARAMS) == 270470
     assert l2.cdra_arena_size(plan, _lib.ARENA_VAL_PARAMS) == 269828
     assert l2.cdra_plan_workspace_bytes(plan) > 0
+    # every BASELINE geometry plans on the host: config 2 (90x120), config 4 (180x240: stage-1 frames exceed shared memory,
+    # the plan falls back to the row-sweep bf16 tower and needs no winner-position / dR hand-off buffers), odd sizes
+    sizes = {}
+    for (h, w) in ((90, 120), (180, 240), (91, 123)):
+        pl = ctypes.c_void_p()
+        assert l2.cdra_plan_create(ctypes.byref(_lib.Config(2, h, w, _lib.BF16, 1)), ctypes.byref(pl)) == 0
+        sizes[(h, w)] = l2.cdra_plan_workspace_bytes(pl)
+        off, dims, es = ctypes.c_int64(), (ctypes.c_int32 * 4)(), ctypes.c_int32()
+        assert l2.cdra_plan_tensor(pl, b'tower.stem', ctypes.byref(off), dims, ctypes.byref(es)) == 0
+        assert list(dims) == [8, (h - 3) // 2 + 1, (w - 3) // 2 + 1, 24] and es.value == 2
+        l2.cdra_plan_destroy(pl)
+    assert sizes[(180, 240)] > 2 * sizes[(90, 120)]
+    # debug switches: known keys only
+    assert l2.cdra_debug_set(b'tc', -1) == 0 and l2.cdra_debug_set(b'fwd_tc', -1) == 0 and l2.cdra_debug_set(b'nope', 1) == -1
+    # shape validation of the self tests happens before any device work
+    assert l2.cdra_debug_umma_selftest(None, None, None, 64, 128, 64, None) == -1
+    assert l2.cdra_debug_umma_selftest_k(ctypes.c_void_p(8), ctypes.c_void_p(8), ctypes.c_void_p(8), 100, 64, 64, None) == -1
     bad = _lib.Config(0, 90, 120, 0, 1)
     assert l2.cdra_plan_create(ctypes.byref(bad), ctypes.byref(ctypes.c_void_p())) == -2
     assert b'batch' in l2.cdra_last_error()
