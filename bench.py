@@ -383,9 +383,9 @@ def run_b200(args):
         if rank == 0:
             out['roofline'] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_rate(2, 1, args.cpu_batch, H, W)
+        rate, sec, cores = cpu_reference_rate(12, 2, args.cpu_batch, H, W)       # ~10 s of host work
         out['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                               'sample': f'2 timed SGD steps of {args.cpu_batch} samples (both passes + clip + Adam), fp32 oracle on the host'}
+                               'sample': f'12 timed SGD steps of {args.cpu_batch} samples (both passes + clip + Adam), fp32 oracle on the host'}
     if rank == 0:
         print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
