@@ -1,15 +1,14 @@
 """ctypes binding of libcdra (include/cdra.h).  PyTorch is used only for device memory / streams.
 
 The product path loads `cdra/libcdra.so` (nvcc, sm_100a) and fails loudly when it is missing — there
-is no CPU fallback.  The CPU logic-check build (`tests/emu/libcdra_emu.so`) can only be selected
-explicitly by the CPU test-suite through `load(emulated=True)`; it is never used by bench / smoke.
+is no CPU fallback and no switch that selects one.  (The CPU test-suite compiles the same sources against a SIMT
+emulator and binds that library itself, under `tests/emu/`, through `bind()`.)
 """
 import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcdra.so')
-EMU_PATH = os.path.join(os.path.dirname(os.path.dirname(HERE)), 'tests', 'emu', 'libcdra_emu.so')
 
 F32, BF16 = 0, 1
 ARENA_DYN_PARAMS, ARENA_DYN_STATE, ARENA_POL_PARAMS, ARENA_POL_STATE, ARENA_VAL_PARAMS, ARENA_VAL_STATE = range(6)
@@ -60,22 +59,25 @@ _SIGNATURES = {
 _loaded = {}
 
 
-def load(emulated=False):
-    """Load the shared library and declare every symbol of include/cdra.h."""
-    key = bool(emulated)
-    if key in _loaded:
-        return _loaded[key]
-    path = EMU_PATH if emulated else LIB_PATH
+def bind(path):
+    """dlopen `path` and declare every symbol of include/cdra.h on it (AttributeError if one is not exported)."""
+    if path in _loaded:
+        return _loaded[path]
     if not os.path.exists(path):
         raise CdraError(f'{path} is missing: build it with `python carla-driving-rl-agent_b200/build.py` '
                         '(there is no fallback path)')
     lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
-        fn = getattr(lib, name)           # AttributeError if the symbol is not exported
+        fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _loaded[key] = lib
+    _loaded[path] = lib
     return lib
+
+
+def load():
+    """The sm_100a library of the product path."""
+    return bind(LIB_PATH)
 
 
 def exported_symbols():

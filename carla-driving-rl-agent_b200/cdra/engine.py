@@ -51,16 +51,13 @@ class Arena:
 
 
 class Engine:
-    def __init__(self, batch, height=90, width=120, dtype='bf16', image_u8=True, device='cuda', emulated=False,
-                 share=None):
+    def __init__(self, batch, height=90, width=120, dtype='bf16', image_u8=True, device='cuda', share=None):
         """`share`: another Engine whose parameter / state / gradient / Adam arenas this one reuses (a plan is
         specific to one batch size; siblings let one network serve several, e.g. a remainder minibatch or B=1
         rollout inference)."""
-        self.lib = _lib.load(emulated=emulated)
+        self.lib = self._open_library()
         self.device = torch.device(device)
-        if not emulated and self.device.type != 'cuda':
-            raise _lib.CdraError('libcdra runs on CUDA devices only (no CPU fallback)')
-        self.emulated = emulated
+        self._check_device()
         self.B, self.H, self.W = batch, height, width
         self.dtype = dtype
         self.image_u8 = bool(image_u8)
@@ -88,9 +85,16 @@ class Engine:
         self.x512, self.d_x512 = f(batch, 512), f(batch, 512)
         self.scalars, self.head_out = f(16), f(batch, 8)
 
+    # the two places that tie an Engine to the GPU build of the library (the CPU test-suite subclasses them away)
+    def _open_library(self):
+        return _lib.load()
+
+    def _check_device(self):
+        if self.device.type != 'cuda':
+            raise _lib.CdraError('libcdra runs on CUDA devices only (no CPU fallback)')
+
     def sibling(self, batch):
-        return Engine(batch, self.H, self.W, dtype=self.dtype, image_u8=self.image_u8, device=self.device,
-                      emulated=self.emulated, share=self)
+        return type(self)(batch, self.H, self.W, dtype=self.dtype, image_u8=self.image_u8, device=self.device, share=self)
 
     def __del__(self):
         try:
@@ -102,14 +106,12 @@ class Engine:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
-        if self.emulated:
-            return None
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def tensor(self, name):
         """View of a named intermediate tensor inside the workspace (parity taps)."""
         off, dims, es = C.c_int64(), (C.c_int32 * 4)(), C.c_int32()
-        if self.dtype == 'bf16' and not self.emulated:
+        if self.dtype == 'bf16':
             # perf mode stores padded, shuffled channel planes: ask the library for the logical layout (fp32 copy)
             if self.lib.cdra_debug_export(self.plan, name.encode(), None, None, dims, None) == 0:
                 out = torch.empty([d for d in dims], dtype=torch.float32, device=self.device)

@@ -12,6 +12,7 @@ from typing import Dict, List
 import numpy as np
 import torch
 
+from cdra import checkpoint
 from cdra.engine import Engine
 from cdra.init import init_arena
 from core import architectures as nn
@@ -59,8 +60,8 @@ class ArenaModel:
     """What the reference gets from a `tf.keras.Model`: variables, get/set_weights, save/load, summary —
     backed by a (trainable arena, state arena) pair of the engine."""
 
-    def __init__(self, name, arena, state, order=None):
-        self.name, self.arena, self.state = name, arena, state
+    def __init__(self, name, arena, state, order=None, kind='dynamics'):
+        self.name, self.arena, self.state, self.kind = name, arena, state, kind
         self._order = order          # Keras `get_weights()` order = layers in creation order, each [trainable..., moving...]
 
     @property
@@ -97,19 +98,16 @@ class ArenaModel:
     def count_params(self):
         return self.arena.size + self.state.size
 
+    def _named_views(self):
+        return [(n, self._view(n)) for n in self.variable_names()]
+
     def save_weights(self, filepath):
-        os.makedirs(os.path.dirname(filepath) or '.', exist_ok=True)
-        np.savez(filepath + '.npz', **{n: self._view(n).detach().cpu().numpy() for n in self.variable_names()})
+        checkpoint.save_model(filepath, self._named_views())
 
     def load_weights(self, filepath, by_name=False):
-        if os.path.exists(filepath + '.npz'):
-            z = np.load(filepath + '.npz')
-            for n in self.variable_names():
-                self._view(n).copy_(torch.from_numpy(z[n]))
-        elif os.path.exists(filepath + '.index'):
-            raise NotImplementedError('TensorFlow-bundle checkpoints are imported with tools/import_tf_checkpoint.py (SURVEY 8f-3)')
-        else:
-            raise FileNotFoundError(filepath)
+        """`<filepath>.npz` (written by save_weights) or the reference's TensorFlow checkpoint `<filepath>.index`
+        (weights/stage-*/, core/networks.py:302-310)."""
+        checkpoint.load_model(filepath, self.kind, self._named_views())
 
     def summary(self):
         print(f'Model: "{self.name}"')
@@ -122,7 +120,7 @@ class OldPolicy(ArenaModel):
     """`old_policy`: a detached copy of the policy arena (core/networks.py:175-176); only read during rollouts."""
 
     def __init__(self, policy: ArenaModel):
-        self.name = 'PolicyNetwork-old'
+        self.name, self.kind = 'PolicyNetwork-old', 'policy'
         self._flat = policy.arena.flat.clone()
         self._state_flat = policy.state.flat.clone()
         self.arena, self.state = policy.arena, policy.state
@@ -141,9 +139,10 @@ class OldPolicy(ArenaModel):
 
 class CARLANetwork(Network):
     """The CARLAgent network (core/networks.py:147-310)."""
+    ENGINE = Engine
 
     def __init__(self, agent, control_policy: dict, control_value: dict, dynamics: dict, update_dynamics=False,
-                 device=None, dtype=None, emulated=False, world_size=1):
+                 device=None, dtype=None):
         super().__init__(agent)
         self.inputs = self._get_input_layers()
         self.inputs['action'] = (agent.num_actions,)
@@ -166,11 +165,11 @@ class CARLANetwork(Network):
         assert C == 3
 
         if device is None:
-            device = 'cpu' if emulated else f'cuda:{torch.cuda.current_device()}'
+            device = f'cuda:{torch.cuda.current_device()}'
         self.device = torch.device(device)
-        self.dtype = dtype or ('f32' if emulated else 'bf16')
+        self.dtype = dtype or 'bf16'
         self.image_u8 = bool(getattr(agent.env, 'image_uint8', False))
-        self.engine = Engine(agent.batch_size, H, W, dtype=self.dtype, image_u8=self.image_u8, device=self.device, emulated=emulated)
+        self.engine = self.ENGINE(agent.batch_size, H, W, dtype=self.dtype, image_u8=self.image_u8, device=self.device)
         self._siblings: Dict[int, Engine] = {agent.batch_size: self.engine}
         from cdra.parallel import GradSync
         self.sync = GradSync(self.engine)            # one rank per GPU under torchrun; a no-op on a single process
@@ -182,9 +181,9 @@ class CARLANetwork(Network):
 
         self.dynamics = ArenaModel('Dynamics-Model', self.engine.dyn, self.engine.dyn_state)
         self.action_index = 0
-        self.value = ArenaModel('Value-Network', self.engine.val, self.engine.val_state)
+        self.value = ArenaModel('Value-Network', self.engine.val, self.engine.val_state, kind='value')
         self.last_value = torch.zeros((1, 2), dtype=torch.float32)                                  # (base, exp), :171
-        self.policy = ArenaModel('PolicyNetwork', self.engine.pol, self.engine.pol_state)
+        self.policy = ArenaModel('PolicyNetwork', self.engine.pol, self.engine.pol_state, kind='policy')
         self.old_policy = OldPolicy(self.policy)
         self.update_old_policy()
 

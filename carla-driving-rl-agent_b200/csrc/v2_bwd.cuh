@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
         }
     }
     float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-    float2 xc0 = make_float2(0.f, 0.f), xc1 = xc0;              // xhat = a * x + y  for this thread's two input channels
+    float4 xc0 = make_float4(1.f, 0.f, 0.f, 0.f), xc1 = xc0;    // (scale, shift, inv_std, -mean * inv_std) of this thread's two input channels
     float2 ac8[8];
     const bool iclamp = a.clamp != 0, xform = a.aff != nullptr || iclamp, want_sums = a.in_bsum != nullptr;
     const double inv_n = 1.0 / ((double)a.B * out_px);
@@ -822,13 +822,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
         }
         __syncthreads();
     };
-    auto xhat_consts = [&](int t, int slot) {
-        if (!a.aff) return make_float2(0.f, 0.f);
-        const float2 af = a.aff[(size_t)t * CP + slot], bp = a.bnp[(size_t)t * CP + slot];
-        if (af.x == 0.f) return make_float2(0.f, 0.f);
-        const float r = bp.y / af.x;                              // inv_std / scale = 1 / gamma
-        return make_float2(r, -af.y * r - bp.x * bp.y);
-    };
+    auto xhat_consts = [&](int t, int slot) { return sum_consts(a.aff, a.bnp, (size_t)t * CP + slot); };
     const int row_step = S * PW * CP;
     int cur_t = -1;
     for (int f = f_lo, it = 0; f < f_hi; ++f, ++it) {
@@ -913,20 +907,20 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
             // data gradient: d in(iy, ix) = sum_{ky,kx} w[ky][kx] * dR((iy + pt - ky)/S, (ix + pl - kx)/S)
             for (int ix = xl; ix < a.Wi; ix += NXL) {
                 bf16* gp = a.din + ((size_t)f * in_px + ix) * CP + 2 * pr;
-                const bf16* ap = Pin + (PW + ix + 1) * CP + 2 * pr;
+                // the sums use the RAW input value (same mask / xhat as every consumer of them, bnbwd_apply): the tile in shared
+                // memory only holds the bf16-rounded activation, so the raw pair is re-read through L2 (TMA just fetched the frame)
+                const bf16* rp = a.in + ((size_t)f * in_px + ix) * CP + 2 * pr;
                 auto finish = [&](float acc0, float acc1) {       // (+ existing share), store, BatchNorm-backward sums of the input
                     if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
                     const uint32_t pk = pack2(acc0, acc1);
                     *reinterpret_cast<uint32_t*>(gp) = pk;
                     if (want_sums) {
                         const float2 gr = unpack2(pk);
-                        const float2 av = unpack2(*reinterpret_cast<const uint32_t*>(ap));
-                        const float d0 = (!iclamp || (av.x > 0.f && av.x < 6.f)) ? gr.x : 0.f;
-                        const float d1 = (!iclamp || (av.y > 0.f && av.y < 6.f)) ? gr.y : 0.f;
-                        s1a += d0; s2a = fmaf(d0, fmaf(av.x, xc0.x, xc0.y), s2a);
-                        s1b += d1; s2b = fmaf(d1, fmaf(av.y, xc1.x, xc1.y), s2b);
+                        const float2 rv = unpack2(__ldg(reinterpret_cast<const unsigned int*>(rp)));
+                        sum_accum(gr.x, rv.x, xc0, iclamp, s1a, s2a);
+                        sum_accum(gr.y, rv.y, xc1, iclamp, s1b, s2b);
                     }
-                    gp += a.Wi * CP; ap += PW * CP;
+                    gp += a.Wi * CP; rp += a.Wi * CP;
                 };
                 if (S == 1) {
                     // d in(iy, ix) = sum w[ky][kx] * dR tile(iy + 2 - ky, ix + 2 - kx): tile rows iy, iy+1, iy+2 <-> ky = 2, 1, 0

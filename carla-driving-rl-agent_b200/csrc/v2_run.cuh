@@ -558,11 +558,39 @@ __global__ void __launch_bounds__(256) export_kernel(const ExportArgs e) {
     if (e.b && ch >= half) { src = e.b; ch -= half; }
     e.out[i] = __bfloat162float(src[r * e.cp + logical_slot(e.map, ch)]);
 }
+// BatchNorm tables of a tower tensor in the logical channel order: out [4][C][2] fp32.  which 0: aff (scale, shift),
+// 1: bnp (mean, inv_std), 2: bsum (sum dz, sum dz * xhat; fp64 in the workspace)
+struct ExportTabArgs { const void* a; const void* b; int cp; SlotMap map; int C, half, which; float* out; };
+__global__ void __launch_bounds__(256) export_tab_kernel(const ExportTabArgs e) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= kT * e.C) return;
+    const int t = i / e.C; int ch = i - t * e.C;
+    const void* src = e.a;
+    if (e.b && ch >= e.half) { src = e.b; ch -= e.half; }
+    const size_t idx = (size_t)t * e.cp + logical_slot(e.map, ch);
+    float2 v;
+    if (e.which == 2) { const double2 d = reinterpret_cast<const double2*>(src)[idx]; v = make_float2((float)d.x, (float)d.y); }
+    else v = reinterpret_cast<const float2*>(src)[idx];
+    e.out[2 * i] = v.x; e.out[2 * i + 1] = v.y;
+}
+
 inline bool export_tensor(const Plan& p, const char* name_c, char* ws, float* out, int32_t dims[4], cudaStream_t st) {
     const V2Plan& v = p.v2;
     std::string n(name_c);
     bool grad = false;
+    int tab = -1;
     if (n.rfind("grad:", 0) == 0) { grad = true; n = n.substr(5); }
+    else if (n.rfind("aff:", 0) == 0) { tab = 0; n = n.substr(4); }
+    else if (n.rfind("bnp:", 0) == 0) { tab = 1; n = n.substr(4); }
+    else if (n.rfind("bsum:", 0) == 0) { tab = 2; n = n.substr(5); }
+    if (tab >= 0 && tab < 2 && (n == "tower.stem")) {          // the stem keeps the legacy (unpadded) table layout
+        const WsTensor& t = p.tensors[p.t_stem];
+        ExportTabArgs e; e.a = ws + (tab == 0 ? t.aff : t.bnp); e.b = nullptr; e.cp = t.C; e.map = SlotMap{t.C, t.C, 0};
+        e.C = t.C; e.half = t.C; e.which = tab; e.out = out;
+        if (dims) { dims[0] = kT; dims[1] = t.C; dims[2] = 2; dims[3] = 1; }
+        if (out) { CDRA_LAUNCH(export_tab_kernel, dim3(cdiv(kT * e.C, 256)), dim3(256), 0, st, e); }
+        return true;
+    }
     int ia = -1, ib = -1;
     auto it = v.index.find(n);
     if (it != v.index.end()) ia = it->second;
@@ -575,6 +603,15 @@ inline bool export_tensor(const Plan& p, const char* name_c, char* ws, float* ou
     }
     if (ia < 0) return false;
     const V2Tensor& ta = v.t[ia];
+    if (tab >= 0) {
+        if (!ta.has_bn) return false;
+        auto sel = [&](const V2Tensor& t) { return (const void*)(ws + (tab == 0 ? t.aff : tab == 1 ? t.bnp : t.bsum)); };
+        ExportTabArgs e; e.a = sel(ta); e.b = ib >= 0 ? sel(v.t[ib]) : nullptr; e.cp = ta.cp; e.map = SlotMap{ta.n0, ta.n0p, ta.n1};
+        e.half = ta.C(); e.C = ta.C() * (ib >= 0 ? 2 : 1); e.which = tab; e.out = out;
+        if (dims) { dims[0] = kT; dims[1] = e.C; dims[2] = 2; dims[3] = 1; }
+        if (out) { CDRA_LAUNCH(export_tab_kernel, dim3(cdiv(kT * e.C, 256)), dim3(256), 0, st, e); }
+        return true;
+    }
     ExportArgs e;
     e.a = (const bf16*)(ws + (grad ? ta.grad : ta.data)); e.b = ib >= 0 ? (const bf16*)(ws + (grad ? v.t[ib].grad : v.t[ib].data)) : nullptr;
     e.cp = ta.cp; e.map = SlotMap{ta.n0, ta.n0p, ta.n1}; e.rows = (long long)4 * ta.Rt; e.C = ta.C() * (ib >= 0 ? 2 : 1); e.out = out;

@@ -307,7 +307,7 @@ inline __host__ __device__ StemBwdSmem stem_bwd_smem(int HB, int Ws, int Wp, int
     off = (off + 127) & ~127;
     s.img = off; off += ((2 * HB + 1) * W3 + 15 + 127) & ~127;
     s.raw = off; off += (HB * Ws * kSC * 2 + 127) & ~127;
-    s.dz = off; off += (HB * Ws * kSC * 2 + 127) & ~127;
+    s.dz = off; off += (HB * Ws * kSC * 4 + 127) & ~127;      // fp32: a pixel can win several windows, the sum is not rounded per add
     s.dp = off; off += (s.nwr_max * Wp * kSC * 2 + 127) & ~127;
     s.idx = off; off += (s.nwr_max * Wp * kSC + 32 + 127) & ~127;
     s.total = off;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_bwd_kernel(const StemBwd
     float* s_red = reinterpret_cast<float*>(smem + L.red);
     const uint8_t* ib = smem + L.img;
     const unsigned short* rawt = reinterpret_cast<const unsigned short*>(smem + L.raw);
-    bf16* dzt = reinterpret_cast<bf16*>(smem + L.dz);
+    float* dzt = reinterpret_cast<float*>(smem + L.dz);
     const bf16* dpt = reinterpret_cast<const bf16*>(smem + L.dp);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
     const int nunits = kT * G.B * a.nbands;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_bwd_kernel(const StemBwd
             cur_t = t;
         }
         // ---- zero the dz tile (overlaps the loads)
-        for (int i = tid; i < (npx * kSC * 2 + 15) / 16; i += kStemThreads) reinterpret_cast<uint4*>(dzt)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < (npx * kSC * 4 + 15) / 16; i += kStemThreads) reinterpret_cast<uint4*>(dzt)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         mbar_wait(&full[0], it & 1);
         // ---- max-pool backward: every window adds its gradient to the stored winner (if that pixel is in this band)
@@ -438,12 +438,9 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_bwd_kernel(const StemBwd
                 const int c0 = code & 0xff, c1 = code >> 8;
                 const int ya0 = 2 * py - G.pad_t + c0 / 3 - y0, xa0 = 2 * px - G.pad_l + c0 % 3;
                 const int ya1 = 2 * py - G.pad_t + c1 / 3 - y0, xa1 = 2 * px - G.pad_l + c1 % 3;
-                if (c0 == c1) {
-                    if (ya0 >= 0 && ya0 < n) red_bf16x2(dzt + ((size_t)ya0 * G.Ws + xa0) * kSC + 2 * cp, d);
-                } else {
-                    if (ya0 >= 0 && ya0 < n) red_bf16x2(dzt + ((size_t)ya0 * G.Ws + xa0) * kSC + 2 * cp, d & 0xffffu);
-                    if (ya1 >= 0 && ya1 < n) red_bf16x2(dzt + ((size_t)ya1 * G.Ws + xa1) * kSC + 2 * cp, d & 0xffff0000u);
-                }
+                const float2 dv = unpack2(d);
+                if (ya0 >= 0 && ya0 < n) atomicAdd(dzt + ((size_t)ya0 * G.Ws + xa0) * kSC + 2 * cp, dv.x);
+                if (ya1 >= 0 && ya1 < n) atomicAdd(dzt + ((size_t)ya1 * G.Ws + xa1) * kSC + 2 * cp + 1, dv.y);
             }
         }
         __syncthreads();
@@ -468,7 +465,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_bwd_kernel(const StemBwd
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const float raw = __uint_as_float((uint32_t)rawt[(size_t)qc * kSC + g + 8 * j] << 16);
-                        const float dzr = __bfloat162float(dzt[(size_t)qc * kSC + g + 8 * j]);
+                        const float dzr = dzt[(size_t)qc * kSC + g + 8 * j];
                         const float uu = fmaf(raw, cst[j].x, cst[j].y);
                         const float dz = (valid[e] && uu > 0.f && uu < 6.f) ? dzr : 0.f;
                         const float xh = valid[e] ? fmaf(raw, cst[j].z, cst[j].w) : 0.f;

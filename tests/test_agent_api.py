@@ -8,13 +8,21 @@ import torch
 H, W = 42, 58
 
 
+@pytest.fixture(autouse=True)
+def _cpu_logic_build(monkeypatch, built_libs):
+    """bind the networks to the CPU logic-check build of the library (tests/emu); the product has no such switch"""
+    from core.networks import CARLANetwork
+    from tests.emu.engine import EmuEngine
+    monkeypatch.setattr(CARLANetwork, 'ENGINE', EmuEngine)
+
+
 def _agent(tmp_path, batch_size=2, **kw):
     from core import CARLAgent, SyntheticCARLAEnvironment
     env = SyntheticCARLAEnvironment(image_shape=(H, W, 3), image_uint8=True, seed=1)
     return CARLAgent(env, batch_size=batch_size, name='t', weights_dir=str(tmp_path / 'w'), evaluation_dir=str(tmp_path / 'e'),
                      seed=7, skip_data=1, drop_batch_remainder=True, log_mode='summary', policy_lr=3e-4, value_lr=3e-4,
                      dynamics_lr=3e-4, entropy_regularization=1.0, clip_ratio=0.2, gamma=0.9999, lambda_=0.999,
-                     network=dict(emulated=True, dtype='f32'), **kw)
+                     network=dict(device='cpu', dtype='f32'), **kw)
 
 
 def test_api_surface_and_defaults(built_libs, tmp_path):

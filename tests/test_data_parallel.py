@@ -20,12 +20,12 @@ def _worker(rank, world, port, out_dir):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    from cdra.engine import Engine
+    from tests.emu.engine import EmuEngine
     from cdra.init import init_engine
     from cdra.parallel import GradSync
     from tests import common as C
     torch.set_num_threads(1)
-    eng = Engine(B, H, W, dtype='f32', image_u8=True, device='cpu', emulated=True)
+    eng = EmuEngine(B, H, W, dtype='f32', image_u8=True, device='cpu')
     init_engine(eng, seed=100 + rank)                       # deliberately different: broadcast must fix it
     sync = GradSync(eng)
     sync.broadcast_parameters(0)
@@ -53,7 +53,7 @@ def test_two_rank_gradient_exchange(built_libs, tmp_path):
     # replicas stay bit-identical after the step
     assert torch.equal(r0['dyn'], r1['dyn']) and torch.equal(r0['pol'], r1['pol'])
     # the per-tensor clip saw the globally averaged gradient: norms are those of mean_g, tensor by tensor
-    from cdra.engine import Engine
-    eng = Engine(B, H, W, dtype='f32', image_u8=True, device='cpu', emulated=True)
+    from tests.emu.engine import EmuEngine
+    eng = EmuEngine(B, H, W, dtype='f32', image_u8=True, device='cpu')
     want = torch.stack([eng.pol.view(n, r0['mean_g']).pow(2).sum() for n in eng.pol.names])
     assert torch.allclose(r0['norms'], want, rtol=1e-4, atol=1e-10)

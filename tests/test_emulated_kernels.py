@@ -13,8 +13,8 @@ B, H, W = 3, 42, 58      # stem 20x28 -> pool 10x14 -> 5x7 -> 3x4 -> 2x2
 
 @pytest.fixture(scope='module')
 def eng(built_libs):
-    from cdra.engine import Engine
-    e = Engine(B, H, W, dtype='f32', image_u8=True, device='cpu', emulated=True)
+    from tests.emu.engine import EmuEngine
+    e = EmuEngine(B, H, W, dtype='f32', image_u8=True, device='cpu')
     return e
 
 
