@@ -43,12 +43,13 @@ _SIGNATURES = {
     'cdra_debug_stem_backward': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     'cdra_dynamics_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     'cdra_dynamics_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    'cdra_policy_head_loss_fwd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int,
+    'cdra_policy_head_loss_fwd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int,
                                                 C.c_float, _P, _P, _P, _P, _P, _P]),
     'cdra_value_head_loss_fwd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P, _P, _P]),
     'cdra_gae': (C.c_int, [_P, _P, _P, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, _P, _P, _P]),
     'cdra_clip_adam': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int64, C.c_float, _P, _P]),
+    'cdra_grad_norms': (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_float, _P, _P]),
     'cdra_gather_rows': (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
     'cdra_launch_count': (C.c_int64, []),
     'cdra_profile_enable': (None, [C.c_int]),

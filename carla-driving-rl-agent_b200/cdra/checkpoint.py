@@ -129,11 +129,11 @@ class TensorBundle:
 # ---------------------------------------------------------------------------------------------- layer order
 def _unit_names(arena_names):
     """tower unit prefixes in construction order, with their stride (a unit with a shortcut branch has stride 2)"""
-    units = []
+    units, have = [], set(arena_names)
     for n in arena_names:
         if n.startswith('tower.s') and n.endswith('.pw1.w'):
             u = n[:-len('.pw1.w')]
-            units.append((u, 2 if (u + '.scdw.w') in arena_names else 1))
+            units.append((u, 2 if (u + '.scdw.w') in have else 1))
     return units
 
 
@@ -144,9 +144,8 @@ def keras_layer_sequence(model, arena_names):
     if model != 'dynamics':
         heads = ('alpha', 'beta', 'similarity', 'speed') if model == 'policy' else ('base', 'exp', 'speed', 'similarity')
         return [('bn1', 'bn'), ('d1', 'dense'), ('bn2', 'bn'), ('d2', 'dense')] + [(h, 'dense') for h in heads]
-    names = set(arena_names)
     seq = [('tower.stem', 'conv'), ('tower.stem', 'bn')]
-    for u, stride in _unit_names(names):
+    for u, stride in _unit_names(list(arena_names)):
         seq += [(u + '.pw1', 'conv'), (u + '.pw1', 'bn')]
         if stride == 2:
             seq += [(u + '.scdw', 'dw'), (u + '.dw', 'dw'), (u + '.scdw', 'bn'), (u + '.dw', 'bn'),

@@ -165,11 +165,11 @@ class Engine:
         return g
 
     def policy_head(self, x512, actions_eval, logp_old, adv, true_speed, true_sim, clip_ratio=0.2, ent_coef=1.0,
-                    training=True, grad_scale=1.0, backward=True, update_moving=True):
+                    training=True, grad_scale=1.0, backward=True, update_moving=True, actions_jac=None):
         p = _lib.ptr
         state = self.pol_state.flat if (update_moving or not training) else None
         _lib.check(self.lib, self.lib.cdra_policy_head_loss_fwd_bwd(
-            self.plan, p(self.pol.flat), p(state), p(x512), p(actions_eval), p(logp_old), p(adv),
+            self.plan, p(self.pol.flat), p(state), p(x512), p(actions_eval), p(actions_jac), p(logp_old), p(adv),
             p(true_speed), p(true_sim), clip_ratio, ent_coef, 1 if training else 0, grad_scale, p(self.scalars),
             p(self.head_out), p(self.d_x512) if backward else None, p(self.g_pol) if backward else None, p(self.ws),
             self._stream()), 'policy_head')
@@ -202,6 +202,16 @@ class Engine:
             p(arena.flat), p(grads), p(m), p(v), p(arena.offsets_dev), len(arena.names), arena.size,
             float(clip_norm) if clip_norm else 0.0, float(lr), beta1, beta2, eps, self.adam_step[which],
             float(grad_scale), p(self.norms[which]), self._stream()), 'clip_adam')
+
+    def grad_norms(self, which, grad_scale=1.0):
+        """per-tensor L2 norms of a gradient arena as ONE device tensor (one launch, no host synchronisation)"""
+        arena = dict(dyn=self.dyn, pol=self.pol, val=self.val)[which]
+        grads = dict(dyn=self.g_dyn, pol=self.g_pol, val=self.g_val)[which]
+        out = torch.empty(len(arena.names), dtype=torch.float32, device=self.device)
+        p = _lib.ptr
+        _lib.check(self.lib, self.lib.cdra_grad_norms(p(grads), p(arena.offsets_dev), len(arena.names), arena.size,
+                                                      float(grad_scale), p(out), self._stream()), 'grad_norms')
+        return out.sqrt_()
 
     def gather_rows(self, src, index, out):
         row_bytes = src[0].numel() * src.element_size()

@@ -1,7 +1,9 @@
 """Keras-default parameter initialisation for the flat arenas (what `CARLANetwork.__init__` gets from
 building its Keras layers, core/networks.py:150-176): glorot-uniform kernels, glorot-uniform biases where
 the reference passes `bias_initializer='glorot_uniform'` (every Dense and GRU; Conv2D/DepthwiseConv2D and
-the alpha/beta heads keep Keras' zero bias), BatchNorm gamma 1 / beta 0 / moving mean 0 / variance 1."""
+the alpha/beta heads keep Keras' zero bias), orthogonal GRU recurrent kernels (Keras `recurrent_initializer='orthogonal'`;
+the reference only overrides the bias initialiser, core/networks.py:47-50), BatchNorm gamma 1 / beta 0 / moving mean 0 /
+variance 1."""
 import math
 
 import torch
@@ -28,6 +30,18 @@ def _fans(name, shape):
 ZERO_BIAS_PREFIXES = ('tower.', 'alpha.', 'beta.')
 
 
+def _orthogonal(shape, gen, device):
+    """Keras Orthogonal initializer [lib] on the full [units, 3*units] recurrent matrix: QR of a normal matrix of the
+    transposed (tall) shape, signs fixed by diag(R), transposed back."""
+    rows, cols = shape
+    a = torch.randn(max(rows, cols), min(rows, cols), generator=gen, device=device, dtype=torch.float32)
+    q, r = torch.linalg.qr(a.double().cpu())
+    q = q * torch.sign(torch.diagonal(r))
+    if rows < cols:
+        q = q.t()
+    return q.to(torch.float32).to(device).contiguous()
+
+
 def init_arena(arena, state, seed):
     gen = torch.Generator(device=arena.flat.device).manual_seed(seed)
     dev = arena.flat.device
@@ -39,6 +53,8 @@ def init_arena(arena, state, seed):
             v.zero_()
         elif name.endswith('.b') and name.startswith(ZERO_BIAS_PREFIXES):
             v.zero_()
+        elif name.startswith('gru.') and name.endswith('.r'):
+            v.copy_(_orthogonal(shape, gen, dev))
         else:
             fi, fo = _fans(name, shape)
             v.copy_(_glorot(shape, fi, fo, gen, dev))

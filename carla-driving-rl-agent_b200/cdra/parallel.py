@@ -43,6 +43,16 @@ class GradSync:
         for w in which:
             dist.all_reduce(dict(dyn=e.g_dyn, pol=e.g_pol, val=e.g_val)[w], op=dist.ReduceOp.SUM)
 
+    def agree_min(self, value: int) -> int:
+        """The smallest `value` over all ranks.  Every rank must issue the same number of gradient all-reduces: the number
+        of minibatches of an update (and whether the update happens at all, core/carla_agent.py:130-133) is a rank-local
+        quantity -- an early `done` shortens one rank's memory -- so it is agreed on before the loop."""
+        if self.world == 1:
+            return int(value)
+        t = torch.tensor([int(value)], dtype=torch.int64, device=self.engine.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
     def shard(self, n_trajectories):
         """Trajectories [lo, hi) owned by this rank (rollouts never move between GPUs)."""
         per = n_trajectories // self.world

@@ -25,6 +25,18 @@ def relu6(x):
     return torch.clamp(x, 0.0, 6.0)
 
 
+def sample_beta_reparameterized(alpha, beta):
+    """A Beta(alpha, beta) sample the way tfp.distributions.Beta draws it [lib] -- x = g1 / (g1 + g2), g1 ~ Gamma(alpha),
+    g2 ~ Gamma(beta) -- with its pathwise derivatives (dx/dalpha, dx/dbeta) from the implicit-reparameterisation gradients
+    of the gamma draws.  Returns (x [B,2] contiguous, jac [B,2,2] contiguous); x is NOT clipped (the kernel clips it like
+    `_clip_actions`, core/networks.py:139-144, and stops the gradient where it did)."""
+    g1, g2 = torch._standard_gamma(alpha), torch._standard_gamma(beta)
+    s = g1 + g2
+    x = g1 / s
+    jac = torch.stack([g2 / (s * s) * torch._standard_gamma_grad(alpha, g1), -g1 / (s * s) * torch._standard_gamma_grad(beta, g2)], dim=-1)
+    return x.contiguous(), jac.contiguous()
+
+
 class FakeCARLAEnvironment:
     """A testing-only environment with the state- and action-space of a CARLA environment
     (core/carla_agent.py:26-52).  Like the reference's it only defines spaces; unlike the reference's it uses the
@@ -114,6 +126,7 @@ class CARLAgent(PPOAgent):
         network_spec.setdefault('dynamics', self.DEFAULT_DYNAMICS)
 
         self.should_update_dynamics = update_dynamics
+        self.reparameterized_actions = kwargs.pop('reparameterized_actions', True)     # False: stored-action style constant
         self.dynamics_path = os.path.join(kwargs.get('weights_dir', 'weights'), name, 'dynamics_model')
         self.load_full = load_full
         super().__init__(*args, name=name, network=network_spec, clip_norm=clip_norm, **kwargs)
@@ -136,7 +149,8 @@ class CARLAgent(PPOAgent):
 
     # ------------------------------------------------------------------ update (core/carla_agent.py:129-145)
     def update(self):
-        if len(self.memory) < self.batch_size:
+        # under data parallelism the decision is collective (a rank that skipped would leave the others' all-reduce hanging)
+        if self.network.sync.agree_min(len(self.memory)) < self.batch_size:
             print('[Not updated] memory too small!')
             self.env.reset_info()
             return
@@ -196,14 +210,17 @@ class CARLAgent(PPOAgent):
             assert self.should_update_dynamics
             grads = self.apply_dynamics_gradients(gradients=gradients['dynamics'])
             super().apply_policy_gradients(gradients=gradients['policy'])
-            self.log(gradients_norm_dynamics=[g.norm() for g in grads])
+            self.log(gradients_norm_dynamics=self._dyn_norms)
         else:
             super().apply_policy_gradients(gradients)
 
     def apply_dynamics_gradients(self, gradients):
         """Adam without clipping (core/carla_agent.py:386-388)."""
-        self.network.sync.allreduce('dyn')
-        self.network.engine.clip_adam('dyn', self.dynamics_lr(), None, self.network.grad_scale)
+        net = self.network
+        net.sync.allreduce('dyn')
+        # what the reference logs as [tf.norm(g) for g in grads] (:382,461): one launch, stays on the device
+        self._dyn_norms = net.engine.grad_norms('dyn', net.grad_scale) if self.statistics.should_log else None
+        net.engine.clip_adam('dyn', self.dynamics_lr(), None, net.grad_scale)
         return gradients
 
     def policy_predict(self, inputs: dict) -> dict:
@@ -216,16 +233,18 @@ class CARLAgent(PPOAgent):
         eng = states['_engine']
         x = states['dynamics']
         B = eng.B
-        # decision D2: the log-prob is evaluated at a detached sample of the *new* policy, like
-        # PolicyNetwork.call (core/networks.py:97-100); sample here from the current parameters
+        # PolicyNetwork.call evaluates log pi_new at a fresh, reparameterised sample of the NEW policy
+        # (core/networks.py:97-100): draw it from the current parameters (one forward-only head call), together with its
+        # pathwise derivatives, which the fused kernel folds into d loss / d (alpha, beta)
         with torch.no_grad():
             z2, z1 = torch.full((B, 2), 0.5, device=eng.device), torch.zeros(B, 1, device=eng.device)
             eng.policy_head(x, z2, z2, z1.view(-1), z1, z1, training=True, backward=False, update_moving=False)
             ho = eng.head_out.view(B, 8)
-            actions_eval = torch.distributions.Beta(ho[:, 0:2], ho[:, 2:4]).sample().clamp(utils.EPSILON, 1 - utils.EPSILON)
-        sc = eng.policy_head(x, actions_eval.contiguous(), old_log_prob.contiguous(), advantages.reshape(-1).contiguous(),
+            actions_eval, actions_jac = sample_beta_reparameterized(ho[:, 0:2], ho[:, 2:4])
+        sc = eng.policy_head(x, actions_eval, old_log_prob.contiguous(), advantages.reshape(-1).contiguous(),
                              true_speed.contiguous(), true_similarity.contiguous(), float(self.clip_ratio()),
-                             float(self.entropy_strength()), training=True, grad_scale=1.0, backward=True)
+                             float(self.entropy_strength()), training=True, grad_scale=1.0, backward=True,
+                             actions_jac=actions_jac if self.reparameterized_actions else None)
         self.log(ratio=sc[5], log_prob=sc[6], entropy=sc[7], entropy_coeff=self.entropy_strength.value,
                  ratio_clip=self.clip_ratio.value, loss_speed_policy=sc[3], loss_policy=sc[1], loss_entropy=sc[2],
                  speed_pi=sc[8], loss_similarity_policy=sc[4], similarity_pi=sc[9])
@@ -248,7 +267,7 @@ class CARLAgent(PPOAgent):
             assert self.should_update_dynamics
             grads = self.apply_dynamics_gradients(gradients=gradients['dynamics'])
             super().apply_value_gradients(gradients=gradients['value'])
-            self.log(gradients_norm_dynamics_v=[g.norm() for g in grads])
+            self.log(gradients_norm_dynamics_v=self._dyn_norms)
         else:
             super().apply_value_gradients(gradients)
 

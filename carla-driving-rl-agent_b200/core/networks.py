@@ -178,6 +178,7 @@ class CARLANetwork(Network):
         init_arena(self.engine.dyn, self.engine.dyn_state, seed)
         init_arena(self.engine.pol, self.engine.pol_state, seed + 1)
         init_arena(self.engine.val, self.engine.val_state, seed + 2)
+        self.sync.broadcast_parameters(0)             # replicas start from rank 0's parameters whatever their seeds
 
         self.dynamics = ArenaModel('Dynamics-Model', self.engine.dyn, self.engine.dyn_state)
         self.action_index = 0

@@ -446,11 +446,11 @@ static void tail_backward(const RunCtx& c, const float* road, const float* vehic
 
 // ----------------------------------------------------------------------------------------------- heads
 static int run_head(bool policy, cdra_plan_t* plan, const float* params, float* state, const float* x512,
-                    const float* actions, const float* logp_old, const float* adv, const float* returns_be,
+                    const float* actions, const float* actions_jac, const float* logp_old, const float* adv, const float* returns_be,
                     const float* true_speed, const float* true_sim, float clip, float ent_coef, int training,
                     float grad_scale, float* scalars, float* head_out, float* d_x512, float* grads, char* ws, cudaStream_t st) {
     const Plan& p = *plan->p; const HeadSpec& h = policy ? p.policy : p.value; const int B = p.B;
-    t_gemm_tf32 = p.cfg.dtype == CDRA_DTYPE_BF16 && getenv("CDRA_NO_TF32") == nullptr;
+    t_gemm_tf32 = false;      // the heads are tiny and feed the loss directly: fp32 GEMMs in both modes (PPO loss rtol 1e-4 given the trunk output)
     float* n1 = F(ws, named_off(p, "head.n1")); float* pre1 = F(ws, named_off(p, "head.pre1")); float* a1 = F(ws, named_off(p, "head.a1"));
     float* n2 = F(ws, named_off(p, "head.n2")); float* pre2 = F(ws, named_off(p, "head.pre2")); float* a2 = F(ws, named_off(p, "head.a2"));
     float2* st1 = (float2*)(ws + named_off(p, "head.st1")); float2* st2 = (float2*)(ws + named_off(p, "head.st2"));
@@ -485,7 +485,7 @@ static int run_head(bool policy, cdra_plan_t* plan, const float* params, float* 
         a.w[i] = params + h.out_w[i]; a.b[i] = params + h.out_b[i]; a.n[i] = h.out_n[i];
         a.dw[i] = gsink + (grads ? h.out_w[i] : (int64_t)i * 1024); a.db[i] = gsink + (grads ? h.out_b[i] : (int64_t)4096 + i * 8);
     }
-    a.actions = actions; a.logp_old = logp_old; a.adv = adv; a.returns_be = returns_be;
+    a.actions = actions; a.actions_jac = actions_jac; a.logp_old = logp_old; a.adv = adv; a.returns_be = returns_be;
     a.true_speed = true_speed; a.true_sim = true_sim; a.clip = clip; a.ent_coef = ent_coef; a.grad_scale = grad_scale;
     a.exp_scale = 6.0f; a.acc = acc; a.scalars = scalars; a.head_out = head_out; a.da2 = da2;
     if (policy) { auto k = head_loss_kernel<true>; CDRA_LAUNCH(k, dim3(cdiv(B, kHeadRows)), dim3(256), 0, st, a); }
@@ -687,6 +687,7 @@ int cdra_debug_set(const char* key, int value) {
 #ifndef CDRA_EMU
     if (std::string(key) == "tc") { v2::tc_override() = value; return CDRA_OK; }
     if (std::string(key) == "fwd_tc") { v2::fwd_tc_override() = value; return CDRA_OK; }
+    if (std::string(key) == "fused") { v2::fused_override() = value; return CDRA_OK; }
 #endif
     return fail(CDRA_ERR_BADARG, "unknown debug key");
 }
@@ -714,7 +715,7 @@ int cdra_debug_stem_backward(cdra_plan_t* plan, const float* params, const void*
 }
 
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
-                                  const float* actions_eval, const float* logp_old, const float* adv,
+                                  const float* actions_eval, const float* actions_jac, const float* logp_old, const float* adv,
                                   const float* true_speed, const float* true_sim, float clip_ratio, float ent_coef,
                                   int training, float grad_scale, float* scalars_out, float* head_out, float* d_x512,
                                   float* grads, void* workspace, void* stream) {
@@ -722,7 +723,7 @@ int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float*
         !head_out || !workspace) return fail(CDRA_ERR_BADARG, "null argument");
     if (grads && !d_x512) return fail(CDRA_ERR_BADARG, "d_x512 required with grads");
     if (!training && !state) return fail(CDRA_ERR_BADARG, "inference needs the moving statistics");
-    return run_head(true, plan, params, state, x512, actions_eval, logp_old, adv, nullptr, true_speed, true_sim,
+    return run_head(true, plan, params, state, x512, actions_eval, actions_jac, logp_old, adv, nullptr, true_speed, true_sim,
                     clip_ratio, ent_coef, training, grad_scale, scalars_out, head_out, d_x512, grads, (char*)workspace,
                     (cudaStream_t)stream);
 }
@@ -735,7 +736,7 @@ int cdra_value_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* 
         return fail(CDRA_ERR_BADARG, "null argument");
     if (grads && !d_x512) return fail(CDRA_ERR_BADARG, "d_x512 required with grads");
     if (!training && !state) return fail(CDRA_ERR_BADARG, "inference needs the moving statistics");
-    return run_head(false, plan, params, state, x512, nullptr, nullptr, nullptr, returns_be, true_speed, true_sim, 0.f,
+    return run_head(false, plan, params, state, x512, nullptr, nullptr, nullptr, nullptr, returns_be, true_speed, true_sim, 0.f,
                     0.f, training, grad_scale, scalars_out, head_out, d_x512, grads, (char*)workspace, (cudaStream_t)stream);
 }
 
@@ -770,6 +771,17 @@ int cdra_clip_adam(float* params, const float* grads, float* m, float* v, const 
     }
     CDRA_LAUNCH(adam_kernel, dim3(blocks), dim3(256), 0, st, a);
     return check_launch("clip_adam");
+}
+
+int cdra_grad_norms(const float* grads, const int64_t* tensor_offsets, int n_tensors, int64_t total, float grad_scale,
+                    float* sq_norms_out, void* stream) {
+    if (!grads || !tensor_offsets || !sq_norms_out || n_tensors < 1 || total < 1) return fail(CDRA_ERR_BADARG, "bad argument");
+    AdamArgs a; memset(&a, 0, sizeof a);
+    a.g = grads; a.offs = tensor_offsets; a.n_tensors = n_tensors; a.grad_scale = grad_scale; a.norms = sq_norms_out; a.total = total;
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_async(sq_norms_out, (size_t)n_tensors * 4, st);
+    CDRA_LAUNCH(sqnorm_kernel, dim3((unsigned)cdiv(total, kAdamChunk)), dim3(256), 0, st, a);
+    return check_launch("grad_norms");
 }
 
 int64_t cdra_launch_count(void) { return (int64_t)g_launches.load(); }

@@ -30,6 +30,7 @@ struct HeadLossArgs {
     const float* w[4]; const float* b[4]; int n[4];     // output heads
     // policy inputs
     const float* actions; const float* logp_old; const float* adv;
+    const float* actions_jac;         // [B][2][2] (d action / d alpha, d action / d beta) of a reparameterised sample, or null
     // value inputs
     const float* returns_be;
     const float* true_speed; const float* true_sim;
@@ -99,6 +100,17 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) head_loss_kernel(HeadLossArgs a) {
                     dlogp_da[i] = log(x) - (pa - pab); dlogp_db[i] = log1p(-x) - (pb - pab);
                     dH_da[i] = -(al - 1.0) * trigamma_d(al) + (al + be - 2.0) * tab;
                     dH_db[i] = -(be - 1.0) * trigamma_d(be) + (al + be - 2.0) * tab;
+                    if (a.actions_jac) {
+                        // the evaluated action is a reparameterised sample x(alpha, beta) of the new policy (PolicyNetwork.call,
+                        // core/networks.py:97-100): d logp / d alpha = partial + d logp / dx * dx / d alpha.  tf.clip_by_value
+                        // passes the gradient only where the sample was not clipped.
+                        const float xr = a.actions[(size_t)row * 2 + i];
+                        if (xr >= kActEps && xr <= 1.f - kActEps) {
+                            const double dlogp_dx = (al - 1.0) / x - (be - 1.0) / (1.0 - x);
+                            dlogp_da[i] += dlogp_dx * (double)a.actions_jac[(size_t)row * 4 + 2 * i];
+                            dlogp_db[i] += dlogp_dx * (double)a.actions_jac[(size_t)row * 4 + 2 * i + 1];
+                        }
+                    }
                     rat[i] = exp(logp - (double)a.logp_old[(size_t)row * 2 + i]);
                     ratio += 0.5 * rat[i]; Hs += H; lps += logp;
                     a.head_out[(size_t)row * 8 + i] = (float)al; a.head_out[(size_t)row * 8 + 2 + i] = (float)be;

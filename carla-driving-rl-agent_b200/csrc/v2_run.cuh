@@ -9,6 +9,7 @@
 #include "v2_stem.cuh"
 #include "v2_umma.cuh"
 #include "v2_pw_tc.cuh"
+#include "v3_pw_bwd.cuh"
 
 namespace cdra {
 namespace v2 {
@@ -111,6 +112,8 @@ inline int& tc_override() { static int v = -1; return v; }      // cdra_debug_se
 inline bool use_tc() { static const bool env = getenv("CDRA_NO_TC") == nullptr; return tc_override() < 0 ? env : tc_override() != 0; }
 inline int& fwd_tc_override() { static int v = -1; return v; }  // cdra_debug_set("fwd_tc", 0 | 1)
 inline bool use_fwd_tc() { static const bool env = getenv("CDRA_NO_FWD_TC") == nullptr; return fwd_tc_override() < 0 ? env : fwd_tc_override() != 0; }
+inline int& fused_override() { static int v = -1; return v; }   // cdra_debug_set("fused", 0 | 1)
+inline bool use_fused() { static const bool env = getenv("CDRA_NO_FUSED") == nullptr; return fused_override() < 0 ? env : fused_override() != 0; }
 inline int num_sms() {
     static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
     return n;
@@ -352,10 +355,43 @@ inline bool try_pw_wgrad_tc(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int
     return true;
 }
 
+// the whole backward of one pointwise layer in ONE warp-specialised tcgen05 kernel (v3_pw_bwd.cuh): every layer whose
+// weight-gradient accumulator [KP x NPall] plus the double-buffered data-gradient tile fit the 512 TMEM columns
+template <int R>
+inline bool try_pw_bwd_fused(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, int min_stages) {
+    int cps[kMaxSrc] = {0, 0, 0}, acc[kMaxSrc] = {0, 0, 0};
+    for (int i = 0; i < hd.nsrc; ++i) { cps[i] = hd.src[i].cp; acc[i] = hd.src[i].accumulate; }
+    const int x1cp = a.x1 ? a.x1cp : 0;
+    const PwBfSmem L0 = pw_bf_smem(R, hd.nsrc, cps, acc, hd.NPall, hd.cols.nplanes, a.cpo, x1cp, 0);
+    if (L0.mbk > 2 || L0.np16 > 256 || L0.cols_dw + 2 * L0.mbk * R > 512 || x1cp > kBfEpilogueThreads) return false;
+    const int nstage = std::min(kBfMaxStages, (kMaxDynSmem - 1024 - L0.ring) / L0.stage_bytes);
+    if (nstage < min_stages) return false;
+    const PwBfSmem L = pw_bf_smem(R, hd.nsrc, cps, acc, hd.NPall, hd.cols.nplanes, a.cpo, x1cp, nstage);
+    if (L.total > kMaxDynSmem) return false;
+    auto k = pw_bwd_fused_kernel<R>;
+    static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nstage; a.direct = 0;
+    const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
+    int gx = std::min(ntile, num_sms());
+    a.tiles_per_cta = (ntile + gx - 1) / gx;
+    gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    CDRA_LAUNCH_PDL(k, dim3(gx), dim3(kBfThreads), L.total, c.stream, a);
+    return true;
+}
+
 // data gradient (+ pass-through, + BN-backward sums of the inputs) and weight gradient of one GEMM launch
 inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a) {
     a.d = desc_dev(c, di);
     a.out_clamp = 1;
+    if (use_tc() && use_fused()) {
+        double fb = 0;
+        for (int i = 0; i < hd.nsrc; ++i) fb += 4.0 * a.Rt * (hd.src[i].map.n0 + hd.src[i].map.n1) * 2 * (2 + hd.src[i].accumulate);    // raw src read, d src written (+ read)
+        fb += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n + a.ncopy) * 2 * 2;                                       // d out, out read
+        if (a.x1) fb += 4.0 * a.Rt * 2 * a.ncopy * 2 * 2;
+        prof_bytes(fb);
+        if (try_pw_bwd_fused<64>(c, a, hd, 4) || try_pw_bwd_fused<32>(c, a, hd, 3) || try_pw_bwd_fused<64>(c, a, hd, 2) || try_pw_bwd_fused<32>(c, a, hd, 2)) return;
+    }
     const int tc_np = (hd.NPall + 15) & ~15, tc_mb = (hd.KP + 127) / 128;
     const bool tc = use_tc() && tc_np <= 256 && tc_mb * tc_np <= 512;       // the [KP x NPall] accumulator fits the SM's TMEM
     a.dr = use_tc() ? (bf16*)(c.ws + c.p->v2.dr_scratch) : nullptr;     // every layer hands dR over; the mma.sync weight gradient takes it too

@@ -1,0 +1,447 @@
+// v3: ONE warp-specialised tcgen05 kernel for the whole backward of a pointwise (1x1) convolution layer --
+// what tape.gradient computes through Conv2D(1x1) + BatchNormalization + ReLU6 (core/architectures.py:130,134,140;
+// core/carla_agent.py:361-365): BatchNorm(+ReLU6) backward of the layer's output gradient, data gradient, weight
+// gradient, pass-through gradient of a stride-1 unit, and the BatchNorm-backward sums of every gradient it writes.
+//
+// Per row tile (R rows, contiguous in HBM):
+//   TMA producer (1 thread)   bulk copies of d out / out (both planes), the raw source rows (+ x1, + the partial gradient
+//                             of a second consumer) into a multi-stage ring; mbarrier complete_tx
+//   transform warps (6)       dR = scale * (dz - S1/n - xhat * S2/n) and act(src) = relu6(scale * raw + shift), written
+//                             straight into 128-byte-swizzled tiles (double buffered)
+//   MMA issuer (1 thread)     dSrc^T [kk][r] = sum_j Wb[kk][j] dR[r][j]     A = weights (K-major, resident), B = dR tile
+//                                                                          (K-major), D in TMEM (double buffered)
+//                             dW [kk][j]   += sum_r act(src)[r][kk] dR[r][j]  A = act tile, B = the SAME dR tile (both
+//                                                                          MN-major), D resident in TMEM for the CTA's life
+//   epilogue warps (8)        tcgen05.ld of dSrc^T: a thread owns ONE channel kk and walks the tile's rows, so the
+//                             BatchNorm-backward sums of the source accumulate in registers with no cross-thread
+//                             reduction; bf16 rows are staged and leave through one TMA bulk store per source
+// No CTA-wide barrier inside the loop: the roles are chained by mbarriers only (ring full/empty, staging full/empty,
+// TMEM full/empty).  Replaces pw_dgrad_kernel + the dR hand-off matrix + pw_wgrad_tc_kernel of v2_bwd.cuh for every
+// layer whose accumulators fit the 512 TMEM columns (stage 1 and stage 2 except the stage-2 stride-2 tail).
+#pragma once
+#ifndef CDRA_EMU
+#include "v2_bwd.cuh"
+#include "v2_stem.cuh"
+
+namespace cdra {
+namespace v2 {
+
+CDRA_DEV void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+CDRA_DEV void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+CDRA_DEV void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr int kBfThreads = 512, kBfTransformWarps = 6, kBfEpilogueWarps = 8, kBfMaxStages = 8;
+constexpr int kBfTransformThreads = kBfTransformWarps * 32, kBfEpilogueThreads = kBfEpilogueWarps * 32;
+
+struct PwBfSmem {
+    int w, dr, xs, st, st2, ring, total;
+    int stage_bytes, dr_bytes, xs_bytes, w_bytes;
+    int o_dout, o_out, o_src[kMaxSrc], o_x1, o_ge[kMaxSrc], st_off[kMaxSrc];
+    int mbk, np16, nkb, cols_dw, tmem_cols;
+};
+// `cps[i]`, `acc[i]`: slots / accumulate flag of source i
+inline __host__ __device__ PwBfSmem pw_bf_smem(int R, int nsrc, const int* cps, const int* acc, int NPall, int nplanes, int cpo, int x1cp, int nstage) {
+    PwBfSmem s;
+    int ksum = 0;
+    for (int i = 0; i < nsrc; ++i) ksum += cps[i];
+    s.mbk = (ksum + 127) / 128; s.np16 = (NPall + 15) & ~15; s.nkb = (s.np16 + 63) / 64;
+    s.cols_dw = s.mbk * s.np16;
+    const int cols = s.cols_dw + 2 * s.mbk * R;
+    s.tmem_cols = 32; while (s.tmem_cols < cols) s.tmem_cols *= 2;
+    // one ring stage: [d out planes][out planes][sources][x1][existing gradients of accumulate sources], R rows each
+    int off = 0;
+    s.o_dout = off; off += nplanes * R * cpo * 2;
+    s.o_out = off; off += nplanes * R * cpo * 2;
+    for (int i = 0; i < kMaxSrc; ++i) { s.o_src[i] = off; if (i < nsrc) off += R * cps[i] * 2; }
+    s.o_x1 = off; off += R * x1cp * 2;
+    for (int i = 0; i < kMaxSrc; ++i) { s.o_ge[i] = off; if (i < nsrc && acc[i]) off += R * cps[i] * 2; }
+    s.stage_bytes = (off + 127) & ~127;
+    s.w_bytes = s.mbk * s.nkb * 128 * 128;
+    s.dr_bytes = s.nkb * R * 128;
+    s.xs_bytes = s.mbk * 2 * R * 128;
+    off = 1024;                                         // mbarriers + TMEM slot
+    s.w = off; off += s.w_bytes;
+    s.dr = off; off += 2 * s.dr_bytes;
+    s.xs = off; off += 2 * s.xs_bytes;
+    s.st = off;
+    { int o = 0; for (int i = 0; i < kMaxSrc; ++i) { s.st_off[i] = o; if (i < nsrc) o += R * cps[i] * 2; } off += (o + 127) & ~127; }
+    s.st2 = off; off += (R * x1cp * 2 + 127) & ~127;
+    off = (off + 1023) & ~1023;
+    s.ring = off;
+    { int ring = nstage * s.stage_bytes; const int scratch = 128 * 65 * 4; if (ring < scratch) ring = scratch; off += ring; }   // doubles as the dW transposition tile
+    s.total = off + 1024;                               // slack for the manual 1024-byte alignment of the base
+    return s;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwdArgs a) {
+    static_assert(R == 32 || R == 64, "row tile");
+    constexpr int HR = R / 2;                           // rows per epilogue half
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const PwDesc& d = *a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    const int NP = d.NPall, gwp = d.cols.gwp, nplanes = d.cols.nplanes, nsrc = d.nsrc, cpo = a.cpo;
+    int cps[kMaxSrc], accs[kMaxSrc], ksum = 0;
+    for (int i = 0; i < kMaxSrc; ++i) { cps[i] = i < nsrc ? d.src[i].cp : 0; accs[i] = i < nsrc ? d.src[i].accumulate : 0; ksum += cps[i]; }
+    const int x1cp = a.x1 ? a.x1cp : 0;
+    const int S = a.nbuf;                               // ring depth
+    const PwBfSmem L = pw_bf_smem(R, nsrc, cps, accs, NP, nplanes, cpo, x1cp, S);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);               // [kBfMaxStages]
+    uint64_t* empty = full + kBfMaxStages;                            // [kBfMaxStages]
+    uint64_t* stg_full = empty + kBfMaxStages;                        // [2]
+    uint64_t* stg_empty = stg_full + 2;                               // [2]
+    uint64_t* tm_full = stg_empty + 2;                                // [2]
+    uint64_t* tm_empty = tm_full + 2;                                 // [2]
+    uint64_t* all_done = tm_empty + 2;                                // [1]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 512);
+    unsigned char* Ws = smem + L.w;
+    unsigned char* ring = smem + L.ring;
+
+    const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
+    const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
+    const int my_tiles = max(0, tile_hi - tile_lo);
+
+    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
+    if (tid == 32) {
+        for (int s = 0; s < kBfMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kBfTransformWarps + kBfEpilogueWarps); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&stg_full[b], kBfTransformWarps); mbar_init(&stg_empty[b], 1);
+            mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], kBfEpilogueWarps);
+        }
+        mbar_init(all_done, 1);
+        mbar_fence_init();
+    }
+    // weights: Wb [KP][NP] (row kk, column j) -> K-major swizzled A operand blocks [mb][kb] of [128 rows][128 bytes]; the
+    // staging tiles start as zeros (K / N padding and the rows of partial tiles contribute nothing)
+    for (int i = tid; i < (L.w_bytes + 2 * L.dr_bytes + 2 * L.xs_bytes) / 16; i += kBfThreads) reinterpret_cast<uint4*>(Ws)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = tid; i < d.KP * (NP >> 3); i += kBfThreads) {
+        const int kk = i / (NP >> 3), c = i - kk * (NP >> 3);
+        if (kk >= L.mbk * 128) continue;
+        *reinterpret_cast<uint4*>(Ws + (size_t)((kk >> 7) * L.nkb + (c >> 3)) * 16384 + sw128_offset(kk & 127, (c & 7) * 8, 128)) =
+            *reinterpret_cast<const uint4*>(d.wb + (size_t)kk * NP + c * 8);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    pdl_wait();                                         // everything above read only this launch's descriptor / prepared weights
+
+    auto tile_geom = [&](int tile, int& t, int& r0, int& rows) { t = tile / tps; r0 = (tile - t * tps) * R; rows = min(R, a.Rt - r0); };
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % S, k = it / S;
+                mbar_wait(&empty[s], (k & 1) ^ 1);
+                int t, r0, rows; tile_geom(tile_lo + it, t, r0, rows);
+                const size_t row = (size_t)t * a.Rt + r0;
+                unsigned char* dst = ring + (size_t)s * L.stage_bytes;
+                uint32_t bytes = (uint32_t)rows * (2 * nplanes * cpo + ksum + x1cp) * 2;
+                for (int i = 0; i < nsrc; ++i) if (accs[i]) bytes += (uint32_t)rows * cps[i] * 2;
+                mbar_expect_tx(&full[s], bytes);
+                for (int p = 0; p < nplanes; ++p) {
+                    bulk_g2s(dst + L.o_dout + (size_t)p * R * cpo * 2, a.dout[p] + row * cpo, rows * cpo * 2, &full[s]);
+                    bulk_g2s(dst + L.o_out + (size_t)p * R * cpo * 2, a.out[p] + row * cpo, rows * cpo * 2, &full[s]);
+                }
+                for (int i = 0; i < nsrc; ++i) {
+                    bulk_g2s(dst + L.o_src[i], d.src[i].data + row * cps[i], rows * cps[i] * 2, &full[s]);
+                    if (accs[i]) bulk_g2s(dst + L.o_ge[i], d.src[i].grad + row * cps[i], rows * cps[i] * 2, &full[s]);
+                }
+                if (x1cp) bulk_g2s(dst + L.o_x1, a.x1 + row * x1cp, rows * x1cp * 2, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_d = umma_idesc(128, R, 0, 0), idesc_w = umma_idesc(128, L.np16, 1, 1);
+            const uint32_t wa = smem_u32(Ws);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int b = it & 1, n = it >> 1;
+                mbar_wait(&stg_full[b], n & 1);
+                mbar_wait(&tm_empty[b], (n & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t ra = smem_u32(smem + L.dr + (size_t)b * L.dr_bytes), xa = smem_u32(smem + L.xs + (size_t)b * L.xs_bytes);
+                for (int mb = 0; mb < L.mbk; ++mb)
+                    for (int ks = 0; ks < (L.np16 >> 4); ++ks) {
+                        const int kb = ks >> 2;
+                        umma_bf16(tmem + (uint32_t)(L.cols_dw + (b * L.mbk + mb) * R),
+                                  umma_desc(wa + (uint32_t)(mb * L.nkb + kb) * 16384u + (uint32_t)(ks & 3) * 32u, 16, 1024),
+                                  umma_desc(ra + (uint32_t)kb * (uint32_t)(R * 128) + (uint32_t)(ks & 3) * 32u, 16, 1024), idesc_d, ks > 0);
+                    }
+                umma_commit(&tm_full[b]);
+                for (int mb = 0; mb < L.mbk; ++mb)
+#pragma unroll
+                    for (int ks = 0; ks < R / 16; ++ks)
+                        umma_bf16(tmem + (uint32_t)(mb * L.np16), umma_desc(xa + (uint32_t)mb * 2u * R * 128u + (uint32_t)ks * 2048u, R * 128, 1024),
+                                  umma_desc(ra + (uint32_t)ks * 2048u, R * 128, 1024), idesc_w, it > 0 || ks > 0);
+                umma_commit(&stg_empty[b]);
+            }
+            umma_commit(all_done);
+            mbar_wait(all_done, 0);
+        }
+    } else if (warp < 2 + kBfTransformWarps) {
+        // ================================================================ transform warps
+        const int ttid = tid - 64;
+        const int nqr = NP >> 3, rq = ttid % nqr, rrl = ttid / nqr, rnrl = kBfTransformThreads / nqr;       // dR chunks
+        const int nqx = ksum >> 3, xq = ttid % nqx, xrl = ttid / nqx, xnrl = kBfTransformThreads / nqx;    // act(src) chunks
+        const int tp = (rq * 8) / gwp, tc = rq * 8 - tp * gwp;
+        int xsrc = 0, xch = xq;
+        while (xsrc < nsrc - 1 && xch >= (cps[xsrc] >> 3)) { xch -= cps[xsrc] >> 3; ++xsrc; }
+        int xcp = 0, o_xsrc = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxSrc; ++i) if (i == xsrc) { xcp = cps[i]; o_xsrc = L.o_src[i]; }
+        const float2* xaff = d.src[xsrc].aff;
+        const int o_dout = L.o_dout, o_out = L.o_out, stage_bytes = L.stage_bytes, o_dr = L.dr, o_xs = L.xs, dr_bytes = L.dr_bytes, xs_bytes = L.xs_bytes;
+        const bool sclamp = d.src[xsrc].clamp != 0, oclamp = a.out_clamp != 0;
+        const double inv_n = 1.0 / (double)a.Rt;
+        float4 c8[8];
+        float2 x8[8];
+        int cur_t = -1;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it % S, k = it / S, b = it & 1, n = it >> 1;
+            int t, r0, rows; tile_geom(tile_lo + it, t, r0, rows);
+            if (t != cur_t) {                           // this thread's chunk constants for the slice (no shared table, no barrier)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    int p, sl, l, nn;
+                    c8[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rrl < rnrl && pw_col(d, rq * 8 + q, p, sl, l, nn)) {
+                        const size_t idx = (size_t)t * cpo + sl;
+                        c8[q] = bnbwd_consts(a.tb[p].aff[idx], a.tb[p].bnp[idx], ld_sum(a.tb[p].bsum + idx), inv_n);
+                    }
+                    x8[q] = (xrl < xnrl && xaff) ? xaff[(size_t)t * xcp + xch * 8 + q] : make_float2(1.f, 0.f);
+                }
+                cur_t = t;
+            }
+            mbar_wait(&full[s], k & 1);
+            mbar_wait(&stg_empty[b], (n & 1) ^ 1);
+            const unsigned char* rb = ring + (size_t)s * stage_bytes;
+            unsigned char* Dr = smem + o_dr + (size_t)b * dr_bytes;
+            unsigned char* Xs = smem + o_xs + (size_t)b * xs_bytes;
+            if (rrl < rnrl) {
+                const uint4* dv = reinterpret_cast<const uint4*>(rb + o_dout + (size_t)tp * R * cpo * 2) + (tc >> 3);
+                const uint4* ov = reinterpret_cast<const uint4*>(rb + o_out + (size_t)tp * R * cpo * 2) + (tc >> 3);
+                const int nch = cpo >> 3;
+                for (int r = rrl; r < R; r += rnrl) {
+                    uint4 dvv = make_uint4(0, 0, 0, 0);
+                    if (r < rows) {
+                        dvv = dv[r * nch]; const uint4 ovv = ov[r * nch];
+                        uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
+                            dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], oclamp), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], oclamp));
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(Dr + sw128_offset(r, rq * 8, R)) = dvv;
+                }
+            }
+            if (xrl < xnrl) {
+                const uint4* sv = reinterpret_cast<const uint4*>(rb + o_xsrc) + xch;
+                const int nch = xcp >> 3;
+                for (int r = xrl; r < R; r += xnrl) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (r < rows) v = affine8(sv[r * nch], x8, sclamp);
+                    *reinterpret_cast<uint4*>(Xs + sw128_offset(r, xq * 8, R)) = v;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&stg_full[b]); mbar_arrive(&empty[s]); }
+        }
+    } else {
+        // ================================================================ epilogue warps
+        const int ew = warp - (2 + kBfTransformWarps), lg = ew & 3, half = ew >> 2, etid = tid - (2 + kBfTransformWarps) * 32;
+        // this thread's data-gradient channel per 128-row block of dSrc^T: kk = mb * 128 + 32 * lg + lane -> (source, slot).
+        // Everything the tile loop needs is hoisted into registers here (no descriptor reads / local arrays in the loop).
+        struct Chan {
+            int cp, o_src, o_ge, st_off, slot; bool on, clamp, want, acc;
+            const float2* aff; const float2* bnp; double2* bsum;
+            float s1, s2; float4 sc;
+        };
+        auto make_chan = [&](int mb) {
+            Chan ch; ch.on = false; ch.cp = 0; ch.o_src = ch.o_ge = ch.st_off = ch.slot = 0; ch.clamp = ch.want = ch.acc = false;
+            ch.aff = ch.bnp = nullptr; ch.bsum = nullptr; ch.s1 = ch.s2 = 0.f; ch.sc = make_float4(1.f, 0.f, 0.f, 0.f);
+            if (mb >= L.mbk) return ch;
+            const int kk = mb * 128 + 32 * lg + lane;
+            int off = 0;
+            for (int i = 0; i < nsrc; ++i) {
+                const int cp = d.src[i].cp;
+                if (kk >= off && kk < off + cp) {
+                    const PwSrc& Sx = d.src[i];
+                    ch.on = true; ch.cp = cp; ch.slot = kk - off; ch.clamp = Sx.clamp != 0; ch.acc = Sx.accumulate != 0;
+                    ch.aff = Sx.aff; ch.bnp = Sx.bnp; ch.bsum = Sx.bsum;
+                    ch.want = Sx.bsum != nullptr && ch.slot >= Sx.sum_lo && ch.slot < Sx.sum_hi;
+                    ch.o_src = L.o_src[i]; ch.o_ge = L.o_ge[i]; ch.st_off = L.st_off[i];
+                }
+                off += cp;
+            }
+            return ch;
+        };
+        Chan ch0 = make_chan(0), ch1 = make_chan(1);
+        const int mbk = L.mbk, cols_dw = L.cols_dw, o_dout = L.o_dout, o_x1 = L.o_x1, o_st = L.st, o_st2 = L.st2, stage_bytes = L.stage_bytes;
+        // pass-through role: thread <-> x1 slot
+        int x_src = -1;                                 // element offset inside the d out region of a stage, -2: padding (zero), -1: no role
+        if (x1cp && etid < x1cp) {
+            const int l = slot_logical(a.x1map, etid);
+            x_src = (l >= 0 && (l >> 1) < a.ncopy) ? (l & 1) * R * cpo + a.copy_dst0 + (l >> 1) : -2;
+        }
+        float xs1 = 0.f, xs2 = 0.f;
+        float4 xc = make_float4(1.f, 0.f, 0.f, 0.f);
+        const bool xclamp = a.x1clamp != 0;
+        // bulk-store plan of thread 0 (one store per gradient tensor)
+        bf16* g_ptr[kMaxSrc]; int g_cp[kMaxSrc], g_off[kMaxSrc];
+#pragma unroll
+        for (int i = 0; i < kMaxSrc; ++i) { g_ptr[i] = i < nsrc ? d.src[i].grad : nullptr; g_cp[i] = cps[i]; g_off[i] = L.st_off[i]; }
+        auto flush_chan = [&](Chan& ch, int t) {
+            if (ch.want && (ch.s1 != 0.f || ch.s2 != 0.f)) {
+                double2* dst = ch.bsum + (size_t)t * ch.cp + ch.slot;
+                atomicAdd(&dst->x, (double)ch.s1); atomicAdd(&dst->y, (double)ch.s2);
+            }
+            ch.s1 = ch.s2 = 0.f;
+        };
+        auto flush = [&](int t) {
+            flush_chan(ch0, t); flush_chan(ch1, t);
+            if (x_src != -1 && a.x1bsum && (xs1 != 0.f || xs2 != 0.f)) {
+                double2* dst = a.x1bsum + (size_t)t * x1cp + etid;
+                atomicAdd(&dst->x, (double)xs1); atomicAdd(&dst->y, (double)xs2);
+            }
+            xs1 = xs2 = 0.f;
+        };
+        auto run_chan = [&](Chan& ch, int mb, int b, int rows, const unsigned char* rb) {
+            float v[HR];
+            const uint32_t taddr = tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(cols_dw + (b * mbk + mb) * R + half * HR);
+            tmem_ld16(taddr, *reinterpret_cast<float(*)[16]>(&v[0]));
+            if (HR == 32) tmem_ld16(taddr + 16, *reinterpret_cast<float(*)[16]>(&v[HR - 16]));
+            if (!ch.on) return;
+            const int cp = ch.cp;
+            const unsigned short* rawp = reinterpret_cast<const unsigned short*>(rb + ch.o_src) + ch.slot + half * HR * cp;
+            const unsigned short* gep = reinterpret_cast<const unsigned short*>(rb + ch.o_ge) + ch.slot + half * HR * cp;
+            unsigned short* stp = reinterpret_cast<unsigned short*>(smem + o_st + ch.st_off) + ch.slot + half * HR * cp;
+            const int nr = min(HR, rows - half * HR);
+            float s1 = ch.s1, s2 = ch.s2;
+            const float4 sc = ch.sc;
+#pragma unroll
+            for (int j = 0; j < HR; ++j) {
+                if (j < nr) {
+                    float g = v[j];
+                    if (ch.acc) g = __bfloat162float(__float2bfloat16_rn(g)) + __uint_as_float((uint32_t)gep[j * cp] << 16);
+                    const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16_rn(g));
+                    stp[j * cp] = gb;
+                    if (ch.want) sum_accum(__uint_as_float((uint32_t)gb << 16), __uint_as_float((uint32_t)rawp[j * cp] << 16), sc, ch.clamp, s1, s2);
+                }
+            }
+            ch.s1 = s1; ch.s2 = s2;
+        };
+        int cur_t = -1;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it % S, k = it / S, b = it & 1, n = it >> 1;
+            int t, r0, rows; tile_geom(tile_lo + it, t, r0, rows);
+            if (t != cur_t) {
+                if (cur_t >= 0) flush(cur_t);
+                if (ch0.on) ch0.sc = sum_consts(ch0.aff, ch0.bnp, (size_t)t * ch0.cp + ch0.slot);
+                if (ch1.on) ch1.sc = sum_consts(ch1.aff, ch1.bnp, (size_t)t * ch1.cp + ch1.slot);
+                if (x_src != -1) xc = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + etid);
+                cur_t = t;
+            }
+            // the previous tile's bulk stores have finished READING the staging rows
+            if (etid == 0) bulk_store_wait_read();
+            named_bar_sync(1, kBfEpilogueThreads);
+            mbar_wait(&full[s], k & 1);                 // (long complete: acquires the TMA writes for this thread)
+            mbar_wait(&tm_full[b], n & 1);
+            tc_fence_after();
+            const unsigned char* rb = ring + (size_t)s * stage_bytes;
+            run_chan(ch0, 0, b, rows, rb);
+            if (mbk > 1) run_chan(ch1, 1, b, rows, rb);
+            tc_fence_before();
+            // pass-through half of a stride-1 unit: d x1[slot(2i + p)] = d out_p[copy_dst0 + i]   (bit-exact gather)
+            if (x_src != -1) {
+                const unsigned short* dreg = reinterpret_cast<const unsigned short*>(rb + o_dout);
+                const unsigned short* xr = reinterpret_cast<const unsigned short*>(rb + o_x1) + etid;
+                unsigned short* dst = reinterpret_cast<unsigned short*>(smem + o_st2) + etid;
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) {
+                    const unsigned short gb = x_src >= 0 ? dreg[x_src + r * cpo] : (unsigned short)0;
+                    dst[r * x1cp] = gb;
+                    sum_accum(__uint_as_float((uint32_t)gb << 16), __uint_as_float((uint32_t)xr[r * x1cp] << 16), xc, xclamp, xs1, xs2);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&tm_empty[b]); mbar_arrive(&empty[s]); }
+            fence_proxy_async();
+            named_bar_sync(2, kBfEpilogueThreads);
+            if (etid == 0) {                            // one TMA bulk store per gradient tensor (a row tile is contiguous in HBM)
+                const size_t row = (size_t)t * a.Rt + r0;
+#pragma unroll
+                for (int i = 0; i < kMaxSrc; ++i)
+                    if (g_ptr[i]) bulk_s2g(g_ptr[i] + row * g_cp[i], smem + o_st + g_off[i], (uint32_t)rows * g_cp[i] * 2);
+                if (x1cp) bulk_s2g(a.dx1 + row * x1cp, smem + o_st2, (uint32_t)rows * x1cp * 2);
+            }
+        }
+        if (cur_t >= 0) flush(cur_t);
+        if (etid == 0) bulk_store_wait_all();
+    }
+
+    // ================================================================ all roles: weight-gradient epilogue
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (my_tiles > 0) {
+        float* Sc = reinterpret_cast<float*>(ring);        // [128][65]
+        for (int mb = 0; mb < L.mbk; ++mb)
+            for (int c0 = 0; c0 < L.np16; c0 += 64) {
+                const int ncol = min(64, L.np16 - c0);
+                if (warp < 4) {
+                    for (int c = 0; c < ncol; c += 8) {
+                        float v[8];
+                        tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mb * L.np16 + c0 + c), v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) Sc[(32 * warp + lane) * 65 + c + i] = v[i];
+                    }
+                }
+                __syncthreads();
+                for (int i = tid; i < 128 * ncol; i += kBfThreads) {
+                    const int rowk = i / ncol, col = i - rowk * ncol;
+                    int lk, kx, p, sl, lj, nn;
+                    const int kk = mb * 128 + rowk, j = c0 + col;
+                    if (kk < d.KP && j < NP && pw_row(d, kk, lk, kx) && pw_col(d, j, p, sl, lj, nn) && lk == lj) {
+                        const LayerP& Lp = d.layer[lk];
+                        atomicAdd(Lp.dw + (size_t)kx * Lp.N + nn, Sc[rowk * 65 + col]);
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
+    // ---- BatchNorm parameter gradients (one CTA): dgamma = sum_t S2, dbeta = sum_t S1
+    if (blockIdx.x == 0) {
+        for (int j = tid; j < NP; j += kBfThreads) {
+            int p, sl, l, nn;
+            if (!pw_col(d, j, p, sl, l, nn)) continue;
+            double gs = 0.0, bs = 0.0;
+            for (int t = 0; t < kT; ++t) { const double2 v = ld_sum(a.tb[p].bsum + (size_t)t * cpo + sl); bs += v.x; gs += v.y; }
+            d.layer[l].dg[nn] = (float)gs; d.layer[l].dbe[nn] = (float)bs;
+        }
+    }
+}
+
+}  // namespace v2
+}  // namespace cdra
+#endif

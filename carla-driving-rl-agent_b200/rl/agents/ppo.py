@@ -118,20 +118,14 @@ class PPOAgent(Agent):
                 self.seed_regularization()
                 total_loss, policy_grads = self.get_policy_gradients(data_batch)
                 self.update_policy(policy_grads)
-                if isinstance(policy_grads, dict):
-                    policy_grads = policy_grads['policy']
-                self.log(loss_total=total_loss, lr_policy=self.policy_lr.value,
-                         gradients_norm_policy=[g.norm() for g in policy_grads])
+                self.log(loss_total=total_loss, lr_policy=self.policy_lr.value, gradients_norm_policy=self._head_norms)
 
         for _ in range(self.optimization_steps['value']):
             for data_batch in value_batches():
                 self.seed_regularization()
                 value_loss, value_grads = self.get_value_gradients(data_batch)
                 self.update_value(value_grads)
-                if isinstance(value_grads, dict):
-                    value_grads = value_grads['value']
-                self.log(loss_value=value_loss, lr_value=self.value_lr.value,
-                         gradients_norm_value=[g.norm() for g in value_grads])
+                self.log(loss_value=value_loss, lr_value=self.value_lr.value, gradients_norm_value=self._head_norms)
 
         if torch.cuda.is_available():
             torch.cuda.synchronize()
@@ -153,15 +147,15 @@ class PPOAgent(Agent):
         """rl/agents/ppo.py:238-252: per-tensor clip -> (old_policy <- policy) -> Adam [-> Polyak]."""
         net = self.network
         clip = self.grad_norm_policy if self.should_clip_policy_grads else None
+        net.sync.allreduce('pol')
+        self._head_norms = net.engine.grad_norms('pol', net.grad_scale) if self.statistics.should_log else None
         if self.should_polyak_average:
             old = net.policy.flat.clone()
             net.update_old_policy(old)
-            net.sync.allreduce('pol')
             net.engine.clip_adam('pol', self.policy_lr(), clip, net.grad_scale)
             utils.polyak_averaging(net.policy.flat, old, alpha=self.polyak_coeff)
         else:
             net.update_old_policy()
-            net.sync.allreduce('pol')
             net.engine.clip_adam('pol', self.policy_lr(), clip, net.grad_scale)
         return gradients
 
@@ -170,6 +164,7 @@ class PPOAgent(Agent):
         net = self.network
         clip = self.grad_norm_value if self.should_clip_value_grads else None
         net.sync.allreduce('val')
+        self._head_norms = net.engine.grad_norms('val', net.grad_scale) if self.statistics.should_log else None
         if self.should_polyak_average:
             old = net.value.flat.clone()
             net.engine.clip_adam('val', self.value_lr(), clip, net.grad_scale)
@@ -190,6 +185,8 @@ class PPOAgent(Agent):
         n = flat[0].shape[0]
         index_lists = utils.index_batches(n, self.batch_size, drop_remainder=self.drop_batch_remainder, skip=self.skip_count,
                                           num_shards=self.obs_skipping, seed=self.seed, **kw)
+        # data parallel: one gradient all-reduce per minibatch, so every rank runs the same number of them
+        index_lists = index_lists[:self.network.sync.agree_min(len(index_lists))]
 
         def gen():
             for idx in index_lists:

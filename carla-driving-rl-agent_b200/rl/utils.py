@@ -108,28 +108,99 @@ def index_batches(n: int, batch_size: int, shuffle_batches=False, seed=None, dro
 
 
 class Summary:
-    """Lightweight stand-in for utils.Summary (rl/utils.py:577-673): collects scalars per key; `mode=None`
-    disables logging.  TensorBoard export is outside the hot path."""
+    """utils.Summary (rl/utils.py:577-673): `agent.log(**kwargs)` collects values per key, `write_summaries()` emits one
+    TensorBoard scalar per collected value (histograms for 'weight-' / 'bias-' keys, images for 'image_' keys) under
+    `<summary_dir>/<name>/<timestamp>` and clears the lists; `mode='log'` only collects, `mode=None` disables.
 
-    def __init__(self, mode='summary', name=None, keys: Optional[List[str]] = None, **_):
+    Values that live on the GPU (losses, ratios, per-tensor gradient norms written by the kernels) are kept as device
+    tensors and reduced / copied to the host ONCE per `write_summaries()` -- logging never synchronises the update loop
+    (the reference's eager `float(x)` per scalar would cost one host round trip per value per SGD step)."""
+
+    def __init__(self, mode='summary', name=None, summary_dir='logs', keys: Optional[List[str]] = None):
+        self.stats: Dict[str, dict] = {}
+        self.allowed_keys = {k: True for k in keys} if isinstance(keys, (list, tuple, set)) else None
+        self.should_log = mode in ('summary', 'log')
+        self.use_summary = mode == 'summary'
         self.mode = mode
         self.name = name
-        self.keys = set(keys) if keys else None
-        self.stats: Dict[str, list] = {}
-        self.should_log = mode is not None
+        self.summary_dir = None
+        self._writer = None
+        self.last: Dict[str, float] = {}
+        if self.use_summary:
+            import datetime
+            self.summary_dir = os.path.join(summary_dir, str(name), datetime.datetime.now().strftime('%Y%m%d-%H%M%S'))
+
+    def should_log_key(self, key: str) -> bool:
+        return True if self.allowed_keys is None else key in self.allowed_keys
 
     def log(self, **kwargs):
         if not self.should_log:
             return
-        for k, v in kwargs.items():
-            if self.keys is not None and k not in self.keys:
+        for key, value in kwargs.items():
+            if not self.should_log_key(key):
                 continue
-            if isinstance(v, torch.Tensor):
-                v = v.detach().float().mean().item() if v.numel() > 1 else v.item()
-            elif isinstance(v, (list, tuple)):
-                v = [float(x) for x in v]
-            self.stats.setdefault(k, []).append(v)
+            entry = self.stats.setdefault(key, dict(step=0, list=[]))
+            if isinstance(value, np.ndarray):
+                value = torch.from_numpy(np.atleast_1d(value))
+            if isinstance(value, torch.Tensor):
+                # a tensor with several elements extends the list row by row (tf: `list.extend(tensor)`); the snapshot is a
+                # device-side copy, so buffers the kernels overwrite every step (loss scalars) can be logged as views
+                v = value.detach()
+                entry['list'].append(v.reshape(v.shape[0], -1).clone() if v.dim() >= 1 and v.numel() > 1 else v.reshape(1, 1).clone())
+            elif isinstance(value, (list, tuple)) and len(value) and isinstance(value[0], torch.Tensor):
+                entry['list'].append(torch.stack([x.detach().float().reshape(-1).mean() for x in value]).reshape(-1, 1))
+            elif hasattr(value, '__iter__'):
+                entry['list'].extend(np.mean(np.asarray(x, dtype=np.float64)) for x in value)
+            else:
+                entry['list'].append(float(value))
+
+    def _collect(self):
+        """{key: [float per logged value]}: every device tensor is reduced to per-row means on its device, all of them
+        travel to the host in ONE copy"""
+        dev_rows, slots = [], []
+        out = {}
+        for key, entry in self.stats.items():
+            vals = []
+            for item in entry['list']:
+                if isinstance(item, torch.Tensor):
+                    m = item.float().mean(dim=1)
+                    if m.device.type == 'cpu':
+                        vals.extend(m.tolist())
+                    else:
+                        slots.append((key, len(vals), m.numel()))
+                        vals.extend([None] * m.numel())
+                        dev_rows.append(m)
+                else:
+                    vals.append(float(item))
+            out[key] = vals
+        if dev_rows:
+            host = torch.cat(dev_rows).cpu().tolist()
+            i = 0
+            for key, pos, n in slots:
+                out[key][pos:pos + n] = host[i:i + n]
+                i += n
+        return out
 
     def write_summaries(self):
-        self.last = {k: v[-1] for k, v in self.stats.items() if v}
-        self.stats = {}
+        data = self._collect()
+        self.last = {k: v[-1] for k, v in data.items() if v}
+        if self.use_summary:
+            if self._writer is None:
+                from torch.utils.tensorboard import SummaryWriter
+                self._writer = SummaryWriter(log_dir=self.summary_dir)
+            for name, values in data.items():
+                step = self.stats[name]['step']
+                if 'weight-' in name or 'bias-' in name:
+                    self._writer.add_histogram(name, np.asarray(values), global_step=step)
+                else:
+                    for i, v in enumerate(values):
+                        self._writer.add_scalar(name, v, global_step=step + i)
+            self._writer.flush()
+        for name, values in data.items():
+            self.stats[name]['step'] += len(values)
+            self.stats[name]['list'].clear()
+
+    def close(self):
+        if self._writer is not None:
+            self._writer.close()
+            self._writer = None

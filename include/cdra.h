@@ -99,7 +99,11 @@ int cdra_dynamics_backward(cdra_plan_t* plan, const float* params, const void* i
  * logp_old [B,2]; adv [B]; true_speed/true_sim [B,1].  scalars_out (16 floats): 0 total, 1 loss_policy,
  * 2 loss_entropy(=coef*H), 3 loss_speed, 4 loss_similarity, 5 ratio mean, 6 log_prob mean, 7 entropy,
  * 8 speed mean, 9 similarity mean.  d_x512 [B,512]; grads = policy gradient arena (overwritten).
- * grad_scale multiplies every gradient (1/world_size under data parallelism). */
+ * grad_scale multiplies every gradient (1/world_size under data parallelism).
+ * actions_jac [B,2,2] (may be NULL): (d a / d alpha, d a / d beta) of each evaluated action when it is a reparameterised
+ * sample of the NEW policy -- the reference's `log_prob(clip(sample))` is differentiated through the sample (TFP Beta is
+ * FULLY_REPARAMETERIZED: x = g1 / (g1 + g2) with implicit gamma gradients [lib]); NULL treats the action as a constant
+ * (the base class's stored-action PPO, rl/agents/ppo.py:324-325). */
 /* The dense GEMM behind the GRU projections, the trunk and the control branches (Keras Dense / GRU kernels,
  * core/networks.py:24-66): C[M][N] (=|+=) opA(A) opB(B) (+ bias[n]) on fp32 row-major device matrices; ta: A is stored
  * [K][M]; tb: B is stored [N][K].  tensor_core = 0: fp32 CUDA-core kernel (parity mode); 1: TF32 mma.sync kernel (bf16
@@ -123,7 +127,7 @@ int cdra_debug_umma_selftest_k(const void* A, const void* B, float* C, int Mw, i
 int cdra_debug_set(const char* key, int value);
 
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
-                                  const float* actions_eval, const float* logp_old, const float* adv,
+                                  const float* actions_eval, const float* actions_jac, const float* logp_old, const float* adv,
                                   const float* true_speed, const float* true_sim, float clip_ratio,
                                   float ent_coef, int training, float grad_scale, float* scalars_out,
                                   float* head_out, float* d_x512, float* grads, void* workspace, void* stream);
@@ -152,6 +156,12 @@ int cdra_gae(const float* rewards, const float* values_be, const float* last_val
 int cdra_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* tensor_offsets,
                    int n_tensors, int64_t total, float clip_norm, float lr, float beta1, float beta2, float eps,
                    int64_t step, float grad_scale, float* norms_out, void* stream);
+
+/* The per-tensor gradient norms the reference logs after every SGD step (`[tf.norm(g) for g in grads]`,
+ * rl/agents/ppo.py:209-210,223-224; core/carla_agent.py:382,461): ONE launch over the flat arena instead of one reduction
+ * (and one host round trip) per tensor.  sq_norms_out [n_tensors] receives sum((grad_scale * g)^2) per tensor. */
+int cdra_grad_norms(const float* grads, const int64_t* tensor_offsets, int n_tensors, int64_t total, float grad_scale,
+                    float* sq_norms_out, void* stream);
 
 /* utils.data_to_batches gather (rl/utils.py:365-393): dst[i] = src[index[i]] for rows of row_bytes. */
 int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst, void* stream);

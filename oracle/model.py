@@ -310,15 +310,35 @@ def beta_entropy(a, b):
             + (a + b - 2.0) * torch.digamma(a + b))
 
 
-def policy_forward(p, x512, actions_eval, training=True, bn_state=None):
-    """PolicyNetwork.call (core/networks.py:96-110).  `actions_eval` replaces the fresh sample the
-    reference draws (decision D2); it is clipped like `_clip_actions` (:139-144)."""
+def beta_sample_reparameterized(alpha, beta, generator=None):
+    """tfp.distributions.Beta._sample_n [lib] (tensorflow-probability 0.11): x = g1 / (g1 + g2) with g1 ~ Gamma(alpha),
+    g2 ~ Gamma(beta); the distribution is FULLY_REPARAMETERIZED, the gamma draws carry implicit-reparameterisation
+    gradients dg/dalpha = -(dF/dalpha) / pdf (tf.random.gamma's RandomGammaGrad; torch exposes the same quantity as
+    torch._standard_gamma_grad).  Returns (sample, jac [..., 2] = (dx/dalpha, dx/dbeta)) as constants."""
+    with torch.no_grad():
+        a, b = alpha.detach(), beta.detach()
+        g1 = torch._standard_gamma(a, generator=generator) if generator is not None else torch._standard_gamma(a)
+        g2 = torch._standard_gamma(b, generator=generator) if generator is not None else torch._standard_gamma(b)
+        s = g1 + g2
+        x = g1 / s
+        dg1, dg2 = torch._standard_gamma_grad(a, g1), torch._standard_gamma_grad(b, g2)
+        jac = torch.stack([g2 / (s * s) * dg1, -g1 / (s * s) * dg2], dim=-1)
+    return x, jac
+
+
+def policy_forward(p, x512, actions_eval, training=True, bn_state=None, actions_jac=None):
+    """PolicyNetwork.call (core/networks.py:96-110).  `actions_eval` stands for the fresh sample of the new policy the
+    reference draws (:97-100; decision D2); it is clipped like `_clip_actions` (:139-144).  With `actions_jac`
+    [B,2,2] = (d a / d alpha, d a / d beta) the action is a reparameterised sample and the log-prob is differentiated through
+    it, as TFP does; without it the action is a constant."""
     h = control_branch(x512, p, training, bn_state)
     alpha = softplus_c(h @ p['alpha.w'] + p['alpha.b'])
     beta = softplus_c(h @ p['beta.w'] + p['beta.b'])
     sim = torch.tanh(h @ p['similarity.w'] + p['similarity.b'])
     speed = 2.0 * torch.sigmoid(h @ p['speed.w'] + p['speed.b'])
-    a = actions_eval.clamp(EPSILON, 1.0 - EPSILON)
+    if actions_jac is not None:          # value of the sample unchanged, first-order dependence on (alpha, beta) attached
+        actions_eval = (actions_eval + actions_jac[..., 0] * (alpha - alpha.detach()) + actions_jac[..., 1] * (beta - beta.detach()))
+    a = actions_eval.clamp(EPSILON, 1.0 - EPSILON)      # tf.clip_by_value: gradient passes where not clipped
     logp = beta_log_prob(alpha, beta, a)
     ent = beta_entropy(alpha, beta)
     mean = alpha / (alpha + beta)

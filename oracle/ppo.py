@@ -120,13 +120,13 @@ def _leaf(params):
 
 
 def policy_pass(dyn, pol, obs, actions_eval, advantages, old_log_prob, true_speed, true_sim,
-                clip_ratio=0.2, ent_coef=1.0):
+                clip_ratio=0.2, ent_coef=1.0, actions_jac=None):
     """CARLAgent.get_policy_gradients (core/carla_agent.py:351-373): loss + grads wrt policy head and
     dynamics.  Returns dict(loss, scalars, g_dyn, g_pol, x512, bn_dyn, bn_pol)."""
     d, h = _leaf(dyn), _leaf(pol)
     bs_d, bs_h = model.BNState(), model.BNState()
     x512 = model.dynamics_forward(d, obs, True, bs_d)
-    out = model.policy_forward(h, x512, actions_eval, True, bs_h)
+    out = model.policy_forward(h, x512, actions_eval, True, bs_h, actions_jac)
     loss, scalars = policy_objective(out, advantages, old_log_prob, true_speed, true_sim, clip_ratio, ent_coef)
     loss.backward()
     return dict(loss=loss.detach(), scalars={k: v.detach() for k, v in scalars.items()},

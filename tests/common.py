@@ -72,7 +72,8 @@ def rel_l2(a, b):
 
 def policy_step_engine(eng, obs, bt, clip=0.2, ent=1.0):
     x = eng.dynamics_forward(obs)
-    sc = eng.policy_head(x, bt['actions'], bt['logp_old'], bt['adv'], bt['true_speed'], bt['true_sim'], clip, ent).clone()
+    sc = eng.policy_head(x, bt['actions'], bt['logp_old'], bt['adv'], bt['true_speed'], bt['true_sim'], clip, ent,
+                         actions_jac=bt.get('actions_jac')).clone()
     eng.dynamics_backward(obs, eng.d_x512)
     return sc
 
@@ -87,7 +88,8 @@ def value_step_engine(eng, obs, bt):
 def policy_step_oracle(dyn, pol, obs, bt, clip=0.2, ent=1.0, dtype=torch.float64):
     c = lambda t: t.detach().cpu().to(dtype)
     return ppo.policy_pass(dyn, pol, oracle_obs(obs, dtype), c(bt['actions']), c(bt['adv']), c(bt['logp_old']),
-                           c(bt['true_speed']), c(bt['true_sim']), clip, ent)
+                           c(bt['true_speed']), c(bt['true_sim']), clip, ent,
+                           actions_jac=c(bt['actions_jac']) if 'actions_jac' in bt else None)
 
 
 def value_step_oracle(dyn, val, obs, bt, dtype=torch.float64):

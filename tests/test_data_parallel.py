@@ -41,6 +41,8 @@ def _worker(rank, world, port, out_dir):
     eng.clip_adam('pol', 3e-4, 1.0, sync.grad_scale)
     torch.save(dict(dyn=eng.dyn.flat.clone(), pol=eng.pol.flat.clone(), norms=eng.norms['pol'].clone(),
                     mean_g=(sum(gathered[1]) / world)), os.path.join(out_dir, f'r{rank}.pt'))
+    # the number of minibatches (= gradient all-reduces) of an update is agreed on: the shortest rank decides
+    assert sync.agree_min(5 + 3 * rank) == 5
     lo, hi = sync.shard(8)
     assert (lo, hi) == (rank * 4, rank * 4 + 4)
     dist.destroy_process_group()

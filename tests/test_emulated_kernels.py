@@ -166,3 +166,40 @@ def test_gather_rows(eng):
     out = torch.empty(3, 5)
     eng.gather_rows(src, torch.tensor([8, 1, 4]), out)
     assert torch.equal(out, src[[8, 1, 4]])
+
+
+def test_policy_head_reparameterized_sample_gradient(eng, params):
+    """PolicyNetwork.call evaluates log pi at a REPARAMETERISED sample of the new policy (core/networks.py:97-100; TFP Beta
+    is FULLY_REPARAMETERIZED [lib]): with the sample's pathwise derivatives handed over (`actions_jac`), the fused head kernel
+    must reproduce the oracle's gradient through the sample; and the jacobian itself is checked against the defining property
+    of a reparameterised sample, d/dalpha E[f(x)] = E[f'(x) dx/dalpha]."""
+    dyn, pol, val = params
+    C.load_engine(eng, dyn, pol, val)
+    g = torch.Generator().manual_seed(11)
+    x512 = torch.randn(B, 512, generator=g)
+    bt = C.synthetic_batch(B, seed=12)
+    alpha = 1.01 + 3.0 * torch.rand(B, 2, generator=g, dtype=torch.float64)
+    beta = 1.01 + 3.0 * torch.rand(B, 2, generator=g, dtype=torch.float64)
+    act, jac = model.beta_sample_reparameterized(alpha, beta, generator=g)
+    act[0, 0] = 1.0                       # a clipped sample: tf.clip_by_value stops its gradient
+    bt['actions'], bt['actions_jac'] = act.float().contiguous(), jac.float().contiguous()
+    grads = {}
+    for use_jac in (True, False):
+        sc = eng.policy_head(x512, bt['actions'], bt['logp_old'], bt['adv'], bt['true_speed'], bt['true_sim'], 0.2, 1.0,
+                             actions_jac=bt['actions_jac'] if use_jac else None).clone()
+        h = {k: (t.clone().requires_grad_(True) if not k.endswith(('.mm', '.mv')) else t) for k, t in pol.items()}
+        xl = x512.double().requires_grad_(True)
+        out = model.policy_forward(h, xl, bt['actions'].double(), True, None, bt['actions_jac'].double() if use_jac else None)
+        loss, _ = ppo.policy_objective(out, bt['adv'].double(), bt['logp_old'].double(), bt['true_speed'].double(), bt['true_sim'].double(), 0.2, 1.0)
+        loss.backward()
+        assert abs(sc[0].item() - loss.item()) < 1e-4 * max(1.0, abs(loss.item()))
+        rows = C.grad_report(eng.pol, eng.g_pol, {k: t.grad for k, t in h.items() if t.requires_grad})
+        assert max(r[2] for r in rows) < 1e-2, sorted(rows, key=lambda r: -r[2])[:3]
+        assert C.rel_max(eng.d_x512, xl.grad) < 1e-2
+        grads[use_jac] = eng.g_pol.clone()
+    assert C.rel_l2(grads[True], grads[False]) > 1e-2          # the pathwise term is not negligible
+    # the jacobian is a pathwise derivative: compare E[x * dx/dalpha-weighted] estimates with the closed form of the mean,
+    # d/dalpha E[x] = beta / (alpha + beta)^2, d/dbeta E[x] = -alpha / (alpha + beta)^2
+    a0, b0 = torch.full((200000,), 2.5, dtype=torch.float64), torch.full((200000,), 1.7, dtype=torch.float64)
+    x, j = model.beta_sample_reparameterized(a0, b0, generator=g)
+    assert abs(j[:, 0].mean().item() - 1.7 / (4.2 ** 2)) < 2e-3 and abs(j[:, 1].mean().item() + 2.5 / (4.2 ** 2)) < 2e-3

@@ -9,7 +9,7 @@ import torch
 from oracle import model, ppo, spec
 from tests import common as C
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason='needs a CUDA device')]
 
 H, W = 90, 120
 
