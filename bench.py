@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """PPO update-step throughput of the B200-native hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (libcdra, sm_100a)
+    python bench.py --gpus N --steps K --warmup W            # this repo (libcdra, sm_100a), BASELINE config C2 per GPU
+    python bench.py --config C4 --gpus 2 ...                 # the other BASELINE.json configurations by name (C2 | C4 | C5)
     python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle restatement of the
                                                              # reference's TF/Keras path on the host cores
 
@@ -9,8 +10,13 @@ A "step" is one SGD minibatch index of the PPO update over the global minibatch 
 policy pass (shared-trunk forward+backward, policy head + clipped-surrogate/entropy/aux loss, gradient
 all-reduce, per-tensor clip + Adam on head and trunk) AND value pass (the same with the value head), i.e.
 every sample goes through both passes like `PPOAgent.update` (rl/agents/ppo.py:190-226); GAE / returns for
-all bs x T transitions run once per update inside the timed region.  Rollout tensors (bs x T samples,
+all bs x T transitions run once per update -- and once inside every timed region.  Rollout tensors (bs x T samples,
 uint8 frames) are resident in HBM before the clock starts; every step gathers its minibatch from them.
+
+`e2e` is the same metric through the reference-facing API with HOST buffers: pinned host transitions ->
+`CARLAMemory.append` (the host->device copies) -> `CARLAgent.end_episode` (returns / GAE) -> `CARLAgent.update()`
+(rl/agents/ppo.py:190-226: index batches, gather, both passes, clip + Adam) -> `write_summaries()` (the losses come
+back to the host), all inside the clock.
 """
 import argparse
 import json
@@ -28,6 +34,11 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 METRIC = 'ppo_update_samples_per_sec'
+CONFIGS = {                                       # BASELINE.json `configs` (per-GPU minibatch 512 in all of them)
+    'C2': dict(bs=512, T=256, height=90, width=120),      # batch_size=512, T=256, 90x120, bf16, 1 GPU  (C3 = the same on 8 GPUs)
+    'C4': dict(bs=512, T=256, height=180, width=240),     # batch_size=1024 over 2 GPUs, 180x240 high-res tower
+    'C5': dict(bs=512, T=512, height=90, width=120),      # batch_size=2048 over 4 GPUs, T=512 GAE / GRU stress
+}
 BYTES_PER_SAMPLE = {('bf16', 90, 120): 41.43e6, ('f32', 90, 120): 82.60e6, ('bf16', 180, 240): 164.33e6}
 
 
@@ -37,6 +48,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=12)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default=None, choices=sorted(CONFIGS), help='BASELINE.json configuration by name')
     ap.add_argument('--bs', type=int, default=512, help='samples per GPU per SGD step (BASELINE config 2: 512)')
     ap.add_argument('--T', type=int, default=256)
     ap.add_argument('--height', type=int, default=90)
@@ -45,7 +57,11 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--cpu-batch', type=int, default=32)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config:
+        for k, v in CONFIGS[a.config].items():
+            setattr(a, k, v)
+    return a
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -156,7 +172,9 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return
-    rate, sec, cores = cpu_reference_rate(args.steps, max(1, min(args.warmup, 2)), args.cpu_batch, args.height, args.width)
+    # every host core, also under torchrun (which pins OMP_NUM_THREADS to 1 for its workers)
+    rate, sec, cores = cpu_reference_rate(args.steps, max(1, min(args.warmup, 2)), args.cpu_batch, args.height, args.width,
+                                          threads=os.cpu_count())
     sample = f'{args.cpu_batch}-sample SGD minibatch per step (policy pass + value pass + clip + Adam), fp32, torch-CPU restatement'
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
@@ -221,17 +239,15 @@ def run_b200(args):
         else:
             eng.gather_rows(state['ret'], idx, mb['returns'])
 
-    def allreduce(*ts):
-        if world > 1:
-            for t in ts:
-                dist.all_reduce(t)
+    from cdra.parallel import GradSync
+    sync = GradSync(eng)            # the library's own NCCL communicator: cdra_allreduce_grads on the compute stream
 
     def policy_pass(m):
         # rl/agents/ppo.py:199-210, core/carla_agent.py:351-388
         x = eng.dynamics_forward(m)
         eng.policy_head(x, m['actions'], m['logp_old'], m['adv'], m['true_speed'], m['true_sim'], 0.2, 1.0)
         eng.dynamics_backward(m, eng.d_x512)
-        allreduce(eng.g_dyn, eng.g_pol)
+        sync.allreduce_pass('policy')                                  # ONE collective: policy head + dynamics gradients
         eng.clip_adam('dyn', 3e-4, None, gscale)
         old_pol.copy_(eng.pol.flat)                                   # update_old_policy before the Adam step (ppo.py:249)
         eng.clip_adam('pol', 3e-4, 1.0, gscale)
@@ -242,78 +258,31 @@ def run_b200(args):
         x = eng.dynamics_forward(m)
         eng.value_head(x, m['returns'], m['true_speed'], m['true_sim'])
         eng.dynamics_backward(m, eng.d_x512)
-        allreduce(eng.g_dyn, eng.g_val)
+        sync.allreduce_pass('value')
         eng.clip_adam('dyn', 3e-4, None, gscale)
         eng.clip_adam('val', 3e-4, 1.0, gscale)
         return eng.scalars[0]
 
-    def sgd_step(i, feeder=None, nxt=None):
-        """one SGD minibatch index through both passes.  feeder = None: minibatches gathered from the HBM-resident rollout;
-        else: minibatches arrive from pinned HOST memory through the feeder's copy stream (end-to-end leg), and `nxt` =
-        (policy, value) host minibatches of the following step, prefetched while this step computes"""
-        if i % T == 0:
-            gae()                                                     # once per update (PPOAgent.end_episode)
+    def sgd_step(i):
+        """one SGD minibatch index through both passes; minibatches gathered from the HBM-resident rollout"""
         lo = (i % T) * bs
-        if feeder is None:
-            gather(perm_p[lo:lo + bs], 'policy')
-            loss_p = policy_pass(mb)
-            gather(perm_v[lo:lo + bs], 'value')
-            return loss_p, value_pass(mb)
-        loss_p = policy_pass(feeder.acquire('p'))
-        feeder.release('p')
-        if nxt is not None:
-            feeder.prefetch('p', nxt[0])
-        loss_v = value_pass(feeder.acquire('v')).clone()
-        feeder.release('v')
-        if nxt is not None:
-            feeder.prefetch('v', nxt[1])
-        return loss_p, loss_v
-
-    class HostFeeder:
-        """double-buffered H2D staging of the two per-step minibatches on a copy stream (pinned host -> device), so the
-        copy of the next pass overlaps the kernels of the current one; events order buffer reuse both ways"""
-        def __init__(self, like_p, like_v):
-            self.cs = torch.cuda.Stream(device=dev)
-            self.bufs = {'p': {k: torch.empty_like(v, device=dev) for k, v in like_p.items()},
-                         'v': {k: torch.empty_like(v, device=dev) for k, v in like_v.items()}}
-            self.ready = {w: torch.cuda.Event() for w in 'pv'}
-            self.free = {w: torch.cuda.Event() for w in 'pv'}
-            for w in 'pv':
-                self.free[w].record(torch.cuda.current_stream())
-
-        def prefetch(self, which, host):
-            with torch.cuda.stream(self.cs):
-                self.cs.wait_event(self.free[which])
-                for k, v in host.items():
-                    self.bufs[which][k].copy_(v, non_blocking=True)
-                self.ready[which].record(self.cs)
-
-        def acquire(self, which):
-            torch.cuda.current_stream().wait_event(self.ready[which])
-            return self.bufs[which]
-
-        def release(self, which):
-            self.free[which].record(torch.cuda.current_stream())
+        gather(perm_p[lo:lo + bs], 'policy')
+        loss_p = policy_pass(mb)
+        gather(perm_v[lo:lo + bs], 'value')
+        return loss_p, value_pass(mb)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, first, host_bufs=None, feeder=None):
+    def timed(nsteps, first):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if host_bufs is not None:                                     # first step's inputs: H2D inside the clock as well
-            feeder.prefetch('p', host_bufs[0][0]); feeder.prefetch('v', host_bufs[0][1])
+        gae()                                                         # returns / GAE of all bs x T transitions: once per update, inside the clock
         for i in range(nsteps):
-            if host_bufs is None:
-                sgd_step(first + i)
-            else:
-                nxt = host_bufs[(i + 1) % len(host_bufs)] if i + 1 < nsteps else None
-                lp, lv = sgd_step(first + i, feeder, nxt)
-                hl = host_loss[i % len(host_loss)]                    # D2H read of the step's result (pinned, asynchronous)
-                hl[0].copy_(lp, non_blocking=True); hl[1].copy_(lv, non_blocking=True)
+            sgd_step(first + i)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -323,6 +292,7 @@ def run_b200(args):
 
     launches0 = eng.lib.cdra_launch_count()
     stage('rollout ready')
+    gae()
     for i in range(args.warmup):
         sgd_step(i)
         if debug:
@@ -339,57 +309,105 @@ def run_b200(args):
     clocks = sampler.finish() if sampler else None
     value = world * bs * args.steps / (ms / 1e3)
 
-    # ---- end-to-end: same step through the public call with HOST buffers (pinned), H2D + D2H inside the clock
-    e2e_keys = keys + ('adv', 'returns')
-    gather(perm_p[:bs], 'policy'); gather(perm_v[:bs], 'value'); torch.cuda.synchronize()
-    host_bufs = []
-    for j in range(2):                                                # (policy-pass minibatch, value-pass minibatch) pairs
-        gather(perm_p[j * bs:(j + 1) * bs], 'policy')
-        hp = {k: mb[k].cpu().pin_memory() for k in keys + ('adv',)}
-        gather(perm_v[j * bs:(j + 1) * bs], 'value')
-        hv = {k: mb[k].cpu().pin_memory() for k in keys + ('returns',)}
-        host_bufs.append((hp, hv))
-    host_loss = [[torch.empty((), pin_memory=True), torch.empty((), pin_memory=True)] for _ in range(4)]
-    h2d = sum(t.numel() * t.element_size() for h in host_bufs[0] for t in h.values())
-    feeder = HostFeeder(host_bufs[0][0], host_bufs[0][1])
+    peak, peak_src = measured_peaks()
+    roof = None
+    if not args.no_profile:
+        # every rank runs the two profiled steps (they contain the gradient all-reduce); rank 0 reports
+        roof = kernel_roofline(eng, sgd_step, args.warmup + args.steps, peak, peak_src)
+    # ---- end-to-end: the same metric through the reference-facing API with HOST buffers (see e2e_agent_leg)
     e2e_steps = max(2, args.steps // 2)
-    timed(1, 1, host_bufs, feeder)
-    ms_e2e = timed(e2e_steps, 1, host_bufs, feeder)
-    assert all(torch.isfinite(h[0]) and torch.isfinite(h[1]) for h in host_loss[:min(4, e2e_steps)])
-    e2e_value = world * bs * e2e_steps / (ms_e2e / 1e3)
+    rollout_gb = roll['state_image'].numel() / 1e9
+    del roll, mb
+    torch.cuda.empty_cache()
+    e2e = e2e_agent_leg(args, torch, dist, dev, world, rank, e2e_steps, barrier)
 
     out = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
         'data': 'synthetic',
         'config': {'workload': workload_text(H, W, bs, world, T),
-                   'step': 'one SGD minibatch index = bs samples/GPU through both passes; GAE once per T steps',
-                   'l2': f'inputs ({roll["state_image"].numel() / 1e9:.1f} GB rollout) and activations exceed L2; no flush needed',
+                   'step': 'one SGD minibatch index = bs samples/GPU through both passes; returns/GAE of all bs x T transitions once inside the timed region',
+                   'l2': f'inputs ({rollout_gb:.1f} GB rollout) and activations exceed L2; no flush needed',
                    'parallelism': f'dp{world}', 'optimizer': 'Keras-style Adam x3, per-tensor clip 1.0 on heads'},
-        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
-                'ms_per_step': ms_e2e / e2e_steps,
-                'note': 'pinned host minibatches -> device on a copy stream (double-buffered, overlapped with the previous pass), losses read back every step'},
+        'e2e': e2e,
         'gpu_launches': int(launches), 'launches_per_step': per_step_launches, 'clocks': clocks,
     }
-    peak, peak_src = measured_peaks()
     bps = BYTES_PER_SAMPLE.get((args.dtype, H, W))
     if bps:
         out['roofline_step'] = {'bound': 'hbm', 'achieved': value / world * bps / 1e9, 'peak': peak, 'unit': 'GB/s',
                                 'frac': value / world * bps / 1e9 / peak, 'bytes_per_sample': bps,
                                 'note': 'canonical algorithmic bytes of SURVEY 8(d) x samples/s/GPU; peak ' + peak_src}
-    if not args.no_profile:
-        # every rank runs the two profiled steps (they contain the gradient all-reduce); rank 0 reports
-        roof = kernel_roofline(eng, sgd_step, args.warmup + args.steps, peak, peak_src)
-        if rank == 0:
-            out['roofline'] = roof
+    if roof is not None and rank == 0:
+        out['roofline'] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_rate(12, 2, args.cpu_batch, H, W)       # ~10 s of host work
+        rate, sec, cores = cpu_reference_rate(12, 2, args.cpu_batch, H, W, threads=os.cpu_count())       # ~10 s of host work
         out['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                'sample': f'12 timed SGD steps of {args.cpu_batch} samples (both passes + clip + Adam), fp32 oracle on the host'}
     if rank == 0:
         print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_agent_leg(args, torch, dist, dev, world, rank, n_steps, barrier):
+    """`e2e`: pinned HOST transitions -> CARLAMemory.append (H2D) -> end_episode (returns / GAE) -> CARLAgent.update()
+    -> write_summaries() (losses D2H), timed as a whole with CUDA events; n_steps environment steps of bs parallel
+    trajectories = n_steps SGD minibatch indices per pass (minibatch = bs samples)."""
+    import tempfile
+    from core import CARLAgent, SyntheticCARLAEnvironment
+    bs, H, W = args.bs, args.height, args.width
+    env = SyntheticCARLAEnvironment(image_shape=(H, W, 3), image_uint8=True, seed=rank)
+    tmp = tempfile.mkdtemp(prefix='cdra_bench_')
+    agent = CARLAgent(env, batch_size=bs, name='bench', weights_dir=os.path.join(tmp, 'w'), evaluation_dir=os.path.join(tmp, 'e'),
+                      seed=42, skip_data=0, drop_batch_remainder=True, shuffle=True, shuffle_batches=False, log_mode='log',
+                      policy_lr=3e-4, value_lr=3e-4, dynamics_lr=3e-4, entropy_regularization=1.0, clip_ratio=0.2, gamma=0.9999,
+                      lambda_=0.999, advantage_scale=2.0, aug_intensity=0.0, network=dict(dtype=args.dtype, device=dev))
+    g = torch.Generator().manual_seed(99 + rank)
+    pin = lambda t: t.contiguous().pin_memory()
+    r = lambda *shape: torch.rand(*shape, generator=g)
+    steps = []
+    for t in range(n_steps):                          # what bs parallel environments hand over at one step (host memory)
+        state = dict(state_image=pin(torch.randint(0, 256, (bs, 4, H, W, 3), dtype=torch.uint8, generator=g)),
+                     state_road=pin(torch.cat([(r(bs, 4, 3) < 0.2).float(), 0.3 + 0.6 * r(bs, 4, 1),
+                                               torch.nn.functional.one_hot(torch.randint(0, 5, (bs, 4), generator=g), 5).float()], -1)),
+                     state_vehicle=pin(torch.cat([r(bs, 4, 1) * 2 - 1, r(bs, 4, 3)], -1)),
+                     state_navigation=pin(torch.sort(r(bs, 4, 5) * 25, dim=-1).values))
+        steps.append(dict(state=state, action=pin(r(bs, 2).clamp(1e-4, 1 - 1e-4)), log_prob=pin(0.5 * torch.randn(bs, 2, generator=g)),
+                          reward=pin((torch.randn(bs, generator=g) * 2 + 1).clamp(-10, 30)),
+                          value=pin(torch.stack([r(bs) * 2 - 1, torch.floor(r(bs) * 6)], -1))))
+    speed, sim = pin(r(n_steps * bs) * 30.0), pin(r(n_steps * bs) * 2 - 1)
+    last = pin(torch.stack([r(bs) * 2 - 1, torch.floor(r(bs) * 6)], -1))
+    h2d = sum(t.numel() * t.element_size() for st in steps for t in list(st['state'].values()) + [st['action'], st['log_prob'], st['reward'], st['value']])
+    h2d += speed.numel() * 4 * 2 + last.numel() * 4
+    mem = agent.get_memory(capacity=n_steps, num_envs=bs)            # preallocated device buffers (outside the clock)
+
+    def run():
+        mem.delete()
+        agent.memory = mem
+        for st in steps:
+            mem.append(st['state'], st['action'], st['reward'], st['value'], st['log_prob'])
+        env.info_buffer = dict(speed=speed.to(dev, non_blocking=True), similarity=sim.to(dev, non_blocking=True))
+        agent.end_episode(last)
+        agent.update()
+        agent.write_summaries()
+        return agent.statistics.last
+
+    run()                                              # warm-up (allocations, first-use costs)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lastv = run()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    assert all(k in lastv and lastv[k] == lastv[k] for k in ('loss_total', 'loss_value')), lastv
+    return {'value': world * bs * n_steps / (ms / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d // n_steps,
+            'd2h_bytes_per_step': max(4, agent.statistics.last_d2h_bytes // n_steps), 'ms_per_step': ms / n_steps, 'steps': n_steps,
+            'note': 'CARLAMemory.append (pinned host -> device buffers) + end_episode (GAE) + CARLAgent.update() + write_summaries() '
+                    'inside the clock; every sample crosses PCIe once and is used by both passes'}
 
 
 def kernel_roofline(eng, sgd_step, first, peak, peak_src):

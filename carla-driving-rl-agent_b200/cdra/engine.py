@@ -67,8 +67,8 @@ class Engine:
         self.ws_bytes = int(self.lib.cdra_plan_workspace_bytes(self.plan))
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
         if share is not None:
-            for k in ('dyn', 'dyn_state', 'pol', 'pol_state', 'val', 'val_state', 'g_dyn', 'g_pol', 'g_val', 'adam',
-                      'adam_step', 'norms'):
+            for k in ('dyn', 'dyn_state', 'pol', 'pol_state', 'val', 'val_state', 'g_all', 'g_dyn', 'g_pol', 'g_val', 'g_policy_pass',
+                      'g_value_pass', 'adam', 'adam_step', 'norms'):
                 setattr(self, k, getattr(share, k))
         else:
             mk = lambda w: Arena(self.lib, self.plan, w, self.device)
@@ -76,7 +76,17 @@ class Engine:
             self.pol, self.pol_state = mk(_lib.ARENA_POL_PARAMS), mk(_lib.ARENA_POL_STATE)
             self.val, self.val_state = mk(_lib.ARENA_VAL_PARAMS), mk(_lib.ARENA_VAL_STATE)
             z = lambda a: torch.zeros_like(a.flat)
-            self.g_dyn, self.g_pol, self.g_val = z(self.dyn), z(self.pol), z(self.val)
+            # ONE flat gradient buffer [policy | dynamics | value] (each part padded to 64 floats): the policy pass's
+            # gradients (policy + dynamics) and the value pass's (dynamics + value) are each one contiguous range, i.e.
+            # one all-reduce per pass under data parallelism (cdra_allreduce_grads)
+            r64 = lambda n: (n + 63) // 64 * 64
+            o_dyn, o_val = r64(self.pol.size), r64(self.pol.size) + r64(self.dyn.size)
+            self.g_all = torch.zeros(o_val + r64(self.val.size), dtype=torch.float32, device=self.device)
+            self.g_pol = self.g_all[:self.pol.size]
+            self.g_dyn = self.g_all[o_dyn:o_dyn + self.dyn.size]
+            self.g_val = self.g_all[o_val:o_val + self.val.size]
+            self.g_policy_pass = self.g_all[:o_dyn + self.dyn.size]          # what the policy pass exchanges
+            self.g_value_pass = self.g_all[o_dyn:o_val + self.val.size]      # what the value pass exchanges
             self.adam = {k: (z(a), z(a)) for k, a in (('dyn', self.dyn), ('pol', self.pol), ('val', self.val))}
             self.adam_step = dict(dyn=0, pol=0, val=0)
             self.norms = {k: torch.zeros(len(a.names), dtype=torch.float32, device=self.device)

@@ -20,10 +20,39 @@ def rank():
 
 
 class GradSync:
+    """Gradient exchange of one engine.  On GPUs the all-reduce is the library's own `cdra_allreduce_grads` (an NCCL
+    communicator created from an id that rank 0 broadcasts through torch.distributed), enqueued on the engine's stream like
+    every kernel; on the CPU test path (gloo) it is `torch.distributed.all_reduce`."""
+
     def __init__(self, engine):
         self.engine = engine
         self.world = world_size()
         self.grad_scale = 1.0 / self.world
+        self.comm = None
+        if self.world > 1 and engine.device.type == 'cuda':
+            import ctypes as C
+            from . import _lib
+            lib = engine.lib
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if rank() == 0:
+                buf = (C.c_ubyte * 128)()
+                _lib.check(lib, lib.cdra_comm_unique_id(buf), 'comm_unique_id')
+                ident = torch.tensor(list(buf), dtype=torch.uint8)
+            ident = ident.to(engine.device)
+            dist.broadcast(ident, 0)
+            raw = (C.c_ubyte * 128)(*ident.cpu().tolist())
+            comm = C.c_void_p()
+            torch.cuda.set_device(engine.device)
+            _lib.check(lib, lib.cdra_comm_create(raw, self.world, rank(), C.byref(comm)), 'comm_create')
+            self.comm = comm
+
+    def __del__(self):
+        try:
+            if self.comm:
+                self.engine.lib.cdra_comm_destroy(self.comm)
+                self.comm = None
+        except Exception:
+            pass
 
     def broadcast_parameters(self, src=0):
         """Make every replica start from rank `src`'s parameters, state and Adam moments."""
@@ -35,13 +64,29 @@ class GradSync:
         for m, v in e.adam.values():
             dist.broadcast(m, src); dist.broadcast(v, src)
 
+    def _sum(self, t):
+        if self.comm is not None:
+            from . import _lib
+            e = self.engine
+            _lib.check(e.lib, e.lib.cdra_allreduce_grads(self.comm, _lib.ptr(t), t.numel(), e._stream()), 'allreduce_grads')
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
     def allreduce(self, *which):
         """Sum the named gradient arenas ('dyn', 'pol', 'val') across ranks, in place, on the current stream."""
         if self.world == 1:
             return
         e = self.engine
         for w in which:
-            dist.all_reduce(dict(dyn=e.g_dyn, pol=e.g_pol, val=e.g_val)[w], op=dist.ReduceOp.SUM)
+            self._sum(dict(dyn=e.g_dyn, pol=e.g_pol, val=e.g_val)[w])
+
+    def allreduce_pass(self, which):
+        """ONE collective for everything a pass produced: 'policy' = policy head + dynamics, 'value' = dynamics + value head
+        (contiguous ranges of the engine's flat gradient buffer)."""
+        if self.world == 1:
+            return
+        e = self.engine
+        self._sum(e.g_policy_pass if which == 'policy' else e.g_value_pass)
 
     def agree_min(self, value: int) -> int:
         """The smallest `value` over all ranks.  Every rank must issue the same number of gradient all-reduces: the number

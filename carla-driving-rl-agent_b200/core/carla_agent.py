@@ -163,12 +163,16 @@ class CARLAgent(PPOAgent):
         self.env.reset_info()
 
     def _aux_targets(self, n):
-        speed = torch.as_tensor(np.asarray(self.env.info_buffer['speed'], dtype=np.float32)).reshape(-1, 1) / 100.0
-        similarity = torch.as_tensor(np.asarray(self.env.info_buffer['similarity'], dtype=np.float32)).reshape(-1, 1)
+        """speed / 100 and similarity from `env.info_buffer` (core/carla_agent.py:328-329,338-347), truncated or zero-padded
+        to the memory length.  The buffers may be python lists (the reference's CARLAEnv) or tensors (vectorised feeders)."""
+        def column(x):
+            t = x.detach().float() if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float32))
+            return t.reshape(-1, 1)
+        speed, similarity = column(self.env.info_buffer['speed']) / 100.0, column(self.env.info_buffer['similarity'])
         if speed.shape[0] >= n:                                                                  # :338-345
             speed, similarity = speed[:n], similarity[:n]
         else:
-            pad = torch.zeros(n - speed.shape[0], 1)
+            pad = torch.zeros(n - speed.shape[0], 1, device=speed.device)
             speed, similarity = torch.cat([speed, pad], 0), torch.cat([similarity, pad], 0)
         return speed, similarity
 
@@ -208,16 +212,20 @@ class CARLAgent(PPOAgent):
     def apply_policy_gradients(self, gradients):
         if isinstance(gradients, dict):
             assert self.should_update_dynamics
-            grads = self.apply_dynamics_gradients(gradients=gradients['dynamics'])
-            super().apply_policy_gradients(gradients=gradients['policy'])
+            # data parallel: ONE collective for everything the pass produced (policy head + dynamics gradients are one
+            # contiguous range of the engine's gradient buffer), then the three fused clip+Adam launches
+            self.network.sync.allreduce_pass('policy')
+            self.apply_dynamics_gradients(gradients=gradients['dynamics'], reduced=True)
+            super().apply_policy_gradients(gradients=gradients['policy'], reduced=True)
             self.log(gradients_norm_dynamics=self._dyn_norms)
         else:
             super().apply_policy_gradients(gradients)
 
-    def apply_dynamics_gradients(self, gradients):
+    def apply_dynamics_gradients(self, gradients, reduced=False):
         """Adam without clipping (core/carla_agent.py:386-388)."""
         net = self.network
-        net.sync.allreduce('dyn')
+        if not reduced:
+            net.sync.allreduce('dyn')
         # what the reference logs as [tf.norm(g) for g in grads] (:382,461): one launch, stays on the device
         self._dyn_norms = net.engine.grad_norms('dyn', net.grad_scale) if self.statistics.should_log else None
         net.engine.clip_adam('dyn', self.dynamics_lr(), None, net.grad_scale)
@@ -265,8 +273,9 @@ class CARLAgent(PPOAgent):
     def apply_value_gradients(self, gradients):
         if isinstance(gradients, dict):
             assert self.should_update_dynamics
-            grads = self.apply_dynamics_gradients(gradients=gradients['dynamics'])
-            super().apply_value_gradients(gradients=gradients['value'])
+            self.network.sync.allreduce_pass('value')
+            self.apply_dynamics_gradients(gradients=gradients['dynamics'], reduced=True)
+            super().apply_value_gradients(gradients=gradients['value'], reduced=True)
             self.log(gradients_norm_dynamics_v=self._dyn_norms)
         else:
             super().apply_value_gradients(gradients)
@@ -280,9 +289,10 @@ class CARLAgent(PPOAgent):
         self.log(speed_v=sc[4], similarity_v=sc[5], loss_v=sc[1], loss_speed_value=sc[2], loss_similarity_value=sc[3])
         return sc[0].clone()
 
-    def get_memory(self):
+    def get_memory(self, capacity=256, num_envs=1):
         return CARLAMemory(state_spec=self.state_spec, num_actions=self.num_actions, time_horizon=self.env.time_horizon,
-                           device=self.network.device)
+                           device=self.network.device, capacity=capacity, num_envs=num_envs,
+                           image_dtype=torch.uint8 if self.network.image_u8 else torch.float32)
 
     def preprocess(self):
         """Augmentation closure of the reference (core/carla_agent.py:523-579); image augmentation is a rollout-time
@@ -303,8 +313,10 @@ class CARLAgent(PPOAgent):
 
 
 class CARLAMemory(PPOMemory):
-    """core/carla_agent.py:586-596: states carry a `time_horizon` axis."""
+    """core/carla_agent.py:586-596: states carry a `time_horizon` axis ([N, 4, H, W, 3] frames, uint8 on the device when the
+    environment delivers uint8)."""
 
-    def __init__(self, state_spec: dict, num_actions: int, time_horizon: int, device='cpu'):
-        super().__init__(state_spec, num_actions, device=device)
+    def __init__(self, state_spec: dict, num_actions: int, time_horizon: int, device='cpu', capacity=256, num_envs=1,
+                 image_dtype=torch.float32):
         self.time_horizon = time_horizon
+        super().__init__(state_spec, num_actions, device=device, capacity=capacity, num_envs=num_envs, image_dtype=image_dtype)

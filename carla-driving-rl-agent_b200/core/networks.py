@@ -194,17 +194,18 @@ class CARLANetwork(Network):
             self._siblings[batch] = self.engine.sibling(batch)
         return self._siblings[batch]
 
-    def gather(self, tensors: List[torch.Tensor], idx: np.ndarray) -> List[torch.Tensor]:
-        """Minibatch gather (the tf.data slicing of rl/utils.py:365-393) with cdra_gather_rows."""
-        index = torch.as_tensor(idx, dtype=torch.int64, device=self.device)
+    def gather_device(self, tensors: List[torch.Tensor], index: torch.Tensor) -> List[torch.Tensor]:
+        """Minibatch gather (the tf.data slicing of rl/utils.py:365-393) with cdra_gather_rows: `tensors` are contiguous
+        device tensors [N, ...], `index` an int64 device vector."""
         out = []
         for t in tensors:
-            t = t if t.device == self.device else t.to(self.device)
-            if t.dim() == 1:
-                t = t.unsqueeze(-1)
-            dst = torch.empty((len(idx),) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
-            out.append(self.engine.gather_rows(t.contiguous(), index, dst))
+            dst = torch.empty((index.numel(),) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            out.append(self.engine.gather_rows(t, index, dst))
         return out
+
+    def gather(self, tensors: List[torch.Tensor], idx: np.ndarray) -> List[torch.Tensor]:
+        index = torch.as_tensor(idx, dtype=torch.int64, device=self.device)
+        return self.gather_device([(t if t.dim() > 1 else t.unsqueeze(-1)).to(self.device).contiguous() for t in tensors], index)
 
     def _obs(self, states: dict):
         img = states['state_image']
@@ -272,7 +273,7 @@ class CARLANetwork(Network):
         inputs = dict(inputs)
         memory = self.agent.memory
         n = len(memory) if memory is not None else 0
-        inputs['action'] = torch.zeros((1, self.agent.num_actions)) if n == 0 else memory._actions[-1]
+        inputs['action'] = torch.zeros((1, self.agent.num_actions)) if n == 0 else memory.last_action()
         return inputs
 
     def predict_last_value(self, state, is_terminal: bool, **kwargs):

@@ -784,6 +784,95 @@ int cdra_grad_norms(const float* grads, const int64_t* tensor_offsets, int n_ten
     return check_launch("grad_norms");
 }
 
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------------------- NCCL (resolved at run time)
+#ifndef CDRA_EMU
+#include <dlfcn.h>
+struct NcclId { char internal[128]; };        // == ncclUniqueId
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+}
+static NcclApi* nccl_api(std::string& err) {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (api.handle) break; }   // the copy torch loaded
+        for (const char* n : names) { if (api.handle) break; api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); }
+        if (api.handle) {
+            api.GetUniqueId = (int (*)(void*))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+            api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+            api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) { err = "libnccl.so.2 not found / incomplete"; return nullptr; }
+    return &api;
+}
+#endif
+struct cdra_comm { void* comm; int world, rank; };
+
+extern "C" {
+int cdra_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(CDRA_ERR_BADARG, "null argument");
+#ifndef CDRA_EMU
+    std::string err; NcclApi* api = nccl_api(err);
+    if (!api) return fail(CDRA_ERR_NCCL, err);
+    const int rc = api->GetUniqueId(id_out);
+    if (rc != 0) return fail(CDRA_ERR_NCCL, std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(rc) : "?"));
+    return CDRA_OK;
+#else
+    return fail(CDRA_ERR_NCCL, "no NCCL in the CPU logic-check build");
+#endif
+}
+int cdra_comm_create(const void* id, int world, int rank, cdra_comm_t** out) {
+    if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(CDRA_ERR_BADARG, "bad argument");
+#ifndef CDRA_EMU
+    std::string err; NcclApi* api = nccl_api(err);
+    if (!api) return fail(CDRA_ERR_NCCL, err);
+    NcclId nid; memcpy(&nid, id, sizeof nid);
+    void* comm = nullptr;
+    const int rc = api->CommInitRank(&comm, world, nid, rank);
+    if (rc != 0) return fail(CDRA_ERR_NCCL, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(rc) : "?"));
+    *out = new cdra_comm{comm, world, rank};
+    return CDRA_OK;
+#else
+    return fail(CDRA_ERR_NCCL, "no NCCL in the CPU logic-check build");
+#endif
+}
+void cdra_comm_destroy(cdra_comm_t* c) {
+#ifndef CDRA_EMU
+    if (c) { std::string err; NcclApi* api = nccl_api(err); if (api && c->comm) api->CommDestroy(c->comm); delete c; }
+#else
+    delete c;
+#endif
+}
+int cdra_allreduce_grads(cdra_comm_t* c, float* grads, int64_t count, void* stream) {
+    if (!c || !grads || count < 1) return fail(CDRA_ERR_BADARG, "bad argument");
+#ifndef CDRA_EMU
+    std::string err; NcclApi* api = nccl_api(err);
+    if (!api) return fail(CDRA_ERR_NCCL, err);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const int rc = api->AllReduce(grads, grads, (size_t)count, /* ncclFloat32 */ 7, /* ncclSum */ 0, c->comm, (cudaStream_t)stream);
+    if (rc != 0) return fail(CDRA_ERR_NCCL, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(rc) : "?"));
+    return CDRA_OK;
+#else
+    return fail(CDRA_ERR_NCCL, "no NCCL in the CPU logic-check build");
+#endif
+}
+}  // extern "C"
+
+extern "C" {
 int64_t cdra_launch_count(void) { return (int64_t)g_launches.load(); }
 void cdra_profile_enable(int on) { g_prof = on != 0; }
 void cdra_profile_reset(void) { g_entries.clear(); }

@@ -363,7 +363,7 @@ inline bool try_pw_bwd_fused(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, in
     for (int i = 0; i < hd.nsrc; ++i) { cps[i] = hd.src[i].cp; acc[i] = hd.src[i].accumulate; }
     const int x1cp = a.x1 ? a.x1cp : 0;
     const PwBfSmem L0 = pw_bf_smem(R, hd.nsrc, cps, acc, hd.NPall, hd.cols.nplanes, a.cpo, x1cp, 0);
-    if (L0.mbk > 2 || L0.np16 > 256 || L0.cols_dw + 2 * L0.mbk * R > 512 || x1cp > kBfEpilogueThreads) return false;
+    if (L0.mbk != 1 || L0.np16 > 256 || L0.cols_dw + 2 * R > 512 || x1cp > kBfEpilogueThreads) return false;
     const int nstage = std::min(kBfMaxStages, (kMaxDynSmem - 1024 - L0.ring) / L0.stage_bytes);
     if (nstage < min_stages) return false;
     const PwBfSmem L = pw_bf_smem(R, hd.nsrc, cps, acc, hd.NPall, hd.cols.nplanes, a.cpo, x1cp, nstage);

@@ -44,7 +44,7 @@ constexpr int kBfThreads = 512, kBfTransformWarps = 6, kBfEpilogueWarps = 8, kBf
 constexpr int kBfTransformThreads = kBfTransformWarps * 32, kBfEpilogueThreads = kBfEpilogueWarps * 32;
 
 struct PwBfSmem {
-    int w, dr, xs, st, st2, ring, total;
+    int maps, w, dr, xs, st, st2, ring, total;
     int stage_bytes, dr_bytes, xs_bytes, w_bytes;
     int o_dout, o_out, o_src[kMaxSrc], o_x1, o_ge[kMaxSrc], st_off[kMaxSrc];
     int mbk, np16, nkb, cols_dw, tmem_cols;
@@ -70,6 +70,8 @@ inline __host__ __device__ PwBfSmem pw_bf_smem(int R, int nsrc, const int* cps, 
     s.dr_bytes = s.nkb * R * 128;
     s.xs_bytes = s.mbk * 2 * R * 128;
     off = 1024;                                         // mbarriers + TMEM slot
+    s.maps = off; off += 2 * 256 * 4;                   // logical row / column maps of the weight-gradient flush
+    off = (off + 1023) & ~1023;
     s.w = off; off += s.w_bytes;
     s.dr = off; off += 2 * s.dr_bytes;
     s.xs = off; off += 2 * s.xs_bytes;
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     uint64_t* tm_empty = tm_full + 2;                                 // [2]
     uint64_t* all_done = tm_empty + 2;                                // [1]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 512);
+    int* s_rmap = reinterpret_cast<int*>(smem + L.maps);              // GEMM row kk    -> (layer << 24 | k), -1 = padding
+    int* s_cmap = s_rmap + 256;                                        // GEMM column j  -> (layer << 24 | n), -1 = padding
     unsigned char* Ws = smem + L.w;
     unsigned char* ring = smem + L.ring;
 
@@ -127,11 +131,22 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     // staging tiles start as zeros (K / N padding and the rows of partial tiles contribute nothing)
     for (int i = tid; i < (L.w_bytes + 2 * L.dr_bytes + 2 * L.xs_bytes) / 16; i += kBfThreads) reinterpret_cast<uint4*>(Ws)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    // narrow layers (KP <= 64 / 32): the weight rows are replicated 2 / 4 times over the 128 M rows, so that EVERY TMEM lane
+    // block holds the data gradient and all epilogue warps share the tile's rows (a warp can only read its own 32 lanes)
+    const int kpad = ksum <= 32 ? 32 : (ksum <= 64 ? 64 : 128);
+    const int copies = min(128 / kpad, R / 16);
     for (int i = tid; i < d.KP * (NP >> 3); i += kBfThreads) {
         const int kk = i / (NP >> 3), c = i - kk * (NP >> 3);
-        if (kk >= L.mbk * 128) continue;
-        *reinterpret_cast<uint4*>(Ws + (size_t)((kk >> 7) * L.nkb + (c >> 3)) * 16384 + sw128_offset(kk & 127, (c & 7) * 8, 128)) =
-            *reinterpret_cast<const uint4*>(d.wb + (size_t)kk * NP + c * 8);
+        if (kk >= 128) continue;
+        const uint4 w = *reinterpret_cast<const uint4*>(d.wb + (size_t)kk * NP + c * 8);
+        for (int q = 0; q < copies; ++q)
+            if (kk < kpad) *reinterpret_cast<uint4*>(Ws + (size_t)(c >> 3) * 16384 + sw128_offset(kk + q * kpad, (c & 7) * 8, 128)) = w;
+    }
+    for (int i = tid; i < 512; i += kBfThreads) {
+        int l, k, p, sl, nn, v = -1;
+        if (i < 256) { if (i < d.KP && pw_row(d, i, l, k)) v = (l << 24) | k; }
+        else if (i - 256 < NP && pw_col(d, i - 256, p, sl, l, nn)) v = (l << 24) | nn;
+        s_rmap[i] = v;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -140,15 +155,19 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     const uint32_t tmem = *s_tmem;
     pdl_wait();                                         // everything above read only this launch's descriptor / prepared weights
 
-    auto tile_geom = [&](int tile, int& t, int& r0, int& rows) { t = tile / tps; r0 = (tile - t * tps) * R; rows = min(R, a.Rt - r0); };
+    // tile cursor: (slice, first row, rows) and (ring stage, ring phase) advance incrementally -- no divisions in the loops
+    struct Cursor { int t, r0, s, k; };
+    const int t_first = tile_lo / tps;
+    auto cursor0 = [&]() { Cursor c; c.t = t_first; c.r0 = (tile_lo - t_first * tps) * R; c.s = 0; c.k = 0; return c; };
+    auto advance = [&](Cursor& c) { c.r0 += R; if (c.r0 >= a.Rt) { c.r0 = 0; ++c.t; } if (++c.s == S) { c.s = 0; c.k ^= 1; } };
 
     if (warp == 0) {
         // ================================================================ TMA producer
         if (lane == 0) {
-            for (int it = 0; it < my_tiles; ++it) {
-                const int s = it % S, k = it / S;
+            Cursor cur = cursor0();
+            for (int it = 0; it < my_tiles; ++it, advance(cur)) {
+                const int s = cur.s, k = cur.k, t = cur.t, r0 = cur.r0, rows = min(R, a.Rt - cur.r0);
                 mbar_wait(&empty[s], (k & 1) ^ 1);
-                int t, r0, rows; tile_geom(tile_lo + it, t, r0, rows);
                 const size_t row = (size_t)t * a.Rt + r0;
                 unsigned char* dst = ring + (size_t)s * L.stage_bytes;
                 uint32_t bytes = (uint32_t)rows * (2 * nplanes * cpo + ksum + x1cp) * 2;
@@ -212,9 +231,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
         float4 c8[8];
         float2 x8[8];
         int cur_t = -1;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int s = it % S, k = it / S, b = it & 1, n = it >> 1;
-            int t, r0, rows; tile_geom(tile_lo + it, t, r0, rows);
+        Cursor cur = cursor0();
+        for (int it = 0; it < my_tiles; ++it, advance(cur)) {
+            const int s = cur.s, k = cur.k, b = it & 1, n = it >> 1, t = cur.t, rows = min(R, a.Rt - cur.r0);
             if (t != cur_t) {                           // this thread's chunk constants for the slice (no shared table, no barrier)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -237,27 +256,47 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 const uint4* dv = reinterpret_cast<const uint4*>(rb + o_dout + (size_t)tp * R * cpo * 2) + (tc >> 3);
                 const uint4* ov = reinterpret_cast<const uint4*>(rb + o_out + (size_t)tp * R * cpo * 2) + (tc >> 3);
                 const int nch = cpo >> 3;
-                for (int r = rrl; r < R; r += rnrl) {
-                    uint4 dvv = make_uint4(0, 0, 0, 0);
-                    if (r < rows) {
-                        dvv = dv[r * nch]; const uint4 ovv = ov[r * nch];
-                        uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
+                for (int rbase = rrl; rbase < R; rbase += 3 * rnrl) {
+                    uint4 dvv[3], ovv[3];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
-                            dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], oclamp), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], oclamp));
+                    for (int u = 0; u < 3; ++u) {
+                        const int r = rbase + u * rnrl;
+                        dvv[u] = make_uint4(0, 0, 0, 0); ovv[u] = dvv[u];
+                        if (r < rows) { dvv[u] = dv[r * nch]; ovv[u] = ov[r * nch]; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int r = rbase + u * rnrl;
+                        if (r < R) {
+                            uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv[u]); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv[u]);
+                            if (r < rows) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
+                                    dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], oclamp), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], oclamp));
+                                }
+                            }
+                            *reinterpret_cast<uint4*>(Dr + sw128_offset(r, rq * 8, R)) = dvv[u];
                         }
                     }
-                    *reinterpret_cast<uint4*>(Dr + sw128_offset(r, rq * 8, R)) = dvv;
                 }
             }
             if (xrl < xnrl) {
                 const uint4* sv = reinterpret_cast<const uint4*>(rb + o_xsrc) + xch;
                 const int nch = xcp >> 3;
-                for (int r = xrl; r < R; r += xnrl) {
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (r < rows) v = affine8(sv[r * nch], x8, sclamp);
-                    *reinterpret_cast<uint4*>(Xs + sw128_offset(r, xq * 8, R)) = v;
+                for (int rbase = xrl; rbase < R; rbase += 3 * xnrl) {
+                    uint4 v[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int r = rbase + u * xnrl;
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (r < rows) v[u] = sv[r * nch];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int r = rbase + u * xnrl;
+                        if (r < R) *reinterpret_cast<uint4*>(Xs + sw128_offset(r, xq * 8, R)) = r < rows ? affine8(v[u], x8, sclamp) : make_uint4(0, 0, 0, 0);
+                    }
                 }
             }
             fence_proxy_async();
@@ -267,18 +306,18 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     } else {
         // ================================================================ epilogue warps
         const int ew = warp - (2 + kBfTransformWarps), lg = ew & 3, half = ew >> 2, etid = tid - (2 + kBfTransformWarps) * 32;
-        // this thread's data-gradient channel per 128-row block of dSrc^T: kk = mb * 128 + 32 * lg + lane -> (source, slot).
-        // Everything the tile loop needs is hoisted into registers here (no descriptor reads / local arrays in the loop).
+        // this thread's data-gradient channel: TMEM lane 32 * lg + lane = copy q of channel kk; it walks rows
+        // [(half * copies + q) * hrt, + hrt) of the tile.  Everything the tile loop needs is hoisted into registers here.
+        const int lane_id = 32 * lg + lane, q_copy = lane_id / kpad, kk = lane_id - q_copy * kpad;
+        const int hrt = R / (2 * copies), row_first = q_copy < copies ? (half * copies + q_copy) * hrt : 0;
         struct Chan {
             int cp, o_src, o_ge, st_off, slot; bool on, clamp, want, acc;
             const float2* aff; const float2* bnp; double2* bsum;
             float s1, s2; float4 sc;
-        };
-        auto make_chan = [&](int mb) {
-            Chan ch; ch.on = false; ch.cp = 0; ch.o_src = ch.o_ge = ch.st_off = ch.slot = 0; ch.clamp = ch.want = ch.acc = false;
-            ch.aff = ch.bnp = nullptr; ch.bsum = nullptr; ch.s1 = ch.s2 = 0.f; ch.sc = make_float4(1.f, 0.f, 0.f, 0.f);
-            if (mb >= L.mbk) return ch;
-            const int kk = mb * 128 + 32 * lg + lane;
+        } ch;
+        ch.on = false; ch.cp = 0; ch.o_src = ch.o_ge = ch.st_off = ch.slot = 0; ch.clamp = ch.want = ch.acc = false;
+        ch.aff = ch.bnp = nullptr; ch.bsum = nullptr; ch.s1 = ch.s2 = 0.f; ch.sc = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (q_copy < copies) {
             int off = 0;
             for (int i = 0; i < nsrc; ++i) {
                 const int cp = d.src[i].cp;
@@ -291,10 +330,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 }
                 off += cp;
             }
-            return ch;
-        };
-        Chan ch0 = make_chan(0), ch1 = make_chan(1);
-        const int mbk = L.mbk, cols_dw = L.cols_dw, o_dout = L.o_dout, o_x1 = L.o_x1, o_st = L.st, o_st2 = L.st2, stage_bytes = L.stage_bytes;
+        }
+        const int cols_dw = L.cols_dw, o_dout = L.o_dout, o_x1 = L.o_x1, o_st = L.st, o_st2 = L.st2, stage_bytes = L.stage_bytes;
         // pass-through role: thread <-> x1 slot
         int x_src = -1;                                 // element offset inside the d out region of a stage, -2: padding (zero), -1: no role
         if (x1cp && etid < x1cp) {
@@ -308,54 +345,53 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
         bf16* g_ptr[kMaxSrc]; int g_cp[kMaxSrc], g_off[kMaxSrc];
 #pragma unroll
         for (int i = 0; i < kMaxSrc; ++i) { g_ptr[i] = i < nsrc ? d.src[i].grad : nullptr; g_cp[i] = cps[i]; g_off[i] = L.st_off[i]; }
-        auto flush_chan = [&](Chan& ch, int t) {
+        auto flush = [&](int t) {
             if (ch.want && (ch.s1 != 0.f || ch.s2 != 0.f)) {
                 double2* dst = ch.bsum + (size_t)t * ch.cp + ch.slot;
                 atomicAdd(&dst->x, (double)ch.s1); atomicAdd(&dst->y, (double)ch.s2);
             }
             ch.s1 = ch.s2 = 0.f;
-        };
-        auto flush = [&](int t) {
-            flush_chan(ch0, t); flush_chan(ch1, t);
             if (x_src != -1 && a.x1bsum && (xs1 != 0.f || xs2 != 0.f)) {
                 double2* dst = a.x1bsum + (size_t)t * x1cp + etid;
                 atomicAdd(&dst->x, (double)xs1); atomicAdd(&dst->y, (double)xs2);
             }
             xs1 = xs2 = 0.f;
         };
-        auto run_chan = [&](Chan& ch, int mb, int b, int rows, const unsigned char* rb) {
-            float v[HR];
-            const uint32_t taddr = tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(cols_dw + (b * mbk + mb) * R + half * HR);
-            tmem_ld16(taddr, *reinterpret_cast<float(*)[16]>(&v[0]));
-            if (HR == 32) tmem_ld16(taddr + 16, *reinterpret_cast<float(*)[16]>(&v[HR - 16]));
-            if (!ch.on) return;
+        auto run_chan = [&](int b, int rows, const unsigned char* rb) {
+            const uint32_t taddr = tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(cols_dw + b * R + row_first);
             const int cp = ch.cp;
-            const unsigned short* rawp = reinterpret_cast<const unsigned short*>(rb + ch.o_src) + ch.slot + half * HR * cp;
-            const unsigned short* gep = reinterpret_cast<const unsigned short*>(rb + ch.o_ge) + ch.slot + half * HR * cp;
-            unsigned short* stp = reinterpret_cast<unsigned short*>(smem + o_st + ch.st_off) + ch.slot + half * HR * cp;
-            const int nr = min(HR, rows - half * HR);
             float s1 = ch.s1, s2 = ch.s2;
             const float4 sc = ch.sc;
+            for (int c8 = 0; c8 < hrt; c8 += 8) {       // 8 rows at a time: one tcgen05.ld, the shared-memory loads up front, then the math
+                float v[8];
+                tmem_ld8(taddr + c8, v);
+                if (!ch.on) continue;
+                const int row0 = row_first + c8;
+                const unsigned short* rawp = reinterpret_cast<const unsigned short*>(rb + ch.o_src) + ch.slot + row0 * cp;
+                const unsigned short* gep = reinterpret_cast<const unsigned short*>(rb + ch.o_ge) + ch.slot + row0 * cp;
+                unsigned short* stp = reinterpret_cast<unsigned short*>(smem + o_st + ch.st_off) + ch.slot + row0 * cp;
+                const int nr = rows - row0;             // rows of this chunk inside the slice (rows past it are staged but never stored)
+                uint32_t rawv[8], gev[8];
 #pragma unroll
-            for (int j = 0; j < HR; ++j) {
-                if (j < nr) {
+                for (int j = 0; j < 8; ++j) { rawv[j] = rawp[j * cp]; gev[j] = ch.acc ? (uint32_t)gep[j * cp] : 0u; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
                     float g = v[j];
-                    if (ch.acc) g = __bfloat162float(__float2bfloat16_rn(g)) + __uint_as_float((uint32_t)gep[j * cp] << 16);
+                    if (ch.acc) g = __bfloat162float(__float2bfloat16_rn(g)) + __uint_as_float(gev[j] << 16);
                     const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16_rn(g));
                     stp[j * cp] = gb;
-                    if (ch.want) sum_accum(__uint_as_float((uint32_t)gb << 16), __uint_as_float((uint32_t)rawp[j * cp] << 16), sc, ch.clamp, s1, s2);
+                    if (ch.want && j < nr) sum_accum(__uint_as_float((uint32_t)gb << 16), __uint_as_float(rawv[j] << 16), sc, ch.clamp, s1, s2);
                 }
             }
             ch.s1 = s1; ch.s2 = s2;
         };
         int cur_t = -1;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int s = it % S, k = it / S, b = it & 1, n = it >> 1;
-            int t, r0, rows; tile_geom(tile_lo + it, t, r0, rows);
+        Cursor cur = cursor0();
+        for (int it = 0; it < my_tiles; ++it, advance(cur)) {
+            const int s = cur.s, k = cur.k, b = it & 1, n = it >> 1, t = cur.t, r0 = cur.r0, rows = min(R, a.Rt - cur.r0);
             if (t != cur_t) {
                 if (cur_t >= 0) flush(cur_t);
-                if (ch0.on) ch0.sc = sum_consts(ch0.aff, ch0.bnp, (size_t)t * ch0.cp + ch0.slot);
-                if (ch1.on) ch1.sc = sum_consts(ch1.aff, ch1.bnp, (size_t)t * ch1.cp + ch1.slot);
+                if (ch.on) ch.sc = sum_consts(ch.aff, ch.bnp, (size_t)t * ch.cp + ch.slot);
                 if (x_src != -1) xc = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + etid);
                 cur_t = t;
             }
@@ -366,8 +402,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
             mbar_wait(&tm_full[b], n & 1);
             tc_fence_after();
             const unsigned char* rb = ring + (size_t)s * stage_bytes;
-            run_chan(ch0, 0, b, rows, rb);
-            if (mbk > 1) run_chan(ch1, 1, b, rows, rb);
+            run_chan(b, rows, rb);
             tc_fence_before();
             // pass-through half of a stride-1 unit: d x1[slot(2i + p)] = d out_p[copy_dst0 + i]   (bit-exact gather)
             if (x_src != -1) {
@@ -415,13 +450,21 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                     }
                 }
                 __syncthreads();
-                for (int i = tid; i < 128 * ncol; i += kBfThreads) {
-                    const int rowk = i / ncol, col = i - rowk * ncol;
-                    int lk, kx, p, sl, lj, nn;
-                    const int kk = mb * 128 + rowk, j = c0 + col;
-                    if (kk < d.KP && j < NP && pw_row(d, kk, lk, kx) && pw_col(d, j, p, sl, lj, nn) && lk == lj) {
-                        const LayerP& Lp = d.layer[lk];
-                        atomicAdd(Lp.dw + (size_t)kx * Lp.N + nn, Sc[rowk * 65 + col]);
+                {
+                    const int col = tid & 63, cm = (col < ncol) ? s_cmap[c0 + col] : -1;
+                    if (cm >= 0) {
+                        float* wl0 = d.layer[0].dw; float* wl1 = d.layer[1].dw;
+                        const int N0 = d.layer[0].N, N1 = d.layer[1].N;
+                        for (int rowk = tid >> 6; rowk < 128; rowk += kBfThreads >> 6) {
+                            const int rm = s_rmap[mb * 128 + rowk];
+                            if (rm >= 0 && (rm >> 24) == (cm >> 24)) {
+                                const float val = Sc[rowk * 65 + col];
+                                if (val != 0.f) {
+                                    if ((rm >> 24) == 0) atomicAdd(wl0 + (size_t)(rm & 0xffffff) * N0 + (cm & 0xffffff), val);
+                                    else atomicAdd(wl1 + (size_t)(rm & 0xffffff) * N1 + (cm & 0xffffff), val);
+                                }
+                            }
+                        }
                     }
                 }
                 __syncthreads();

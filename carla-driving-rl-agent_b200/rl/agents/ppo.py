@@ -143,11 +143,13 @@ class PPOAgent(Agent):
     def update_value(self, gradients):
         return self.apply_value_gradients(gradients), True
 
-    def apply_policy_gradients(self, gradients):
-        """rl/agents/ppo.py:238-252: per-tensor clip -> (old_policy <- policy) -> Adam [-> Polyak]."""
+    def apply_policy_gradients(self, gradients, reduced=False):
+        """rl/agents/ppo.py:238-252: per-tensor clip -> (old_policy <- policy) -> Adam [-> Polyak].  `reduced`: the caller
+        already exchanged the gradients across the data-parallel ranks."""
         net = self.network
         clip = self.grad_norm_policy if self.should_clip_policy_grads else None
-        net.sync.allreduce('pol')
+        if not reduced:
+            net.sync.allreduce('pol')
         self._head_norms = net.engine.grad_norms('pol', net.grad_scale) if self.statistics.should_log else None
         if self.should_polyak_average:
             old = net.policy.flat.clone()
@@ -159,11 +161,12 @@ class PPOAgent(Agent):
             net.engine.clip_adam('pol', self.policy_lr(), clip, net.grad_scale)
         return gradients
 
-    def apply_value_gradients(self, gradients):
+    def apply_value_gradients(self, gradients, reduced=False):
         """rl/agents/ppo.py:264-275."""
         net = self.network
         clip = self.grad_norm_value if self.should_clip_value_grads else None
-        net.sync.allreduce('val')
+        if not reduced:
+            net.sync.allreduce('val')
         self._head_norms = net.engine.grad_norms('val', net.grad_scale) if self.statistics.should_log else None
         if self.should_polyak_average:
             old = net.value.flat.clone()
@@ -180,17 +183,24 @@ class PPOAgent(Agent):
         return self.memory.states, self.memory.advantages, self.memory.actions, self.memory.log_probabilities
 
     def _batches(self, tensors, **kw):
-        """Callable that yields gathered minibatches (tuples shaped like `tensors`) — the data_to_batches role."""
+        """Callable that yields gathered minibatches (tuples shaped like `tensors`) -- the data_to_batches role
+        (rl/utils.py:365-393).  The rollout tensors are made device-resident ONCE, the index lists travel in one copy,
+        every minibatch is one `cdra_gather_rows` per tensor."""
         flat, tree = _flatten(tensors)
         n = flat[0].shape[0]
         index_lists = utils.index_batches(n, self.batch_size, drop_remainder=self.drop_batch_remainder, skip=self.skip_count,
                                           num_shards=self.obs_skipping, seed=self.seed, **kw)
         # data parallel: one gradient all-reduce per minibatch, so every rank runs the same number of them
         index_lists = index_lists[:self.network.sync.agree_min(len(index_lists))]
+        dev = self.network.device
+        flat = [(t if t.dim() > 1 else t.unsqueeze(-1)).to(dev).contiguous() for t in flat]
+        sizes = [len(ix) for ix in index_lists]
+        all_idx = torch.as_tensor(np.concatenate(index_lists) if index_lists else np.zeros(0, np.int64), dtype=torch.int64).to(dev)
+        starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 
         def gen():
-            for idx in index_lists:
-                yield _unflatten(self.network.gather(flat, idx), tree)
+            for j, m in enumerate(sizes):
+                yield _unflatten(self.network.gather_device(flat, all_idx[starts[j]:starts[j] + m]), tree)
         return gen
 
     def get_value_batches(self):
@@ -258,9 +268,7 @@ class PPOAgent(Agent):
                     self.update()
                     self.memory.delete()
                     self.memory = self.get_memory()
-                elif self.update_frequency > 1:
-                    self.memory.rewards = self.memory.rewards[:-1]
-                    self.memory.values = self.memory.values[:-1]
+                # (update_frequency > 1: the reference trims the bootstrap entries here, :551-553; update_index already did)
                 self.log(episode_rewards=episode_reward)
                 self.write_summaries()
                 if self.should_record:
@@ -349,85 +357,161 @@ def _unflatten(flat, spec):
 
 
 class PPOMemory:
-    """Recent memory used in PPOAgent (rl/agents/ppo.py:629-754).  Transitions are appended to python lists and
-    stacked once per trajectory (the reference re-`tf.concat`s every tensor at every step)."""
+    """Recent memory used in PPOAgent (rl/agents/ppo.py:629-754) as PREALLOCATED DEVICE BUFFERS: every `append` is one
+    row write (host -> device copy straight into the buffer, uint8 frames stay uint8), the update's minibatches are
+    gathered from the buffers by `cdra_gather_rows`, returns / advantages are written by `cdra_gae`.  (The reference
+    re-`tf.concat`s every tensor at every step -- O(N^2) copies -- and keeps fp32 frames on the host.)
 
-    def __init__(self, state_spec: dict, num_actions: int, device='cpu'):
-        self.index = 0
+    `num_envs` > 1 stores vectorised rollouts: one `append` carries the transition of every environment; rows are
+    time-major (row = step * num_envs + env), trajectories are the columns."""
+
+    def __init__(self, state_spec: dict, num_actions: int, device='cpu', capacity=256, num_envs=1, image_dtype=torch.float32):
+        self.index = 0                              # first step of the trajectory being collected
         self.device = torch.device(device)
         self.simple_state = list(state_spec.keys()) == ['state']
         self.state_spec = state_spec
-        self._states = [] if self.simple_state else {k: [] for k in state_spec}
-        self._actions, self._log_probs, self._values, self._rewards = [], [], [], []
         self.num_actions = num_actions
-        self.states = None if self.simple_state else {}
-        self.rewards = torch.zeros(0)
-        self.values = torch.zeros(0, 2)
-        self.actions = torch.zeros(0, num_actions)
-        self.log_probabilities = torch.zeros(0, num_actions)
+        self.num_envs = int(num_envs)
+        self.capacity = max(1, int(capacity))       # environment steps
+        self.size = 0                               # environment steps stored
+        self.image_dtype = image_dtype
+        self._buf = None
+        self._finished = False                      # end_trajectory has appended the bootstrap row
         self.returns = None
         self.advantages = None
 
+    # ------------------------------------------------------------------ storage
+    def _alloc(self, steps):
+        E, dev = self.num_envs, self.device
+        f = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
+        buf = dict(actions=f(steps * E, self.num_actions), log_probs=f(steps * E, self.num_actions),
+                   values=f((steps + 1) * E, 2), rewards=f((steps + 1) * E), states={})
+        for k, shape in self.state_spec.items():
+            dtype = self.image_dtype if k.endswith('image') else torch.float32
+            lead = () if self.simple_state else (getattr(self, 'time_horizon', None),)
+            lead = tuple(x for x in lead if x)
+            buf['states'][k] = torch.zeros((steps * E,) + lead + tuple(shape), dtype=dtype, device=dev)
+        return buf
+
+    def _ensure(self, steps):
+        if self._buf is None:
+            self._buf = self._alloc(self.capacity)
+        if steps <= self.capacity:
+            return
+        cap = self.capacity
+        while cap < steps:
+            cap *= 2
+        new, n, E = self._alloc(cap), self.size, self.num_envs
+        for k in ('actions', 'log_probs'):
+            new[k][:n * E].copy_(self._buf[k][:n * E])
+        for k in ('values', 'rewards'):
+            new[k][:(n + 1) * E].copy_(self._buf[k][:(n + 1) * E])
+        for k, v in self._buf['states'].items():
+            new['states'][k][:n * E].copy_(v[:n * E])
+        self._buf, self.capacity = new, cap
+
     def __len__(self):
-        return len(self._actions) if self._actions else self.actions.shape[0]
+        return self.size * self.num_envs
 
     def delete(self):
-        self._states = self._actions = self._log_probs = self._values = self._rewards = None
-        self.states = self.rewards = self.values = self.actions = self.log_probabilities = self.returns = self.advantages = None
+        self._buf = None
+        self.size = self.index = 0
+        self.returns = self.advantages = None
+
+    def _rows(self, x, width=None):
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+        return t.reshape(self.num_envs, -1) if width is None else t.reshape(self.num_envs, width)
 
     def append(self, state, action, reward, value, log_prob):
-        if self.simple_state:
-            self._states.append(state)
-        else:
-            assert isinstance(state, dict)
-            for k, v in state.items():
-                self._states[k].append(v)
-        self._actions.append(torch.as_tensor(action, dtype=torch.float32).reshape(1, -1))
-        self._rewards.append(float(reward))
-        self._values.append(torch.as_tensor(value, dtype=torch.float32).reshape(1, 2))
-        self._log_probs.append(torch.as_tensor(log_prob, dtype=torch.float32).reshape(1, -1))
+        """One transition per environment (rl/agents/ppo.py:678-690).  Tensors may live on the host (pinned memory makes
+        the copies asynchronous) or on the device; state tensors carry a leading axis of `num_envs`."""
+        assert not self._finished, 'append after end_trajectory: call update_index / delete first'
+        self._ensure(self.size + 1)
+        E, lo = self.num_envs, self.size * self.num_envs
+        b = self._buf
+        states = {'state': state} if self.simple_state else state
+        for k, dst in b['states'].items():
+            src = states[k] if isinstance(states[k], torch.Tensor) else torch.as_tensor(np.asarray(states[k]))
+            dst[lo:lo + E].copy_(src.reshape(dst[lo:lo + E].shape), non_blocking=True)
+        b['actions'][lo:lo + E].copy_(self._rows(action, self.num_actions), non_blocking=True)
+        b['log_probs'][lo:lo + E].copy_(self._rows(log_prob, self.num_actions), non_blocking=True)
+        b['values'][lo:lo + E].copy_(self._rows(value, 2), non_blocking=True)
+        r = reward if isinstance(reward, torch.Tensor) else torch.as_tensor(np.asarray(reward, dtype=np.float32))
+        b['rewards'][lo:lo + E].copy_(r.reshape(E), non_blocking=True)
+        self.size += 1
 
-    def _materialise(self):
-        cat = lambda xs: torch.cat([torch.as_tensor(x) for x in xs], dim=0).to(self.device)
-        if self.simple_state:
-            self.states = cat(self._states)
-        else:
-            self.states = {k: cat(v).contiguous() for k, v in self._states.items()}
-        self.actions = cat(self._actions)
-        self.log_probabilities = cat(self._log_probs)
+    def last_action(self):
+        E = self.num_envs
+        return self._buf['actions'][(self.size - 1) * E: self.size * E]
 
+    # ------------------------------------------------------------------ views the agent batches over
+    @property
+    def states(self):
+        n = len(self)
+        views = {k: v[:n] for k, v in self._buf['states'].items()}
+        return views['state'] if self.simple_state else views
+
+    @property
+    def actions(self):
+        return self._buf['actions'][:len(self)]
+
+    @property
+    def log_probabilities(self):
+        return self._buf['log_probs'][:len(self)]
+
+    @property
+    def values(self):
+        return self._buf['values'][:(self.size + (1 if self._finished else 0)) * self.num_envs]
+
+    @property
+    def rewards(self):
+        return self._buf['rewards'][:(self.size + (1 if self._finished else 0)) * self.num_envs]
+
+    # ------------------------------------------------------------------ returns / advantages
     def end_trajectory(self, last_value: torch.Tensor):
-        """Adds the value of the terminal state (rl/agents/ppo.py:692-697)."""
-        self._materialise()
-        last_value = torch.as_tensor(last_value, dtype=torch.float32).reshape(1, 2).cpu()
-        self._last_value = last_value
-        self.values = torch.cat([torch.cat(self._values, 0).cpu(), last_value], 0)
-        v_T = (last_value[:, 0].double() * torch.pow(torch.tensor(10.0, dtype=torch.float64), last_value[:, 1].double())).float()
-        self.rewards = torch.cat([torch.tensor(self._rewards, dtype=torch.float32), v_T], 0)
+        """Adds the value of the terminal state (rl/agents/ppo.py:692-697): values gets (base, exp), rewards gets
+        v_T = base * 10^exp as the bootstrap.  last_value: [num_envs, 2] (zeros for terminal states)."""
+        self._ensure(self.size + 1)
+        E, lo = self.num_envs, self.size * self.num_envs
+        lv = torch.as_tensor(last_value, dtype=torch.float32).reshape(E, 2).to(self.device)
+        self._buf['values'][lo:lo + E].copy_(lv)
+        v_T = (lv[:, 0].double() * torch.pow(torch.tensor(10.0, dtype=torch.float64, device=self.device), lv[:, 1].double())).float()
+        self._buf['rewards'][lo:lo + E].copy_(v_T)
+        self._finished = True
 
     def compute_returns_and_advantages(self, engine, gamma: float, lambda_: float, scale=2.0, append=False):
-        """compute_returns + compute_advantages (rl/agents/ppo.py:699-727) in one cdra_gae call."""
+        """compute_returns + compute_advantages (rl/agents/ppo.py:699-727) of the trajectory (per environment) that just
+        ended, in one cdra_gae call; results are stored time-major like every other buffer."""
+        assert self._finished
+        E, n0, n1 = self.num_envs, self.index, self.size
+        T = n1 - n0
         dev = engine.device
-        r = self.rewards[self.index:-1].reshape(1, -1).contiguous().to(dev)
-        vbe = self.values[self.index:-1].reshape(1, -1, 2).contiguous().to(dev)
-        last = self.values[-1:].reshape(1, 2).contiguous().to(dev)
-        returns_be, adv = engine.gae(r, vbe, last, gamma, lambda_, scale)
-        new_returns, new_adv = returns_be[0].to(self.device), adv[0].to(self.device)
+        r = self._buf['rewards'][n0 * E:n1 * E].view(T, E).t().contiguous().to(dev)
+        vbe = self._buf['values'][n0 * E:n1 * E].view(T, E, 2).transpose(0, 1).contiguous().to(dev)
+        last = self._buf['values'][n1 * E:(n1 + 1) * E].contiguous().to(dev)
+        returns_be, adv = engine.gae(r, vbe, last, gamma, lambda_, scale)               # [E,T,2], [E,T]
+        new_returns = returns_be.transpose(0, 1).reshape(T * E, 2).to(self.device)
+        new_adv = adv.t().reshape(T * E).to(self.device)
         if (self.returns is None) or (not append):
             self.returns, self.advantages = new_returns, new_adv
         else:
             self.returns = torch.cat([self.returns, new_returns], 0)
             self.advantages = torch.cat([self.advantages, new_adv], 0)
-        values = self.values[self.index:, 0] * torch.pow(torch.tensor(10.0), self.values[self.index:, 1])
-        returns = new_returns[:, 0] * torch.pow(torch.tensor(10.0, device=new_returns.device), new_returns[:, 1])
+        ten = torch.tensor(10.0, device=self.device)
+        vals = self._buf['values'][n0 * E:(n1 + 1) * E]
+        values = vals[:, 0] * torch.pow(ten, vals[:, 1])
+        returns = new_returns[:, 0] * torch.pow(ten, new_returns[:, 1])
         return returns, values, new_adv
 
     def update_index(self, append=False):
-        self.index = self.rewards.shape[0] - 1 if append else self.rewards.shape[0]
+        """rl/agents/ppo.py:729-733: the next trajectory starts after this one; with `append` (update_frequency > 1)
+        the bootstrap row is dropped and collection continues."""
+        self.index = self.size
+        self._finished = False
 
     def serialize(self, episode: int, save_path: str):
         filename = f'trace-{episode}-{time.strftime("%Y%m%d-%H%M%S")}.npz'
-        buffer = dict(reward=self.rewards.numpy(), action=self.actions.cpu().numpy(), value=self.values.numpy(),
+        buffer = dict(reward=self.rewards.cpu().numpy(), action=self.actions.cpu().numpy(), value=self.values.cpu().numpy(),
                       log_prob=self.log_probabilities.cpu().numpy())
         if self.simple_state:
             buffer['state'] = self.states.cpu().numpy()

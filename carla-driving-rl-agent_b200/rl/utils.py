@@ -126,6 +126,7 @@ class Summary:
         self.summary_dir = None
         self._writer = None
         self.last: Dict[str, float] = {}
+        self.last_d2h_bytes = 0
         if self.use_summary:
             import datetime
             self.summary_dir = os.path.join(summary_dir, str(name), datetime.datetime.now().strftime('%Y%m%d-%H%M%S'))
@@ -173,8 +174,11 @@ class Summary:
                 else:
                     vals.append(float(item))
             out[key] = vals
+        self.last_d2h_bytes = 0
         if dev_rows:
-            host = torch.cat(dev_rows).cpu().tolist()
+            packed = torch.cat(dev_rows)
+            self.last_d2h_bytes = packed.numel() * 4
+            host = packed.cpu().tolist()
             i = 0
             for key, pos, n in slots:
                 out[key][pos:pos + n] = host[i:i + n]

@@ -166,6 +166,19 @@ int cdra_grad_norms(const float* grads, const int64_t* tensor_offsets, int n_ten
 /* utils.data_to_batches gather (rl/utils.py:365-393): dst[i] = src[index[i]] for rows of row_bytes. */
 int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst, void* stream);
 
+/* Data-parallel gradient exchange (nothing like it exists in the single-process reference): one NCCL sum
+ * all-reduce of a flat fp32 gradient range per pass, enqueued on `stream` like every kernel of the library so that a whole
+ * SGD step stays on one stream / is capturable in a CUDA graph.  libnccl is resolved at run time (dlopen; the copy PyTorch
+ * already loaded is reused), so the library itself has no link-time dependency on it.
+ *   cdra_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller broadcasts it to the other ranks by any means
+ *   cdra_comm_create    : every rank, on its own device (cudaSetDevice done by the caller); collective
+ *   cdra_allreduce_grads: in-place sum over ranks of grads[0 .. count) */
+typedef struct cdra_comm cdra_comm_t;
+int cdra_comm_unique_id(void* id_out_128_bytes);
+int cdra_comm_create(const void* id_128_bytes, int world_size, int rank, cdra_comm_t** out);
+void cdra_comm_destroy(cdra_comm_t* comm);
+int cdra_allreduce_grads(cdra_comm_t* comm, float* grads, int64_t count, void* stream);
+
 /* Launch accounting (bench.py's `gpu_launches`) and optional per-kernel CUDA-event timing on the launch
  * stream (bench.py's live roofline numbers).  Profiling serialises every launch; never leave it on
  * inside a timed region.  cdra_profile_report writes "name\tcount\ttotal_ms\talgorithmic_bytes\n" lines

@@ -19,10 +19,11 @@ def _cpu_logic_build(monkeypatch, built_libs):
 def _agent(tmp_path, batch_size=2, **kw):
     from core import CARLAgent, SyntheticCARLAEnvironment
     env = SyntheticCARLAEnvironment(image_shape=(H, W, 3), image_uint8=True, seed=1)
+    base = dict(seed=7, skip_data=1, drop_batch_remainder=True, log_mode='summary', policy_lr=3e-4, value_lr=3e-4,
+                dynamics_lr=3e-4, entropy_regularization=1.0, clip_ratio=0.2, gamma=0.9999, lambda_=0.999)
+    base.update(kw)
     return CARLAgent(env, batch_size=batch_size, name='t', weights_dir=str(tmp_path / 'w'), evaluation_dir=str(tmp_path / 'e'),
-                     seed=7, skip_data=1, drop_batch_remainder=True, log_mode='summary', policy_lr=3e-4, value_lr=3e-4,
-                     dynamics_lr=3e-4, entropy_regularization=1.0, clip_ratio=0.2, gamma=0.9999, lambda_=0.999,
-                     network=dict(device='cpu', dtype='f32'), **kw)
+                     network=dict(device='cpu', dtype='f32'), **base)
 
 
 def test_api_surface_and_defaults(built_libs, tmp_path):
@@ -124,3 +125,35 @@ def test_dynamic_parameters():
     q = PolynomialDecay(1.0, 0.0, decay_steps=4)
     q.step = 2
     assert abs(q() - 0.5) < 1e-12
+
+
+def test_vectorised_device_memory(built_libs, tmp_path):
+    """the rollout memory as preallocated buffers: vectorised appends (one transition per environment),
+    growth, time-major rows, per-environment returns / advantages equal to the single-trajectory oracle
+    (rl/agents/ppo.py:692-727), and an update() over it"""
+    from oracle import ppo
+    E, T = 2, 3
+    agent = _agent(tmp_path, batch_size=E * T, skip_data=0)
+    mem = agent.get_memory(capacity=2, num_envs=E)                      # forces a growth step
+    rng = np.random.RandomState(4)
+    rew = (rng.randn(T, E) * 2 + 1).astype(np.float32)
+    val = np.stack([rng.rand(T, E) * 2 - 1, np.floor(rng.rand(T, E) * 4)], -1).astype(np.float32)
+    img = rng.randint(0, 256, size=(T, E, 4, H, W, 3)).astype(np.uint8)
+    for t in range(T):
+        state = dict(state_image=torch.from_numpy(img[t]), state_road=torch.rand(E, 4, 9), state_vehicle=torch.rand(E, 4, 4),
+                     state_navigation=torch.rand(E, 4, 5))
+        mem.append(state, torch.rand(E, 2), torch.from_numpy(rew[t]), torch.from_numpy(val[t]), torch.randn(E, 2) * 0.3)
+    assert len(mem) == T * E and mem.capacity >= T and mem.states['state_image'].dtype == torch.uint8
+    assert torch.equal(mem.states['state_image'].view(T, E, 4, H, W, 3)[2, 1], torch.from_numpy(img[2, 1]))     # time-major rows
+    last = np.array([[0.5, 1.0], [0.0, 0.0]], np.float32)
+    agent.memory = mem
+    agent.end_episode(torch.from_numpy(last))
+    ret, adv = mem.returns.view(T, E, 2).numpy(), mem.advantages.view(T, E).numpy()
+    for e in range(E):
+        r_ref, a_ref, _ = ppo.end_trajectory(rew[:, e], val[:, e], last[e], agent.gamma, agent.lambda_, 2.0)
+        assert np.array_equal(ret[:, e, 1], r_ref[:, 1]) and np.abs(ret[:, e, 0] - r_ref[:, 0]).max() < 2e-7
+        assert np.abs(adv[:, e] - a_ref).max() < 1e-6
+    agent.env.info_buffer = dict(speed=torch.rand(T * E) * 30, similarity=torch.rand(T * E) * 2 - 1)         # tensors are accepted too
+    p0 = agent.network.policy.flat.clone()
+    agent.update()
+    assert agent.network.engine.adam_step == dict(dyn=2, pol=1, val=1) and not torch.equal(agent.network.policy.flat, p0)

@@ -35,7 +35,7 @@ def _worker(rank, world, port, out_dir):
     gathered = [[torch.zeros_like(t) for _ in range(world)] for t in local]
     for t, g in zip(local, gathered):
         dist.all_gather(g, t)
-    sync.allreduce('dyn', 'pol')
+    sync.allreduce_pass('policy')              # ONE collective over the contiguous [policy | dynamics] gradient range
     assert torch.allclose(eng.g_dyn, sum(gathered[0]), atol=1e-6) and torch.allclose(eng.g_pol, sum(gathered[1]), atol=1e-6)
     eng.clip_adam('dyn', 3e-4, None, sync.grad_scale)
     eng.clip_adam('pol', 3e-4, 1.0, sync.grad_scale)
