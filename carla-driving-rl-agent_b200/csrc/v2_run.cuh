@@ -151,14 +151,16 @@ inline bool try_pw_fwd(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd, int colm
 // plain-output layers (pw1 of every unit) on tcgen05: one CTA per SM, TMEM accumulator, weights resident in the swizzled layout
 inline bool try_pw_fwd_tc(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
     constexpr int NT = 512;
-    if (hd.cols.nplanes != 1 || a.x1 || hd.cols.interleave || a.gwv != a.cpo) return false;
+    if (hd.cols.nplanes > 2 || (a.gwv & 1)) return false;
     int sum = 0;
     for (int i = 0; i < hd.nsrc; ++i) sum += hd.src[i].cp;
-    const PwFwdTcSmem L0 = pw_fwd_tc_smem(hd.KP, hd.NPall, a.cpo, sum, 0, NT);
-    if (L0.np > 256 || L0.nkb > 4 || (NT / (a.cpo >> 3)) < 1 || (NT / (sum >> 3)) < 1) return false;
+    const int x1cp = a.x1 ? a.x1cp : 0, nq = hd.cols.nplanes * (a.cpo >> 3);
+    const PwFwdTcSmem L0 = pw_fwd_tc_smem(hd.KP, hd.NPall, a.cpo, sum, 0, NT, hd.cols.nplanes, x1cp);
+    if (L0.np > 256 || L0.nkb > 4 || (NT / nq) < 1 || (NT / (sum >> 3)) < 1) return false;
+    if (a.x1 && NT / (2 * ((a.ncopy + 1) >> 1)) < 1) return false;
     const int nbuf = std::min(8, (kMaxDynSmem - L0.total) / L0.raw_stride);
     if (nbuf < 2) return false;
-    const PwFwdTcSmem L = pw_fwd_tc_smem(hd.KP, hd.NPall, a.cpo, sum, nbuf, NT);
+    const PwFwdTcSmem L = pw_fwd_tc_smem(hd.KP, hd.NPall, a.cpo, sum, nbuf, NT, hd.cols.nplanes, x1cp);
     auto k = pw_fwd_tc_kernel<NT>;
     static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
     (void)attr_done;

@@ -327,3 +327,13 @@ def test_full_size_layer_slice_bf16(built_libs):
                 dR = L.bf16r(a1t[t, :, 0] * (dz - bs[t, :, 0] / n - xhat * bs[t, :, 1] / n))
                 d_in, _ = L.pw_backward(dR, xin, p(name + '.pw1.w'))
                 assert C.rel_l2(gx[f][..., Cx // 2:], L.bf16r(d_in)) <= GRAD_TOL, (name, f)
+        # the unit tail (pw2 + channel shuffle + pass-through) of the same unit: branch channels against the layer oracle,
+        # pass-through channels bit-exact
+        r2 = eng.tensor(name + '.dw'); out = eng.tensor(name + '.out')
+        a2t = eng.tensor('aff:' + name + '.dw').squeeze(-1).double().cpu()
+        for t, b in ((0, 1), (2, B - 2)):
+            f = t * B + b
+            a2 = L.bf16r(L.f32r(r2[f].double().cpu() * a2t[t, :, 0] + a2t[t, :, 1]))
+            cat = L.unshuffle(out[f].double().cpu())
+            assert C.rel_l2(cat[..., Cx // 2:], L.pw_forward(a2, p(name + '.pw2.w'), p(name + '.pw2.b'))) <= FWD_TOL, (name, f)
+            assert torch.equal(cat[..., :Cx // 2], x[f].double().cpu()[..., :Cx // 2]), (name, f)
