@@ -226,6 +226,7 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
         for (auto& t : v.t) if (t.name != "tower.pool") t.grad = alloc(t.bytes() + 256);
         auto pwalloc = [&](V2Pw& g) {
             g.wf = alloc((size_t)g.NPall * g.KP * 2); g.wb = alloc((size_t)g.NPall * g.KP * 2); g.bias = alloc((size_t)g.NPall * 4);
+            g.wfs = alloc((size_t)((g.KP + 63) / 64) * g.NPall * 128 + 16384); g.wbs = alloc((size_t)((g.NPall + 63) / 64) * g.KP * 128 + 16384);
         };
         for (auto& u : v.u) { pwalloc(u.pw1); pwalloc(u.tail); }
         pwalloc(v.head_pw);

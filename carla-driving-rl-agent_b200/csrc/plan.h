@@ -100,6 +100,7 @@ struct V2Tensor {
 struct V2Pw {                    // one GEMM launch (pw1 / unit tail / head conv)
     int KP = 0, NPall = 0, nplanes = 1, gwp = 0;
     size_t wf = 0, wb = 0, bias = 0;    // workspace byte offsets of the prepared bf16 operands
+    size_t wfs = 0, wbs = 0;            // the same operands cut into 64-column blocks of 128-byte-swizzled rows (v4_pwg.cuh)
     int counter = -1, bcounter = -1;
 };
 struct V2Unit {

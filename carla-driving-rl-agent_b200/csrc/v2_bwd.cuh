@@ -61,6 +61,7 @@ struct PwBwdArgs {
     // dR = BatchNorm(+ReLU6) backward of d out, [4*Rt][NPall] bf16: written once by the data-gradient kernel (it builds
     // the tile anyway), consumed by the tcgen05 weight-gradient kernel, which then needs no transform of its own
     bf16* dr;
+    GBlock blk[kGMaxBlk]; int nblk;   // v4_pwg.cuh: blockIdx.y = M block
 };
 
 struct PwDgradSmem { int colc, srcc, x1c, stat, w, raw, dr, st, st2, total, raw_stride, ldr, ldw, lds, lds2; };

@@ -44,6 +44,10 @@ struct PwDesc {
     bf16* wf;               // [NPall][KP]   wf[j][k]  (forward B operand, k contiguous)
     bf16* wb;               // [KP][NPall]   wb[k][j]  (data-gradient B operand, j contiguous)
     float* bias;            // [NPall]
+    // the same operands as 64-column blocks of 128-byte-swizzled rows (chunk c of row r at c ^ (r & 7)): a contiguous run
+    // of rows of one block is a ready-made K-major tcgen05 operand tile, fetched by ONE bulk copy (v4_pwg.cuh)
+    bf16* wfs;              // [ceil(KP/64)][NPall][64]    block kb, row j  : wf[j][64 kb ..]
+    bf16* wbs;              // [ceil(NPall/64)][KP][64]    block jb, row kk : wb[kk][64 jb ..]
 };
 
 // GEMM row kk -> (layer, logical k) ; returns false for padding
@@ -97,7 +101,27 @@ __global__ void __launch_bounds__(256) pw_prep_kernel(const PwDesc* __restrict__
             int p, s, l, n;
             d.bias[j] = pw_col(d, j, p, s, l, n) ? d.layer[l].b[n] : 0.f;
         }
+    // swizzled blocks (zero beyond KP / NPall inside the last block)
+    const int nkb = (d.KP + 63) >> 6, njb = (d.NPall + 63) >> 6;
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < nkb * d.NPall * 64; i += gridDim.y * 256) {
+        const int kb = i / (d.NPall * 64), rem = i - kb * d.NPall * 64, j = rem >> 6, c = rem & 63, kk = kb * 64 + c;
+        int lk, k, p, s, lj, n;
+        float v = 0.f;
+        if (kk < d.KP && pw_row(d, kk, lk, k) && pw_col(d, j, p, s, lj, n) && lk == lj) v = d.layer[lk].w[(size_t)k * d.layer[lk].N + n];
+        d.wfs[((size_t)kb * d.NPall + j) * 64 + ((((c >> 3) ^ (j & 7)) << 3) | (c & 7))] = __float2bfloat16_rn(v);
+    }
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < njb * d.KP * 64; i += gridDim.y * 256) {
+        const int jb = i / (d.KP * 64), rem = i - jb * d.KP * 64, kk = rem >> 6, c = rem & 63, j = jb * 64 + c;
+        int lk, k, p, s, lj, n;
+        float v = 0.f;
+        if (j < d.NPall && pw_row(d, kk, lk, k) && pw_col(d, j, p, s, lj, n) && lk == lj) v = d.layer[lk].w[(size_t)k * d.layer[lk].N + n];
+        d.wbs[((size_t)jb * d.KP + kk) * 64 + ((((c >> 3) ^ (kk & 7)) << 3) | (c & 7))] = __float2bfloat16_rn(v);
+    }
 }
+
+// one M block (<= 128 GEMM columns / rows) of the tcgen05 GEMM family of v4_pwg.cuh
+constexpr int kGMaxBlk = 8;
+struct GBlock { int base, n, aux0, aux1; };   // forward: first GEMM column, columns, plane, first slot; data gradient: first GEMM row, rows, source, first slot
 
 // ======================================================================================== forward
 struct PwFwdArgs {
@@ -115,6 +139,7 @@ struct PwFwdArgs {
     int ntiles_n;               // colmode 1: N tiles per plane
     int tiles_per_cta;
     int nbuf;                   // tcgen05 kernel: depth of the TMA ring
+    GBlock blk[kGMaxBlk]; int nblk;   // v4_pwg.cuh: blockIdx.y = M block
 };
 
 template <int R, int WM, int WN, int MT, int NBW>

@@ -10,6 +10,7 @@
 #include "v2_umma.cuh"
 #include "v2_pw_tc.cuh"
 #include "v3_pw_bwd.cuh"
+#include "v4_pwg.cuh"
 
 namespace cdra {
 namespace v2 {
@@ -46,6 +47,7 @@ struct UnitDescs { PwDesc pw1, tail; };
 inline void fill_pw(PwDesc& d, const RunCtx& c, const V2Pw& g) {
     d.KP = g.KP; d.NPall = g.NPall;
     d.wf = (bf16*)(c.ws + g.wf); d.wb = (bf16*)(c.ws + g.wb); d.bias = (float*)(c.ws + g.bias);
+    d.wfs = (bf16*)(c.ws + g.wfs); d.wbs = (bf16*)(c.ws + g.wbs);
     d.cols.nplanes = g.nplanes; d.cols.gwp = g.gwp;
 }
 inline PwDesc desc_pw1(const RunCtx& c, int ui) {
@@ -114,6 +116,10 @@ inline int& fwd_tc_override() { static int v = -1; return v; }  // cdra_debug_se
 inline bool use_fwd_tc() { static const bool env = getenv("CDRA_NO_FWD_TC") == nullptr; return fwd_tc_override() < 0 ? env : fwd_tc_override() != 0; }
 inline int& fused_override() { static int v = -1; return v; }   // cdra_debug_set("fused", 0 | 1)
 inline bool use_fused() { static const bool env = getenv("CDRA_NO_FUSED") == nullptr; return fused_override() < 0 ? env : fused_override() != 0; }
+inline int& pwg_override() { static int v = -1; return v; }     // cdra_debug_set("pwg", 0 | 1)
+inline bool use_pwg() { static const bool env = getenv("CDRA_NO_PWG") == nullptr; return pwg_override() < 0 ? env : pwg_override() != 0; }
+// the GEMM family of v4_pwg.cuh takes every pointwise launch whose reduction length reaches this (stage 3 and the head)
+inline int pwg_min_k() { static const int v = getenv("CDRA_PWG_MINK") ? atoi(getenv("CDRA_PWG_MINK")) : 192; return v; }
 inline int num_sms() {
     static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
     return n;
@@ -173,6 +179,56 @@ inline bool try_pw_fwd_tc(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
     return true;
 }
 
+// shared-memory plan of a v4_pwg launch: resident weights when they leave room for >= 3 ring stages, else streamed
+inline bool pwg_plan(int kdim, int tab_bytes, int extra, int& ares, int& nstage, int& smem) {
+    ares = 1;
+    PwgSmem L0 = pwg_smem(kdim, tab_bytes, true, 128, 0, extra);
+    nstage = (kMaxDynSmem - L0.total) / L0.stage_bytes;
+    if (nstage < 3) {
+        ares = 0;
+        L0 = pwg_smem(kdim, tab_bytes, false, 128, 0, extra);
+        nstage = (kMaxDynSmem - L0.total) / L0.stage_bytes;
+        if (nstage < 3) return false;
+    }
+    nstage = std::min(nstage, kGMaxStages);
+    smem = pwg_smem(kdim, tab_bytes, ares != 0, 128, nstage, extra).total;
+    return true;
+}
+inline void pwg_grid(int Rt, int nblk, int& gx, int& tiles_per_cta) {
+    const int tps = (Rt + kGRows - 1) / kGRows, ntile = kT * tps;
+    const int per_blk = std::max(1, num_sms() / nblk);
+    tiles_per_cta = (ntile + per_blk - 1) / per_blk;
+    gx = (ntile + tiles_per_cta - 1) / tiles_per_cta;
+}
+
+inline bool try_pwg_fwd(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
+    if (hd.KP < pwg_min_k() || hd.KP > 768 || (a.gwv & 1)) return false;
+    a.nblk = 0;
+    for (int p = 0; p < hd.cols.nplanes; ++p)
+        for (int s0 = 0; s0 < hd.cols.gwp; s0 += 128) {
+            if (a.gwv - s0 <= 0) continue;
+            if (a.nblk == kGMaxBlk) return false;
+            a.blk[a.nblk++] = GBlock{p * hd.cols.gwp + s0, std::min(128, hd.cols.gwp - s0), p, s0};
+        }
+    int ares, nstage, smem;
+    if (!pwg_plan(hd.KP, ((hd.KP + 63) & ~63) * 8, 0, ares, nstage, smem)) return false;
+    static bool attr_done = (cudaFuncSetAttribute(pwg_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem),
+                             cudaFuncSetAttribute(pwg_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nstage;
+    int gx; pwg_grid(a.Rt, a.nblk, gx, a.tiles_per_cta);
+    if (nstage >= 5) CDRA_LAUNCH_PDL(pwg_fwd_kernel<4>, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
+    else CDRA_LAUNCH_PDL(pwg_fwd_kernel<2>, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
+    if (a.x1) {       // pass-through half of a stride-1 unit
+        PassFwdArgs q; q.x1 = a.x1; q.x1cp = a.x1cp; q.x1map = a.x1map; q.out[0] = a.out[0]; q.out[1] = a.out[1]; q.cpo = a.cpo;
+        q.ncopy = a.ncopy; q.copy_dst0 = a.copy_dst0; q.rows = (long long)kT * a.Rt;
+        prof_bytes(4.0 * a.Rt * 2 * a.ncopy * 2 * 2);
+        const long long total = q.rows * q.ncopy;
+        CDRA_LAUNCH_PDL(pass_fwd_kernel, dim3((unsigned)std::min<long long>((total + 255) / 256, 8 * num_sms())), dim3(256), 0, c.stream, q);
+    }
+    return true;
+}
+
 inline void launch_pw_fwd(const RunCtx& c, int di, const PwDesc& hd, PwFwdArgs& a, bool allow_full_cols) {
     a.d = desc_dev(c, di);
     a.training = c.training;
@@ -182,6 +238,7 @@ inline void launch_pw_fwd(const RunCtx& c, int di, const PwDesc& hd, PwFwdArgs& 
     if (a.x1) bytes += 4.0 * a.Rt * 2 * a.ncopy * 2;
     prof_bytes(bytes);
     bool ok = false;
+    if (use_tc() && use_pwg() && try_pwg_fwd(c, a, hd)) return;
     if (allow_full_cols && use_tc() && use_fwd_tc() && try_pw_fwd_tc(c, a, hd)) return;
     if (allow_full_cols) {
         if (hd.NPall <= 64) ok = try_pw_fwd<128, 8, 1, 1, 8>(c, a, hd, 0, 2) || try_pw_fwd<64, 4, 2, 1, 4>(c, a, hd, 0, 1);
@@ -382,6 +439,42 @@ inline bool try_pw_bwd_fused(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, in
     return true;
 }
 
+inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
+    if (hd.KP < pwg_min_k() || hd.NPall > 768) return false;
+    a.nblk = 0;
+    int off = 0;
+    for (int i = 0; i < hd.nsrc; ++i) {
+        for (int s0 = 0; s0 < hd.src[i].cp; s0 += 128) {
+            if (a.nblk == kGMaxBlk) return false;
+            a.blk[a.nblk++] = GBlock{off + s0, std::min(128, hd.src[i].cp - s0), i, s0};
+        }
+        off += hd.src[i].cp;
+    }
+    int ares, nstage, smem;
+    if (!pwg_plan(hd.NPall, ((hd.NPall + 63) & ~63) * 16, 16384, ares, nstage, smem)) return false;
+    static bool attr_done = (cudaFuncSetAttribute(pwg_dgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nstage;
+    int gx; pwg_grid(a.Rt, a.nblk, gx, a.tiles_per_cta);
+    CDRA_LAUNCH_PDL(pwg_dgrad_kernel<2>, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
+    for (int i = 0; i < hd.nsrc; ++i) {      // BatchNorm-backward sums of the gradients just written
+        const PwSrc& Sx = hd.src[i];
+        if (!Sx.bsum || Sx.sum_hi <= Sx.sum_lo) continue;
+        BsumArgs q; q.x = Sx.data; q.dx = Sx.grad; q.cp = Sx.cp; q.lo = Sx.sum_lo; q.hi = Sx.sum_hi; q.clamp = Sx.clamp; q.aff = Sx.aff; q.bnp = Sx.bnp;
+        q.bsum = Sx.bsum; q.Rt = a.Rt; q.rows_per_cta = 64;
+        prof_bytes(4.0 * a.Rt * (Sx.sum_hi - Sx.sum_lo) * 2 * 2);
+        CDRA_LAUNCH_PDL(bsum_kernel, dim3((a.Rt + 63) / 64, kT, (Sx.sum_hi - Sx.sum_lo + 255) / 256), dim3(256), 0, c.stream, q);
+    }
+    if (a.x1) {
+        PassBwdArgs q; q.x1 = a.x1; q.dx1 = a.dx1; q.x1cp = a.x1cp; q.x1map = a.x1map; q.x1aff = a.x1aff; q.x1bnp = a.x1bnp; q.x1bsum = a.x1bsum;
+        q.x1clamp = a.x1clamp; q.dout[0] = a.dout[0]; q.dout[1] = a.dout[1]; q.cpo = a.cpo; q.ncopy = a.ncopy; q.copy_dst0 = a.copy_dst0; q.Rt = a.Rt;
+        q.rows_per_cta = 64;
+        prof_bytes(4.0 * a.Rt * 2 * a.ncopy * 2 * 3);
+        CDRA_LAUNCH_PDL(pass_bwd_kernel, dim3((a.Rt + q.rows_per_cta - 1) / q.rows_per_cta, kT), dim3(256), 0, c.stream, q);
+    }
+    return true;
+}
+
 // data gradient (+ pass-through, + BN-backward sums of the inputs) and weight gradient of one GEMM launch
 inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a) {
     a.d = desc_dev(c, di);
@@ -405,7 +498,8 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
     if (a.x1) bytes += 4.0 * a.Rt * 2 * a.ncopy * 2 * 2;
     prof_bytes(bytes);
     bool ok;
-    if (max_cp <= 64)
+    if (use_tc() && use_pwg() && a.x1cp <= 256 && try_pwg_dgrad(c, a, hd)) ok = true;
+    else if (max_cp <= 64)
         ok = try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 2, 0, 2) || try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 1, 0, 2) ||
              try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 2, 0, 1) || try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 1, 0, 1) ||
              try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 0, 1) || try_pw_dgrad<32, 2, 4, 1, 2>(c, a, hd, 1, 1, 1);
