@@ -20,6 +20,7 @@ back to the host), all inside the clock.
 """
 import argparse
 import json
+import re
 import os
 import statistics
 import subprocess
@@ -410,6 +411,25 @@ def e2e_agent_leg(args, torch, dist, dev, world, rank, n_steps, barrier):
                     'inside the clock; every sample crosses PCIe once and is used by both passes'}
 
 
+def _demangle_short(name):
+    """_ZN4cdra2v213dw_bwd_kernelILi120ELi1EEEv... -> dw_bwd<120,1> (length-prefixed Itanium identifiers)"""
+    if not name.startswith('_ZN'):
+        return name
+    i, ident = 3, None
+    while i < len(name) and name[i].isdigit():
+        j = i
+        while name[j].isdigit():
+            j += 1
+        n = int(name[i:j]); ident = name[j:j + n]; i = j + n
+    if not ident:
+        return name
+    ints = []
+    if i < len(name) and name[i] == 'I':
+        ints = re.findall(r'L[ib](\d+)E', name[i:name.find('Ev', i) + 1 if name.find('Ev', i) > 0 else len(name)])
+    ident = ident[:-7] if ident.endswith('_kernel') else ident
+    return ident + ('<' + ','.join(ints) + '>' if ints else '')
+
+
 def kernel_roofline(eng, sgd_step, first, peak, peak_src):
     """Per-kernel CUDA-event timing on the launch stream (serialised; outside the timed region)."""
     import ctypes
@@ -432,17 +452,22 @@ def kernel_roofline(eng, sgd_step, first, peak, peak_src):
                     'sqnorm', 'adam', 'gather_rows'):
             if tag in name:
                 short = tag
+        if short == name:                            # mangled name of a templated kernel: keep the kernel name + template integers
+            short = _demangle_short(name)
         rows.append((short, int(cnt), float(ms), float(by)))
     agg = {}
     for s, c, m, b in rows:
         a = agg.setdefault(s, [0, 0.0, 0.0]); a[0] += c; a[1] += m; a[2] += b
     total = sum(a[1] for a in agg.values())
     top = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    for k, v in top:                                 # full table (two steps) for the logs
+        print(f'[profile] {k:32s} n={v[0]:4d} ms/step={v[1] / 2:7.3f} us/launch={1e3 * v[1] / max(v[0], 1):7.1f} '
+              f'GB/s={(v[2] / (v[1] / 1e3) / 1e9) if v[1] > 0 and v[2] > 0 else 0:7.1f}', file=sys.stderr)
     name, (cnt, ms, by) = top[0]
     ach = by / (ms / 1e3) / 1e9 if ms > 0 else 0.0
     traffic = None                                   # DRAM bytes per launch of that kernel from the committed ncu capture
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
         if tj.get('kernel') == name:
             traffic = tj['dram_bytes_per_launch']
     except (OSError, ValueError, KeyError):
@@ -451,7 +476,7 @@ def kernel_roofline(eng, sgd_step, first, peak, peak_src):
             'algorithmic_bytes_per_launch': by / max(cnt, 1),
             'launches': cnt, 'avg_ms': ms / max(cnt, 1), 'share_of_step': ms / total if total else None, 'peak_source': peak_src,
             'by_kernel': {k: {'launches': v[0], 'ms': round(v[1], 3), 'share': round(v[1] / total, 4),
-                              'GBps': round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None} for k, v in top[:14]}}
+                              'GBps': round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None} for k, v in top[:20]}}
 
 
 def _quiet_stdout():

@@ -120,6 +120,8 @@ inline int& pwg_override() { static int v = -1; return v; }     // cdra_debug_se
 inline bool use_pwg() { static const bool env = getenv("CDRA_NO_PWG") == nullptr; return pwg_override() < 0 ? env : pwg_override() != 0; }
 // the GEMM family of v4_pwg.cuh takes every pointwise launch whose reduction length reaches this (stage 3 and the head)
 inline int pwg_min_k() { static const int v = getenv("CDRA_PWG_MINK") ? atoi(getenv("CDRA_PWG_MINK")) : 192; return v; }
+inline bool use_pwg_wgrad() { static const bool env = getenv("CDRA_NO_PWG_WGRAD") == nullptr; return env; }
+inline int pwg_min_k_bwd() { static const int v = getenv("CDRA_PWG_MINK_BWD") ? atoi(getenv("CDRA_PWG_MINK_BWD")) : 192; return v; }
 inline int num_sms() {
     static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
     return n;
@@ -440,7 +442,7 @@ inline bool try_pw_bwd_fused(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, in
 }
 
 inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
-    if (hd.KP < pwg_min_k() || hd.NPall > 768) return false;
+    if (hd.KP < pwg_min_k_bwd() || hd.NPall > 768) return false;
     a.nblk = 0;
     int off = 0;
     for (int i = 0; i < hd.nsrc; ++i) {
@@ -475,6 +477,39 @@ inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
     return true;
 }
 
+// split-K tcgen05 weight gradient over the dR hand-off (v4_pwg.cuh)
+inline bool try_pwg_wgrad(const RunCtx& c, const PwBwdArgs& b, const PwDesc& hd) {
+    if (hd.KP < pwg_min_k_bwd() || hd.KP > 768 || b.dr == nullptr) return false;
+    PwgWgArgs a; memset(&a, 0, sizeof a);
+    a.d = b.d; a.Rt = b.Rt; a.dr = b.dr; a.tb[0] = b.tb[0]; a.tb[1] = b.tb[1]; a.cpo = b.cpo;
+    int off = 0;
+    for (int i = 0; i < hd.nsrc; ++i) {
+        for (int s0 = 0; s0 < hd.src[i].cp; s0 += 128) {
+            if (a.nblk == kGMaxBlk) return false;
+            a.blk[a.nblk++] = GBlock{off + s0, std::min(128, hd.src[i].cp - s0), i, s0};
+        }
+        off += hd.src[i].cp;
+    }
+    a.nnb = (hd.NPall + 255) / 256;
+    const int nbk = (std::min(256, hd.NPall) + 63) / 64;
+    const PwgWgSmem L0 = pwg_wg_smem(hd.KP, nbk, 0);
+    int nstage = std::min(kGMaxStages, (kMaxDynSmem - L0.total) / L0.stage_bytes);
+    if (nstage < 2) return false;
+    const int smem = pwg_wg_smem(hd.KP, nbk, nstage).total;
+    static bool attr_done = (cudaFuncSetAttribute(pwg_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem),
+                             cudaFuncSetAttribute(pwg_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
+    (void)attr_done;
+    a.nbuf = nstage;
+    const int gy = a.nblk * a.nnb;
+    const int tps = (a.Rt + kGRows - 1) / kGRows, ntile = kT * tps;
+    const int splits = std::max(1, num_sms() / gy);
+    a.tiles_per_cta = (ntile + splits - 1) / splits;
+    const int gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    if (nstage >= 3) CDRA_LAUNCH_PDL(pwg_wgrad_kernel<2>, dim3(gx, gy), dim3(kGThreads), smem, c.stream, a);
+    else CDRA_LAUNCH_PDL(pwg_wgrad_kernel<1>, dim3(gx, gy), dim3(kGThreads), smem, c.stream, a);
+    return true;
+}
+
 // data gradient (+ pass-through, + BN-backward sums of the inputs) and weight gradient of one GEMM launch
 inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a) {
     a.d = desc_dev(c, di);
@@ -497,8 +532,8 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
     bytes += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n + a.ncopy) * 2 * 2;                      // d out, out read
     if (a.x1) bytes += 4.0 * a.Rt * 2 * a.ncopy * 2 * 2;
     prof_bytes(bytes);
-    bool ok;
-    if (use_tc() && use_pwg() && a.x1cp <= 256 && try_pwg_dgrad(c, a, hd)) ok = true;
+    bool ok, pwg = false;
+    if (use_tc() && use_pwg() && a.x1cp <= 256 && try_pwg_dgrad(c, a, hd)) ok = pwg = true;
     else if (max_cp <= 64)
         ok = try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 2, 0, 2) || try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 1, 0, 2) ||
              try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 2, 0, 1) || try_pw_dgrad<64, 4, 2, 1, 4>(c, a, hd, 1, 0, 1) ||
@@ -513,6 +548,7 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
     for (int i = 0; i < hd.nsrc; ++i) bytes += 4.0 * a.Rt * (hd.src[i].map.n0 + hd.src[i].map.n1) * 2;
     bytes += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n) * 2 * 2;
     prof_bytes(bytes);
+    if (pwg && use_pwg_wgrad() && try_pwg_wgrad(c, a, hd)) return;
     if (tc && (try_pw_wgrad_tc<128>(c, a, hd, 3) || try_pw_wgrad_tc<64>(c, a, hd, 4) || try_pw_wgrad_tc<32>(c, a, hd, 4) || try_pw_wgrad_tc<16>(c, a, hd, 3) ||
                      try_pw_wgrad_tc<32>(c, a, hd, 2) || try_pw_wgrad_tc<16>(c, a, hd, 2))) return;
     if (hd.cols.gwp <= 64)

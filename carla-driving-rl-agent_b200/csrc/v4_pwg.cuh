@@ -567,6 +567,243 @@ __global__ void __launch_bounds__(256) bsum_kernel(const BsumArgs a) {
     }
 }
 
+// ======================================================================================== weight gradient
+// dW[kk][j] += sum_r act(src)[r][kk] * dR[r][j] as a split-K tcgen05 GEMM: an output tile is (M block of <= 128 source
+// slots) x (N block of <= 256 GEMM columns), blockIdx.y; the rows are split over blockIdx.x.  Both operands are
+// MN-major views of row tiles: the same [128 rows][64 channels] swizzled blocks the forward uses as K-major tiles
+// (v2_umma.cuh), so the producers are the forward's (cp.async + in-place BatchNorm affine / ReLU6 for act(src)) plus a
+// plain copy of the dR hand-off matrix the data-gradient kernel left.  The accumulator stays in TMEM for the CTA's life;
+// the epilogue transposes it through shared memory and adds it to the fp32 gradient arena with coalesced atomics.
+struct PwgWgSmem { int ck, tab, maps, ring, total, stage_bytes; };
+inline __host__ __device__ PwgWgSmem pwg_wg_smem(int KP, int nbk, int nstage) {
+    PwgWgSmem s;
+    int off = 1024;
+    s.ck = off; off += 128 * 4;
+    s.tab = off; off += ((KP + 63) & ~63) * 8;
+    s.maps = off; off += (128 + 256) * 4;
+    off = (off + 1023) & ~1023;
+    s.stage_bytes = (2 + nbk) * 16384;
+    s.ring = off; off += nstage * s.stage_bytes;
+    s.total = off + 1024;
+    return s;
+}
+struct PwgWgArgs {
+    const PwDesc* d; int Rt; const bf16* dr;             // dR hand-off [4*Rt][NPall]
+    GBlock blk[kGMaxBlk]; int nblk;                      // M blocks: first GEMM row, rows, source, first slot
+    int nnb;                                             // N blocks of 256 GEMM columns; blockIdx.y = mblock * nnb + nblock
+    int tiles_per_cta, nbuf;
+    Tables tb[2]; int cpo;                               // for the BatchNorm parameter gradients (dgamma, dbeta)
+};
+
+template <int D>
+__global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const PwDesc& d = *a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    const int KP = d.KP, NP = d.NPall, nsrc = d.nsrc, S = a.nbuf, Rt = a.Rt;
+    const int mbi = blockIdx.y / a.nnb, nbi = blockIdx.y - mbi * a.nnb;
+    const GBlock gb = a.blk[mbi];
+    const int j_lo = nbi * 256, ncol = min(256, NP - j_lo), nbk = (ncol + 63) >> 6, npad = nbk * 64;
+    const PwgWgSmem L = pwg_wg_smem(KP, (min(256, NP) + 63) >> 6, S);
+    const int stage_bytes = (2 + ((min(256, NP) + 63) >> 6)) * 16384;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kGMaxStages;
+    uint64_t* acc_full = empty + kGMaxStages;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 512);
+    int* s_ck = reinterpret_cast<int*>(smem + L.ck);
+    float2* s_aff = reinterpret_cast<float2*>(smem + L.tab);
+    int* s_rmap = reinterpret_cast<int*>(smem + L.maps);
+    int* s_cmap = s_rmap + 128;
+    unsigned char* ring = smem + L.ring;
+
+    const int tps = (Rt + kGRows - 1) / kGRows, ntile = kT * tps;
+    const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
+    const int my_tiles = max(0, tile_hi - tile_lo);
+    const int t_first = tile_lo / tps, r_first = (tile_lo - t_first * tps) * kGRows;
+
+    if (warp == 0) tmem_alloc(s_tmem, 256);
+    if (tid == 32) {
+        for (int s = 0; s < kGMaxStages; ++s) { mbar_init(&full[s], kGProd); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    const int nkc = ((KP + 63) & ~63) >> 3;
+    for (int ck = tid; ck < nkc; ck += kGThreads) {
+        int v = -1, off = 0;
+        for (int i = 0; i < nsrc; ++i) {
+            const int nch = d.src[i].cp >> 3;
+            if (ck >= off && ck < off + nch) v = (i << 24) | ((d.src[i].clamp ? 1 : 0) << 23) | ((ck - off) * 8);
+            off += nch;
+        }
+        s_ck[ck] = v;
+    }
+    for (int i = tid; i < 128 + 256; i += kGThreads) {
+        int l, k, p, sl, nn, v = -1;
+        if (i < 128) { if (i < gb.n && pw_row(d, gb.base + i, l, k)) v = (l << 24) | k; }
+        else if (i - 128 < ncol && pw_col(d, j_lo + i - 128, p, sl, l, nn)) v = (l << 24) | nn;
+        s_rmap[i] = v;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(128, npad, 1, 1);
+            int s = 0, ph = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes), sb = sa + 32768u;
+#pragma unroll
+                for (int ks = 0; ks < kGRows / 16; ++ks)
+                    umma_bf16(tmem, umma_desc(sa + ks * 2048, kGRows * 128, 1024), umma_desc(sb + ks * 2048, kGRows * 128, 1024), idesc, (it | ks) != 0);
+                umma_commit(&empty[s]);
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else if (warp >= 2 && warp < 2 + kGProd) {
+        const int pt = tid - 64, c = pt & 7, rl = pt >> 3;
+        const uint32_t swz = (uint32_t)((c ^ (rl & 7)) << 4);
+        const bf16* sp0 = d.src[0].data; const bf16* sp1 = nsrc > 1 ? d.src[1].data : nullptr; const bf16* sp2 = nsrc > 2 ? d.src[2].data : nullptr;
+        const int cp0 = d.src[0].cp, cp1 = nsrc > 1 ? d.src[1].cp : 0, cp2 = nsrc > 2 ? d.src[2].cp : 0;
+        // this thread's two act chunks (one per 64-channel block of the M block): table entries, validity
+        int ea[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) ea[b] = (b * 64 + c * 8 < gb.n) ? s_ck[(gb.base >> 3) + b * 8 + c] : -1;
+        int is = 0, iph = 0;
+        int lt = t_first, lr0 = r_first;                // issue cursor
+        auto issue = [&]() {
+            mbar_wait(&empty[is], iph ^ 1);
+            const int rows = min(kGRows, Rt - lr0);
+            unsigned char* st = ring + (size_t)is * stage_bytes + swz + rl * 128;
+            const size_t row = (size_t)lt * Rt + lr0 + rl;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int e = ea[b], si = e >> 24;
+                const bf16* sp = si <= 0 ? sp0 : (si == 1 ? sp1 : sp2);
+                const int cp = si <= 0 ? cp0 : (si == 1 ? cp1 : cp2);
+                const bf16* base = sp + row * cp + (e >= 0 ? (e & 0xffff) : 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool ok = e >= 0 && rl + 32 * i < rows;
+                    cp_async16(st + b * 16384 + i * 32 * 128, ok ? base + (size_t)(32 * i) * cp : sp0, ok);
+                }
+            }
+            for (int b = 0; b < nbk; ++b) {
+                const int j0 = j_lo + b * 64 + c * 8;
+                const bf16* base = a.dr + row * NP + j0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool ok = j0 < NP && rl + 32 * i < rows;
+                    cp_async16(st + 32768 + b * 16384 + i * 32 * 128, ok ? base + (size_t)(32 * i) * NP : a.dr, ok);
+                }
+            }
+            if (++is == S) { is = 0; iph ^= 1; }
+            lr0 += kGRows; if (lr0 >= Rt) { lr0 = 0; ++lt; }
+        };
+        for (int j = 0; j < D; ++j) { if (j < my_tiles) issue(); cp_async_commit(); }
+        int s = 0, cur_t = -1, t = t_first, r0 = r_first;
+        for (int q = 0; q < my_tiles; ++q) {
+            if (q + D < my_tiles) issue();
+            cp_async_commit();
+            if (t != cur_t) {
+                named_bar_sync(2, kGProdThreads);
+                for (int kk = pt; kk < nkc * 8; kk += kGProdThreads) {
+                    const int e = s_ck[kk >> 3];
+                    float2 v = make_float2(1.f, 0.f);
+                    if (e >= 0) {
+                        const PwSrc& Sx = d.src[e >> 24];
+                        if (Sx.aff) v = Sx.aff[(size_t)t * Sx.cp + (e & 0xffff) + (kk & 7)];
+                    }
+                    s_aff[kk] = v;
+                }
+                named_bar_sync(2, kGProdThreads);
+                cur_t = t;
+            }
+            const int rows = min(kGRows, Rt - r0);
+            cp_async_wait<D>();
+            unsigned char* st = ring + (size_t)s * stage_bytes + swz + rl * 128;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int e = ea[b];
+                if (e < 0) continue;
+                float2 c8[8];
+                const float4* ap = reinterpret_cast<const float4*>(s_aff + gb.base + b * 64 + c * 8);
+                const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
+                c8[0] = make_float2(a0.x, a0.y); c8[1] = make_float2(a0.z, a0.w); c8[2] = make_float2(a1.x, a1.y); c8[3] = make_float2(a1.z, a1.w);
+                c8[4] = make_float2(a2.x, a2.y); c8[5] = make_float2(a2.z, a2.w); c8[6] = make_float2(a3.x, a3.y); c8[7] = make_float2(a3.z, a3.w);
+                const bool clamp = ((e >> 23) & 1) != 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (rl + 32 * i < rows) {
+                        uint4* bp = reinterpret_cast<uint4*>(st + b * 16384 + i * 32 * 128);
+                        *bp = affine8(*bp, c8, clamp);
+                    }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (++s == S) s = 0;
+            r0 += kGRows; if (r0 >= Rt) { r0 = 0; ++t; }
+        }
+    }
+    // ================================================================ all roles: accumulator -> gradient arena
+    __syncthreads();
+    if (my_tiles > 0) {
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        float* Sc = reinterpret_cast<float*>(ring);        // [128][65]
+        float* wl0 = d.layer[0].dw; float* wl1 = d.layer[1].dw;
+        const int N0 = d.layer[0].N, N1 = d.layer[1].N;
+        for (int c0 = 0; c0 < npad; c0 += 64) {
+            if (warp < 4) {
+#pragma unroll
+                for (int cq = 0; cq < 64; cq += 16) {
+                    float v[16];
+                    tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(c0 + cq), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) Sc[(32 * warp + lane) * 65 + cq + i] = v[i];
+                }
+            }
+            __syncthreads();
+            {
+                const int col = tid & 63, cm = (c0 + col < ncol) ? s_cmap[c0 + col] : -1;
+                if (cm >= 0)
+                    for (int rowk = tid >> 6; rowk < 128; rowk += kGThreads >> 6) {
+                        const int rm = s_rmap[rowk];
+                        if (rm >= 0 && (rm >> 24) == (cm >> 24)) {
+                            const float val = Sc[rowk * 65 + col];
+                            if (val != 0.f) {
+                                if ((rm >> 24) == 0) atomicAdd(wl0 + (size_t)(rm & 0xffffff) * N0 + (cm & 0xffffff), val);
+                                else atomicAdd(wl1 + (size_t)(rm & 0xffffff) * N1 + (cm & 0xffffff), val);
+                            }
+                        }
+                    }
+            }
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+    // ---- BatchNorm parameter gradients (one CTA): dgamma = sum_t S2, dbeta = sum_t S1
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int j = tid; j < NP; j += kGThreads) {
+            int p, sl, l, nn;
+            if (!pw_col(d, j, p, sl, l, nn)) continue;
+            double gs = 0.0, bs = 0.0;
+            for (int t = 0; t < kT; ++t) { const double2 v = ld_sum(a.tb[p].bsum + (size_t)t * a.cpo + sl); bs += v.x; gs += v.y; }
+            d.layer[l].dg[nn] = (float)gs; d.layer[l].dbe[nn] = (float)bs;
+        }
+    }
+}
+
 // pass-through half of a stride-1 unit, backward: d x1[slot(2i + p)] = d out_p[n0p + i] (bit-exact gather) and the
 // BatchNorm-backward sums of x1.  grid = (row chunks, slices), one thread per x1 slot.
 struct PassBwdArgs {
