@@ -316,7 +316,7 @@ def run_b200(args):
         # every rank runs the two profiled steps (they contain the gradient all-reduce); rank 0 reports
         roof = kernel_roofline(eng, sgd_step, args.warmup + args.steps, peak, peak_src)
     # ---- end-to-end: the same metric through the reference-facing API with HOST buffers (see e2e_agent_leg)
-    e2e_steps = max(2, args.steps // 2)
+    e2e_steps = max(4, args.steps)                   # as many environment steps per update as timed SGD steps (amortises the per-update fixed work the same way)
     rollout_gb = roll['state_image'].numel() / 1e9
     del roll, mb
     torch.cuda.empty_cache()

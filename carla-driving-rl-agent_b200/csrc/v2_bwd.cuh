@@ -763,7 +763,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
     const int tid = threadIdx.x;
     pdl_trigger();
     const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo, PW = a.Wi + 2, QW = a.Wo + 2;
-    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, true);
+    const bool sep = a.sep != 0;
+    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, true, sep);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     float* s_stat = reinterpret_cast<float*>(smem + L.stat);
     float* s_wred = reinterpret_cast<float*>(smem + L.wred);
@@ -775,15 +776,16 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     for (int i = tid; i < CP * 2; i += kDwThreads) s_stat[i] = 0.f;
     for (int i = tid; i < CP * 9; i += kDwThreads) s_wred[i] = 0.f;
-    for (int i = tid; i < a.nbuf * L.pin_stride / 4; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + L.pin)[i] = 0u;
+    for (int i = tid; i < (sep ? 1 : a.nbuf) * L.pin_stride / 4; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + L.pin)[i] = 0u;
     for (int i = tid; i < (a.Ho + 2) * QW * (CP / 2); i += kDwThreads) reinterpret_cast<uint32_t*>(Pdr)[i] = 0u;
     __syncthreads();
     auto issue = [&](int f, int buf) {
         mbar_expect_tx(&full[buf], 2 * out_bytes + row_bytes * a.Hi);
         bulk_g2s(smem + L.raw_dout + (size_t)buf * L.out_stride, a.dout + (size_t)f * out_px * CP, out_bytes, &full[buf]);
         bulk_g2s(smem + L.raw_out + (size_t)buf * L.out_stride, a.out + (size_t)f * out_px * CP, out_bytes, &full[buf]);
-        unsigned char* dst = smem + L.pin + (size_t)buf * L.pin_stride + (PW + 1) * CP * 2;
         const bf16* src = a.in + (size_t)f * in_px * CP;
+        if (sep) { bulk_g2s(smem + L.rawin + (size_t)buf * L.in_stride, src, row_bytes * a.Hi, &full[buf]); return; }
+        unsigned char* dst = smem + L.pin + (size_t)buf * L.pin_stride + (PW + 1) * CP * 2;
         for (int y = 0; y < a.Hi; ++y) bulk_g2s(dst + (size_t)y * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
     };
     pdl_wait();
@@ -834,7 +836,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
             for (int s = tid; s < CP; s += kDwThreads) {
                 const int l = slot_logical(a.map, s);
                 const size_t idx = (size_t)t * CP + s;
-                s_colc[s] = l >= 0 ? bnbwd_consts(a.tb.aff[idx], a.tb.bnp[idx], a.tb.bsum[idx], inv_n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // chunk-transposed (constant q of every 8-slot chunk contiguous): the 16-byte reads below are conflict free
+                s_colc[(s & 7) * NCH + (s >> 3)] = l >= 0 ? bnbwd_consts(a.tb.aff[idx], a.tb.bnp[idx], a.tb.bsum[idx], inv_n) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (tpl < TNPL) {
 #pragma unroll
@@ -845,11 +848,12 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
             __syncthreads();
         }
         mbar_wait(&full[buf], (it / a.nbuf) & 1);
-        bf16* Pin = reinterpret_cast<bf16*>(smem + L.pin + (size_t)buf * L.pin_stride);
+        bf16* Pin = reinterpret_cast<bf16*>(smem + L.pin + (sep ? 0 : (size_t)buf * L.pin_stride));
+        const bf16* Rin = reinterpret_cast<const bf16*>(smem + L.rawin + (size_t)buf * L.in_stride);
         if (tpl < TNPL) {
             float4 c8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = s_colc[tch * 8 + q];
+            for (int q = 0; q < 8; ++q) c8[q] = s_colc[q * NCH + tch];
             const uint4* dv = reinterpret_cast<const uint4*>(smem + L.raw_dout + (size_t)buf * L.out_stride) + tch;
             const uint4* ov = reinterpret_cast<const uint4*>(smem + L.raw_out + (size_t)buf * L.out_stride) + tch;
             uint4* qv = reinterpret_cast<uint4*>(Pdr) + tch;
@@ -864,7 +868,15 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                 }
                 qv[((wo.y + 1) * QW + wo.x + 1) * NCH] = dvv;
             }
-            if (xform) {
+            if (sep) {                                  // raw frame -> activated halo tile
+                uint4* pv = reinterpret_cast<uint4*>(Pin) + tch;
+                const uint4* rv = reinterpret_cast<const uint4*>(Rin) + tch;
+                PxWalk wi(tpl, TNPL, a.Wi);
+                for (int px = tpl; px < in_px; px += TNPL, wi.next()) {
+                    const uint4 v = rv[px * NCH];
+                    pv[((wi.y + 1) * PW + wi.x + 1) * NCH] = xform ? affine8(v, ac8, iclamp) : v;
+                }
+            } else if (xform) {
                 uint4* pv = reinterpret_cast<uint4*>(Pin) + tch;
                 PxWalk wi(tpl, TNPL, a.Wi);
                 for (int px = tpl; px < in_px; px += TNPL, wi.next()) {
@@ -910,14 +922,14 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                 bf16* gp = a.din + ((size_t)f * in_px + ix) * CP + 2 * pr;
                 // the sums use the RAW input value (same mask / xhat as every consumer of them, bnbwd_apply): the tile in shared
                 // memory only holds the bf16-rounded activation, so the raw pair is re-read through L2 (TMA just fetched the frame)
-                const bf16* rp = a.in + ((size_t)f * in_px + ix) * CP + 2 * pr;
+                const bf16* rp = sep ? Rin + (size_t)ix * CP + 2 * pr : a.in + ((size_t)f * in_px + ix) * CP + 2 * pr;
                 auto finish = [&](float acc0, float acc1) {       // (+ existing share), store, BatchNorm-backward sums of the input
                     if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
                     const uint32_t pk = pack2(acc0, acc1);
                     *reinterpret_cast<uint32_t*>(gp) = pk;
                     if (want_sums) {
                         const float2 gr = unpack2(pk);
-                        const float2 rv = unpack2(__ldg(reinterpret_cast<const unsigned int*>(rp)));
+                        const float2 rv = unpack2(sep ? *reinterpret_cast<const uint32_t*>(rp) : __ldg(reinterpret_cast<const unsigned int*>(rp)));
                         sum_accum(gr.x, rv.x, xc0, iclamp, s1a, s2a);
                         sum_accum(gr.y, rv.y, xc1, iclamp, s1b, s2b);
                     }

@@ -23,13 +23,16 @@ struct DwArgs {
     int training;
     unsigned* counter;
     int frames_per_cta, nbuf;
+    int sep;                                                             // backward: raw input frames kept next to ONE activated halo tile
 };
 
 // shared-memory carve-up of the depthwise kernels (host + device).  The input frame lives in a halo-padded tile
 // [(Hi+2)][(Wi+2)][cp] (zero border = TF SAME padding): TMA row copies land in its interior and the producer's
 // BatchNorm affine (+ReLU6) is applied in place, so the stencils need no bounds checks.
-struct DwSmem { int stat, wred, colc, pin, raw_out, raw_dout, pdr, total, pin_stride, out_stride; };
-inline __host__ __device__ DwSmem dw_smem(int cp, int Hi, int Wi, int Ho, int Wo, int nbuf, bool backward) {
+struct DwSmem { int stat, wred, colc, pin, raw_out, raw_dout, pdr, total, pin_stride, out_stride, rawin, in_stride; };
+// sep (backward only): the TMA ring holds the RAW input frames (one contiguous bulk copy each; the BatchNorm-backward
+// sums of the input need the raw values) and the activated, halo-padded tile exists once
+inline __host__ __device__ DwSmem dw_smem(int cp, int Hi, int Wi, int Ho, int Wo, int nbuf, bool backward, bool sep = false) {
     DwSmem s;
     int off = 64;
     s.stat = off; off += cp * 8;
@@ -38,7 +41,9 @@ inline __host__ __device__ DwSmem dw_smem(int cp, int Hi, int Wi, int Ho, int Wo
     off = (off + 127) & ~127;
     s.pin_stride = ((Hi + 2) * (Wi + 2) * cp * 2 + 127) & ~127;
     s.out_stride = (Ho * Wo * cp * 2 + 127) & ~127;
-    s.pin = off; off += nbuf * s.pin_stride;
+    s.in_stride = (Hi * Wi * cp * 2 + 127) & ~127;
+    s.pin = off; off += (sep ? 1 : nbuf) * s.pin_stride;
+    s.rawin = off; off += sep ? nbuf * s.in_stride : 0;
     s.raw_out = off; off += backward ? nbuf * s.out_stride : 0;
     s.raw_dout = off; off += backward ? nbuf * s.out_stride : 0;
     s.pdr = off; off += backward ? (((Ho + 2) * (Wo + 2) * cp * 2 + 127) & ~127) : 0;   // dR with a zero halo
@@ -77,7 +82,7 @@ CDRA_DEV void dw_grad_row(const float2 (&r)[3], float2 dr, float* g0, float* g1)
 
 // forward: out(oy, ox) = b + sum_{ky,kx} w[ky][kx] * act(in)(oy*S - pt + ky, ox*S - pl + kx)   (zero outside the frame)
 template <int CP, int S>
-__global__ void __launch_bounds__(kDwThreads) dw_fwd_kernel(const DwArgs a) {
+__global__ void __launch_bounds__(kDwThreads, 2) dw_fwd_kernel(const DwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NPAIR = CP / 2, NCH = CP / 8, NXL = kDwThreads / NPAIR, TNPL = kDwThreads / NCH;
     const int tid = threadIdx.x;

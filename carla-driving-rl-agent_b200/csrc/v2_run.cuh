@@ -578,8 +578,9 @@ inline void launch_dw_bwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
         case 1202: k = dw_bwd_kernel<120, 2>; break;  case 2322: k = dw_bwd_kernel<232, 2>; break;
     }
     if (!k) { fprintf(stderr, "libcdra: no depthwise kernel for cp=%d stride=%d\n", in.cp, u.stride); return; }
-    a.nbuf = 2;
-    DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true);
+    a.nbuf = 2; a.sep = (a.in_bsum != nullptr && getenv("CDRA_NO_DW_SEP") == nullptr) ? 1 : 0;
+    DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true, a.sep != 0);
+    if (L.total > kMaxDynSmem && a.sep) { a.sep = 0; L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true); }
     if (L.total > kMaxDynSmem) { a.nbuf = 1; L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, 1, true); }
     if (L.total > kMaxDynSmem) { fprintf(stderr, "libcdra: dw_bwd frame does not fit in shared memory (%d bytes)\n", L.total); return; }
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
