@@ -55,6 +55,7 @@ _SIGNATURES = {
     'cdra_comm_create': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     'cdra_comm_destroy': (None, [_P]),
     'cdra_allreduce_grads': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'cdra_augment': (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     'cdra_launch_count': (C.c_int64, []),
     'cdra_profile_enable': (None, [C.c_int]),
     'cdra_profile_reset': (None, []),

@@ -1,8 +1,8 @@
 """CARLAgent — the reference's core/carla_agent.py agent surface (constructor kwargs, update path, losses,
 gradient application order, memory, fake environment) with the numerics executed by libcdra.
 
-Not mirrored: `record` / `evaluate` (CARLA roll-outs) and `augment` (rollout-time image augmentation,
-SURVEY §8f-4) — they need the simulator / are outside the update hot path.
+Not mirrored: `record` / `evaluate` (CARLA roll-outs) — they need the simulator.  `augment` / `preprocess` run the
+reference's image augmentation on the device (`cdra_augment`).
 """
 import os
 from typing import Union
@@ -295,17 +295,41 @@ class CARLAgent(PPOAgent):
                            image_dtype=torch.uint8 if self.network.image_u8 else torch.float32)
 
     def preprocess(self):
-        """Augmentation closure of the reference (core/carla_agent.py:523-579); image augmentation is a rollout-time
-        "next" row: this build batches the observation dict and leaves the image untouched."""
-        if self.aug_intensity > 0.0:
-            print('[preprocess] image augmentation is not built; observations are passed through unchanged')
+        """Augmentation function used during the reinforcement learning phase (core/carla_agent.py:523-525)."""
+        return self.augment()
+
+    def augment(self):
+        """Augmentation closure of the reference (core/carla_agent.py:527-579) on the DEVICE: `prepare` batches the list of
+        observation dicts, then -- when `aug_intensity` > 0 -- one `cdra_augment` call applies colour jitter, blur,
+        salt & pepper, gaussian noise, per-sample min-max normalisation, cutout and coarse dropout with the reference's
+        chance gates (cdra/augment.py draws the per-call scalars; the image stays on the GPU as float32 in [0, 1])."""
+        alpha = float(self.aug_intensity)
+        rng = np.random.default_rng(self.seed)
+        device = self.network.device
 
         def prepare(state):
             if isinstance(state, list):
-                state = {k: np.stack([s[k] for s in state], 0) for k in state[0]}
+                state = {k: np.stack([np.asarray(s[k]) for s in state], 0) for k in state[0]}
                 state = {f'state_{k}': v for k, v in state.items()}
             return state
-        return prepare
+
+        def augment_fn(states):
+            state = prepare(states)
+            if alpha <= 0.0:
+                return state
+            from cdra import augment as A
+            image = state['state_image']
+            image = image if isinstance(image, torch.Tensor) else torch.as_tensor(np.asarray(image))
+            if image.dtype != torch.uint8:
+                image = image.float()
+            image = image.to(device).contiguous()
+            group = int(image.shape[1]) if image.dim() == 5 else int(image.shape[0]) if image.dim() == 4 else 1     # one sample = its time_horizon frames
+            params, mask = A.draw_params(rng, alpha, group=group)
+            state = dict(state)
+            state['state_image'] = A.augment(image, params, mask)
+            return state
+
+        return augment_fn
 
     def load_weights(self):
         print('loading weights...')

@@ -210,7 +210,8 @@ class CARLANetwork(Network):
     def _obs(self, states: dict):
         img = states['state_image']
         if self.image_u8 and img.dtype != torch.uint8:
-            img = img.to(torch.uint8)
+            # float frames (e.g. augmented ones, in [0, 1]) for a uint8 engine: quantise to the byte grid the stem reads
+            img = (img.float().clamp(0.0, 1.0) * 255.0).round().to(torch.uint8) if img.is_floating_point() else img.to(torch.uint8)
         elif not self.image_u8 and img.dtype != torch.float32:
             img = img.float()
         obs = dict(state_image=img.contiguous().to(self.device))

@@ -8,6 +8,7 @@
 #include "v2_run.cuh"
 #include "tail.cuh"
 #include "ppo.cuh"
+#include "augment.cuh"
 
 using namespace cdra;
 
@@ -138,10 +139,11 @@ static cudaStream_t side_stream(const RunCtx& c) {
     if (off || g_prof) return c.stream;
     const Plan& p = *c.p;
     if (!p.side_stream) {
-        cudaStream_t s; cudaEvent_t e0, e1;
+        cudaStream_t s; cudaEvent_t e0, e1, e2;
         cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&e0, cudaEventDisableTiming); cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
-        p.side_stream = s; p.ev_fork = e0; p.ev_join = e1;
+        cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
+        p.side_stream = s; p.ev_fork = e0; p.ev_join = e1; p.ev_prep = e2;
     }
     return (cudaStream_t)p.side_stream;
 }
@@ -158,8 +160,8 @@ static void side_join(const RunCtx& c, cudaStream_t sd) {
 static void side_destroy(Plan* p) {
     if (p->side_stream) {
         cudaStreamDestroy((cudaStream_t)p->side_stream);
-        cudaEventDestroy((cudaEvent_t)p->ev_fork); cudaEventDestroy((cudaEvent_t)p->ev_join);
-        p->side_stream = p->ev_fork = p->ev_join = nullptr;
+        cudaEventDestroy((cudaEvent_t)p->ev_fork); cudaEventDestroy((cudaEvent_t)p->ev_join); cudaEventDestroy((cudaEvent_t)p->ev_prep);
+        p->side_stream = p->ev_fork = p->ev_join = p->ev_prep = nullptr;
     }
 }
 #else
@@ -599,13 +601,20 @@ int cdra_dynamics_forward(cdra_plan_t* plan, const float* params, float* state, 
     const bool bf = p.cfg.dtype == CDRA_DTYPE_BF16, u8 = p.cfg.image_u8 != 0;
     cudaStream_t sd = side_stream(c);
     side_fork(c, sd);
+#ifndef CDRA_EMU
+    if (p.v2.on) {               // GEMM operand preparation runs next to the stem (nothing before the first pointwise layer needs it)
+        RunCtx cs = c; cs.stream = sd;
+        v2::tower_prepare(cs);
+        if (sd != c.stream) cudaEventRecord((cudaEvent_t)p.ev_prep, sd);
+    }
+#endif
     tail_forward(c, road, vehicle, navigation, out512, sd, 1);       // feature MLPs + their GRUs, next to the image tower
 #ifndef CDRA_EMU
     if (p.v2.on) {               // bf16 perf mode: legacy stem + pool, then the v2 tower (padded planes, TMA tiles)
-        v2::tower_prepare(c);
         if (p.v2.stem_on) v2::stem_forward(c, (const uint8_t*)image);
         else if (u8) tower_forward<bf16, uint8_t>(c, (const uint8_t*)image, true);
         else tower_forward<bf16, float>(c, (const float*)image, true);
+        if (sd != c.stream) cudaStreamWaitEvent(c.stream, (cudaEvent_t)p.ev_prep, 0);     // a full dependency: the tower's PDL prologues read the prepared operands
         v2::tower_forward(c);
     } else
 #endif
@@ -898,6 +907,32 @@ int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t r
     unsigned gy = cdiv(row_bytes, 256 * 16 * 8); if (gy < 1) gy = 1; if (gy > 64) gy = 64;
     CDRA_LAUNCH(gather_rows_kernel, dim3((unsigned)n, gy), dim3(256), 0, (cudaStream_t)stream, a);
     return check_launch("gather_rows");
+}
+
+int cdra_augment(const void* image, int image_u8, int64_t frames, int height, int width, const cdra_augment_params* params,
+                 const uint8_t* dropout_mask, float* out, void* scratch, void* stream) {
+#ifdef CDRA_EMU
+    (void)image; (void)image_u8; (void)frames; (void)height; (void)width; (void)params; (void)dropout_mask; (void)out; (void)scratch; (void)stream;
+    return fail(CDRA_ERR_BADARG, "cdra_augment needs the CUDA build");
+#else
+    if (!image || !params || !out || !scratch || frames < 1 || height < 1 || width < 1) return fail(CDRA_ERR_BADARG, "bad argument");
+    const cdra_augment_params& p = *params;
+    if (p.blur_size != 0 && p.blur_size != 3 && p.blur_size != 5) return fail(CDRA_ERR_BADARG, "blur_size must be 0, 3 or 5");
+    if (p.normalize && p.group < 1) return fail(CDRA_ERR_BADARG, "group must be >= 1");
+    if (p.dropout_size > 0 && !dropout_mask) return fail(CDRA_ERR_BADARG, "dropout_mask missing");
+    if ((long long)height * width >= (1 << 27)) return fail(CDRA_ERR_BADARG, "frame too large for the per-pixel hash");
+    cudaStream_t st = (cudaStream_t)stream;
+    aug::AugArgs a; memset(&a, 0, sizeof a);
+    a.img = image; a.u8 = image_u8; a.frames = frames; a.H = height; a.W = width; a.p = p; a.dropout_mask = dropout_mask; a.out = out;
+    const long long groups = p.normalize ? (frames + p.group - 1) / p.group : 1;
+    a.mean = (float*)scratch; a.kmin = (uint32_t*)scratch + 3 * frames; a.kmax = a.kmin + groups;
+    if (p.normalize) { cudaMemsetAsync(a.kmin, 0xff, (size_t)groups * 4, st); cudaMemsetAsync(a.kmax, 0, (size_t)groups * 4, st); }
+    const dim3 grid((unsigned)cdiv((long long)height * width, 256), (unsigned)frames);
+    if (p.jitter) CDRA_LAUNCH(aug::aug_mean_kernel, dim3((unsigned)frames), dim3(256), 0, st, a);
+    CDRA_LAUNCH(aug::aug_main_kernel, grid, dim3(256), 0, st, a);
+    if (p.normalize || p.cutout_size > 0 || p.dropout_size > 0) CDRA_LAUNCH(aug::aug_finish_kernel, grid, dim3(256), 0, st, a);
+    return check_launch("augment");
+#endif
 }
 
 }  // extern "C"

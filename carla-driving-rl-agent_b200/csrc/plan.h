@@ -161,6 +161,7 @@ struct Plan {
     mutable void* side_stream = nullptr;
     mutable void* ev_fork = nullptr;
     mutable void* ev_join = nullptr;
+    mutable void* ev_prep = nullptr;      // GEMM operand preparation (side stream) -> first pointwise kernel of the tower
 };
 
 Plan* build_plan(const cdra_config& cfg, std::string& err);

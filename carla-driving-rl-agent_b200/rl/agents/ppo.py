@@ -432,6 +432,8 @@ class PPOMemory:
         states = {'state': state} if self.simple_state else state
         for k, dst in b['states'].items():
             src = states[k] if isinstance(states[k], torch.Tensor) else torch.as_tensor(np.asarray(states[k]))
+            if dst.dtype == torch.uint8 and src.is_floating_point():     # float frames in [0, 1] (augmented) -> the byte grid the stem reads
+                src = (src.clamp(0.0, 1.0) * 255.0).round()
             dst[lo:lo + E].copy_(src.reshape(dst[lo:lo + E].shape), non_blocking=True)
         b['actions'][lo:lo + E].copy_(self._rows(action, self.num_actions), non_blocking=True)
         b['log_probs'][lo:lo + E].copy_(self._rows(log_prob, self.num_actions), non_blocking=True)

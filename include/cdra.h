@@ -179,6 +179,29 @@ int cdra_comm_create(const void* id_128_bytes, int world_size, int rank, cdra_co
 void cdra_comm_destroy(cdra_comm_t* comm);
 int cdra_allreduce_grads(cdra_comm_t* comm, float* grads, int64_t count, void* stream);
 
+/* On-device image augmentation: the `augment_fn` closure of the reference (core/carla_agent.py:527-579;
+ * rl/augmentations/augmentations.py:44-263, rl/augmentations/simclr.py:44-58) over a batch of frames.  The scalars TF
+ * draws once per call are passed explicitly (the host mirror draws them); per-pixel draws come from a counter-based hash
+ * of (seed, frame, pixel, stream) that oracle/augment.py restates bit for bit.
+ *   image   [frames][H][W][3] uint8 (value / 255 is augmented) or fp32
+ *   out     [frames][H][W][3] fp32
+ *   scratch >= 3 * frames + 2 * ceil(frames / group) 32-bit words (channel means, per-sample min / max keys)
+ *   dropout_mask [dropout_size^2] uint8 on the device (1 = keep), may be NULL when dropout_size == 0 */
+typedef struct cdra_augment_params {
+    uint32_t seed;                       /* stream of the per-pixel hash */
+    int32_t jitter;                      /* colour jitter: brightness -> contrast -> saturation -> hue -> clip [0, 1] */
+    float brightness, contrast, saturation, hue;    /* delta, factor, factor, delta (fraction of a turn) */
+    int32_t blur_size;                   /* 0 | 3 | 5: depthwise SAME convolution with blur_kernel [size][size][3] */
+    float blur_kernel[75];
+    int32_t salt_pepper; float sp_amount;            /* select p = amount / 10, salt with p = 1/2 */
+    int32_t gauss_noise; float gn_amount, gn_std;    /* select p = amount, add clip(N(0, std), 0, 1) */
+    int32_t normalize, group; float eps;             /* (x - min) / (max - min + eps) over every `group` consecutive frames */
+    int32_t cutout_size, cutout_cell;                /* zero grid cell `cutout_cell` of a size x size grid stretched over the frame */
+    int32_t dropout_size;                            /* coarse dropout grid (0 = off) */
+} cdra_augment_params;
+int cdra_augment(const void* image, int image_u8, int64_t frames, int height, int width, const cdra_augment_params* params,
+                 const uint8_t* dropout_mask, float* out, void* scratch, void* stream);
+
 /* Launch accounting (bench.py's `gpu_launches`) and optional per-kernel CUDA-event timing on the launch
  * stream (bench.py's live roofline numbers).  Profiling serialises every launch; never leave it on
  * inside a timed region.  cdra_profile_report writes "name\tcount\ttotal_ms\talgorithmic_bytes\n" lines

@@ -49,7 +49,7 @@ def test_cuda_library_exports_every_symbol(built_libs):
         assert l2.cdra_plan_tensor(pl, b'tower.stem', ctypes.byref(off), dims, ctypes.byref(es)) == 0
         assert list(dims) == [8, (h - 3) // 2 + 1, (w - 3) // 2 + 1, 24] and es.value == 2
         l2.cdra_plan_destroy(pl)
-    assert sizes[(180, 240)] > 2 * sizes[(90, 120)]
+    assert sizes[(180, 240)] > 1.5 * sizes[(90, 120)]       # 4x the activations; the fixed GEMM-operand buffers do not scale
     # debug switches: known keys only
     assert l2.cdra_debug_set(b'tc', -1) == 0 and l2.cdra_debug_set(b'fwd_tc', -1) == 0 and l2.cdra_debug_set(b'nope', 1) == -1
     # shape validation of the self tests happens before any device work

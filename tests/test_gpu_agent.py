@@ -92,3 +92,23 @@ def test_rollout_inference_matches_oracle_on_the_trained_agent(built_libs, tmp_p
     # inference must not touch the moving statistics
     got = net.engine.dyn_state.to_dict()
     assert all(torch.equal(got[k].cpu(), dyn[k]) for k in got)
+
+
+def test_augmented_rollout_on_cuda(built_libs, tmp_path, monkeypatch):
+    """`aug_intensity` > 0 (stages 4-5 of the curriculum, main.py:79,88): the preprocess closure augments on the device and
+    the rollout / update run on the augmented frames."""
+    monkeypatch.chdir(tmp_path)
+    agent = _agent(tmp_path, batch_size=8, aug_intensity=1.0, name='aug')
+    fn = agent.preprocess()
+    states = [agent.env.reset() for _ in range(3)]
+    batch = fn(states)                                       # list of observation dicts -> batched dict, image augmented
+    img = batch['state_image']
+    assert img.is_cuda and img.dtype == torch.float32 and tuple(img.shape) == (3, 4, H, Wd, 3)
+    assert torch.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0 + 1e-6
+    for b in range(3):                                       # per-sample min-max normalisation (cutout / dropout only add zeros)
+        assert img[b].min() == 0.0 and img[b].max() > 0.99
+    raw = torch.as_tensor(np.stack([s['image'] for s in states], 0)).float() / 255
+    assert not torch.allclose(img.cpu(), raw, atol=1e-3)
+    agent.learn(episodes=1, timesteps=17, save_every='end', close=False)
+    assert agent.network.engine.adam_step == dict(dyn=4, pol=2, val=2)
+    assert np.isfinite(agent.statistics.last['loss_total'])
