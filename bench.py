@@ -382,15 +382,26 @@ def e2e_agent_leg(args, torch, dist, dev, world, rank, n_steps, barrier):
     h2d += speed.numel() * 4 * 2 + last.numel() * 4
     mem = agent.get_memory(capacity=n_steps, num_envs=bs)            # preallocated device buffers (outside the clock)
 
+    marks = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e, time.perf_counter()))
+
     def run():
+        del marks[:]
+        mark('start')
         mem.delete()
         agent.memory = mem
         for st in steps:
             mem.append(st['state'], st['action'], st['reward'], st['value'], st['log_prob'])
+        mark('append')
         env.info_buffer = dict(speed=speed.to(dev, non_blocking=True), similarity=sim.to(dev, non_blocking=True))
         agent.end_episode(last)
+        mark('end_episode')
         agent.update()
+        mark('update')
         agent.write_summaries()
+        mark('summaries')
         return agent.statistics.last
 
     run()                                              # warm-up (allocations, first-use costs)
@@ -404,6 +415,10 @@ def e2e_agent_leg(args, torch, dist, dev, world, rank, n_steps, barrier):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
+    if rank == 0:                                      # where the end-to-end time goes (device time | host time per phase)
+        torch.cuda.synchronize()
+        for (n0, ev0, h0), (n1, ev1, h1) in zip(marks[:-1], marks[1:]):
+            print(f'[e2e] {n1:12s} device {ev0.elapsed_time(ev1):8.2f} ms   host {1e3 * (h1 - h0):8.2f} ms', file=sys.stderr)
     assert all(k in lastv and lastv[k] == lastv[k] for k in ('loss_total', 'loss_value')), lastv
     return {'value': world * bs * n_steps / (ms / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d // n_steps,
             'd2h_bytes_per_step': max(4, agent.statistics.last_d2h_bytes // n_steps), 'ms_per_step': ms / n_steps, 'steps': n_steps,

@@ -954,20 +954,33 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                         if (iy + 2 < a.Hi) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += QW * CP; }
                     }
                 } else {
+                    // stride 2: input pixel (iy, ix) only sees the taps whose parity matches, d in = sum dR((iy+pt-ky)/2, (ix+pl-kx)/2) * w[ky][kx]
+                    // over even (iy+pt-ky), (ix+pl-kx).  The column taps are fixed per thread (kx = 0, 2 at tile columns cA, cA - 1 when
+                    // ix + pl is even; kx = 1 at cA otherwise) and selected ONCE; the row taps alternate with the parity of iy + pt.
+                    const int xs = ix + a.pad_l;
+                    const bool xe = (xs & 1) == 0;
+                    const int cA = (xs >> 1) + 1, cB = xe ? cA - 1 : cA;
+                    float wa0[3], wa1[3], wb0[3], wb1[3];
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        wa0[ky] = xe ? w0[ky * 3] : w0[ky * 3 + 1]; wa1[ky] = xe ? w1[ky * 3] : w1[ky * 3 + 1];
+                        wb0[ky] = xe ? w0[ky * 3 + 2] : 0.f;         wb1[ky] = xe ? w1[ky * 3 + 2] : 0.f;
+                    }
+                    const bf16* pa = Pdr + cA * CP + 2 * pr; const bf16* pb = Pdr + cB * CP + 2 * pr;
                     for (int iy = 0; iy < a.Hi; ++iy) {
-                        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const int ny = iy + a.pad_t - ky;
-                            if (ny & 1) continue;
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const int nx = ix + a.pad_l - kx;
-                                if (nx & 1) continue;
-                                const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(Pdr + (((ny >> 1) + 1) * QW + (nx >> 1) + 1) * CP + 2 * pr));
-                                acc0 = fmaf(dr.x, w0[ky * 3 + kx], acc0);
-                                acc1 = fmaf(dr.y, w1[ky * 3 + kx], acc1);
-                            }
+                        const int ys = iy + a.pad_t;
+                        float acc0, acc1;
+                        if ((ys & 1) == 0) {                      // ky = 0 at tile row ys/2 + 1, ky = 2 at tile row ys/2
+                            const int r = ((ys >> 1) + 1) * QW * CP;
+                            const float2 a0 = unpack2(*reinterpret_cast<const uint32_t*>(pa + r)), b0 = unpack2(*reinterpret_cast<const uint32_t*>(pb + r));
+                            const float2 a2 = unpack2(*reinterpret_cast<const uint32_t*>(pa + r - QW * CP)), b2 = unpack2(*reinterpret_cast<const uint32_t*>(pb + r - QW * CP));
+                            acc0 = fmaf(a0.x, wa0[0], fmaf(b0.x, wb0[0], fmaf(a2.x, wa0[2], b2.x * wb0[2])));
+                            acc1 = fmaf(a0.y, wa1[0], fmaf(b0.y, wb1[0], fmaf(a2.y, wa1[2], b2.y * wb1[2])));
+                        } else {                                  // ky = 1 at tile row (ys - 1)/2 + 1
+                            const int r = (((ys - 1) >> 1) + 1) * QW * CP;
+                            const float2 a1 = unpack2(*reinterpret_cast<const uint32_t*>(pa + r)), b1 = unpack2(*reinterpret_cast<const uint32_t*>(pb + r));
+                            acc0 = fmaf(a1.x, wa0[1], b1.x * wb0[1]);
+                            acc1 = fmaf(a1.y, wa1[1], b1.y * wb1[1]);
                         }
                         finish(acc0, acc1);
                     }

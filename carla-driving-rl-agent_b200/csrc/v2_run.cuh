@@ -443,6 +443,8 @@ inline bool try_pw_bwd_fused(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, in
 
 inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
     if (hd.KP < pwg_min_k_bwd() || hd.NPall > 768) return false;
+    for (int i = 0; i < hd.nsrc; ++i)            // the vectorised sums kernel covers whole 8-slot chunks
+        if (hd.src[i].bsum && hd.src[i].sum_hi > hd.src[i].sum_lo && ((hd.src[i].sum_lo & 7) || ((hd.src[i].sum_hi - hd.src[i].sum_lo) & 7) || hd.src[i].sum_hi - hd.src[i].sum_lo > 256)) return false;
     a.nblk = 0;
     int off = 0;
     for (int i = 0; i < hd.nsrc; ++i) {
@@ -463,9 +465,10 @@ inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
         const PwSrc& Sx = hd.src[i];
         if (!Sx.bsum || Sx.sum_hi <= Sx.sum_lo) continue;
         BsumArgs q; q.x = Sx.data; q.dx = Sx.grad; q.cp = Sx.cp; q.lo = Sx.sum_lo; q.hi = Sx.sum_hi; q.clamp = Sx.clamp; q.aff = Sx.aff; q.bnp = Sx.bnp;
-        q.bsum = Sx.bsum; q.Rt = a.Rt; q.rows_per_cta = 64;
+        static const int bsum_rows = getenv("CDRA_BSUM_ROWS") ? atoi(getenv("CDRA_BSUM_ROWS")) : 64;
+        q.bsum = Sx.bsum; q.Rt = a.Rt; q.rows_per_cta = bsum_rows;
         prof_bytes(4.0 * a.Rt * (Sx.sum_hi - Sx.sum_lo) * 2 * 2);
-        CDRA_LAUNCH_PDL(bsum_kernel, dim3((a.Rt + 63) / 64, kT, (Sx.sum_hi - Sx.sum_lo + 255) / 256), dim3(256), 0, c.stream, q);
+        CDRA_LAUNCH_PDL(bsum_kernel, dim3((a.Rt + q.rows_per_cta - 1) / q.rows_per_cta, kT), dim3(256), 0, c.stream, q);
     }
     if (a.x1) {
         PassBwdArgs q; q.x1 = a.x1; q.dx1 = a.dx1; q.x1cp = a.x1cp; q.x1map = a.x1map; q.x1aff = a.x1aff; q.x1bnp = a.x1bnp; q.x1bsum = a.x1bsum;

@@ -547,23 +547,47 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_dgrad_kernel(const PwBwdArgs
 // BatchNorm-backward sums S1 = sum dz, S2 = sum dz * xhat of a freshly written gradient tensor (slots [lo, hi)):
 // grid = (row chunks, slices), one thread per slot, 2-byte loads coalesced along the row
 struct BsumArgs { const bf16* x; const bf16* dx; int cp, lo, hi, clamp; const float2* aff; const float2* bnp; double2* bsum; int Rt, rows_per_cta; };
+// vectorised: thread <-> (8-slot chunk, row lane), 16-byte loads; row lanes are reduced through shared memory.
+// Needs lo % 8 == 0 and (hi - lo) % 8 == 0 (every tower tensor: cp is a multiple of 8 and the sums cover [0, cp)).
 __global__ void __launch_bounds__(256) bsum_kernel(const BsumArgs a) {
+    __shared__ float2 s_part[8 * 256];                 // [row lane][slot] partial (S1, S2); <= 8 row lanes are used
     pdl_trigger();
-    const int s = a.lo + blockIdx.z * 256 + threadIdx.x, t = blockIdx.y;
+    const int nsl = a.hi - a.lo, nch = nsl >> 3, t = blockIdx.y, tid = threadIdx.x;
+    const int ch = tid % nch, rl = tid / nch, nrl = min(8, 256 / nch);
     const int r_lo = blockIdx.x * a.rows_per_cta, r_hi = min(a.Rt, r_lo + a.rows_per_cta);
     pdl_wait();
-    if (s >= a.hi) return;
-    const float4 sc = sum_consts(a.aff, a.bnp, (size_t)t * a.cp + s);
-    const bool clamp = a.clamp != 0;
-    const unsigned short* xr = reinterpret_cast<const unsigned short*>(a.x) + ((size_t)t * a.Rt) * a.cp + s;
-    const unsigned short* gr = reinterpret_cast<const unsigned short*>(a.dx) + ((size_t)t * a.Rt) * a.cp + s;
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-    for (int r = r_lo; r < r_hi; ++r)
-        sum_accum(__uint_as_float((uint32_t)gr[(size_t)r * a.cp] << 16), __uint_as_float((uint32_t)xr[(size_t)r * a.cp] << 16), sc, clamp, s1, s2);
-    if (s1 != 0.f || s2 != 0.f) {
-        double2* dst = a.bsum + (size_t)t * a.cp + s;
-        atomicAdd(&dst->x, (double)s1); atomicAdd(&dst->y, (double)s2);
+    if (rl < nrl) {
+        const int s0 = a.lo + ch * 8;
+        float4 sc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sc[q] = sum_consts(a.aff, a.bnp, (size_t)t * a.cp + s0 + q);
+        const bool clamp = a.clamp != 0;
+        float s1[8], s2[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { s1[q] = 0.f; s2[q] = 0.f; }
+        const size_t base = ((size_t)t * a.Rt) * a.cp + s0;
+#pragma unroll 4
+        for (int r = r_lo + rl; r < r_hi; r += nrl) {
+            const uint4 g = ldg_cg16(a.dx + base + (size_t)r * a.cp), x = ldg_cg16(a.x + base + (size_t)r * a.cp);
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g); const uint32_t* xw = reinterpret_cast<const uint32_t*>(&x);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 gg = unpack2(gw[i]), xx = unpack2(xw[i]);
+                sum_accum(gg.x, xx.x, sc[2 * i], clamp, s1[2 * i], s2[2 * i]);
+                sum_accum(gg.y, xx.y, sc[2 * i + 1], clamp, s1[2 * i + 1], s2[2 * i + 1]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_part[rl * nsl + ch * 8 + q] = make_float2(s1[q], s2[q]);
+    }
+    __syncthreads();
+    for (int i = tid; i < nsl; i += 256) {
+        float v1 = 0.f, v2 = 0.f;
+        for (int l = 0; l < nrl; ++l) { const float2 v = s_part[l * nsl + i]; v1 += v.x; v2 += v.y; }
+        if (v1 != 0.f || v2 != 0.f) {
+            double2* dst = a.bsum + (size_t)t * a.cp + a.lo + i;
+            atomicAdd(&dst->x, (double)v1); atomicAdd(&dst->y, (double)v2);
+        }
     }
 }
 

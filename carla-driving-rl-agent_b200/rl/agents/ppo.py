@@ -127,9 +127,10 @@ class PPOAgent(Agent):
                 self.update_value(value_grads)
                 self.log(loss_value=value_loss, lr_value=self.value_lr.value, gradients_norm_value=self._head_norms)
 
+        t1 = time.time()                                 # host time to enqueue the update (the device runs behind it)
         if torch.cuda.is_available():
             torch.cuda.synchronize()
-        print(f'Update took {round(time.time() - t0, 3)}s')
+        print(f'Update took {round(time.time() - t0, 3)}s (enqueued in {round(t1 - t0, 3)}s)')
 
     def get_policy_gradients(self, batch):
         raise NotImplementedError
