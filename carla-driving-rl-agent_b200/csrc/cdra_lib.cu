@@ -698,6 +698,7 @@ int cdra_debug_set(const char* key, int value) {
     if (std::string(key) == "fwd_tc") { v2::fwd_tc_override() = value; return CDRA_OK; }
     if (std::string(key) == "fused") { v2::fused_override() = value; return CDRA_OK; }
     if (std::string(key) == "pwg") { v2::pwg_override() = value; return CDRA_OK; }
+    if (std::string(key) == "dw_band") { v2::dw_band_cap() = value < 0 ? 0 : value; return CDRA_OK; }
 #endif
     return fail(CDRA_ERR_BADARG, "unknown debug key");
 }

@@ -129,19 +129,7 @@ Plan* build_plan(const cdra_config& cfg, std::string& err) {
 
     // ---- v2 tower tensors (bf16 perf mode): padded planes, see v2_common.cuh
     p.v2.on = (p.elem == 2);
-    if (p.v2.on) {
-        // the v2 depthwise kernels keep whole frames in shared memory (halo-padded input + dR tile + raw output pair in the
-        // backward): frames that do not fit (e.g. 180x240 at stage 1) send the plan to the row-sweep bf16 kernels instead
-        auto r8c = [](int x) { return (x + 7) / 8 * 8; };
-        for (const Unit& un : p.units) {
-            const int cps[2] = {r8c(un.half), un.stride == 2 ? r8c(un.cin >= 64 ? un.cin / 2 : un.cin) : 0};
-            for (int cp : cps) {
-                if (!cp) continue;
-                const size_t bwd = ((size_t)(un.Hi + 2) * (un.Wi + 2) + 2 * (size_t)un.Ho * un.Wo + (size_t)(un.Ho + 2) * (un.Wo + 2)) * cp * 2 + cp * 64 + 1024;
-                if (bwd > 224 * 1024) p.v2.on = false;
-            }
-        }
-    }
+    // (the v2 depthwise kernels band frames that do not fit shared memory -- 180x240 at stage 1 -- so every geometry stays on v2)
     if (p.v2.on) {
         V2Plan& v = p.v2;
         auto r8 = [](int x) { return (x + 7) / 8 * 8; };

@@ -763,33 +763,36 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
     const int tid = threadIdx.x;
     pdl_trigger();
     const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo, PW = a.Wi + 2, QW = a.Wo + 2;
-    const bool sep = a.sep != 0;
-    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, true, sep);
+    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, true, a.band_rows, S);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     float* s_stat = reinterpret_cast<float*>(smem + L.stat);
     float* s_wred = reinterpret_cast<float*>(smem + L.wred);
     float4* s_colc = reinterpret_cast<float4*>(smem + L.colc);
+    bf16* Pin = reinterpret_cast<bf16*>(smem + L.pin);
     bf16* Pdr = reinterpret_cast<bf16*>(smem + L.pdr);
-    const uint32_t out_bytes = (uint32_t)out_px * CP * 2, row_bytes = (uint32_t)a.Wi * CP * 2;
-    const int nframes = kT * a.B;
-    const int f_lo = blockIdx.x * a.frames_per_cta, f_hi = min(nframes, f_lo + a.frames_per_cta);
+    const uint32_t orow_bytes = (uint32_t)a.Wo * CP * 2, row_bytes = (uint32_t)a.Wi * CP * 2;
+    const int nitems = kT * a.B * a.nbands;
+    const int it_lo = blockIdx.x * a.frames_per_cta, it_hi = min(nitems, it_lo + a.frames_per_cta);
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     for (int i = tid; i < CP * 2; i += kDwThreads) s_stat[i] = 0.f;
     for (int i = tid; i < CP * 9; i += kDwThreads) s_wred[i] = 0.f;
-    for (int i = tid; i < (sep ? 1 : a.nbuf) * L.pin_stride / 4; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + L.pin)[i] = 0u;
-    for (int i = tid; i < (a.Ho + 2) * QW * (CP / 2); i += kDwThreads) reinterpret_cast<uint32_t*>(Pdr)[i] = 0u;
+    for (int i = tid; i < L.pin_stride / 4; i += kDwThreads) reinterpret_cast<uint32_t*>(Pin)[i] = 0u;
+    for (int i = tid; i < (a.band_rows + 2) * QW * (CP / 2); i += kDwThreads) reinterpret_cast<uint32_t*>(Pdr)[i] = 0u;
     __syncthreads();
-    auto issue = [&](int f, int buf) {
-        mbar_expect_tx(&full[buf], 2 * out_bytes + row_bytes * a.Hi);
-        bulk_g2s(smem + L.raw_dout + (size_t)buf * L.out_stride, a.dout + (size_t)f * out_px * CP, out_bytes, &full[buf]);
-        bulk_g2s(smem + L.raw_out + (size_t)buf * L.out_stride, a.out + (size_t)f * out_px * CP, out_bytes, &full[buf]);
-        const bf16* src = a.in + (size_t)f * in_px * CP;
-        if (sep) { bulk_g2s(smem + L.rawin + (size_t)buf * L.in_stride, src, row_bytes * a.Hi, &full[buf]); return; }
-        unsigned char* dst = smem + L.pin + (size_t)buf * L.pin_stride + (PW + 1) * CP * 2;
-        for (int y = 0; y < a.Hi; ++y) bulk_g2s(dst + (size_t)y * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
+    // rows of (d out, out) a band needs: its own and one neighbour row on either side (the data gradient of the band's
+    // input rows reaches them)
+    auto out_rows = [&](const DwBand& b, int& o_lo, int& o_hi) { o_lo = max(0, b.oy0 - 1); o_hi = min(a.Ho - 1, b.oy0 + b.bho); };
+    auto issue = [&](int item, int buf) {
+        const DwBand b = dw_band(a, item, S);
+        int o_lo, o_hi; out_rows(b, o_lo, o_hi);
+        const uint32_t ob = orow_bytes * (uint32_t)(o_hi - o_lo + 1), ib = row_bytes * (uint32_t)(b.i_hi - b.i_lo + 1);
+        mbar_expect_tx(&full[buf], 2 * ob + ib);
+        bulk_g2s(smem + L.raw_dout + (size_t)buf * L.out_stride, a.dout + ((size_t)b.f * out_px + (size_t)o_lo * a.Wo) * CP, ob, &full[buf]);
+        bulk_g2s(smem + L.raw_out + (size_t)buf * L.out_stride, a.out + ((size_t)b.f * out_px + (size_t)o_lo * a.Wo) * CP, ob, &full[buf]);
+        bulk_g2s(smem + L.rawin + (size_t)buf * L.in_stride, a.in + ((size_t)b.f * in_px + (size_t)b.i_lo * a.Wi) * CP, ib, &full[buf]);
     };
     pdl_wait();
-    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (f_lo + b < f_hi) issue(f_lo + b, b);
+    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (it_lo + b < it_hi) issue(it_lo + b, b);
 
     const int tch = tid % NCH, tpl = tid / NCH;
     const int pr = tid % NPAIR, xl = tid / NPAIR;
@@ -807,7 +810,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
     float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
     float4 xc0 = make_float4(1.f, 0.f, 0.f, 0.f), xc1 = xc0;    // (scale, shift, inv_std, -mean * inv_std) of this thread's two input channels
     float2 ac8[8];
-    const bool iclamp = a.clamp != 0, xform = a.aff != nullptr || iclamp, want_sums = a.in_bsum != nullptr;
+    const bool iclamp = a.clamp != 0, xform = a.aff != nullptr || iclamp, want_sums = a.in_bsum != nullptr, banded = a.nbands > 1;
     const double inv_n = 1.0 / ((double)a.B * out_px);
     auto flush = [&](int t) {
         if (active) {
@@ -828,8 +831,10 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
     auto xhat_consts = [&](int t, int slot) { return sum_consts(a.aff, a.bnp, (size_t)t * CP + slot); };
     const int row_step = S * PW * CP;
     int cur_t = -1;
-    for (int f = f_lo, it = 0; f < f_hi; ++f, ++it) {
-        const int buf = it % a.nbuf, t = f / a.B;
+    for (int item = it_lo, it = 0; item < it_hi; ++item, ++it) {
+        const DwBand bd = dw_band(a, item, S);
+        int o_lo, o_hi; out_rows(bd, o_lo, o_hi);
+        const int buf = it % a.nbuf, f = bd.f, t = f / a.B;
         if (t != cur_t) {
             if (cur_t >= 0) flush(cur_t);
             __syncthreads();
@@ -848,7 +853,6 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
             __syncthreads();
         }
         mbar_wait(&full[buf], (it / a.nbuf) & 1);
-        bf16* Pin = reinterpret_cast<bf16*>(smem + L.pin + (sep ? 0 : (size_t)buf * L.pin_stride));
         const bf16* Rin = reinterpret_cast<const bf16*>(smem + L.rawin + (size_t)buf * L.in_stride);
         if (tpl < TNPL) {
             float4 c8[8];
@@ -857,40 +861,49 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
             const uint4* dv = reinterpret_cast<const uint4*>(smem + L.raw_dout + (size_t)buf * L.out_stride) + tch;
             const uint4* ov = reinterpret_cast<const uint4*>(smem + L.raw_out + (size_t)buf * L.out_stride) + tch;
             uint4* qv = reinterpret_cast<uint4*>(Pdr) + tch;
-            PxWalk wo(tpl, TNPL, a.Wo);
-            for (int px = tpl; px < out_px; px += TNPL, wo.next()) {
-                uint4 dvv = dv[px * NCH]; const uint4 ovv = ov[px * NCH];
-                uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
+            {   // dR rows o_lo .. o_hi -> tile rows (oy - oy0 + 1)
+                PxWalk wo(tpl, TNPL, a.Wo);
+                const int npx = (o_hi - o_lo + 1) * a.Wo, roff = o_lo - bd.oy0 + 1;
+                for (int px = tpl; px < npx; px += TNPL, wo.next()) {
+                    uint4 dvv = dv[px * NCH]; const uint4 ovv = ov[px * NCH];
+                    uint32_t* dw = reinterpret_cast<uint32_t*>(&dvv); const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovv);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
-                    dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], false), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], false));
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 dd = unpack2(dw[i]), oo = unpack2(ow[i]);
+                        dw[i] = pack2(bnbwd_apply(dd.x, oo.x, c8[2 * i], false), bnbwd_apply(dd.y, oo.y, c8[2 * i + 1], false));
+                    }
+                    qv[((wo.y + roff) * QW + wo.x + 1) * NCH] = dvv;
                 }
-                qv[((wo.y + 1) * QW + wo.x + 1) * NCH] = dvv;
+                if (banded) {                               // halo rows outside the frame must read as zero
+                    if (bd.oy0 == 0) for (int x = tpl; x < QW; x += TNPL) qv[x * NCH] = make_uint4(0, 0, 0, 0);
+                    if (bd.oy0 + bd.bho >= a.Ho) for (int x = tpl; x < QW; x += TNPL) qv[((bd.bho + 1) * QW + x) * NCH] = make_uint4(0, 0, 0, 0);
+                }
             }
-            if (sep) {                                  // raw frame -> activated halo tile
+            {   // raw input rows i_lo .. i_hi -> activated halo tile, tile row (iy - row0)
                 uint4* pv = reinterpret_cast<uint4*>(Pin) + tch;
                 const uint4* rv = reinterpret_cast<const uint4*>(Rin) + tch;
                 PxWalk wi(tpl, TNPL, a.Wi);
-                for (int px = tpl; px < in_px; px += TNPL, wi.next()) {
+                const int npx = (bd.i_hi - bd.i_lo + 1) * a.Wi, roff = bd.i_lo - bd.row0;
+                for (int px = tpl; px < npx; px += TNPL, wi.next()) {
                     const uint4 v = rv[px * NCH];
-                    pv[((wi.y + 1) * PW + wi.x + 1) * NCH] = xform ? affine8(v, ac8, iclamp) : v;
+                    pv[((wi.y + roff) * PW + wi.x + 1) * NCH] = xform ? affine8(v, ac8, iclamp) : v;
                 }
-            } else if (xform) {
-                uint4* pv = reinterpret_cast<uint4*>(Pin) + tch;
-                PxWalk wi(tpl, TNPL, a.Wi);
-                for (int px = tpl; px < in_px; px += TNPL, wi.next()) {
-                    uint4* q = pv + ((wi.y + 1) * PW + wi.x + 1) * NCH;
-                    *q = affine8(*q, ac8, iclamp);
+                if (banded) {
+                    const int th = (bd.bho - 1) * S + 3;
+                    for (int tr = 0; tr < th; ++tr) {
+                        const int iy = bd.row0 + tr;
+                        if (iy >= 0 && iy < a.Hi) continue;
+                        for (int x = tpl; x < PW; x += TNPL) pv[(tr * PW + x) * NCH] = make_uint4(0, 0, 0, 0);
+                    }
                 }
             }
         }
         __syncthreads();
         if (active) {
-            // weight gradient: dw[ky][kx] += act(in)(oy*S - pt + ky, ox*S - pl + kx) * dR(oy, ox)   (rows shared between
-            // consecutive outputs stay in registers)
+            // weight gradient over the band's own output rows: dw[ky][kx] += act(in)(oy*S - pt + ky, ox*S - pl + kx) * dR(oy, ox)
+            // (rows shared between consecutive outputs stay in registers)
             for (int ox = xl; ox < a.Wo; ox += NXL) {
-                const bf16* win = Pin + ((1 - a.pad_t) * PW + ox * S + 1 - a.pad_l) * CP + 2 * pr;
+                const bf16* win = Pin + (ox * S + 1 - a.pad_l) * CP + 2 * pr;
                 const bf16* dp = Pdr + (QW + ox + 1) * CP + 2 * pr;
                 auto emit = [&](const float2 (&A)[3], const float2 (&B)[3], const float2 (&C)[3]) {
                     const float2 dr = unpack2(*reinterpret_cast<const uint32_t*>(dp));
@@ -901,14 +914,14 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                 if (S == 1) {
                     dw_ldrow<CP>(win, A); dw_ldrow<CP>(win + PW * CP, B);
                     const bf16* nxt = win + 2 * PW * CP;
-                    for (int oy = 0; oy < a.Ho; oy += 3) {
+                    for (int oy = 0; oy < bd.bho; oy += 3) {
                         dw_ldrow<CP>(nxt, C); emit(A, B, C); nxt += PW * CP;
-                        if (oy + 1 < a.Ho) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += PW * CP; }
-                        if (oy + 2 < a.Ho) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += PW * CP; }
+                        if (oy + 1 < bd.bho) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += PW * CP; }
+                        if (oy + 2 < bd.bho) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += PW * CP; }
                     }
                 } else {
                     dw_ldrow<CP>(win, A);
-                    for (int oy = 0; oy < a.Ho; ++oy) {
+                    for (int oy = 0; oy < bd.bho; ++oy) {
                         dw_ldrow<CP>(win + PW * CP, B); dw_ldrow<CP>(win + 2 * PW * CP, C);
                         emit(A, B, C);
 #pragma unroll
@@ -917,26 +930,27 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                     }
                 }
             }
-            // data gradient: d in(iy, ix) = sum_{ky,kx} w[ky][kx] * dR((iy + pt - ky)/S, (ix + pl - kx)/S)
+            // data gradient of the input rows the band owns: [oy0 * S, (oy0 + bho) * S) (clipped to the frame)
+            //     d in(iy, ix) = sum_{ky,kx} w[ky][kx] * dR((iy + pt - ky)/S, (ix + pl - kx)/S)
+            const int own_lo = bd.oy0 * S, own_hi = min(a.Hi, (bd.oy0 + bd.bho) * S);
             for (int ix = xl; ix < a.Wi; ix += NXL) {
-                bf16* gp = a.din + ((size_t)f * in_px + ix) * CP + 2 * pr;
-                // the sums use the RAW input value (same mask / xhat as every consumer of them, bnbwd_apply): the tile in shared
-                // memory only holds the bf16-rounded activation, so the raw pair is re-read through L2 (TMA just fetched the frame)
-                const bf16* rp = sep ? Rin + (size_t)ix * CP + 2 * pr : a.in + ((size_t)f * in_px + ix) * CP + 2 * pr;
+                bf16* gp = a.din + ((size_t)f * in_px + (size_t)own_lo * a.Wi + ix) * CP + 2 * pr;
+                // the sums use the RAW input value (same mask / xhat as every consumer of them, bnbwd_apply): the ring holds it
+                const bf16* rp = Rin + ((size_t)(own_lo - bd.i_lo) * a.Wi + ix) * CP + 2 * pr;
                 auto finish = [&](float acc0, float acc1) {       // (+ existing share), store, BatchNorm-backward sums of the input
                     if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
                     const uint32_t pk = pack2(acc0, acc1);
                     *reinterpret_cast<uint32_t*>(gp) = pk;
                     if (want_sums) {
                         const float2 gr = unpack2(pk);
-                        const float2 rv = unpack2(sep ? *reinterpret_cast<const uint32_t*>(rp) : __ldg(reinterpret_cast<const unsigned int*>(rp)));
+                        const float2 rv = unpack2(*reinterpret_cast<const uint32_t*>(rp));
                         sum_accum(gr.x, rv.x, xc0, iclamp, s1a, s2a);
                         sum_accum(gr.y, rv.y, xc1, iclamp, s1b, s2b);
                     }
                     gp += a.Wi * CP; rp += a.Wi * CP;
                 };
                 if (S == 1) {
-                    // d in(iy, ix) = sum w[ky][kx] * dR tile(iy + 2 - ky, ix + 2 - kx): tile rows iy, iy+1, iy+2 <-> ky = 2, 1, 0
+                    // own row li = iy - oy0 sees dR rows iy - 1 .. iy + 1 = tile rows li .. li + 2 <-> ky = 2, 1, 0
                     auto emit = [&](const float2 (&A)[3], const float2 (&B)[3], const float2 (&C)[3]) {
                         float acc0 = 0.f, acc1 = 0.f;
                         dw_mac_row<true>(A, w0 + 6, w1 + 6, acc0, acc1);
@@ -944,19 +958,20 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                         dw_mac_row<true>(C, w0, w1, acc0, acc1);
                         finish(acc0, acc1);
                     };
+                    const int nown = own_hi - own_lo;
                     const bf16* dwin = Pdr + ix * CP + 2 * pr;
                     float2 A[3], B[3], C[3];
                     dw_ldrow<CP>(dwin, A); dw_ldrow<CP>(dwin + QW * CP, B);
                     const bf16* nxt = dwin + 2 * QW * CP;
-                    for (int iy = 0; iy < a.Hi; iy += 3) {
+                    for (int li = 0; li < nown; li += 3) {
                         dw_ldrow<CP>(nxt, C); emit(A, B, C); nxt += QW * CP;
-                        if (iy + 1 < a.Hi) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += QW * CP; }
-                        if (iy + 2 < a.Hi) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += QW * CP; }
+                        if (li + 1 < nown) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += QW * CP; }
+                        if (li + 2 < nown) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += QW * CP; }
                     }
                 } else {
-                    // stride 2: input pixel (iy, ix) only sees the taps whose parity matches, d in = sum dR((iy+pt-ky)/2, (ix+pl-kx)/2) * w[ky][kx]
-                    // over even (iy+pt-ky), (ix+pl-kx).  The column taps are fixed per thread (kx = 0, 2 at tile columns cA, cA - 1 when
-                    // ix + pl is even; kx = 1 at cA otherwise) and selected ONCE; the row taps alternate with the parity of iy + pt.
+                    // stride 2: input pixel (iy, ix) only sees the taps whose parity matches, over even (iy+pt-ky), (ix+pl-kx).
+                    // The column taps are fixed per thread (kx = 0, 2 at tile columns cA, cA - 1 when ix + pl is even; kx = 1 at
+                    // cA otherwise) and selected ONCE; the row taps alternate with the parity of iy + pt.  dR row n = tile row n - oy0 + 1.
                     const int xs = ix + a.pad_l;
                     const bool xe = (xs & 1) == 0;
                     const int cA = (xs >> 1) + 1, cB = xe ? cA - 1 : cA;
@@ -967,17 +982,17 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                         wb0[ky] = xe ? w0[ky * 3 + 2] : 0.f;         wb1[ky] = xe ? w1[ky * 3 + 2] : 0.f;
                     }
                     const bf16* pa = Pdr + cA * CP + 2 * pr; const bf16* pb = Pdr + cB * CP + 2 * pr;
-                    for (int iy = 0; iy < a.Hi; ++iy) {
+                    for (int iy = own_lo; iy < own_hi; ++iy) {
                         const int ys = iy + a.pad_t;
                         float acc0, acc1;
-                        if ((ys & 1) == 0) {                      // ky = 0 at tile row ys/2 + 1, ky = 2 at tile row ys/2
-                            const int r = ((ys >> 1) + 1) * QW * CP;
+                        if ((ys & 1) == 0) {                      // ky = 0 at dR row ys/2, ky = 2 at dR row ys/2 - 1
+                            const int r = ((ys >> 1) - bd.oy0 + 1) * QW * CP;
                             const float2 a0 = unpack2(*reinterpret_cast<const uint32_t*>(pa + r)), b0 = unpack2(*reinterpret_cast<const uint32_t*>(pb + r));
                             const float2 a2 = unpack2(*reinterpret_cast<const uint32_t*>(pa + r - QW * CP)), b2 = unpack2(*reinterpret_cast<const uint32_t*>(pb + r - QW * CP));
                             acc0 = fmaf(a0.x, wa0[0], fmaf(b0.x, wb0[0], fmaf(a2.x, wa0[2], b2.x * wb0[2])));
                             acc1 = fmaf(a0.y, wa1[0], fmaf(b0.y, wb1[0], fmaf(a2.y, wa1[2], b2.y * wb1[2])));
-                        } else {                                  // ky = 1 at tile row (ys - 1)/2 + 1
-                            const int r = (((ys - 1) >> 1) + 1) * QW * CP;
+                        } else {                                  // ky = 1 at dR row (ys - 1)/2
+                            const int r = (((ys - 1) >> 1) - bd.oy0 + 1) * QW * CP;
                             const float2 a1 = unpack2(*reinterpret_cast<const uint32_t*>(pa + r)), b1 = unpack2(*reinterpret_cast<const uint32_t*>(pb + r));
                             acc0 = fmaf(a1.x, wa0[1], b1.x * wb0[1]);
                             acc1 = fmaf(a1.y, wa1[1], b1.y * wb1[1]);
@@ -988,7 +1003,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
             }
         }
         __syncthreads();
-        if (tid == 0 && f + a.nbuf < f_hi) issue(f + a.nbuf, buf);
+        if (tid == 0 && item + a.nbuf < it_hi) issue(item + a.nbuf, buf);
     }
     if (cur_t >= 0) flush(cur_t);
     // ---- weight gradients of this CTA

@@ -22,33 +22,49 @@ struct DwArgs {
     bf16* out; const bf16* dout; Tables tb;                              // output tensor [4*B*Ho*Wo][cp] (raw) + tables
     int training;
     unsigned* counter;
-    int frames_per_cta, nbuf;
-    int sep;                                                             // backward: raw input frames kept next to ONE activated halo tile
+    int frames_per_cta, nbuf;                                            // work items (frame, band) per CTA; depth of the TMA ring
+    int band_rows, nbands;                                               // output rows per band; bands per frame (1: whole frames)
 };
 
-// shared-memory carve-up of the depthwise kernels (host + device).  The input frame lives in a halo-padded tile
-// [(Hi+2)][(Wi+2)][cp] (zero border = TF SAME padding): TMA row copies land in its interior and the producer's
-// BatchNorm affine (+ReLU6) is applied in place, so the stencils need no bounds checks.
-struct DwSmem { int stat, wred, colc, pin, raw_out, raw_dout, pdr, total, pin_stride, out_stride, rawin, in_stride; };
-// sep (backward only): the TMA ring holds the RAW input frames (one contiguous bulk copy each; the BatchNorm-backward
-// sums of the input need the raw values) and the activated, halo-padded tile exists once
-inline __host__ __device__ DwSmem dw_smem(int cp, int Hi, int Wi, int Ho, int Wo, int nbuf, bool backward, bool sep = false) {
+// shared-memory carve-up of the depthwise kernels (host + device).  The unit of work is a BAND of `bh` output rows of one
+// frame (the whole frame when it fits): the activated input rows the band needs live in a halo-padded tile
+// [(bh - 1) * S + 3][(Wi + 2)][cp] whose row 0 is input row oy0 * S - pad_t (rows / columns outside the frame are zero = TF
+// SAME padding), so the stencils need no bounds checks.  Forward: the TMA row copies land in the tile's interior and the
+// producer's BatchNorm affine (+ReLU6) is applied in place.  Backward: the ring holds the RAW input rows (one contiguous
+// bulk copy per band; the BatchNorm-backward sums of the input need the raw values) next to the rows oy0 - 1 .. oy0 + bh of
+// (d out, out); the activated input tile and the dR tile (with a one-row halo of REAL neighbour rows) exist once.
+struct DwSmem { int stat, wred, colc, pin, raw_out, raw_dout, pdr, total, pin_stride, out_stride, rawin, in_stride, th; };
+inline __host__ __device__ DwSmem dw_smem(int cp, int Hi, int Wi, int Ho, int Wo, int nbuf, bool backward, int bh, int S) {
     DwSmem s;
     int off = 64;
     s.stat = off; off += cp * 8;
     s.wred = off; off += backward ? cp * 9 * 4 : 0;
     s.colc = off; off += backward ? cp * 16 : 0;
     off = (off + 127) & ~127;
-    s.pin_stride = ((Hi + 2) * (Wi + 2) * cp * 2 + 127) & ~127;
-    s.out_stride = (Ho * Wo * cp * 2 + 127) & ~127;
-    s.in_stride = (Hi * Wi * cp * 2 + 127) & ~127;
-    s.pin = off; off += (sep ? 1 : nbuf) * s.pin_stride;
-    s.rawin = off; off += sep ? nbuf * s.in_stride : 0;
+    s.th = (bh - 1) * S + 3;
+    const int in_rows = s.th < Hi ? s.th : Hi;          // input rows a band loads at most
+    s.pin_stride = (s.th * (Wi + 2) * cp * 2 + 127) & ~127;
+    s.in_stride = (in_rows * Wi * cp * 2 + 127) & ~127;
+    s.out_stride = ((bh + 2 < Ho ? bh + 2 : Ho) * Wo * cp * 2 + 127) & ~127;
+    s.pin = off; off += (backward ? 1 : nbuf) * s.pin_stride;
+    s.rawin = off; off += backward ? nbuf * s.in_stride : 0;
     s.raw_out = off; off += backward ? nbuf * s.out_stride : 0;
     s.raw_dout = off; off += backward ? nbuf * s.out_stride : 0;
-    s.pdr = off; off += backward ? (((Ho + 2) * (Wo + 2) * cp * 2 + 127) & ~127) : 0;   // dR with a zero halo
+    s.pdr = off; off += backward ? (((bh + 2) * (Wo + 2) * cp * 2 + 127) & ~127) : 0;   // dR rows oy0 - 1 .. oy0 + bh
     s.total = off;
     return s;
+}
+// one work item: frame f, output rows [oy0, oy0 + bho); tile row 0 = input row `row0`; the band loads input rows [i_lo, i_hi]
+struct DwBand { int f, oy0, bho, row0, i_lo, i_hi; };
+CDRA_DEV DwBand dw_band(const DwArgs& a, int item, int S) {
+    DwBand b;
+    b.f = item / a.nbands;
+    b.oy0 = (item - b.f * a.nbands) * a.band_rows;
+    b.bho = min(a.band_rows, a.Ho - b.oy0);
+    b.row0 = b.oy0 * S - a.pad_t;
+    b.i_lo = max(0, b.row0);
+    b.i_hi = min(a.Hi - 1, b.row0 + (b.bho - 1) * S + 2);
+    return b;
 }
 
 // per-thread (y, x) walker over the pixels px = lane, lane + step, ... of a W-wide frame without divisions in the loop
@@ -88,24 +104,25 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_fwd_kernel(const DwArgs a) {
     const int tid = threadIdx.x;
     pdl_trigger();
     const int in_px = a.Hi * a.Wi, out_px = a.Ho * a.Wo, PW = a.Wi + 2;
-    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, false);
+    const DwSmem L = dw_smem(CP, a.Hi, a.Wi, a.Ho, a.Wo, a.nbuf, false, a.band_rows, S);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     float* s_stat = reinterpret_cast<float*>(smem + L.stat);
     const uint32_t row_bytes = (uint32_t)a.Wi * CP * 2;
-    const int nframes = kT * a.B;
-    const int f_lo = blockIdx.x * a.frames_per_cta, f_hi = min(nframes, f_lo + a.frames_per_cta);
+    const int nitems = kT * a.B * a.nbands;
+    const int it_lo = blockIdx.x * a.frames_per_cta, it_hi = min(nitems, it_lo + a.frames_per_cta);
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     for (int i = tid; i < CP * 2; i += kDwThreads) s_stat[i] = 0.f;
     for (int i = tid; i < a.nbuf * L.pin_stride / 4; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + L.pin)[i] = 0u;
     __syncthreads();
-    auto issue = [&](int f, int buf) {
-        mbar_expect_tx(&full[buf], row_bytes * a.Hi);
-        unsigned char* dst = smem + L.pin + (size_t)buf * L.pin_stride + (PW + 1) * CP * 2;
-        const bf16* src = a.in + (size_t)f * in_px * CP;
-        for (int y = 0; y < a.Hi; ++y) bulk_g2s(dst + (size_t)y * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
+    auto issue = [&](int item, int buf) {
+        const DwBand b = dw_band(a, item, S);
+        mbar_expect_tx(&full[buf], row_bytes * (uint32_t)(b.i_hi - b.i_lo + 1));
+        unsigned char* dst = smem + L.pin + (size_t)buf * L.pin_stride + CP * 2;        // column 1 of tile row 0
+        const bf16* src = a.in + (size_t)b.f * in_px * CP;
+        for (int y = b.i_lo; y <= b.i_hi; ++y) bulk_g2s(dst + (size_t)(y - b.row0) * PW * CP * 2, src + (size_t)y * a.Wi * CP, row_bytes, &full[buf]);
     };
     pdl_wait();
-    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (f_lo + b < f_hi) issue(f_lo + b, b);
+    if (tid == 0) for (int b = 0; b < a.nbuf; ++b) if (it_lo + b < it_hi) issue(it_lo + b, b);
 
     const int tch = tid % NCH, tpl = tid / NCH;                       // transform role
     const int pr = tid % NPAIR, xl = tid / NPAIR;                     // stencil role
@@ -137,11 +154,12 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_fwd_kernel(const DwArgs a) {
         }
         __syncthreads();
     };
-    const bool clamp = a.clamp != 0, xform = a.aff != nullptr || clamp;
+    const bool clamp = a.clamp != 0, xform = a.aff != nullptr || clamp, banded = a.nbands > 1;
     const int row_step = S * PW * CP, ostep = a.Wo * CP;
     int cur_t = -1;
-    for (int f = f_lo, it = 0; f < f_hi; ++f, ++it) {
-        const int buf = it % a.nbuf, t = f / a.B;
+    for (int item = it_lo, it = 0; item < it_hi; ++item, ++it) {
+        const DwBand bd = dw_band(a, item, S);
+        const int buf = it % a.nbuf, f = bd.f, t = f / a.B;
         if (t != cur_t) {
             if (cur_t >= 0 && a.training) flush(cur_t);
             if (tpl < TNPL) {
@@ -152,21 +170,32 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_fwd_kernel(const DwArgs a) {
         }
         mbar_wait(&full[buf], (it / a.nbuf) & 1);
         bf16* Pin = reinterpret_cast<bf16*>(smem + L.pin + (size_t)buf * L.pin_stride);
-        if (xform) {                                                  // producer's BatchNorm affine (+ReLU6), in place
+        if (xform || banded) {
             if (tpl < TNPL) {
                 uint4* pv = reinterpret_cast<uint4*>(Pin) + tch;
-                PxWalk w(tpl, TNPL, a.Wi);
-                for (int px = tpl; px < in_px; px += TNPL, w.next()) {
-                    uint4* q = pv + ((w.y + 1) * PW + w.x + 1) * NCH;
-                    *q = affine8(*q, c8, clamp);
+                if (xform) {                                          // producer's BatchNorm affine (+ReLU6), in place, on the loaded rows
+                    PxWalk w(tpl, TNPL, a.Wi);
+                    const int npx = (bd.i_hi - bd.i_lo + 1) * a.Wi, roff = bd.i_lo - bd.row0;
+                    for (int px = tpl; px < npx; px += TNPL, w.next()) {
+                        uint4* q = pv + ((w.y + roff) * PW + w.x + 1) * NCH;
+                        *q = affine8(*q, c8, clamp);
+                    }
+                }
+                if (banded) {                                         // tile rows outside the frame: a previous band left data there
+                    const int th = (bd.bho - 1) * S + 3;
+                    for (int tr = 0; tr < th; ++tr) {
+                        const int iy = bd.row0 + tr;
+                        if (iy >= 0 && iy < a.Hi) continue;
+                        for (int x = tpl; x < PW; x += TNPL) pv[(tr * PW + x) * NCH] = make_uint4(0, 0, 0, 0);
+                    }
                 }
             }
             __syncthreads();
         }
         if (active) {
             for (int ox = xl; ox < a.Wo; ox += NXL) {
-                const bf16* win = Pin + ((1 - a.pad_t) * PW + ox * S + 1 - a.pad_l) * CP + 2 * pr;
-                bf16* optr = a.out + ((size_t)f * out_px + ox) * CP + 2 * pr;
+                const bf16* win = Pin + (ox * S + 1 - a.pad_l) * CP + 2 * pr;         // tile row 0 = tap ky 0 of the band's first row
+                bf16* optr = a.out + ((size_t)f * out_px + (size_t)bd.oy0 * a.Wo + ox) * CP + 2 * pr;
                 auto emit = [&](const float2 (&A)[3], const float2 (&B)[3], const float2 (&C)[3]) {
                     float acc0 = b0, acc1 = b1;
                     dw_mac_row<false>(A, w0, w1, acc0, acc1);
@@ -183,14 +212,14 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_fwd_kernel(const DwArgs a) {
                 if (S == 1) {
                     dw_ldrow<CP>(win, A); dw_ldrow<CP>(win + PW * CP, B);
                     const bf16* nxt = win + 2 * PW * CP;
-                    for (int oy = 0; oy < a.Ho; oy += 3) {
+                    for (int oy = 0; oy < bd.bho; oy += 3) {
                         dw_ldrow<CP>(nxt, C); emit(A, B, C); nxt += PW * CP;
-                        if (oy + 1 < a.Ho) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += PW * CP; }
-                        if (oy + 2 < a.Ho) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += PW * CP; }
+                        if (oy + 1 < bd.bho) { dw_ldrow<CP>(nxt, A); emit(B, C, A); nxt += PW * CP; }
+                        if (oy + 2 < bd.bho) { dw_ldrow<CP>(nxt, B); emit(C, A, B); nxt += PW * CP; }
                     }
                 } else {
                     dw_ldrow<CP>(win, A);
-                    for (int oy = 0; oy < a.Ho; ++oy) {
+                    for (int oy = 0; oy < bd.bho; ++oy) {
                         dw_ldrow<CP>(win + PW * CP, B); dw_ldrow<CP>(win + 2 * PW * CP, C);
                         emit(A, B, C);
 #pragma unroll
@@ -201,7 +230,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_fwd_kernel(const DwArgs a) {
             }
         }
         __syncthreads();
-        if (tid == 0 && f + a.nbuf < f_hi) issue(f + a.nbuf, buf);
+        if (tid == 0 && item + a.nbuf < it_hi) issue(item + a.nbuf, buf);
     }
     if (cur_t >= 0 && a.training) flush(cur_t);
     if (a.counter == nullptr) return;

@@ -120,6 +120,7 @@ inline int& pwg_override() { static int v = -1; return v; }     // cdra_debug_se
 inline bool use_pwg() { static const bool env = getenv("CDRA_NO_PWG") == nullptr; return pwg_override() < 0 ? env : pwg_override() != 0; }
 // the GEMM family of v4_pwg.cuh takes every pointwise launch whose reduction length reaches this (stage 3 and the head)
 inline int pwg_min_k() { static const int v = getenv("CDRA_PWG_MINK") ? atoi(getenv("CDRA_PWG_MINK")) : 192; return v; }
+inline int& dw_band_cap() { static int v = 0; return v; }        // cdra_debug_set("dw_band", rows): 0 = automatic
 inline bool use_pwg_wgrad() { static const bool env = getenv("CDRA_NO_PWG_WGRAD") == nullptr; return env; }
 inline int pwg_min_k_bwd() { static const int v = getenv("CDRA_PWG_MINK_BWD") ? atoi(getenv("CDRA_PWG_MINK_BWD")) : 192; return v; }
 inline int num_sms() {
@@ -251,6 +252,23 @@ inline void launch_pw_fwd(const RunCtx& c, int di, const PwDesc& hd, PwFwdArgs& 
     if (!ok) fprintf(stderr, "libcdra: no pw_fwd configuration fits (KP=%d NPall=%d)\n", hd.KP, hd.NPall);
 }
 
+// output rows per band of a depthwise launch: the whole frame if its double-buffered footprint stays under `limit`, else the
+// largest band that does (evened out over the bands)
+inline bool dw_pick_band(int cp, const Unit& u, bool backward, int limit, int& band_rows, int& nbands) {
+    auto total = [&](int bh) { return dw_smem(cp, u.Hi, u.Wi, u.Ho, u.Wo, 2, backward, bh, u.stride).total; };
+    int bh = u.Ho;
+    if (total(bh) > limit) {
+        bh = 1;
+        if (total(bh) > kMaxDynSmem) return false;
+        const int lim = total(1) > limit ? kMaxDynSmem : limit;
+        while (bh < u.Ho && total(bh + 1) <= lim) ++bh;
+    }
+    if (dw_band_cap() > 0) bh = std::min(bh, dw_band_cap());     // test switch: force banding on frames that would fit
+    nbands = (u.Ho + bh - 1) / bh;
+    band_rows = (u.Ho + nbands - 1) / nbands;
+    return true;
+}
+
 inline void launch_dw_fwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, bool clamp, int kbase, const V2Tensor& out,
                           const Unit& u, int counter) {
     DwArgs a; memset(&a, 0, sizeof a);
@@ -269,15 +287,15 @@ inline void launch_dw_fwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
     }
     if (!k) { fprintf(stderr, "libcdra: no depthwise kernel for cp=%d stride=%d\n", in.cp, u.stride); return; }
     a.nbuf = 2;
-    DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, false);
-    if (L.total > kMaxDynSmem) { a.nbuf = 1; L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, 1, false); }
-    if (L.total > kMaxDynSmem) { fprintf(stderr, "libcdra: depthwise frame does not fit in shared memory (%d bytes)\n", L.total); return; }
+    // whole frames when two CTAs of them fit an SM, else the largest row band that does
+    if (!dw_pick_band(in.cp, u, false, 110 * 1024, a.band_rows, a.nbands)) { fprintf(stderr, "libcdra: depthwise band does not fit in shared memory (cp=%d)\n", in.cp); return; }
+    const DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, false, a.band_rows, u.stride);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
-    const int nframes = kT * a.B;
-    int gx = std::min(nframes, num_sms() * per_sm);
-    a.frames_per_cta = (nframes + gx - 1) / gx;
-    gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
+    const int nitems = kT * a.B * a.nbands;
+    int gx = std::min(nitems, num_sms() * per_sm);
+    a.frames_per_cta = (nitems + gx - 1) / gx;
+    gx = (nitems + a.frames_per_cta - 1) / a.frames_per_cta;
     prof_bytes(4.0 * a.B * ((double)u.Hi * u.Wi + (double)u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
     CDRA_LAUNCH_PDL(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
 }
@@ -465,7 +483,7 @@ inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
         const PwSrc& Sx = hd.src[i];
         if (!Sx.bsum || Sx.sum_hi <= Sx.sum_lo) continue;
         BsumArgs q; q.x = Sx.data; q.dx = Sx.grad; q.cp = Sx.cp; q.lo = Sx.sum_lo; q.hi = Sx.sum_hi; q.clamp = Sx.clamp; q.aff = Sx.aff; q.bnp = Sx.bnp;
-        static const int bsum_rows = getenv("CDRA_BSUM_ROWS") ? atoi(getenv("CDRA_BSUM_ROWS")) : 64;
+        static const int bsum_rows = getenv("CDRA_BSUM_ROWS") ? atoi(getenv("CDRA_BSUM_ROWS")) : 128;
         q.bsum = Sx.bsum; q.Rt = a.Rt; q.rows_per_cta = bsum_rows;
         prof_bytes(4.0 * a.Rt * (Sx.sum_hi - Sx.sum_lo) * 2 * 2);
         CDRA_LAUNCH_PDL(bsum_kernel, dim3((a.Rt + q.rows_per_cta - 1) / q.rows_per_cta, kT), dim3(256), 0, c.stream, q);
@@ -581,17 +599,14 @@ inline void launch_dw_bwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
         case 1202: k = dw_bwd_kernel<120, 2>; break;  case 2322: k = dw_bwd_kernel<232, 2>; break;
     }
     if (!k) { fprintf(stderr, "libcdra: no depthwise kernel for cp=%d stride=%d\n", in.cp, u.stride); return; }
-    a.nbuf = 2; a.sep = (a.in_bsum != nullptr && getenv("CDRA_NO_DW_SEP") == nullptr) ? 1 : 0;
-    DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true, a.sep != 0);
-    if (L.total > kMaxDynSmem && a.sep) { a.sep = 0; L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true); }
-    if (L.total > kMaxDynSmem) { a.nbuf = 1; L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, 1, true); }
-    if (L.total > kMaxDynSmem) { fprintf(stderr, "libcdra: dw_bwd frame does not fit in shared memory (%d bytes)\n", L.total); return; }
+    a.nbuf = 2;
+    if (!dw_pick_band(in.cp, u, true, kMaxDynSmem, a.band_rows, a.nbands)) { fprintf(stderr, "libcdra: dw_bwd band does not fit in shared memory (cp=%d)\n", in.cp); return; }
+    const DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true, a.band_rows, u.stride);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
-    const int nframes = kT * a.B;
-    int gx = std::min(nframes, num_sms() * per_sm);
-    a.frames_per_cta = (nframes + gx - 1) / gx;
-    gx = (nframes + a.frames_per_cta - 1) / a.frames_per_cta;
+    const int nitems = kT * a.B * a.nbands;
+    int gx = std::min(nitems, num_sms());
+    a.frames_per_cta = (nitems + gx - 1) / gx;
+    gx = (nitems + a.frames_per_cta - 1) / a.frames_per_cta;
     prof_bytes(4.0 * a.B * (2.0 * u.Hi * u.Wi + 2.0 * u.Ho * u.Wo) * (in.n0 + in.n1) * 2);
     CDRA_LAUNCH_PDL(k, dim3(gx), dim3(kDwThreads), L.total, c.stream, a);
 }

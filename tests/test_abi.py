@@ -39,7 +39,7 @@ def test_cuda_library_exports_every_symbol(built_libs):
     assert l2.cdra_arena_size(plan, _lib.ARENA_VAL_PARAMS) == 269828
     assert l2.cdra_plan_workspace_bytes(plan) > 0
     # every BASELINE geometry plans on the host: config 2 (90x120), config 4 (180x240: stage-1 frames exceed shared memory,
-    # the plan falls back to the row-sweep bf16 tower and needs no winner-position / dR hand-off buffers), odd sizes
+    # the depthwise kernels band them), odd sizes
     sizes = {}
     for (h, w) in ((90, 120), (180, 240), (91, 123)):
         pl = ctypes.c_void_p()

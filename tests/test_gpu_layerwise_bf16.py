@@ -290,6 +290,30 @@ def test_every_bf16_layer_matches_the_oracle(built_libs, weights):
     assert C.rel_l2(eng.d_x512, x512.grad) < 2e-3
 
 
+@pytest.mark.parametrize('band', [3, 2])
+def test_banded_depthwise_matches_the_oracle(built_libs, band):
+    """The depthwise kernels work on row bands of a frame when it does not fit shared memory (180x240, BASELINE config 4):
+    the test switch forces `band`-row bands on the 90x120 frames, where every layer is compared with the layer oracle at the
+    same tolerances as the whole-frame kernels (halo rows re-read across bands, out-of-frame tile rows re-zeroed, each
+    input row's gradient and each output row's weight-gradient share counted exactly once)."""
+    from cdra import _lib
+    lib = _lib.load()
+    B = 8
+    dyn, pol, val = C.trained_params(torch.float64)
+    eng = _engine(B)
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = _dev(C.synthetic_obs(B, H, W, seed=101)), _dev(C.synthetic_batch(B, seed=102))
+    assert lib.cdra_debug_set(b'dw_band', band) == 0
+    try:
+        sc = C.policy_step_engine(eng, obs, bt).cpu()
+        torch.cuda.synchronize()
+        assert torch.isfinite(sc[:10]).all()
+        rep = _layerwise(eng, dyn, obs)
+    finally:
+        lib.cdra_debug_set(b'dw_band', 0)
+    _assert_report(rep, f'B={B} trained weights, depthwise bands of {band} rows')
+
+
 def test_full_size_layer_slice_bf16(built_libs):
     """BASELINE config-2 minibatch (B = 512): the same per-layer comparison on one slice of rows of one stage-1, one
     stage-2 and one stage-3 pointwise layer (forward output, stored input gradient) -- the grids, tile schedules and TMA ring

@@ -333,8 +333,8 @@ def test_pointwise_wgrad_tcgen05_vs_mma(built_libs):
 
 
 def test_high_res_tower_bf16(built_libs, params):
-    """BASELINE config 4 geometry (180x240): stage-1 frames exceed shared memory, so the plan routes the bf16 tower through
-    the row-sweep kernels; perf mode must still track the fp32 parity mode of the same weights"""
+    """BASELINE config 4 geometry (180x240): stage-1 frames exceed shared memory, so the depthwise kernels work on row BANDS
+    of a frame (halo rows re-read, out-of-frame tile rows re-zeroed per band); perf mode must track the fp32 parity mode"""
     B, h, w = 2, 180, 240
     dyn, pol, val = C.trained_params(torch.float64)
     obs, bt = _dev(C.synthetic_obs(B, h, w, seed=81)), _dev(C.synthetic_batch(B, seed=82))
