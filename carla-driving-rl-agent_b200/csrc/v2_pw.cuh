@@ -80,6 +80,15 @@ CDRA_DEV bool pw_col(const PwDesc& d, int j, int& plane, int& slot, int& layer, 
     return true;
 }
 
+// The launch's descriptor copied once into (dynamic) shared memory: every role reads its fields many times, and each
+// dependent read of the global copy costs an L2 round trip in the kernels' prologues.  Ends with a CTA barrier.
+static_assert(sizeof(PwDesc) <= 504 && sizeof(PwDesc) % 4 == 0, "PwDesc must fit the 504 bytes the kernels reserve at offset 520 of their header");
+CDRA_DEV const PwDesc& pw_desc_to_smem(const PwDesc* g, void* s) {
+    for (int i = threadIdx.x; i < (int)(sizeof(PwDesc) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(s)[i] = reinterpret_cast<const uint32_t*>(g)[i];
+    __syncthreads();
+    return *reinterpret_cast<const PwDesc*>(s);
+}
+
 // ---- bf16 operand matrices in slot order, rebuilt at the start of every forward (weights change every SGD step)
 constexpr int kPrepMax = 36;
 struct PrepArgs { PwDesc d[kPrepMax]; int n; };

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     constexpr int HR = R / 2;                           // rows per epilogue half
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const PwDesc& d = *a.d;
+    const PwDesc& d = pw_desc_to_smem(a.d, smem + 520);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
     const int NP = d.NPall, gwp = d.cols.gwp, nplanes = d.cols.nplanes, nsrc = d.nsrc, cpo = a.cpo;

@@ -61,7 +61,7 @@ template <int D>       // D: K blocks in flight per producer thread (ring depth 
 __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a, const int ares) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const PwDesc& d = *a.d;
+    const PwDesc& d = pw_desc_to_smem(a.d, smem + 520);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
     const int KP = d.KP, NPall = d.NPall, nsrc = d.nsrc, S = a.nbuf, Rt = a.Rt;
@@ -325,7 +325,7 @@ template <int D>
 __global__ void __launch_bounds__(kGThreads, 1) pwg_dgrad_kernel(const PwBwdArgs a, const int ares) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const PwDesc& d = *a.d;
+    const PwDesc& d = pw_desc_to_smem(a.d, smem + 520);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
     const int KP = d.KP, NP = d.NPall, gwp = d.cols.gwp, S = a.nbuf, Rt = a.Rt, cpo = a.cpo;
@@ -623,7 +623,7 @@ template <int D>
 __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const PwDesc& d = *a.d;
+    const PwDesc& d = pw_desc_to_smem(a.d, smem + 520);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
     const int KP = d.KP, NP = d.NPall, nsrc = d.nsrc, S = a.nbuf, Rt = a.Rt;
