@@ -57,6 +57,7 @@ def parse():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--e2e-profile', action='store_true', help='print a torch.profiler table of one agent update (stderr)')
     ap.add_argument('--cpu-batch', type=int, default=32)
     a = ap.parse_args()
     if a.config:
@@ -405,6 +406,12 @@ def e2e_agent_leg(args, torch, dist, dev, world, rank, n_steps, barrier):
         return agent.statistics.last
 
     run()                                              # warm-up (allocations, first-use costs)
+    if getattr(args, 'e2e_profile', False) and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            run()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=60), file=sys.stderr)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
