@@ -314,6 +314,32 @@ def test_banded_depthwise_matches_the_oracle(built_libs, band):
     _assert_report(rep, f'B={B} trained weights, depthwise bands of {band} rows')
 
 
+@pytest.mark.parametrize('route', ['fused=0', 'pwg=0', 'tc=0', 'fwd_tc=0'])
+def test_every_kernel_route_matches_the_oracle(built_libs, route):
+    """The library keeps alternative kernels for every pointwise layer (test switches of `cdra_debug_set`): `fused=0` = separate
+    data-gradient (mma.sync) + tcgen05 weight-gradient kernels with the dR hand-off instead of the fused backward, `pwg=0` = the
+    stage-3 / head layers on those kernels instead of the tcgen05 GEMM family, `tc=0` = mma.sync everywhere, `fwd_tc=0` =
+    mma.sync forward.  Each route is held to the SAME per-layer oracle tolerances as the default one (this replaces the
+    round-1 chained kernel-vs-kernel comparison and its 0.15 / 0.5 bounds)."""
+    from cdra import _lib
+    lib = _lib.load()
+    key, val_ = route.split('=')
+    B = 8
+    dyn, pol, val = C.trained_params(torch.float64)
+    eng = _engine(B)
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = _dev(C.synthetic_obs(B, H, W, seed=101)), _dev(C.synthetic_batch(B, seed=102))
+    assert lib.cdra_debug_set(key.encode(), int(val_)) == 0
+    try:
+        sc = C.policy_step_engine(eng, obs, bt).cpu()
+        torch.cuda.synchronize()
+        assert torch.isfinite(sc[:10]).all()
+        rep = _layerwise(eng, dyn, obs)
+    finally:
+        lib.cdra_debug_set(key.encode(), -1)
+    _assert_report(rep, f'B={B} trained weights, kernel route {route}')
+
+
 def test_full_size_layer_slice_bf16(built_libs):
     """BASELINE config-2 minibatch (B = 512): the same per-layer comparison on one slice of rows of one stage-1, one
     stage-2 and one stage-3 pointwise layer (forward output, stored input gradient) -- the grids, tile schedules and TMA ring

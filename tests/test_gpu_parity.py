@@ -300,38 +300,6 @@ def test_tcgen05_selftest(built_libs, shape):
     assert ((Cm.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
 
 
-def test_pointwise_wgrad_tcgen05_vs_mma(built_libs):
-    """the TMEM-resident tcgen05 weight-gradient kernel against the mma.sync kernel on the same saved activations:
-    every pointwise weight / gamma / beta gradient of the tower (all layers but the 464->768 head use tcgen05)"""
-    from cdra import _lib
-    lib = _lib.load()
-    B = 8
-    dyn, pol, val = C.trained_params(torch.float64)
-    eng = _engine(B, 'bf16')
-    C.load_engine(eng, dyn, pol, val)
-    obs, bt = _dev(C.synthetic_obs(B, H, W, seed=71)), _dev(C.synthetic_batch(B, seed=72))
-    x = eng.dynamics_forward(obs)
-    eng.policy_head(x, bt['actions'], bt['logp_old'], bt['adv'], bt['true_speed'], bt['true_sim'], 0.2, 1.0)
-    grads = {}
-    try:
-        for tc in (1, 0):
-            assert lib.cdra_debug_set(b'tc', tc) == 0
-            eng.dynamics_backward(obs, eng.d_x512)
-            torch.cuda.synchronize()
-            grads[tc] = eng.dyn.to_dict(eng.g_dyn.clone())
-    finally:
-        lib.cdra_debug_set(b'tc', -1)
-    worst = 0.0
-    for k, g in grads[0].items():
-        if not (k.startswith('tower.') and ('.pw' in k or '.scpw' in k or k.startswith('tower.head'))) or g.abs().max().item() < 1e-12:
-            continue
-        e = C.rel_l2(grads[1][k], g)
-        worst = max(worst, e)
-        # the last unit sees identical inputs in both runs (same bf16 operands, fp32 accumulation in a different order);
-        # further upstream the run-to-run order of the fp64 / bf16 atomics already moves the gradients by a few 1e-3
-        assert e < (2e-3 if k.startswith('tower.s3.u3') else (0.15 if k.endswith('.w') else 0.5)), (k, e)
-
-
 def test_high_res_tower_bf16(built_libs, params):
     """BASELINE config 4 geometry (180x240): stage-1 frames exceed shared memory, so the depthwise kernels work on row BANDS
     of a frame (halo rows re-read, out-of-frame tile rows re-zeroed per band); perf mode must track the fp32 parity mode"""
