@@ -126,6 +126,7 @@ struct V2Plan {
     int stem_fwd_hb = 0, stem_bwd_hb = 0, pool_pb = 0;
     mutable std::vector<char> host_descs_buf;
     void* host_descs = nullptr;
+    mutable const char* desc_ws[2] = {nullptr, nullptr};    // workspace whose (forward, backward) descriptor copies match host_descs
 };
 
 struct Plan {

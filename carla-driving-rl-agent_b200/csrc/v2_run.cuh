@@ -97,16 +97,25 @@ inline PwDesc desc_head(const RunCtx& c) {
     return d;
 }
 
-inline size_t desc_slot(const Plan& p, int i) { return p.v2.desc_off + (size_t)i * sizeof(PwDesc); }
+// the forward (no gradient pointers) and the backward descriptor sets live side by side in the workspace, so that neither
+// call invalidates the other's device copy
+inline size_t desc_slot(const Plan& p, int i, int which) { return p.v2.desc_off + (size_t)which * 32768 + (size_t)i * sizeof(PwDesc); }
 // launch index: 2*ui = pw1, 2*ui+1 = tail, 2*nunits = head
-inline const PwDesc* desc_dev(const RunCtx& c, int i) { return (const PwDesc*)(c.ws + desc_slot(*c.p, i)); }
+inline const PwDesc* desc_dev(const RunCtx& c, int i) { return (const PwDesc*)(c.ws + desc_slot(*c.p, i, c.grads ? 1 : 0)); }
 
 inline void upload_descs(const RunCtx& c) {
-    const Plan& p = *c.p; const int nu = (int)p.v2.u.size(), n = 2 * nu + 1;
+    const Plan& p = *c.p; const int nu = (int)p.v2.u.size(), n = 2 * nu + 1, which = c.grads ? 1 : 0;
+    static_assert(3 * kPrepMax * sizeof(PwDesc) <= 64 * 1024 && kPrepMax * sizeof(PwDesc) <= 32768, "descriptor buffers");
     PwDesc* host = (PwDesc*)p.v2.host_descs;
+    PwDesc* prev = host + (1 + which) * kPrepMax;    // what the device copy of this set holds
     for (int ui = 0; ui < nu; ++ui) { host[2 * ui] = desc_pw1(c, ui); host[2 * ui + 1] = desc_tail(c, ui); }
     host[2 * nu] = desc_head(c);
-    cudaMemcpyAsync(c.ws + p.v2.desc_off, host, (size_t)n * sizeof(PwDesc), cudaMemcpyHostToDevice, c.stream);
+    // the descriptors only hold pointers into the caller's arenas / workspace: with the same buffers as in the previous call
+    // of the same kind (every SGD step after the first) the device copy is already right
+    if (p.v2.desc_ws[which] == c.ws && memcmp(prev, host, (size_t)n * sizeof(PwDesc)) == 0) return;
+    memcpy(prev, host, (size_t)n * sizeof(PwDesc));
+    p.v2.desc_ws[which] = c.ws;
+    cudaMemcpyAsync(c.ws + desc_slot(p, 0, which), prev, (size_t)n * sizeof(PwDesc), cudaMemcpyHostToDevice, c.stream);
 }
 
 constexpr int kMaxDynSmem = 226 * 1024;      // 227 KB opt-in limit minus the kernels' few static bytes

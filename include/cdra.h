@@ -8,7 +8,9 @@
  *   - all tensor arguments are raw DEVICE pointers owned by the caller (torch.Tensor.data_ptr());
  *     `stream` is a cudaStream_t passed as void*.  All work is enqueued asynchronously on it.
  *   - the library allocates nothing after cdra_plan_create; scratch memory is one caller-owned
- *     workspace of cdra_plan_workspace_bytes() bytes that must be zeroed once before first use.
+ *     workspace of cdra_plan_workspace_bytes() bytes that must be zeroed once before first use and then
+ *     belongs to the plan: the library keeps launch descriptors in it across calls (re-uploaded only when an
+ *     arena pointer changes), so use ONE workspace per plan and do not overwrite or re-create it in between.
  *   - a plan is thread-compatible, not thread-safe: one plan per (process, device).
  */
 #ifndef CDRA_H_
