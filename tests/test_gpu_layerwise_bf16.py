@@ -80,7 +80,7 @@ def _layerwise(eng, dyn, obs):
     rep = {'fwd': {}, 'grad': {}, 'pgrad': {}, 'exact': {}, 'sums': {}}
     B = eng.B
     img = obs['state_image'].cpu()                                   # [B,4,H,W,3] u8
-    frames = img.permute(1, 0, 2, 3, 4).reshape(4 * B, H, W, 3).double()
+    frames = img.permute(1, 0, 2, 3, 4).reshape(4 * B, img.shape[2], img.shape[3], 3).double()
 
     def rel(a, b):
         return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
@@ -312,6 +312,22 @@ def test_banded_depthwise_matches_the_oracle(built_libs, band):
     finally:
         lib.cdra_debug_set(b'dw_band', 0)
     _assert_report(rep, f'B={B} trained weights, depthwise bands of {band} rows')
+
+
+def test_high_res_geometry_matches_the_oracle(built_libs):
+    """BASELINE config 4 geometry (180x240): the stage-1 frames do not fit shared memory, the depthwise kernels band them on
+    their own (no test switch), the stem / pool kernels run more bands; every layer against the layer oracle at the same
+    tolerances as at 90x120."""
+    B, h, w = 2, 180, 240
+    dyn, pol, val = C.trained_params(torch.float64)
+    eng = _engine(B, h, w)
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = _dev(C.synthetic_obs(B, h, w, seed=121)), _dev(C.synthetic_batch(B, seed=122))
+    sc = C.policy_step_engine(eng, obs, bt).cpu()
+    torch.cuda.synchronize()
+    assert torch.isfinite(sc[:10]).all()
+    rep = _layerwise(eng, dyn, obs)
+    _assert_report(rep, f'B={B} trained weights, 180x240 frames')
 
 
 @pytest.mark.parametrize('route', ['fused=0', 'pwg=0', 'tc=0', 'fwd_tc=0'])
