@@ -40,6 +40,7 @@ _SIGNATURES = {
     'cdra_debug_umma_selftest_k': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     'cdra_debug_umma_selftest': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     'cdra_debug_set': (C.c_int, [C.c_char_p, C.c_int]),
+    'cdra_debug_timeline': (C.c_int, [_P]),
     'cdra_debug_stem_backward': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     'cdra_dynamics_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     'cdra_dynamics_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -910,6 +910,19 @@ int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t r
     return check_launch("gather_rows");
 }
 
+int cdra_debug_timeline(uint64_t* out32) {
+    if (!out32) return fail(CDRA_ERR_BADARG, "null argument");
+#ifndef CDRA_EMU
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, v2::g_pwg_ts, 16 * 8);
+    cudaMemcpyFromSymbol(out32 + 16, v2::g_bf_ts, 16 * 8);
+    return check_launch("debug_timeline");
+#else
+    for (int i = 0; i < 32; ++i) out32[i] = 0;
+    return CDRA_OK;
+#endif
+}
+
 int cdra_augment(const void* image, int image_u8, int64_t frames, int height, int width, const cdra_augment_params* params,
                  const uint8_t* dropout_mask, float* out, void* scratch, void* stream) {
 #ifdef CDRA_EMU

@@ -62,6 +62,7 @@ struct PwBwdArgs {
     // the tile anyway), consumed by the tcgen05 weight-gradient kernel, which then needs no transform of its own
     bf16* dr;
     GBlock blk[kGMaxBlk]; int nblk;   // v4_pwg.cuh: blockIdx.y = M block
+    int timeline;                     // record the role timeline of block 0 (cdra_debug_timeline)
 };
 
 struct PwDgradSmem { int colc, srcc, x1c, stat, w, raw, dr, st, st2, total, raw_stride, ldr, ldw, lds, lds2; };

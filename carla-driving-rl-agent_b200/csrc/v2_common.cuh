@@ -172,13 +172,18 @@ CDRA_DEV void bn_finalize_channel(const Tables& tb, int cp, int slot, const Laye
     const float g = L.g[n_logical], b = L.be[n_logical];
     float mm = L.mm ? L.mm[n_logical] : 0.f, mv = L.mv ? L.mv[n_logical] : 1.f;
     const float mm0 = mm, mv0 = mv;
+    // this runs in the LAST CTA while the rest of the GPU idles: all four slices' sums are fetched before any arithmetic, so
+    // the L2 round trips overlap instead of alternating with the double-precision math
+    double2 s[kT];
+#pragma unroll
+    for (int t = 0; t < kT; ++t) s[t] = training ? ld_sum(tb.fsum + (size_t)t * cp + slot) : make_double2(0.0, 0.0);
+#pragma unroll
     for (int t = 0; t < kT; ++t) {
         BnFin f;
         if (training) {
-            const double2 s = ld_sum(tb.fsum + (size_t)t * cp + slot);
-            f = bn_from_sums(s.x, s.y, n, g, b);
-            const double mean = s.x / n;
-            double var = s.y / n - mean * mean;
+            f = bn_from_sums(s[t].x, s[t].y, n, g, b);
+            const double mean = s[t].x / n;
+            double var = s[t].y / n - mean * mean;
             if (var < 0.0) var = 0.0;
             const double vm = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
             mm -= (mm - (float)mean) * (1.f - kBnMomentum);

@@ -149,6 +149,7 @@ struct PwFwdArgs {
     int tiles_per_cta;
     int nbuf;                   // tcgen05 kernel: depth of the TMA ring
     GBlock blk[kGMaxBlk]; int nblk;   // v4_pwg.cuh: blockIdx.y = M block
+    int timeline;                     // record the role timeline of block (0, 0) (cdra_debug_timeline)
 };
 
 template <int R, int WM, int WN, int MT, int NBW>

@@ -129,6 +129,7 @@ inline int& pwg_override() { static int v = -1; return v; }     // cdra_debug_se
 inline bool use_pwg() { static const bool env = getenv("CDRA_NO_PWG") == nullptr; return pwg_override() < 0 ? env : pwg_override() != 0; }
 // the GEMM family of v4_pwg.cuh takes every pointwise launch whose reduction length reaches this (stage 3 and the head)
 inline int pwg_min_k() { static const int v = getenv("CDRA_PWG_MINK") ? atoi(getenv("CDRA_PWG_MINK")) : 192; return v; }
+inline int use_timeline() { static const int v = getenv("CDRA_TIMELINE") != nullptr; return v; }
 inline int& dw_band_cap() { static int v = 0; return v; }        // cdra_debug_set("dw_band", rows): 0 = automatic
 inline bool use_pwg_wgrad() { static const bool env = getenv("CDRA_NO_PWG_WGRAD") == nullptr; return env; }
 inline int pwg_min_k_bwd() { static const int v = getenv("CDRA_PWG_MINK_BWD") ? atoi(getenv("CDRA_PWG_MINK_BWD")) : 192; return v; }
@@ -193,16 +194,13 @@ inline bool try_pw_fwd_tc(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
 
 // shared-memory plan of a v4_pwg launch: resident weights when they leave room for >= 3 ring stages, else streamed
 inline bool pwg_plan(int kdim, int tab_bytes, int extra, int& ares, int& nstage, int& smem) {
-    ares = 1;
-    PwgSmem L0 = pwg_smem(kdim, tab_bytes, true, 128, 0, extra);
-    nstage = (kMaxDynSmem - L0.total) / L0.stage_bytes;
-    if (nstage < 3) {
-        ares = 0;
-        L0 = pwg_smem(kdim, tab_bytes, false, 128, 0, extra);
-        nstage = (kMaxDynSmem - L0.total) / L0.stage_bytes;
-        if (nstage < 3) return false;
-    }
-    nstage = std::min(nstage, kGMaxStages);
+    // bytes in flight hide the load latency (one 16 KB activation block per ring stage): resident weights only when they
+    // still leave a deep ring, else the weights stream through the ring next to the activations
+    const PwgSmem La = pwg_smem(kdim, tab_bytes, true, 128, 0, extra), Ls = pwg_smem(kdim, tab_bytes, false, 128, 0, extra);
+    const int na = std::min(kGMaxStages, (kMaxDynSmem - La.total) / La.stage_bytes);
+    const int ns = std::min(kGMaxStages, (kMaxDynSmem - Ls.total) / Ls.stage_bytes);
+    if (na >= 5 || na >= ns) { ares = 1; nstage = na; } else { ares = 0; nstage = ns; }
+    if (nstage < 3) return false;
     smem = pwg_smem(kdim, tab_bytes, ares != 0, 128, nstage, extra).total;
     return true;
 }
@@ -224,13 +222,18 @@ inline bool try_pwg_fwd(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
         }
     int ares, nstage, smem;
     if (!pwg_plan(hd.KP, ((hd.KP + 63) & ~63) * 8, 0, ares, nstage, smem)) return false;
-    static bool attr_done = (cudaFuncSetAttribute(pwg_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem),
-                             cudaFuncSetAttribute(pwg_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
-    (void)attr_done;
     a.nbuf = nstage;
+    a.timeline = use_timeline();
     int gx; pwg_grid(a.Rt, a.nblk, gx, a.tiles_per_cta);
-    if (nstage >= 5) CDRA_LAUNCH_PDL(pwg_fwd_kernel<4>, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
-    else CDRA_LAUNCH_PDL(pwg_fwd_kernel<2>, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
+    // K blocks in flight per producer thread: two ring stages of slack, so that a producer never waits for the MMA round trip
+    // (full -> tcgen05.mma -> commit -> empty) of the block it has just handed over
+    const int depth = std::max(1, std::min(4, nstage - 2));
+    auto launch = [&](auto k) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        CDRA_LAUNCH_PDL(k, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
+    };
+    if (depth == 4) launch(pwg_fwd_kernel<4>); else if (depth == 3) launch(pwg_fwd_kernel<3>);
+    else if (depth == 2) launch(pwg_fwd_kernel<2>); else launch(pwg_fwd_kernel<1>);
     if (a.x1) {       // pass-through half of a stride-1 unit
         PassFwdArgs q; q.x1 = a.x1; q.x1cp = a.x1cp; q.x1map = a.x1map; q.out[0] = a.out[0]; q.out[1] = a.out[1]; q.cpo = a.cpo;
         q.ncopy = a.ncopy; q.copy_dst0 = a.copy_dst0; q.rows = (long long)kT * a.Rt;
@@ -483,11 +486,15 @@ inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
     }
     int ares, nstage, smem;
     if (!pwg_plan(hd.NPall, ((hd.NPall + 63) & ~63) * 16, 16384, ares, nstage, smem)) return false;
-    static bool attr_done = (cudaFuncSetAttribute(pwg_dgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
-    (void)attr_done;
     a.nbuf = nstage;
     int gx; pwg_grid(a.Rt, a.nblk, gx, a.tiles_per_cta);
-    CDRA_LAUNCH_PDL(pwg_dgrad_kernel<2>, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
+    const int depth = std::max(1, std::min(4, nstage - 2));
+    auto launch = [&](auto k) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        CDRA_LAUNCH_PDL(k, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
+    };
+    if (depth == 4) launch(pwg_dgrad_kernel<4>); else if (depth == 3) launch(pwg_dgrad_kernel<3>);
+    else if (depth == 2) launch(pwg_dgrad_kernel<2>); else launch(pwg_dgrad_kernel<1>);
     for (int i = 0; i < hd.nsrc; ++i) {      // BatchNorm-backward sums of the gradients just written
         const PwSrc& Sx = hd.src[i];
         if (!Sx.bsum || Sx.sum_hi <= Sx.sum_lo) continue;
@@ -526,17 +533,18 @@ inline bool try_pwg_wgrad(const RunCtx& c, const PwBwdArgs& b, const PwDesc& hd)
     int nstage = std::min(kGMaxStages, (kMaxDynSmem - L0.total) / L0.stage_bytes);
     if (nstage < 2) return false;
     const int smem = pwg_wg_smem(hd.KP, nbk, nstage).total;
-    static bool attr_done = (cudaFuncSetAttribute(pwg_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem),
-                             cudaFuncSetAttribute(pwg_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
-    (void)attr_done;
     a.nbuf = nstage;
     const int gy = a.nblk * a.nnb;
-    const int tps = (a.Rt + kGRows - 1) / kGRows, ntile = kT * tps;
+    const int tps = (a.Rt + kWgRows - 1) / kWgRows, ntile = kT * tps;
     const int splits = std::max(1, num_sms() / gy);
     a.tiles_per_cta = (ntile + splits - 1) / splits;
     const int gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    if (nstage >= 3) CDRA_LAUNCH_PDL(pwg_wgrad_kernel<2>, dim3(gx, gy), dim3(kGThreads), smem, c.stream, a);
-    else CDRA_LAUNCH_PDL(pwg_wgrad_kernel<1>, dim3(gx, gy), dim3(kGThreads), smem, c.stream, a);
+    const int depth = std::max(1, std::min(3, nstage - 2));          // two ring stages of slack (see try_pwg_fwd)
+    auto launch = [&](auto k) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        CDRA_LAUNCH_PDL(k, dim3(gx, gy), dim3(kGThreads), smem, c.stream, a);
+    };
+    if (depth == 3) launch(pwg_wgrad_kernel<3>); else if (depth == 2) launch(pwg_wgrad_kernel<2>); else launch(pwg_wgrad_kernel<1>);
     return true;
 }
 
@@ -544,6 +552,7 @@ inline bool try_pwg_wgrad(const RunCtx& c, const PwBwdArgs& b, const PwDesc& hd)
 inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a) {
     a.d = desc_dev(c, di);
     a.out_clamp = 1;
+    a.timeline = use_timeline();
     if (use_tc() && use_fused()) {
         double fb = 0;
         for (int i = 0; i < hd.nsrc; ++i) fb += 4.0 * a.Rt * (hd.src[i].map.n0 + hd.src[i].map.n1) * 2 * (2 + hd.src[i].accumulate);    // raw src read, d src written (+ read)

@@ -29,6 +29,11 @@ namespace v2 {
 CDRA_DEV void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+CDRA_DEV void bulk_s2g_nc(void* dst, const void* src, uint32_t bytes) {      // bulk store shared -> global, not yet committed
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+CDRA_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+CDRA_DEV void bulk_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 CDRA_DEV void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 CDRA_DEV void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -40,6 +45,10 @@ CDRA_DEV void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// role timeline of block 0 (see v4_pwg.cuh / cdra_debug_timeline)
+__device__ unsigned long long g_bf_ts[16];
+CDRA_DEV unsigned long long gtimer3() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define BF_TS(i) do { if (a.timeline && blockIdx.x == 0) g_bf_ts[i] = gtimer3(); } while (0)
 constexpr int kBfThreads = 512, kBfTransformWarps = 6, kBfEpilogueWarps = 8, kBfMaxStages = 8;
 constexpr int kBfTransformThreads = kBfTransformWarps * 32, kBfEpilogueThreads = kBfEpilogueWarps * 32;
 
@@ -48,6 +57,7 @@ struct PwBfSmem {
     int stage_bytes, dr_bytes, xs_bytes, w_bytes;
     int o_dout, o_out, o_src[kMaxSrc], o_x1, o_ge[kMaxSrc], st_off[kMaxSrc];
     int mbk, np16, nkb, cols_dw, tmem_cols;
+    int st_bytes, st2_bytes;
 };
 // `cps[i]`, `acc[i]`: slots / accumulate flag of source i
 inline __host__ __device__ PwBfSmem pw_bf_smem(int R, int nsrc, const int* cps, const int* acc, int NPall, int nplanes, int cpo, int x1cp, int nstage) {
@@ -75,9 +85,10 @@ inline __host__ __device__ PwBfSmem pw_bf_smem(int R, int nsrc, const int* cps, 
     s.w = off; off += s.w_bytes;
     s.dr = off; off += 2 * s.dr_bytes;
     s.xs = off; off += 2 * s.xs_bytes;
-    s.st = off;
-    { int o = 0; for (int i = 0; i < kMaxSrc; ++i) { s.st_off[i] = o; if (i < nsrc) o += R * cps[i] * 2; } off += (o + 127) & ~127; }
-    s.st2 = off; off += (R * x1cp * 2 + 127) & ~127;
+    s.st = off;                                         // gradient rows staged for the bulk stores: DOUBLE buffered (the stores of tile i
+    { int o = 0; for (int i = 0; i < kMaxSrc; ++i) { s.st_off[i] = o; if (i < nsrc) o += R * cps[i] * 2; } s.st_bytes = (o + 127) & ~127; off += 2 * s.st_bytes; }     // read buffer i & 1 while tile i + 1 fills the other)
+    s.st2_bytes = (R * x1cp * 2 + 127) & ~127;
+    s.st2 = off; off += 2 * s.st2_bytes;
     off = (off + 1023) & ~1023;
     s.ring = off;
     { int ring = nstage * s.stage_bytes; const int scratch = 128 * 65 * 4; if (ring < scratch) ring = scratch; off += ring; }   // doubles as the dW transposition tile
@@ -91,6 +102,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     constexpr int HR = R / 2;                           // rows per epilogue half
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    if (threadIdx.x == 0) BF_TS(0);
     const PwDesc& d = pw_desc_to_smem(a.d, smem + 520);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
@@ -153,7 +165,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    if (tid == 0) BF_TS(1);
     pdl_wait();                                         // everything above read only this launch's descriptor / prepared weights
+    if (tid == 0) BF_TS(2);
 
     // tile cursor: (slice, first row, rows) and (ring stage, ring phase) advance incrementally -- no divisions in the loops
     struct Cursor { int t, r0, s, k; };
@@ -192,6 +206,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, n = it >> 1;
                 mbar_wait(&stg_full[b], n & 1);
+                if (it == 0) BF_TS(4); if (it == 8) BF_TS(10);
                 mbar_wait(&tm_empty[b], (n & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t ra = smem_u32(smem + L.dr + (size_t)b * L.dr_bytes), xa = smem_u32(smem + L.xs + (size_t)b * L.xs_bytes);
@@ -248,6 +263,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 cur_t = t;
             }
             mbar_wait(&full[s], k & 1);
+            if (ttid == 0 && it == 0) BF_TS(3);
             mbar_wait(&stg_empty[b], (n & 1) ^ 1);
             const unsigned char* rb = ring + (size_t)s * stage_bytes;
             unsigned char* Dr = smem + o_dr + (size_t)b * dr_bytes;
@@ -331,7 +347,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 off += cp;
             }
         }
-        const int cols_dw = L.cols_dw, o_dout = L.o_dout, o_x1 = L.o_x1, o_st = L.st, o_st2 = L.st2, stage_bytes = L.stage_bytes;
+        const int cols_dw = L.cols_dw, o_dout = L.o_dout, o_x1 = L.o_x1, stage_bytes = L.stage_bytes;
+        int o_st = L.st, o_st2 = L.st2;                   // this tile's staging buffers (alternate per tile)
         // pass-through role: thread <-> x1 slot
         int x_src = -1;                                 // element offset inside the d out region of a stage, -2: padding (zero), -1: no role
         if (x1cp && etid < x1cp) {
@@ -396,13 +413,16 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 cur_t = t;
             }
             // the previous tile's bulk stores have finished READING the staging rows
-            if (etid == 0) bulk_store_wait_read();
+            o_st = L.st + (it & 1) * L.st_bytes; o_st2 = L.st2 + (it & 1) * L.st2_bytes;
+            if (etid == 0) bulk_store_wait_read1();        // the stores of tile it - 2 (same buffers) have finished READING them
             named_bar_sync(1, kBfEpilogueThreads);
             mbar_wait(&full[s], k & 1);                 // (long complete: acquires the TMA writes for this thread)
             mbar_wait(&tm_full[b], n & 1);
+            if (etid == 0 && it == 0) BF_TS(5);
             tc_fence_after();
             const unsigned char* rb = ring + (size_t)s * stage_bytes;
             run_chan(b, rows, rb);
+            if (etid == 0 && it == 0) BF_TS(6);
             tc_fence_before();
             // pass-through half of a stride-1 unit: d x1[slot(2i + p)] = d out_p[copy_dst0 + i]   (bit-exact gather)
             if (x_src != -1) {
@@ -424,10 +444,12 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 const size_t row = (size_t)t * a.Rt + r0;
 #pragma unroll
                 for (int i = 0; i < kMaxSrc; ++i)
-                    if (g_ptr[i]) bulk_s2g(g_ptr[i] + row * g_cp[i], smem + o_st + g_off[i], (uint32_t)rows * g_cp[i] * 2);
-                if (x1cp) bulk_s2g(a.dx1 + row * x1cp, smem + o_st2, (uint32_t)rows * x1cp * 2);
+                    if (g_ptr[i]) bulk_s2g_nc(g_ptr[i] + row * g_cp[i], smem + o_st + g_off[i], (uint32_t)rows * g_cp[i] * 2);
+                if (x1cp) bulk_s2g_nc(a.dx1 + row * x1cp, smem + o_st2, (uint32_t)rows * x1cp * 2);
+                bulk_commit();                          // ONE bulk group per tile
             }
         }
+        if (etid == 0) BF_TS(7);
         if (cur_t >= 0) flush(cur_t);
         if (etid == 0) bulk_store_wait_all();
     }
@@ -435,6 +457,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     // ================================================================ all roles: weight-gradient epilogue
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) BF_TS(8);
     tc_fence_after();
     if (my_tiles > 0) {
         float* Sc = reinterpret_cast<float*>(ring);        // [128][65]
@@ -472,6 +495,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) BF_TS(9);
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
     // ---- BatchNorm parameter gradients (one CTA): dgamma = sum_t S2, dbeta = sum_t S1
     if (blockIdx.x == 0) {
@@ -482,6 +506,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
             for (int t = 0; t < kT; ++t) { const double2 v = ld_sum(a.tb[p].bsum + (size_t)t * cpo + sl); bs += v.x; gs += v.y; }
             d.layer[l].dg[nn] = (float)gs; d.layer[l].dbe[nn] = (float)bs;
         }
+        __syncthreads();
+        if (tid == 0) BF_TS(11);
     }
 }
 

@@ -55,12 +55,18 @@ inline __host__ __device__ PwgSmem pwg_smem(int kdim, int tab_bytes, bool ares, 
 }
 
 struct GCur { int it, kb, t, r0; };
+// role timeline of block (0, 0) in %globaltimer nanoseconds, recorded when the launch was made with CDRA_TIMELINE=1 and read
+// back by cdra_debug_timeline (profiles/pwg_timeline_probe.py): where a launch's time goes between the roles' hand-offs
+__device__ unsigned long long g_pwg_ts[16];
+CDRA_DEV unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PWG_TS(i) do { if (a.timeline && blockIdx.x == 0 && blockIdx.y == 0) g_pwg_ts[i] = gtimer(); } while (0)
 
 // ======================================================================================== forward
 template <int D>       // D: K blocks in flight per producer thread (ring depth >= D + 1)
 __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a, const int ares) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    if (threadIdx.x == 0) PWG_TS(0);
     const PwDesc& d = pw_desc_to_smem(a.d, smem + 520);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
@@ -110,11 +116,13 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    if (tid == 0) PWG_TS(1);
     if (ares && tid == 32) {                            // resident weights (prepared long before this launch)
         mbar_expect_tx(a_full, (uint32_t)nkb * gb.n * 128);
         for (int kb = 0; kb < nkb; ++kb) bulk_g2s(As + (size_t)kb * 16384, d.wfs + ((size_t)kb * NPall + gb.base) * 64, gb.n * 128, a_full);
     }
     pdl_wait();
+    if (tid == 0) PWG_TS(2);
 
     auto advance = [&](GCur& c) { if (++c.kb == nkb) { c.kb = 0; ++c.it; c.r0 += kGRows; if (c.r0 >= Rt) { c.r0 = 0; ++c.t; } } };
 
@@ -123,6 +131,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(128, kGRows, 0, 0);
             if (ares) mbar_wait(a_full, 0);
+            PWG_TS(3);
             int s = 0, ph = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1;
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
                 tc_fence_after();
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[s], ph);
+                    if (it == 0 && kb == 0) PWG_TS(4);
                     tc_fence_after();
                     const uint32_t sb = smem_u32(ring + (size_t)s * stage_bytes);
                     const uint32_t aa = ares ? smem_u32(As) + (uint32_t)kb * 16384u : sb, ba = ares ? sb : sb + 16384u;
@@ -221,6 +231,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
+
             if (++s == S) s = 0;
             advance(pc);
         }
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
             const int b = it & 1, rows = min(kGRows, Rt - r0);
             if (t != cur_t) { if (cur_t >= 0) flush(cur_t); cur_t = t; }
             mbar_wait(&tm_full[b], (it >> 1) & 1);
+            if (et == 0 && it == 0) PWG_TS(5);
             tc_fence_after();
             named_bar_sync(1, kGEpiThreads);               // the previous tile's rows have left the staging tile
             const uint32_t taddr = tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(b * kGRows);
@@ -278,17 +290,22 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
                     for (int w = 0; w < ntail; ++w)
                         *reinterpret_cast<uint32_t*>(orow + (size_t)r * cpo + cc * 8 + 2 * w) = *reinterpret_cast<const uint32_t*>(St + r * stw + cc * 8 + 2 * w);
             }
+            if (et == 0 && it == 0) PWG_TS(6);
             r0 += kGRows; if (r0 >= Rt) { r0 = 0; ++t; }
         }
+        if (et == 0) PWG_TS(7);
         if (cur_t >= 0) flush(cur_t);
+        if (et == 0) PWG_TS(8);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) PWG_TS(9);
     if (warp == 0) tmem_dealloc(tmem, 2 * kGRows);
     // ---- last CTA: BatchNorm tables of every output channel (+ the pass-through slots' tables)
     if (a.counter == nullptr) return;
     if (!last_cta(a.counter, gridDim.x * gridDim.y)) return;
+    if (tid == 0 && a.timeline) g_pwg_ts[10] = gtimer();
     for (int j = tid; j < NPall; j += kGThreads) {
         int p, s, l, n;
         if (pw_col(d, j, p, s, l, n)) bn_finalize_channel(a.tb[p], a.cpo, s, d.layer[l], n, (double)Rt, a.training);
@@ -304,6 +321,8 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
             a.tb[p].bnp[(size_t)t * a.cpo + a.copy_dst0 + c] = a.x1bnp ? a.x1bnp[(size_t)t * a.x1cp + ss] : make_float2(0.f, 1.f);
         }
     }
+    __syncthreads();
+    if (tid == 0 && a.timeline) g_pwg_ts[11] = gtimer();
 }
 
 // pass-through half of a stride-1 unit (core/architectures.py:142-144): out_p[n0p + i] = x1[logical 2i + p], bit exact
@@ -598,6 +617,8 @@ __global__ void __launch_bounds__(256) bsum_kernel(const BsumArgs a) {
 // (v2_umma.cuh), so the producers are the forward's (cp.async + in-place BatchNorm affine / ReLU6 for act(src)) plus a
 // plain copy of the dR hand-off matrix the data-gradient kernel left.  The accumulator stays in TMEM for the CTA's life;
 // the epilogue transposes it through shared memory and adds it to the fp32 gradient arena with coalesced atomics.
+constexpr int kWgRows = 64;            // rows per ring stage of the weight gradient (4 tcgen05.mma K steps): small stages, so that the
+                                       // ring is deep enough for the producers never to wait for an MMA round trip
 struct PwgWgSmem { int ck, tab, maps, ring, total, stage_bytes; };
 inline __host__ __device__ PwgWgSmem pwg_wg_smem(int KP, int nbk, int nstage) {
     PwgWgSmem s;
@@ -606,7 +627,7 @@ inline __host__ __device__ PwgWgSmem pwg_wg_smem(int KP, int nbk, int nstage) {
     s.tab = off; off += ((KP + 63) & ~63) * 8;
     s.maps = off; off += (128 + 256) * 4;
     off = (off + 1023) & ~1023;
-    s.stage_bytes = (2 + nbk) * 16384;
+    s.stage_bytes = (2 + nbk) * kWgRows * 128;
     s.ring = off; off += nstage * s.stage_bytes;
     s.total = off + 1024;
     return s;
@@ -631,7 +652,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
     const GBlock gb = a.blk[mbi];
     const int j_lo = nbi * 256, ncol = min(256, NP - j_lo), nbk = (ncol + 63) >> 6, npad = nbk * 64;
     const PwgWgSmem L = pwg_wg_smem(KP, (min(256, NP) + 63) >> 6, S);
-    const int stage_bytes = (2 + ((min(256, NP) + 63) >> 6)) * 16384;
+    const int stage_bytes = (2 + ((min(256, NP) + 63) >> 6)) * kWgRows * 128;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + kGMaxStages;
     uint64_t* acc_full = empty + kGMaxStages;
@@ -642,10 +663,10 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
     int* s_cmap = s_rmap + 128;
     unsigned char* ring = smem + L.ring;
 
-    const int tps = (Rt + kGRows - 1) / kGRows, ntile = kT * tps;
+    const int tps = (Rt + kWgRows - 1) / kWgRows, ntile = kT * tps;
     const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(ntile, tile_lo + a.tiles_per_cta);
     const int my_tiles = max(0, tile_hi - tile_lo);
-    const int t_first = tile_lo / tps, r_first = (tile_lo - t_first * tps) * kGRows;
+    const int t_first = tile_lo / tps, r_first = (tile_lo - t_first * tps) * kWgRows;
 
     if (warp == 0) tmem_alloc(s_tmem, 256);
     if (tid == 32) {
@@ -682,10 +703,10 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
             for (int it = 0; it < my_tiles; ++it) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes), sb = sa + 32768u;
+                const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes), sb = sa + 2u * kWgRows * 128u;
 #pragma unroll
-                for (int ks = 0; ks < kGRows / 16; ++ks)
-                    umma_bf16(tmem, umma_desc(sa + ks * 2048, kGRows * 128, 1024), umma_desc(sb + ks * 2048, kGRows * 128, 1024), idesc, (it | ks) != 0);
+                for (int ks = 0; ks < kWgRows / 16; ++ks)
+                    umma_bf16(tmem, umma_desc(sa + ks * 2048, kWgRows * 128, 1024), umma_desc(sb + ks * 2048, kWgRows * 128, 1024), idesc, (it | ks) != 0);
                 umma_commit(&empty[s]);
                 if (++s == S) { s = 0; ph ^= 1; }
             }
@@ -704,7 +725,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
         int lt = t_first, lr0 = r_first;                // issue cursor
         auto issue = [&]() {
             mbar_wait(&empty[is], iph ^ 1);
-            const int rows = min(kGRows, Rt - lr0);
+            const int rows = min(kWgRows, Rt - lr0);
             unsigned char* st = ring + (size_t)is * stage_bytes + swz + rl * 128;
             const size_t row = (size_t)lt * Rt + lr0 + rl;
 #pragma unroll
@@ -714,22 +735,22 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
                 const int cp = si <= 0 ? cp0 : (si == 1 ? cp1 : cp2);
                 const bf16* base = sp + row * cp + (e >= 0 ? (e & 0xffff) : 0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < kWgRows / 32; ++i) {
                     const bool ok = e >= 0 && rl + 32 * i < rows;
-                    cp_async16(st + b * 16384 + i * 32 * 128, ok ? base + (size_t)(32 * i) * cp : sp0, ok);
+                    cp_async16(st + b * (kWgRows * 128) + i * 32 * 128, ok ? base + (size_t)(32 * i) * cp : sp0, ok);
                 }
             }
             for (int b = 0; b < nbk; ++b) {
                 const int j0 = j_lo + b * 64 + c * 8;
                 const bf16* base = a.dr + row * NP + j0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < kWgRows / 32; ++i) {
                     const bool ok = j0 < NP && rl + 32 * i < rows;
-                    cp_async16(st + 32768 + b * 16384 + i * 32 * 128, ok ? base + (size_t)(32 * i) * NP : a.dr, ok);
+                    cp_async16(st + (2 + b) * (kWgRows * 128) + i * 32 * 128, ok ? base + (size_t)(32 * i) * NP : a.dr, ok);
                 }
             }
             if (++is == S) { is = 0; iph ^= 1; }
-            lr0 += kGRows; if (lr0 >= Rt) { lr0 = 0; ++lt; }
+            lr0 += kWgRows; if (lr0 >= Rt) { lr0 = 0; ++lt; }
         };
         for (int j = 0; j < D; ++j) { if (j < my_tiles) issue(); cp_async_commit(); }
         int s = 0, cur_t = -1, t = t_first, r0 = r_first;
@@ -750,7 +771,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
                 named_bar_sync(2, kGProdThreads);
                 cur_t = t;
             }
-            const int rows = min(kGRows, Rt - r0);
+            const int rows = min(kWgRows, Rt - r0);
             cp_async_wait<D>();
             unsigned char* st = ring + (size_t)s * stage_bytes + swz + rl * 128;
 #pragma unroll
@@ -764,9 +785,9 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
                 c8[4] = make_float2(a2.x, a2.y); c8[5] = make_float2(a2.z, a2.w); c8[6] = make_float2(a3.x, a3.y); c8[7] = make_float2(a3.z, a3.w);
                 const bool clamp = ((e >> 23) & 1) != 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < kWgRows / 32; ++i)
                     if (rl + 32 * i < rows) {
-                        uint4* bp = reinterpret_cast<uint4*>(st + b * 16384 + i * 32 * 128);
+                        uint4* bp = reinterpret_cast<uint4*>(st + b * (kWgRows * 128) + i * 32 * 128);
                         *bp = affine8(*bp, c8, clamp);
                     }
             }
@@ -774,7 +795,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
             if (++s == S) s = 0;
-            r0 += kGRows; if (r0 >= Rt) { r0 = 0; ++t; }
+            r0 += kWgRows; if (r0 >= Rt) { r0 = 0; ++t; }
         }
     }
     // ================================================================ all roles: accumulator -> gradient arena

@@ -1,0 +1,26 @@
+"""Role timeline of one launch of the tcgen05 forward GEMM family (head conv) and of the fused pointwise backward (s1.u0.pw1)
+at the benchmark size: python profiles/pwg_timeline_probe.py   (needs a B200; CDRA_TIMELINE=1 is set here)."""
+import os, sys, ctypes, torch
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/carla-driving-rl-agent_b200')
+os.environ['CDRA_TIMELINE'] = '1'
+from cdra.engine import Engine
+from tests import common as C
+for B in (512,):
+    eng = Engine(B, 90, 120, dtype='bf16', image_u8=True, device='cuda')
+    dyn, pol, val = C.fresh_params(torch.float64)
+    C.load_engine(eng, dyn, pol, val)
+    obs = {k: v.cuda() for k, v in C.synthetic_obs(B, 90, 120, seed=1).items()}
+    bt = {k: v.cuda() for k, v in C.synthetic_batch(B, seed=2).items()}
+    for _ in range(3): C.policy_step_engine(eng, obs, bt)
+    torch.cuda.synchronize()
+    ts = (ctypes.c_ulonglong * 32)()
+    eng.lib.cdra_debug_timeline(ts)
+    t = list(ts)
+    names = ['start', 'prologue done', 'pdl_wait done', 'weights landed (MMA thr)', 'first full (MMA thr)', 'first tm_full (epi)', 'first item copied', 'last item done', 'flush done', 'final sync', 'last_cta elected', 'finalize done']
+    print('B =', B, '(head conv = last pwg_fwd launch, block (0,0))')
+    for i, n in enumerate(names):
+        print(f'  {n:28s} {(t[i] - t[0]) / 1e3:8.2f} us')
+    names3 = ['start', 'prologue done', 'pdl_wait done', 'first full (transform)', 'first stg_full (MMA)', 'first tm_full (epi)', 'first tile epilogue done', 'last tile done (epi)', 'roles joined', 'dW flush done', 'MMA tile 8 staged', 'BN param grads done']
+    print('fused backward, last launch (s1.u0.pw1), block 0')
+    for i, n in enumerate(names3):
+        print(f'  {n:28s} {(t[16 + i] - t[16]) / 1e3:8.2f} us')
