@@ -20,7 +20,8 @@ for B in (512,):
     print('B =', B, '(head conv = last pwg_fwd launch, block (0,0))')
     for i, n in enumerate(names):
         print(f'  {n:28s} {(t[i] - t[0]) / 1e3:8.2f} us')
-    names3 = ['start', 'prologue done', 'pdl_wait done', 'first full (transform)', 'first stg_full (MMA)', 'first tm_full (epi)', 'first tile epilogue done', 'last tile done (epi)', 'roles joined', 'dW flush done', 'MMA tile 8 staged', 'BN param grads done']
+    names3 = ['start', 'prologue done', 'pdl_wait done', 'first full (transform)', 'first stg_full (MMA)', 'first tm_full (epi)', 'tile 20: epilogue channel loop done', 'last tile done (epi)', 'roles joined', 'dW flush done', 'MMA tile 8 staged', 'BN param grads done']
     print('fused backward, last launch (s1.u0.pw1), block 0')
     for i, n in enumerate(names3):
         print(f'  {n:28s} {(t[16 + i] - t[16]) / 1e3:8.2f} us')
+    print('  tile 20: transform got its input %.2f, got a free staging tile %.2f, handed over %.2f; epilogue got the accumulator %.2f' % tuple((t[16 + i] - t[16]) / 1e3 for i in (12, 13, 14, 15)))
