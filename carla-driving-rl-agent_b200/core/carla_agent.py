@@ -194,7 +194,12 @@ class CARLAgent(PPOAgent):
 
     # ------------------------------------------------------------------ gradients (:351-388, :430-463)
     def _named_grads(self, arena, flat):
-        return [arena.view(n, flat) for n in arena.names]
+        # the per-tensor views of a gradient buffer never change: build them once per (arena, buffer), not per minibatch
+        cache = self.__dict__.setdefault('_grad_views', {})
+        key = (id(arena), flat.data_ptr())
+        if key not in cache:
+            cache[key] = [arena.view(n, flat) for n in arena.names]
+        return cache[key]
 
     def get_policy_gradients(self, batch):
         states, advantages, log_probabilities, speed, similarity = batch

@@ -1,6 +1,8 @@
 // v2 tower: host-side launch sequences (forward, backward) and the logical-layout export used by the parity taps.
 #pragma once
 #ifndef CDRA_EMU
+#include <mutex>
+#include <set>
 #include "plan.h"
 #include "tower_run.cuh"
 #include "v2_pw.cuh"
@@ -133,6 +135,14 @@ inline int use_timeline() { static const int v = getenv("CDRA_TIMELINE") != null
 inline int& dw_band_cap() { static int v = 0; return v; }        // cdra_debug_set("dw_band", rows): 0 = automatic
 inline bool use_pwg_wgrad() { static const bool env = getenv("CDRA_NO_PWG_WGRAD") == nullptr; return env; }
 inline int pwg_min_k_bwd() { static const int v = getenv("CDRA_PWG_MINK_BWD") ? atoi(getenv("CDRA_PWG_MINK_BWD")) : 192; return v; }
+// opt a kernel into the full dynamic shared memory ONCE (the attribute call costs microseconds; the launchers run ~500 times a step)
+template <typename K>
+inline void max_smem_once(K k) {
+    static std::mutex mu;
+    static std::set<const void*> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert((const void*)k).second) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+}
 inline int num_sms() {
     static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
     return n;
@@ -229,7 +239,7 @@ inline bool try_pwg_fwd(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
     // (full -> tcgen05.mma -> commit -> empty) of the block it has just handed over
     const int depth = std::max(1, std::min(4, nstage - 2));
     auto launch = [&](auto k) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        max_smem_once(k);
         CDRA_LAUNCH_PDL(k, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
     };
     if (depth == 4) launch(pwg_fwd_kernel<4>); else if (depth == 3) launch(pwg_fwd_kernel<3>);
@@ -302,7 +312,7 @@ inline void launch_dw_fwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
     // whole frames when two CTAs of them fit an SM, else the largest row band that does
     if (!dw_pick_band(in.cp, u, false, 110 * 1024, a.band_rows, a.nbands)) { fprintf(stderr, "libcdra: depthwise band does not fit in shared memory (cp=%d)\n", in.cp); return; }
     const DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, false, a.band_rows, u.stride);
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    max_smem_once(k);
     const int per_sm = std::max(1, std::min(2, (227 * 1024) / (L.total + 1024)));
     const int nitems = kT * a.B * a.nbands;
     int gx = std::min(nitems, num_sms() * per_sm);
@@ -490,7 +500,7 @@ inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
     int gx; pwg_grid(a.Rt, a.nblk, gx, a.tiles_per_cta);
     const int depth = std::max(1, std::min(4, nstage - 2));
     auto launch = [&](auto k) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        max_smem_once(k);
         CDRA_LAUNCH_PDL(k, dim3(gx, a.nblk), dim3(kGThreads), smem, c.stream, a, ares);
     };
     if (depth == 4) launch(pwg_dgrad_kernel<4>); else if (depth == 3) launch(pwg_dgrad_kernel<3>);
@@ -541,7 +551,7 @@ inline bool try_pwg_wgrad(const RunCtx& c, const PwBwdArgs& b, const PwDesc& hd)
     const int gx = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
     const int depth = std::max(1, std::min(3, nstage - 2));          // two ring stages of slack (see try_pwg_fwd)
     auto launch = [&](auto k) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        max_smem_once(k);
         CDRA_LAUNCH_PDL(k, dim3(gx, gy), dim3(kGThreads), smem, c.stream, a);
     };
     if (depth == 3) launch(pwg_wgrad_kernel<3>); else if (depth == 2) launch(pwg_wgrad_kernel<2>); else launch(pwg_wgrad_kernel<1>);
@@ -620,7 +630,7 @@ inline void launch_dw_bwd(const RunCtx& c, const BnConv& l, const V2Tensor& in, 
     a.nbuf = 2;
     if (!dw_pick_band(in.cp, u, true, kMaxDynSmem, a.band_rows, a.nbands)) { fprintf(stderr, "libcdra: dw_bwd band does not fit in shared memory (cp=%d)\n", in.cp); return; }
     const DwSmem L = dw_smem(in.cp, u.Hi, u.Wi, u.Ho, u.Wo, a.nbuf, true, a.band_rows, u.stride);
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    max_smem_once(k);
     const int nitems = kT * a.B * a.nbands;
     int gx = std::min(nitems, num_sms());
     a.frames_per_cta = (nitems + gx - 1) / gx;

@@ -86,13 +86,22 @@ def index_batches(n: int, batch_size: int, shuffle_batches=False, seed=None, dro
     idx = list(range(skip, n))
 
     def buffered_shuffle(items, buffer_size):
-        out, buf = [], []
-        for it in items:
-            buf.append(it)
-            if len(buf) > buffer_size:
-                out.append(buf.pop(rng.randint(len(buf))))
-        while buf:
-            out.append(buf.pop(rng.randint(len(buf))))
+        """tf.data `shuffle(buffer_size)`: the buffer fills up, every further item pushes out a uniformly drawn one, the rest
+        drains uniformly.  O(1) per item (swap-remove: the order inside the buffer has no meaning) with the random draws
+        taken in bulk -- the update starts with this call while the GPU waits."""
+        items = list(items)
+        n, B = len(items), int(buffer_size)
+        buf = items[:B]
+        out = []
+        if n > B:
+            for x, j in zip(items[B:], rng.randint(0, B + 1, size=n - B).tolist()):
+                buf.append(x)
+                out.append(buf[j]); buf[j] = buf[-1]; buf.pop()
+        m = len(buf)
+        if m:
+            sizes = np.arange(m, 0, -1)
+            for j in np.minimum((rng.random_sample(m) * sizes).astype(np.int64), sizes - 1).tolist():
+                out.append(buf[j]); buf[j] = buf[-1]; buf.pop()
         return out
 
     if shuffle:
