@@ -148,17 +148,6 @@ struct LayerP {
 // kT sequential Keras moving-average updates (core/architectures.py:44-57 applies the same layer object to every
 // time slice; FusedBatchNorm feeds the unbiased variance to the moving average).
 struct BnFin { float scale, shift, mean, inv; };
-CDRA_DEV BnFin bn_from_sums(double sx, double sxx, double n, float g, float b) {
-    const double mean = sx / n;
-    double var = sxx / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    BnFin r;
-    r.inv = (float)(1.0 / sqrt(var + (double)kBnEps));
-    r.mean = (float)mean;
-    r.scale = g * r.inv;
-    r.shift = b - r.mean * r.scale;
-    return r;
-}
 CDRA_DEV BnFin bn_from_moving(float mm, float mv, float g, float b) {
     BnFin r;
     r.inv = 1.0f / sqrtf(mv + kBnEps);
@@ -174,6 +163,7 @@ CDRA_DEV void bn_finalize_channel(const Tables& tb, int cp, int slot, const Laye
     const float mm0 = mm, mv0 = mv;
     // this runs in the LAST CTA while the rest of the GPU idles: all four slices' sums are fetched before any arithmetic, so
     // the L2 round trips overlap instead of alternating with the double-precision math
+    const double inv_n = 1.0 / n, unbias = n / (n > 1.0 ? n - 1.0 : 1.0);     // FusedBatchNorm feeds the unbiased variance to the moving average
     double2 s[kT];
 #pragma unroll
     for (int t = 0; t < kT; ++t) s[t] = training ? ld_sum(tb.fsum + (size_t)t * cp + slot) : make_double2(0.0, 0.0);
@@ -181,13 +171,15 @@ CDRA_DEV void bn_finalize_channel(const Tables& tb, int cp, int slot, const Laye
     for (int t = 0; t < kT; ++t) {
         BnFin f;
         if (training) {
-            f = bn_from_sums(s[t].x, s[t].y, n, g, b);
-            const double mean = s[t].x / n;
-            double var = s[t].y / n - mean * mean;
+            const double mean = s[t].x * inv_n;
+            double var = s[t].y * inv_n - mean * mean;
             if (var < 0.0) var = 0.0;
-            const double vm = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
+            f.inv = (float)rsqrt(var + (double)kBnEps);
+            f.mean = (float)mean;
+            f.scale = g * f.inv;
+            f.shift = b - f.mean * f.scale;
             mm -= (mm - (float)mean) * (1.f - kBnMomentum);
-            mv -= (mv - (float)vm) * (1.f - kBnMomentum);
+            mv -= (mv - (float)(var * unbias)) * (1.f - kBnMomentum);
         } else {
             f = bn_from_moving(mm0, mv0, g, b);
         }
