@@ -309,6 +309,12 @@ def run_b200(args):
     launches = eng.lib.cdra_launch_count() - l0
     stage('timed region done')
     clocks = sampler.finish() if sampler else None
+    # host time to ENQUEUE one step on an idle queue (no synchronisation inside): far below ms_per_step = the GPU, not the launch path, is the limit
+    torch.cuda.synchronize()
+    h0 = time.perf_counter()
+    sgd_step(args.warmup + args.steps)
+    host_ms = 1e3 * (time.perf_counter() - h0)
+    torch.cuda.synchronize()
     value = world * bs * args.steps / (ms / 1e3)
 
     peak, peak_src = measured_peaks()
@@ -332,7 +338,8 @@ def run_b200(args):
                    'l2': f'inputs ({rollout_gb:.1f} GB rollout) and activations exceed L2; no flush needed',
                    'parallelism': f'dp{world}', 'optimizer': 'Keras-style Adam x3, per-tensor clip 1.0 on heads'},
         'e2e': e2e,
-        'gpu_launches': int(launches), 'launches_per_step': per_step_launches, 'clocks': clocks,
+        'gpu_launches': int(launches), 'launches_per_step': per_step_launches,
+        'host_enqueue_ms_per_step': host_ms, 'clocks': clocks,
     }
     bps = BYTES_PER_SAMPLE.get((args.dtype, H, W))
     if bps:

@@ -31,11 +31,16 @@ inline __host__ __device__ PwFwdTcSmem pw_fwd_tc_smem(int KP, int NPall, int cpo
     return s;
 }
 
+// role timeline of block 0 (cdra_debug_timeline, CDRA_TIMELINE=1): tile 2 of the CTA's schedule phase by phase
+__device__ unsigned long long g_tc_ts[16];
+CDRA_DEV unsigned long long gtimer_tc() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TC_TS(i) do { if (a.timeline && blockIdx.x == 0 && threadIdx.x == 0) g_tc_ts[i] = gtimer_tc(); } while (0)
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
     constexpr int R = 128;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    TC_TS(0);
     const PwDesc& d = *a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
@@ -88,7 +93,9 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
         }
         if (x1cp) bulk_g2s(dst + (size_t)R * src_cp_sum * 2, a.x1 + ((size_t)t * a.Rt + r0) * x1cp, rows * x1cp * 2, &full[buf]);
     };
+    TC_TS(1);
     pdl_wait();
+    TC_TS(2);
     if (tid == 32) for (int b = 0; b < a.nbuf; ++b) if (tile_lo + b < tile_hi) issue(tile_lo + b, b);
 
     // transform role: thread <-> one 8-slot chunk over the concatenated sources, row lanes stride the rows
@@ -156,7 +163,9 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) c8[q] = s_aff[xq * 8 + q];
         }
+        if (it == 2) TC_TS(3);
         mbar_wait(&full[buf], (it / a.nbuf) & 1);
+        if (it == 2) TC_TS(4);
         const unsigned char* rb = raw + (size_t)buf * L.raw_stride;
         // ---- transform: raw rows -> BN affine (+ReLU6) -> swizzled K-major tile (rows past the slice end are zero)
         if (xrl < xnrl) {
@@ -170,6 +179,7 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
         }
         fence_proxy_async();
         __syncthreads();
+        if (it == 2) TC_TS(5);
         if (tid == 0) {
             tc_fence_after();
             const uint32_t aa = smem_u32(As), wa = smem_u32(Ws);
@@ -181,6 +191,7 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
             umma_commit(mma_done);
         }
         mbar_wait(mma_done, it & 1);
+        if (it == 2) TC_TS(6);
         tc_fence_after();
         // ---- epilogue: TMEM -> registers -> + bias -> bf16 -> staging rows
         {
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
         }
         tc_fence_before();
         __syncthreads();
+        if (it == 2) TC_TS(7);
         if (tid == 32 && tile + a.nbuf < tile_hi) issue(tile + a.nbuf, buf);       // the raw rows (sources and x1) are consumed
         // ---- store + statistics
         if (vrl < vnrl) {
@@ -233,10 +245,13 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
                 orow += ostep; srow += sstep;
             }
         }
+        if (it == 2) TC_TS(8);
     }
+    TC_TS(9);
     if (cur_t >= 0 && a.training) flush_stats(cur_t);
     tc_fence_before();
     __syncthreads();
+    TC_TS(10);
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
 
     // ---- last CTA: BatchNorm tables of every output channel

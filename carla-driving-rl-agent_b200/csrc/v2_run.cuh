@@ -193,7 +193,7 @@ inline bool try_pw_fwd_tc(const RunCtx& c, PwFwdArgs& a, const PwDesc& hd) {
     auto k = pw_fwd_tc_kernel<NT>;
     static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
     (void)attr_done;
-    a.nbuf = nbuf; a.colmode = 0; a.ntiles_n = 1;
+    a.nbuf = nbuf; a.colmode = 0; a.ntiles_n = 1; a.timeline = use_timeline();
     const int tps = (a.Rt + 127) / 128, ntile = kT * tps;
     int gx = std::min(ntile, num_sms());
     a.tiles_per_cta = (ntile + gx - 1) / gx;

@@ -75,6 +75,17 @@ CDRA_DEV void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 consecutive accumulator columns (one tcgen05.wait::ld per 16 values)
+CDRA_DEV void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---------------------------------------------------------------------------------------------- self test
 // C[Mw][Nw] (fp32) = X^T Y for row-major bf16 X [rows][Mw], Y [rows][Nw]: both operands MN-major, 64-row tiles accumulated
 // in TMEM (the weight-gradient shape).  Mw in {128, 256}, Nw % 16 == 0, Nw <= 256, Mw/128 * Nw <= 512, rows % 64 == 0.

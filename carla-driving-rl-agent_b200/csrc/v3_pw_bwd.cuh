@@ -26,24 +26,11 @@
 namespace cdra {
 namespace v2 {
 
-CDRA_DEV void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 CDRA_DEV void bulk_s2g_nc(void* dst, const void* src, uint32_t bytes) {      // bulk store shared -> global, not yet committed
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 CDRA_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 CDRA_DEV void bulk_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-CDRA_DEV void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-CDRA_DEV void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // role timeline of block 0 (see v4_pwg.cuh / cdra_debug_timeline)
 __device__ unsigned long long g_bf_ts[16];
@@ -503,7 +490,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
             int p, sl, l, nn;
             if (!pw_col(d, j, p, sl, l, nn)) continue;
             double gs = 0.0, bs = 0.0;
-            for (int t = 0; t < kT; ++t) { const double2 v = ld_sum(a.tb[p].bsum + (size_t)t * cpo + sl); bs += v.x; gs += v.y; }
+            double2 v[kT];                               // all four loads in flight before the sums (block 0 ends the kernel)
+#pragma unroll
+            for (int t = 0; t < kT; ++t) v[t] = ld_sum(a.tb[p].bsum + (size_t)t * cpo + sl);
+#pragma unroll
+            for (int t = 0; t < kT; ++t) { bs += v[t].x; gs += v[t].y; }
             d.layer[l].dg[nn] = (float)gs; d.layer[l].dbe[nn] = (float)bs;
         }
         __syncthreads();

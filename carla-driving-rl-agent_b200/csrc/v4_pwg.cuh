@@ -843,7 +843,11 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_wgrad_kernel(const PwgWgArgs
             int p, sl, l, nn;
             if (!pw_col(d, j, p, sl, l, nn)) continue;
             double gs = 0.0, bs = 0.0;
-            for (int t = 0; t < kT; ++t) { const double2 v = ld_sum(a.tb[p].bsum + (size_t)t * a.cpo + sl); bs += v.x; gs += v.y; }
+            double2 v[kT];                               // all four loads in flight before the sums (block 0 ends the kernel)
+#pragma unroll
+            for (int t = 0; t < kT; ++t) v[t] = ld_sum(a.tb[p].bsum + (size_t)t * a.cpo + sl);
+#pragma unroll
+            for (int t = 0; t < kT; ++t) { bs += v[t].x; gs += v[t].y; }
             d.layer[l].dg[nn] = (float)gs; d.layer[l].dbe[nn] = (float)bs;
         }
     }

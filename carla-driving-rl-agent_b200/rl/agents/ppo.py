@@ -14,61 +14,69 @@ from rl.agents.agents import Agent
 from rl.parameters import DynamicParameter, LearningRateSchedule
 
 
+_Schedule = Union[float, LearningRateSchedule, DynamicParameter]
+# the schedules that live in config.json next to the weights (rl/agents/ppo.py:598-617), attribute name == config key
+_SCHEDULED = ('policy_lr', 'value_lr', 'adv_scale', 'entropy_strength', 'clip_ratio')
+
+
+def _every(spec, total, name):
+    """`save_every` / `render_every` of learn(): False / None -> never, True -> every episode, 'end' -> once after the last."""
+    if spec is False or spec is None:
+        return total + 1
+    if spec is True:
+        return 1
+    if spec == 'end':
+        return total
+    if name == 'save_every' and total % spec:
+        raise AssertionError(f'episodes ({total}) must be a multiple of {name} ({spec})')
+    return spec
+
+
 class PPOAgent(Agent):
-    def __init__(self, *args, policy_lr: Union[float, LearningRateSchedule, DynamicParameter] = 1e-3, gamma=0.99,
-                 lambda_=0.95, value_lr: Union[float, LearningRateSchedule, DynamicParameter] = 3e-4, load=False,
-                 optimization_steps=(1, 1), name='ppo-agent', optimizer='adam', clip_norm=(1.0, 1.0),
-                 clip_ratio: Union[float, LearningRateSchedule, DynamicParameter] = 0.2, seed_regularization=False,
-                 entropy_regularization: Union[float, LearningRateSchedule, DynamicParameter] = 0.0,
-                 network: Union[dict, object] = None, update_frequency=1, polyak=1.0, repeat_action=1,
-                 advantage_scale: Union[float, LearningRateSchedule, DynamicParameter] = 2.0, **kwargs):
-        assert 0.0 < polyak <= 1.0                              # rl/agents/ppo.py:33-34
-        assert repeat_action >= 1
+    def __init__(self, *args, policy_lr: _Schedule = 1e-3, gamma=0.99, lambda_=0.95, value_lr: _Schedule = 3e-4, load=False,
+                 optimization_steps=(1, 1), name='ppo-agent', optimizer='adam', clip_norm=(1.0, 1.0), clip_ratio: _Schedule = 0.2,
+                 seed_regularization=False, entropy_regularization: _Schedule = 0.0, network: Union[dict, object] = None,
+                 update_frequency=1, polyak=1.0, repeat_action=1, advantage_scale: _Schedule = 2.0, **kwargs):
+        # keyword names, defaults and the checks below: rl/agents/ppo.py:20-111
+        if not 0.0 < polyak <= 1.0:
+            raise AssertionError('polyak must lie in (0, 1]')
+        if repeat_action < 1:
+            raise AssertionError('repeat_action must be >= 1')
+        if isinstance(clip_ratio, float) and clip_ratio < 0.0:
+            raise AssertionError('clip_ratio must be >= 0')
+        if not isinstance(network, dict) or 'network' not in network:
+            raise ValueError('this build only implements the CARLANetwork family: pass network=dict(network=CARLANetwork, ...)')
         super().__init__(*args, name=name, **kwargs)
 
         self.memory: PPOMemory = None
-        self.gamma = gamma
-        self.lambda_ = lambda_
-        self.repeat_action = repeat_action
-        self.adv_scale = DynamicParameter.create(value=advantage_scale)
+        self.gamma, self.lambda_ = gamma, lambda_
+        self.repeat_action, self.update_frequency = repeat_action, update_frequency
+        self.polyak_coeff, self.should_polyak_average = polyak, polyak < 1.0
+        self.optimization_steps = dict(zip(('policy', 'value'), optimization_steps))
 
-        if seed_regularization:                                  # :44-52
-            def _seed_regularization():
-                self.set_random_seed(random.randint(a=0, b=2 ** 32 - 1))
-            self.seed_regularization = _seed_regularization
-            self.seed_regularization()
-        else:
-            self.seed_regularization = lambda: None
+        # every schedulable hyper-parameter is a DynamicParameter (constant, schedule or user-provided)
+        for attr, value in (('policy_lr', policy_lr), ('value_lr', value_lr), ('adv_scale', advantage_scale),
+                            ('entropy_strength', entropy_regularization), ('clip_ratio', clip_ratio)):
+            setattr(self, attr, DynamicParameter.create(value=value))
 
-        self.entropy_strength = DynamicParameter.create(value=entropy_regularization)
-        if isinstance(clip_ratio, float):
-            assert clip_ratio >= 0.0
-        self.clip_ratio = DynamicParameter.create(value=clip_ratio)
+        # re-seed with a fresh random seed before every minibatch when asked to (a regulariser of the reference)
+        self.seed_regularization = self._reseed if seed_regularization else (lambda: None)
+        self.seed_regularization()
 
         self._init_action_space()
-        print('state_spec:', self.state_spec)
-        print('action_shape:', self.num_actions)
-        print('distribution:', self.distribution_type)
+        for label, what in (('state_spec', self.state_spec), ('action_shape', self.num_actions), ('distribution', self.distribution_type)):
+            print(f'{label}:', what)
         self._init_gradient_clipping(clip_norm)
 
-        self.weights_path = dict(policy=os.path.join(self.base_path, 'policy_net'),
-                                 value=os.path.join(self.base_path, 'value_net'))
-        if not isinstance(network, dict) or 'network' not in network:
-            raise ValueError('this build only implements the CARLANetwork family: pass network=dict(network=CARLANetwork, ...)')
-        network = dict(network)
-        network_class = network.pop('network')
-        self.network = network_class(agent=self, **network)
-
-        self.update_frequency = update_frequency
-        self.policy_lr = DynamicParameter.create(value=policy_lr)
-        self.value_lr = DynamicParameter.create(value=value_lr)
-        self.optimization_steps = dict(policy=optimization_steps[0], value=optimization_steps[1])
-        self.policy_optimizer = utils.get_optimizer_by_name(optimizer, learning_rate=self.policy_lr)
-        self.value_optimizer = utils.get_optimizer_by_name(optimizer, learning_rate=self.value_lr)
-        self.should_polyak_average = polyak < 1.0
-        self.polyak_coeff = polyak
+        spec = dict(network)
+        self.network = spec.pop('network')(agent=self, **spec)
+        self.policy_optimizer, self.value_optimizer = (utils.get_optimizer_by_name(optimizer, learning_rate=lr)
+                                                       for lr in (self.policy_lr, self.value_lr))
         if load:
             self.load()
+
+    def _reseed(self):
+        self.set_random_seed(random.randint(a=0, b=2 ** 32 - 1))
 
     def _init_gradient_clipping(self, clip_norm):
         """rl/agents/ppo.py:114-146."""
@@ -108,29 +116,26 @@ class PPOAgent(Agent):
 
     # ------------------------------------------------------------------ update (rl/agents/ppo.py:190-226)
     def update(self):
-        t0 = time.time()
+        """All policy minibatches, then all value minibatches, each `optimization_steps[...]` times; every minibatch is
+        gradients -> (all-reduce) -> clip -> Adam on the device, nothing is read back here."""
+        started = time.time()
         self.seed_regularization()
-        value_batches = self.get_value_batches()
-        policy_batches = self.get_policy_batches()
+        # both iterators are built up front (the reference draws the value shuffle first)
+        batches = dict(value=self.get_value_batches(), policy=self.get_policy_batches())
+        phases = (('policy', self.get_policy_gradients, self.update_policy, self.policy_lr, 'loss_total'),
+                  ('value', self.get_value_gradients, self.update_value, self.value_lr, 'loss_value'))
+        for tag, gradients_of, apply, lr, loss_key in phases:
+            for _ in range(self.optimization_steps[tag]):
+                for minibatch in batches[tag]():
+                    self.seed_regularization()
+                    loss, grads = gradients_of(minibatch)
+                    apply(grads)
+                    self.log(**{loss_key: loss, f'lr_{tag}': lr.value, f'gradients_norm_{tag}': self._head_norms})
 
-        for _ in range(self.optimization_steps['policy']):
-            for data_batch in policy_batches():
-                self.seed_regularization()
-                total_loss, policy_grads = self.get_policy_gradients(data_batch)
-                self.update_policy(policy_grads)
-                self.log(loss_total=total_loss, lr_policy=self.policy_lr.value, gradients_norm_policy=self._head_norms)
-
-        for _ in range(self.optimization_steps['value']):
-            for data_batch in value_batches():
-                self.seed_regularization()
-                value_loss, value_grads = self.get_value_gradients(data_batch)
-                self.update_value(value_grads)
-                self.log(loss_value=value_loss, lr_value=self.value_lr.value, gradients_norm_value=self._head_norms)
-
-        t1 = time.time()                                 # host time to enqueue the update (the device runs behind it)
+        enqueued = time.time()                           # host time to enqueue the update (the device runs behind it)
         if torch.cuda.is_available():
             torch.cuda.synchronize()
-        print(f'Update took {round(time.time() - t0, 3)}s (enqueued in {round(t1 - t0, 3)}s)')
+        print(f'Update took {round(time.time() - started, 3)}s (enqueued in {round(enqueued - started, 3)}s)')
 
     def get_policy_gradients(self, batch):
         raise NotImplementedError
@@ -215,62 +220,19 @@ class PPOAgent(Agent):
     # ------------------------------------------------------------------ rollout (rl/agents/ppo.py:464-568)
     def learn(self, episodes: int, timesteps: int, save_every: Union[bool, str, int] = False,
               render_every: Union[bool, str, int] = False, close=True):
-        assert episodes % self.update_frequency == 0
-        if (save_every is False) or (save_every is None):
-            save_every = episodes + 1
-        elif save_every is True:
-            save_every = 1
-        elif save_every == 'end':
-            save_every = episodes
-        else:
-            assert episodes % save_every == 0
-        if render_every is False:
-            render_every = episodes + 1
-        elif render_every is True:
-            render_every = 1
+        if episodes % self.update_frequency:
+            raise AssertionError('episodes must be a multiple of update_frequency')
+        save_every, render_every = _every(save_every, episodes, 'save_every'), _every(render_every, episodes, 'render_every')
         try:
             self.memory = self.get_memory()
             for episode in range(1, episodes + 1):
-                self.seed_regularization()
-                self.on_episode_start()
-                preprocess_fn = self.preprocess()
-                self.reset()
-                state = self.env.reset()
-                episode_reward = 0.0
-                t0 = time.time()
-                render = episode % render_every == 0
-                for t in range(1, timesteps + 1):
-                    if render:
-                        self.env.render()
-                    if isinstance(state, dict):
-                        state = {f'state_{k}': v for k, v in state.items()}
-                    state = utils.to_tensor(preprocess_fn(state))
-                    action, mean, std, log_prob, value = self.predict(state)
-                    action_env = self.convert_action(action)
-                    for _ in range(self.repeat_action):
-                        next_state, reward, done, _ = self.env.step(action_env)
-                        episode_reward += reward
-                        if done:
-                            break
-                    self.log(actions=action, action_env=action_env, rewards=reward, distribution_mean=mean, distribution_std=std)
-                    self.memory.append(state, action, reward, value, log_prob)
-                    state = next_state
-                    if done or (t == timesteps):
-                        print(f'Episode {episode} terminated after {t} timesteps in {round((time.time() - t0), 3)}s ' +
-                              f'with reward {round(episode_reward, 3)}.')
-                        self.log(timestep=t)
-                        if isinstance(state, dict):
-                            state = {f'state_{k}': v for k, v in state.items()}
-                        state = utils.to_tensor(preprocess_fn(state))
-                        last_value = self.network.predict_last_value(state, timestep=(t + 1) / timesteps, is_terminal=done)
-                        self.end_episode(last_value, append=self.update_frequency > 1)
-                        break
+                reward = self._collect_episode(episode, timesteps, render=episode % render_every == 0)
                 if episode % self.update_frequency == 0:
                     self.update()
                     self.memory.delete()
                     self.memory = self.get_memory()
                 # (update_frequency > 1: the reference trims the bootstrap entries here, :551-553; update_index already did)
-                self.log(episode_rewards=episode_reward)
+                self.log(episode_rewards=reward)
                 self.write_summaries()
                 if self.should_record:
                     self.record(episode)
@@ -281,6 +243,44 @@ class PPOAgent(Agent):
             if close:
                 print('closing...')
                 self.env.close()
+
+    def _observe(self, state, preprocess_fn):
+        """environment observation -> the `state_*` tensor dict the network consumes"""
+        if isinstance(state, dict):
+            state = {f'state_{k}': v for k, v in state.items()}
+        return utils.to_tensor(preprocess_fn(state))
+
+    def _collect_episode(self, episode, timesteps, render=False):
+        """One trajectory of at most `timesteps` decisions into `self.memory`, closed with the bootstrap value and its
+        returns / advantages (the body of the reference's episode loop, :497-545).  Returns the episode reward."""
+        self.seed_regularization()
+        self.on_episode_start()
+        preprocess_fn = self.preprocess()
+        self.reset()
+        state, total, started = self.env.reset(), 0.0, time.time()
+        for t in range(1, timesteps + 1):
+            if render:
+                self.env.render()
+            state = self._observe(state, preprocess_fn)
+            action, mean, std, log_prob, value = self.predict(state)
+            action_env = self.convert_action(action)
+            for _ in range(self.repeat_action):              # the same action `repeat_action` times, rewards summed
+                next_state, reward, done, _ = self.env.step(action_env)
+                total += reward
+                if done:
+                    break
+            self.log(actions=action, action_env=action_env, rewards=reward, distribution_mean=mean, distribution_std=std)
+            self.memory.append(state, action, reward, value, log_prob)
+            state = next_state
+            if done or t == timesteps:
+                print(f'Episode {episode} terminated after {t} timesteps in {round(time.time() - started, 3)}s '
+                      f'with reward {round(total, 3)}.')
+                self.log(timestep=t)
+                last_value = self.network.predict_last_value(self._observe(state, preprocess_fn), timestep=(t + 1) / timesteps,
+                                                             is_terminal=done)
+                self.end_episode(last_value, append=self.update_frequency > 1)
+                break
+        return total
 
     def get_memory(self):
         return PPOMemory(state_spec=self.state_spec, num_actions=self.num_actions)
@@ -309,19 +309,14 @@ class PPOAgent(Agent):
 
     def save_config(self):
         print('save config')
-        self.update_config(policy_lr=self.policy_lr.serialize(), value_lr=self.value_lr.serialize(),
-                           adv_scale=self.adv_scale.serialize(), entropy_strength=self.entropy_strength.serialize(),
-                           clip_ratio=self.clip_ratio.serialize())
+        self.update_config(**{key: getattr(self, key).serialize() for key in _SCHEDULED})
         super().save_config()
 
     def load_config(self):
         print('load config')
         super().load_config()
-        self.policy_lr.load(config=self.config.get('policy_lr', {}))
-        self.value_lr.load(config=self.config.get('value_lr', {}))
-        self.adv_scale.load(config=self.config.get('adv_scale', {}))
-        self.entropy_strength.load(config=self.config.get('entropy_strength', {}))
-        self.clip_ratio.load(config=self.config.get('clip_ratio', {}))
+        for key in _SCHEDULED:
+            getattr(self, key).load(config=self.config.get(key, {}))
 
     def reset(self):
         super().reset()
@@ -329,9 +324,8 @@ class PPOAgent(Agent):
 
     def on_episode_end(self):
         super().on_episode_end()
-        self.policy_lr.on_episode()
-        self.value_lr.on_episode()
-        self.adv_scale.on_episode()
+        for schedule in (self.policy_lr, self.value_lr, self.adv_scale):
+            schedule.on_episode()
 
 
 def _flatten(tree):

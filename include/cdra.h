@@ -129,11 +129,12 @@ int cdra_debug_umma_selftest_k(const void* A, const void* B, float* C, int Mw, i
 int cdra_debug_set(const char* key, int value);
 
 /* Role timeline of the warp-specialised tcgen05 kernels (test / profiling aid): with CDRA_TIMELINE=1 in the environment, block 0
- * of every pwg_fwd_kernel / pw_bwd_fused_kernel launch records %globaltimer nanoseconds at its hand-offs (prologue done,
+ * of every pwg_fwd_kernel / pw_bwd_fused_kernel / pw_fwd_tc_kernel launch records %globaltimer nanoseconds at its hand-offs (prologue done,
  * griddepcontrol.wait passed, first operand block staged, first accumulator complete, first / last tile stored, statistics
  * flushed, last-CTA finalisation).  Synchronises the device and copies the stamps of the LAST such launches:
- * out32[0..15] forward GEMM family, out32[16..31] fused backward (profiles/pwg_timeline_probe.py names the slots). */
-int cdra_debug_timeline(uint64_t* out32);
+ * out48[0..15] forward GEMM family, out48[16..31] fused backward, out48[32..47] pw_fwd_tc_kernel
+ * (profiles/pwg_timeline_probe.py names the slots). */
+int cdra_debug_timeline(uint64_t* out48);
 
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
                                   const float* actions_eval, const float* actions_jac, const float* logp_old, const float* adv,

@@ -13,7 +13,7 @@ for B in (512,):
     bt = {k: v.cuda() for k, v in C.synthetic_batch(B, seed=2).items()}
     for _ in range(3): C.policy_step_engine(eng, obs, bt)
     torch.cuda.synchronize()
-    ts = (ctypes.c_ulonglong * 32)()
+    ts = (ctypes.c_ulonglong * 48)()
     eng.lib.cdra_debug_timeline(ts)
     t = list(ts)
     names = ['start', 'prologue done', 'pdl_wait done', 'weights landed (MMA thr)', 'first full (MMA thr)', 'first tm_full (epi)', 'first item copied', 'last item done', 'flush done', 'final sync', 'last_cta elected', 'finalize done']
@@ -25,3 +25,7 @@ for B in (512,):
     for i, n in enumerate(names3):
         print(f'  {n:28s} {(t[16 + i] - t[16]) / 1e3:8.2f} us')
     print('  tile 20: transform got its input %.2f, got a free staging tile %.2f, handed over %.2f; epilogue got the accumulator %.2f' % tuple((t[16 + i] - t[16]) / 1e3 for i in (12, 13, 14, 15)))
+    names4 = ['start', 'prologue done', 'pdl_wait done', 'tile 2: loop top', 'tile 2: raw rows landed', 'tile 2: transformed + CTA barrier', 'tile 2: MMA complete', 'tile 2: TMEM -> staging + CTA barrier', 'tile 2: stored + statistics', 'all tiles done', 'statistics flushed']
+    print('pw_fwd_tc, last launch of the backward-free forward (s3.u0.pw1 is pwg; this is the last stage-2 pw1), block 0')
+    for i, n in enumerate(names4):
+        print(f'  {n:40s} {(t[32 + i] - t[32]) / 1e3:8.2f} us')
