@@ -910,17 +910,18 @@ int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t r
     return check_launch("gather_rows");
 }
 
-int cdra_debug_timeline(uint64_t* out48) {
-    uint64_t* out32 = out48;
+int cdra_debug_timeline(uint64_t* out64) {
+    uint64_t* out32 = out64;
     if (!out32) return fail(CDRA_ERR_BADARG, "null argument");
 #ifndef CDRA_EMU
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out32, v2::g_pwg_ts, 16 * 8);
     cudaMemcpyFromSymbol(out32 + 16, v2::g_bf_ts, 16 * 8);
     cudaMemcpyFromSymbol(out32 + 32, v2::g_tc_ts, 16 * 8);
+    cudaMemcpyFromSymbol(out32 + 48, v2::g_bf_ts, 16 * 8, 16 * 8);
     return check_launch("debug_timeline");
 #else
-    for (int i = 0; i < 48; ++i) out32[i] = 0;
+    for (int i = 0; i < 64; ++i) out32[i] = 0;
     return CDRA_OK;
 #endif
 }

@@ -473,6 +473,7 @@ inline bool try_pw_bwd_fused(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd, in
     static bool attr_done = (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), true);
     (void)attr_done;
     a.nbuf = nstage; a.direct = 0;
+    { static const int only_r = getenv("CDRA_TIMELINE_R") ? atoi(getenv("CDRA_TIMELINE_R")) : 0; if (only_r && only_r != R) a.timeline = 0; }
     const int tps = (a.Rt + R - 1) / R, ntile = kT * tps;
     int gx = std::min(ntile, num_sms());
     a.tiles_per_cta = (ntile + gx - 1) / gx;
@@ -569,7 +570,8 @@ inline void launch_pw_bwd(const RunCtx& c, int di, const PwDesc& hd, PwBwdArgs a
         fb += 4.0 * a.Rt * hd.cols.nplanes * (hd.cols.seg0n + hd.cols.seg1n + a.ncopy) * 2 * 2;                                       // d out, out read
         if (a.x1) fb += 4.0 * a.Rt * 2 * a.ncopy * 2 * 2;
         prof_bytes(fb);
-        if (try_pw_bwd_fused<64>(c, a, hd, 4) || try_pw_bwd_fused<32>(c, a, hd, 3) || try_pw_bwd_fused<64>(c, a, hd, 2) || try_pw_bwd_fused<32>(c, a, hd, 2)) return;
+        static const int min64 = getenv("CDRA_BF_MIN64") ? atoi(getenv("CDRA_BF_MIN64")) : 4;      // ring depth below which 32-row tiles are preferred
+        if (try_pw_bwd_fused<64>(c, a, hd, min64) || try_pw_bwd_fused<32>(c, a, hd, 3) || try_pw_bwd_fused<64>(c, a, hd, 2) || try_pw_bwd_fused<32>(c, a, hd, 2)) return;
     }
     const int tc_np = (hd.NPall + 15) & ~15, tc_mb = (hd.KP + 127) / 128;
     const bool tc = use_tc() && tc_np <= 256 && tc_mb * tc_np <= 512;       // the [KP x NPall] accumulator fits the SM's TMEM

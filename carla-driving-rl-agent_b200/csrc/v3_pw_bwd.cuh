@@ -33,11 +33,12 @@ CDRA_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "me
 CDRA_DEV void bulk_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // role timeline of block 0 (see v4_pwg.cuh / cdra_debug_timeline)
-__device__ unsigned long long g_bf_ts[16];
+__device__ unsigned long long g_bf_ts[32];
 CDRA_DEV unsigned long long gtimer3() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define BF_TS(i) do { if (a.timeline && blockIdx.x == 0) g_bf_ts[i] = gtimer3(); } while (0)
 constexpr int kBfThreads = 512, kBfTransformWarps = 6, kBfEpilogueWarps = 8, kBfMaxStages = 8;
 constexpr int kBfTransformThreads = kBfTransformWarps * 32, kBfEpilogueThreads = kBfEpilogueWarps * 32;
+constexpr int kBfGroupWarps = 4, kBfGroupThreads = kBfGroupWarps * 32;     // one epilogue GROUP (4 warps = the 4 TMEM lane blocks) per tile; two groups alternate tiles
 
 struct PwBfSmem {
     int maps, w, dr, xs, st, st2, ring, total;
@@ -86,7 +87,6 @@ inline __host__ __device__ PwBfSmem pw_bf_smem(int R, int nsrc, const int* cps, 
 template <int R>
 __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwdArgs a) {
     static_assert(R == 32 || R == 64, "row tile");
-    constexpr int HR = R / 2;                           // rows per epilogue half
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     if (threadIdx.x == 0) BF_TS(0);
@@ -118,10 +118,10 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
 
     if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
     if (tid == 32) {
-        for (int s = 0; s < kBfMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kBfTransformWarps + kBfEpilogueWarps); }
+        for (int s = 0; s < kBfMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kBfTransformWarps + kBfGroupWarps); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&stg_full[b], kBfTransformWarps); mbar_init(&stg_empty[b], 1);
-            mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], kBfEpilogueWarps);
+            mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], kBfGroupWarps);
         }
         mbar_init(all_done, 1);
         mbar_fence_init();
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
     for (int i = tid; i < (L.w_bytes + 2 * L.dr_bytes + 2 * L.xs_bytes) / 16; i += kBfThreads) reinterpret_cast<uint4*>(Ws)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     // narrow layers (KP <= 64 / 32): the weight rows are replicated 2 / 4 times over the 128 M rows, so that EVERY TMEM lane
-    // block holds the data gradient and all epilogue warps share the tile's rows (a warp can only read its own 32 lanes)
+    // block holds the data gradient and all four warps of an epilogue group share the tile's rows (a warp can only read its own 32 lanes)
     const int kpad = ksum <= 32 ? 32 : (ksum <= 64 ? 64 : 128);
-    const int copies = min(128 / kpad, R / 16);
+    const int copies = min(128 / kpad, R / 8);
     for (int i = tid; i < d.KP * (NP >> 3); i += kBfThreads) {
         const int kk = i / (NP >> 3), c = i - kk * (NP >> 3);
         if (kk >= 128) continue;
@@ -164,26 +164,28 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
 
     if (warp == 0) {
         // ================================================================ TMA producer
-        if (lane == 0) {
-            Cursor cur = cursor0();
-            for (int it = 0; it < my_tiles; ++it, advance(cur)) {
-                const int s = cur.s, k = cur.k, t = cur.t, r0 = cur.r0, rows = min(R, a.Rt - cur.r0);
-                mbar_wait(&empty[s], (k & 1) ^ 1);
-                const size_t row = (size_t)t * a.Rt + r0;
-                unsigned char* dst = ring + (size_t)s * L.stage_bytes;
-                uint32_t bytes = (uint32_t)rows * (2 * nplanes * cpo + ksum + x1cp) * 2;
-                for (int i = 0; i < nsrc; ++i) if (accs[i]) bytes += (uint32_t)rows * cps[i] * 2;
-                mbar_expect_tx(&full[s], bytes);
-                for (int p = 0; p < nplanes; ++p) {
-                    bulk_g2s(dst + L.o_dout + (size_t)p * R * cpo * 2, a.dout[p] + row * cpo, rows * cpo * 2, &full[s]);
-                    bulk_g2s(dst + L.o_out + (size_t)p * R * cpo * 2, a.out[p] + row * cpo, rows * cpo * 2, &full[s]);
-                }
-                for (int i = 0; i < nsrc; ++i) {
-                    bulk_g2s(dst + L.o_src[i], d.src[i].data + row * cps[i], rows * cps[i] * 2, &full[s]);
-                    if (accs[i]) bulk_g2s(dst + L.o_ge[i], d.src[i].grad + row * cps[i], rows * cps[i] * 2, &full[s]);
-                }
-                if (x1cp) bulk_g2s(dst + L.o_x1, a.x1 + row * x1cp, rows * x1cp * 2, &full[s]);
-            }
+        // One copy stream per LANE (d out / out of each plane, every source, its partial gradient, x1): a single thread issuing the
+        // tile's 7-11 small bulk copies one after the other needs ~2 us per tile, which was the kernel's tile period.
+        const bf16* my_base = nullptr; int my_cp = 0, my_off = 0;
+        {
+            int id = 0;
+            auto claim = [&](const bf16* base, int cp, int off) { if (id++ == lane) { my_base = base; my_cp = cp; my_off = off; } };
+            for (int p = 0; p < nplanes; ++p) { claim(a.dout[p], cpo, L.o_dout + p * R * cpo * 2); claim(a.out[p], cpo, L.o_out + p * R * cpo * 2); }
+            for (int i = 0; i < nsrc; ++i) { claim(d.src[i].data, cps[i], L.o_src[i]); if (accs[i]) claim(d.src[i].grad, cps[i], L.o_ge[i]); }
+            if (x1cp) claim(a.x1, x1cp, L.o_x1);
+        }
+        int row_elems = 2 * nplanes * cpo + ksum + x1cp;
+        for (int i = 0; i < nsrc; ++i) if (accs[i]) row_elems += cps[i];
+        Cursor cur = cursor0();
+        for (int it = 0; it < my_tiles; ++it, advance(cur)) {
+            const int s = cur.s, k = cur.k, t = cur.t, r0 = cur.r0, rows = min(R, a.Rt - cur.r0);
+            if (lane == 0 && it == 20) BF_TS(16);
+            mbar_wait(&empty[s], (k & 1) ^ 1);
+            if (lane == 0 && it == 20) BF_TS(17);
+            if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)rows * row_elems * 2);
+            const size_t row = (size_t)t * a.Rt + r0;
+            if (my_base) bulk_g2s(ring + (size_t)s * L.stage_bytes + my_off, my_base + row * my_cp, rows * my_cp * 2, &full[s]);
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
@@ -192,9 +194,12 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
             const uint32_t wa = smem_u32(Ws);
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, n = it >> 1;
+                if (it == 20) BF_TS(18);
                 mbar_wait(&stg_full[b], n & 1);
                 if (it == 0) BF_TS(4); if (it == 8) BF_TS(10);
+                if (it == 20) BF_TS(19);
                 mbar_wait(&tm_empty[b], (n & 1) ^ 1);
+                if (it == 20) BF_TS(20);
                 tc_fence_after();
                 const uint32_t ra = smem_u32(smem + L.dr + (size_t)b * L.dr_bytes), xa = smem_u32(smem + L.xs + (size_t)b * L.xs_bytes);
                 for (int mb = 0; mb < L.mbk; ++mb)
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                         umma_bf16(tmem + (uint32_t)(mb * L.np16), umma_desc(xa + (uint32_t)mb * 2u * R * 128u + (uint32_t)ks * 2048u, R * 128, 1024),
                                   umma_desc(ra + (uint32_t)ks * 2048u, R * 128, 1024), idesc_w, it > 0 || ks > 0);
                 umma_commit(&stg_empty[b]);
+                if (it == 20) BF_TS(21);
             }
             umma_commit(all_done);
             mbar_wait(all_done, 0);
@@ -249,9 +255,12 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 }
                 cur_t = t;
             }
+            if (ttid == 0 && it == 20) BF_TS(22);
             mbar_wait(&full[s], k & 1);
             if (ttid == 0 && it == 0) BF_TS(3);
+            if (ttid == 0 && it == 20) BF_TS(23);
             mbar_wait(&stg_empty[b], (n & 1) ^ 1);
+            if (ttid == 0 && it == 20) BF_TS(24);
             const unsigned char* rb = ring + (size_t)s * stage_bytes;
             unsigned char* Dr = smem + o_dr + (size_t)b * dr_bytes;
             unsigned char* Xs = smem + o_xs + (size_t)b * xs_bytes;
@@ -305,14 +314,18 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&stg_full[b]); mbar_arrive(&empty[s]); }
+            if (ttid == 0 && it == 20) BF_TS(25);
+            if (ttid == 0 && it == 21) BF_TS(26);
         }
     } else {
         // ================================================================ epilogue warps
-        const int ew = warp - (2 + kBfTransformWarps), lg = ew & 3, half = ew >> 2, etid = tid - (2 + kBfTransformWarps) * 32;
+        // Two GROUPS of four warps alternate tiles (group g owns tiles it = g, g + 2, ...: TMEM accumulator g, staging buffers g), so
+        // the per-tile latency chain of one group (barrier -> tcgen05.ld -> shared-memory gather -> bulk store) overlaps the other's.
+        const int ew = warp - (2 + kBfTransformWarps), lg = ew & 3, grp = ew >> 2, etid = tid - (2 + kBfTransformWarps) * 32, gtid = etid & (kBfGroupThreads - 1);
         // this thread's data-gradient channel: TMEM lane 32 * lg + lane = copy q of channel kk; it walks rows
-        // [(half * copies + q) * hrt, + hrt) of the tile.  Everything the tile loop needs is hoisted into registers here.
+        // [q * hrt, + hrt) of its group's tile.  Everything the tile loop needs is hoisted into registers here.
         const int lane_id = 32 * lg + lane, q_copy = lane_id / kpad, kk = lane_id - q_copy * kpad;
-        const int hrt = R / (2 * copies), row_first = q_copy < copies ? (half * copies + q_copy) * hrt : 0;
+        const int hrt = R / copies, row_first = q_copy < copies ? q_copy * hrt : 0;
         struct Chan {
             int cp, o_src, o_ge, st_off, slot; bool on, clamp, want, acc;
             const float2* aff; const float2* bnp; double2* bsum;
@@ -335,15 +348,19 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
             }
         }
         const int cols_dw = L.cols_dw, o_dout = L.o_dout, o_x1 = L.o_x1, stage_bytes = L.stage_bytes;
-        int o_st = L.st, o_st2 = L.st2;                   // this tile's staging buffers (alternate per tile)
-        // pass-through role: thread <-> x1 slot
-        int x_src = -1;                                 // element offset inside the d out region of a stage, -2: padding (zero), -1: no role
-        if (x1cp && etid < x1cp) {
-            const int l = slot_logical(a.x1map, etid);
-            x_src = (l >= 0 && (l >> 1) < a.ncopy) ? (l & 1) * R * cpo + a.copy_dst0 + (l >> 1) : -2;
+        const int o_st = L.st + grp * L.st_bytes, o_st2 = L.st2 + grp * L.st2_bytes;       // this group's staging buffers
+        // pass-through role: thread <-> x1 slots gtid and gtid + 128
+        int x_src[2] = {-1, -1};                        // element offset inside the d out region of a stage, -2: padding (zero), -1: no role
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int slot = gtid + h * kBfGroupThreads;
+            if (x1cp && slot < x1cp) {
+                const int l = slot_logical(a.x1map, slot);
+                x_src[h] = (l >= 0 && (l >> 1) < a.ncopy) ? (l & 1) * R * cpo + a.copy_dst0 + (l >> 1) : -2;
+            }
         }
-        float xs1 = 0.f, xs2 = 0.f;
-        float4 xc = make_float4(1.f, 0.f, 0.f, 0.f);
+        float xs1[2] = {0.f, 0.f}, xs2[2] = {0.f, 0.f};
+        float4 xc[2] = {make_float4(1.f, 0.f, 0.f, 0.f), make_float4(1.f, 0.f, 0.f, 0.f)};
         const bool xclamp = a.x1clamp != 0;
         // bulk-store plan of thread 0 (one store per gradient tensor)
         bf16* g_ptr[kMaxSrc]; int g_cp[kMaxSrc], g_off[kMaxSrc];
@@ -355,11 +372,14 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 atomicAdd(&dst->x, (double)ch.s1); atomicAdd(&dst->y, (double)ch.s2);
             }
             ch.s1 = ch.s2 = 0.f;
-            if (x_src != -1 && a.x1bsum && (xs1 != 0.f || xs2 != 0.f)) {
-                double2* dst = a.x1bsum + (size_t)t * x1cp + etid;
-                atomicAdd(&dst->x, (double)xs1); atomicAdd(&dst->y, (double)xs2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (x_src[h] != -1 && a.x1bsum && (xs1[h] != 0.f || xs2[h] != 0.f)) {
+                    double2* dst = a.x1bsum + (size_t)t * x1cp + gtid + h * kBfGroupThreads;
+                    atomicAdd(&dst->x, (double)xs1[h]); atomicAdd(&dst->y, (double)xs2[h]);
+                }
+                xs1[h] = xs2[h] = 0.f;
             }
-            xs1 = xs2 = 0.f;
         };
         auto run_chan = [&](int b, int rows, const unsigned char* rb) {
             const uint32_t taddr = tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(cols_dw + b * R + row_first);
@@ -378,56 +398,77 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 uint32_t rawv[8], gev[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { rawv[j] = rawp[j * cp]; gev[j] = ch.acc ? (uint32_t)gep[j * cp] : 0u; }
+                uint32_t gbv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float g = v[j];
                     if (ch.acc) g = __bfloat162float(__float2bfloat16_rn(g)) + __uint_as_float(gev[j] << 16);
-                    const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16_rn(g));
-                    stp[j * cp] = gb;
-                    if (ch.want && j < nr) sum_accum(__uint_as_float((uint32_t)gb << 16), __uint_as_float(rawv[j] << 16), sc, ch.clamp, s1, s2);
+                    gbv[j] = __bfloat16_as_ushort(__float2bfloat16_rn(g));
+                    stp[j * cp] = (unsigned short)gbv[j];
+                }
+                if (ch.want) {
+                    if (nr >= 8) {                      // every tile but a slice's last: no per-row guards (warp-uniform: one copy index per warp)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sum_accum(__uint_as_float(gbv[j] << 16), __uint_as_float(rawv[j] << 16), sc, ch.clamp, s1, s2);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nr) sum_accum(__uint_as_float(gbv[j] << 16), __uint_as_float(rawv[j] << 16), sc, ch.clamp, s1, s2);
+                    }
                 }
             }
             ch.s1 = s1; ch.s2 = s2;
         };
         int cur_t = -1;
         Cursor cur = cursor0();
-        for (int it = 0; it < my_tiles; ++it, advance(cur)) {
-            const int s = cur.s, k = cur.k, b = it & 1, n = it >> 1, t = cur.t, r0 = cur.r0, rows = min(R, a.Rt - cur.r0);
+        if (grp) advance(cur);
+        const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+        for (int it = grp; it < my_tiles; it += 2, advance(cur), advance(cur)) {
+            const int s = cur.s, k = cur.k, b = grp, n = it >> 1, t = cur.t, r0 = cur.r0, rows = min(R, a.Rt - cur.r0);
             if (t != cur_t) {
                 if (cur_t >= 0) flush(cur_t);
                 if (ch.on) ch.sc = sum_consts(ch.aff, ch.bnp, (size_t)t * ch.cp + ch.slot);
-                if (x_src != -1) xc = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + etid);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (x_src[h] != -1) xc[h] = sum_consts(a.x1aff, a.x1bnp, (size_t)t * x1cp + gtid + h * kBfGroupThreads);
                 cur_t = t;
             }
-            // the previous tile's bulk stores have finished READING the staging rows
-            o_st = L.st + (it & 1) * L.st_bytes; o_st2 = L.st2 + (it & 1) * L.st2_bytes;
-            if (etid == 0) bulk_store_wait_read1();        // the stores of tile it - 2 (same buffers) have finished READING them
-            named_bar_sync(1, kBfEpilogueThreads);
+            if (etid == 0 && it == 20) BF_TS(27);
+            if (gtid == 0) bulk_store_wait_read();         // this group's previous stores (same staging buffers) have finished READING them
+            named_bar_sync(bar_a, kBfGroupThreads);
+            if (etid == 0 && it == 20) BF_TS(28);
             mbar_wait(&full[s], k & 1);                 // (long complete: acquires the TMA writes for this thread)
             mbar_wait(&tm_full[b], n & 1);
             if (etid == 0 && it == 0) BF_TS(5);
+            if (etid == 0 && it == 20) BF_TS(29);
             tc_fence_after();
             const unsigned char* rb = ring + (size_t)s * stage_bytes;
             run_chan(b, rows, rb);
             if (etid == 0 && it == 0) BF_TS(6);
+            if (etid == 0 && it == 20) BF_TS(30);
             tc_fence_before();
             // pass-through half of a stride-1 unit: d x1[slot(2i + p)] = d out_p[copy_dst0 + i]   (bit-exact gather)
-            if (x_src != -1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (x_src[h] == -1) continue;
+                const int slot = gtid + h * kBfGroupThreads, xo = x_src[h];
                 const unsigned short* dreg = reinterpret_cast<const unsigned short*>(rb + o_dout);
-                const unsigned short* xr = reinterpret_cast<const unsigned short*>(rb + o_x1) + etid;
-                unsigned short* dst = reinterpret_cast<unsigned short*>(smem + o_st2) + etid;
+                const unsigned short* xr = reinterpret_cast<const unsigned short*>(rb + o_x1) + slot;
+                unsigned short* dst = reinterpret_cast<unsigned short*>(smem + o_st2) + slot;
+                float a1 = xs1[h], a2 = xs2[h];
 #pragma unroll 4
                 for (int r = 0; r < rows; ++r) {
-                    const unsigned short gb = x_src >= 0 ? dreg[x_src + r * cpo] : (unsigned short)0;
+                    const unsigned short gb = xo >= 0 ? dreg[xo + r * cpo] : (unsigned short)0;
                     dst[r * x1cp] = gb;
-                    sum_accum(__uint_as_float((uint32_t)gb << 16), __uint_as_float((uint32_t)xr[r * x1cp] << 16), xc, xclamp, xs1, xs2);
+                    sum_accum(__uint_as_float((uint32_t)gb << 16), __uint_as_float((uint32_t)xr[r * x1cp] << 16), xc[h], xclamp, a1, a2);
                 }
+                xs1[h] = a1; xs2[h] = a2;
             }
             __syncwarp();
             if (lane == 0) { mbar_arrive(&tm_empty[b]); mbar_arrive(&empty[s]); }
             fence_proxy_async();
-            named_bar_sync(2, kBfEpilogueThreads);
-            if (etid == 0) {                            // one TMA bulk store per gradient tensor (a row tile is contiguous in HBM)
+            named_bar_sync(bar_b, kBfGroupThreads);
+            if (gtid == 0) {                            // one TMA bulk store per gradient tensor (a row tile is contiguous in HBM)
                 const size_t row = (size_t)t * a.Rt + r0;
 #pragma unroll
                 for (int i = 0; i < kMaxSrc; ++i)
@@ -435,10 +476,12 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 if (x1cp) bulk_s2g_nc(a.dx1 + row * x1cp, smem + o_st2, (uint32_t)rows * x1cp * 2);
                 bulk_commit();                          // ONE bulk group per tile
             }
+            if (etid == 0 && it == 20) BF_TS(31);
+            if (etid == 0 && it == 22) BF_TS(12);
         }
         if (etid == 0) BF_TS(7);
         if (cur_t >= 0) flush(cur_t);
-        if (etid == 0) bulk_store_wait_all();
+        if (gtid == 0) bulk_store_wait_all();
     }
 
     // ================================================================ all roles: weight-gradient epilogue

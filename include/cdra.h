@@ -132,9 +132,10 @@ int cdra_debug_set(const char* key, int value);
  * of every pwg_fwd_kernel / pw_bwd_fused_kernel / pw_fwd_tc_kernel launch records %globaltimer nanoseconds at its hand-offs (prologue done,
  * griddepcontrol.wait passed, first operand block staged, first accumulator complete, first / last tile stored, statistics
  * flushed, last-CTA finalisation).  Synchronises the device and copies the stamps of the LAST such launches:
- * out48[0..15] forward GEMM family, out48[16..31] fused backward, out48[32..47] pw_fwd_tc_kernel
- * (profiles/pwg_timeline_probe.py names the slots). */
-int cdra_debug_timeline(uint64_t* out48);
+ * out64[0..15] forward GEMM family, out64[16..31] fused backward, out64[32..47] pw_fwd_tc_kernel, out64[48..63] fused
+ * backward, steady state (tile 20 of block 0, role by role); profiles/pwg_timeline_probe.py names the slots.
+ * CDRA_TIMELINE_R=32|64 restricts the fused-backward stamps to launches of that row-tile size. */
+int cdra_debug_timeline(uint64_t* out64);
 
 int cdra_policy_head_loss_fwd_bwd(cdra_plan_t* plan, const float* params, float* state, const float* x512,
                                   const float* actions_eval, const float* actions_jac, const float* logp_old, const float* adv,
