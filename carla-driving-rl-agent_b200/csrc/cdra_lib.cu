@@ -399,9 +399,11 @@ static void tower_backward(const RunCtx& c, const TIn* image, bool stem_only = f
 static void tail_backward(const RunCtx& c, const float* road, const float* vehicle, const float* nav, const float* d_out512) {
     const Plan& p = *c.p; const int B = p.B; cudaStream_t st = c.stream;
     float* dn = F(c.ws, named_off(p, "d.trunk.n"));
-    // Dense 512
-    gemm(st, true, false, F(c.ws, p.trunk_n), 352, d_out512, 512, c.grads + p.trunk_w, 512, nullptr, 352, 512, B, false);
-    colsum(st, d_out512, 512, B, 512, c.grads + p.trunk_b, false);
+    // Dense 512: weight / bias gradients are leaves (side stream), the input gradient continues the chain
+    cudaStream_t sd = side_stream(c);
+    side_fork(c, sd);
+    gemm(sd, true, false, F(c.ws, p.trunk_n), 352, d_out512, 512, c.grads + p.trunk_w, 512, nullptr, 352, 512, B, false);
+    colsum(sd, d_out512, 512, B, 512, c.grads + p.trunk_b, false);
     gemm(st, false, true, d_out512, 512, c.params + p.trunk_w, 512, dn, 352, nullptr, B, 352, 512, false);
     {
         Bn1dArgs a; memset(&a, 0, sizeof a);
@@ -410,9 +412,14 @@ static void tail_backward(const RunCtx& c, const float* road, const float* vehic
         a.dgamma = c.grads + p.trunk_g; a.dbeta = c.grads + p.trunk_be; a.B = B; a.C = 352;
         CDRA_LAUNCH(bn1d_bwd_kernel, dim3(cdiv(352, 32)), dim3(256), 0, st, a);
     }
-    cudaStream_t sd = side_stream(c);    // leaf parameter gradients + feature-MLP backward: nothing downstream reads them
-    int col = 0;
+    // Side stream: everything the tower's backward does not wait for -- the three feature GRUs' whole backward chains (their input
+    // gradients only feed the feature-MLP backward, a leaf), every leaf parameter gradient and the feature-MLP backward.
+    // Only the image GRU's chain (d x_in -> global-average-pool backward -> tower) stays on the caller's stream.
+    side_fork(c, sd);                    // d(dyn_in) is final
+    int col = 0, gi = 0;
     for (const GruSpec& g : p.grus) {
+        const bool image = gi++ == 0;
+        cudaStream_t cs = image ? st : sd;
         const int u = g.units, u3 = 3 * u;
         const float* K = c.params + g.k; const float* R = c.params + g.r;
         float* dhbuf = F(c.ws, g.dh);
@@ -425,21 +432,20 @@ static void tail_backward(const RunCtx& c, const float* road, const float* vehic
             else { a.dh = dhbuf + (size_t)((t + 1) & 1) * B * u; a.lddh = u; }
             a.dxp = F(c.ws, g.dxp) + (size_t)t * B * u3; a.dhp = F(c.ws, g.dhp) + (size_t)t * B * u3;
             if (t > 0) { a.dhprev = dhbuf + (size_t)(t & 1) * B * u; a.lddhp = u; }
-            CDRA_LAUNCH(gru_gate_bwd_kernel, dim3(cdiv((long long)B * u, 256)), dim3(256), 0, st, a);
+            CDRA_LAUNCH(gru_gate_bwd_kernel, dim3(cdiv((long long)B * u, 256)), dim3(256), 0, cs, a);
             if (t > 0)      // dh_{t-1} += dhp_t R^T
-                gemm(st, false, true, a.dhp, u3, R, u3, a.dhprev, u, nullptr, B, u, u3, true);
+                gemm(cs, false, true, a.dhp, u3, R, u3, a.dhprev, u, nullptr, B, u, u3, true);
         }
-        // parameter gradients (side stream)
-        side_fork(c, sd);
+        gemm(cs, false, true, F(c.ws, g.dxp), u3, K, u3, F(c.ws, g.dx_in), g.din, nullptr, 4 * B, g.din, u3, false);
+        // parameter gradients (side stream; the image GRU's wait for its chain on the caller's stream)
+        if (image) side_fork(c, sd);
         gemm(sd, true, false, F(c.ws, g.hs), u, F(c.ws, g.dhp) + (size_t)B * u3, u3, c.grads + g.r, u3, nullptr, u, u3, 3 * B, false);
         colsum(sd, F(c.ws, g.dxp), u3, 4 * B, u3, c.grads + g.b, false);
         colsum(sd, F(c.ws, g.dhp), u3, 4 * B, u3, c.grads + g.b + u3, false);
         gemm(sd, true, false, F(c.ws, g.x_in), g.din, F(c.ws, g.dxp), u3, c.grads + g.k, u3, nullptr, g.din, u3, 4 * B, false);
-        gemm(st, false, true, F(c.ws, g.dxp), u3, K, u3, F(c.ws, g.dx_in), g.din, nullptr, 4 * B, g.din, u3, false);
         col += u;
     }
-    {
-        side_fork(c, sd);
+    {   // feature-MLP backward: after the feature GRUs' d x_in (same stream)
         FeatArgs3 aa; const float* x[3] = {road, vehicle, nav};
         feat_args(p, c.ws, c.params, nullptr, c.grads, x, 1, aa);
         CDRA_LAUNCH(featnet_bwd_kernel, dim3(3), dim3(kFeatThreads), 0, sd, aa);
