@@ -938,8 +938,9 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                 bf16* gp = a.din + ((size_t)f * in_px + (size_t)own_lo * a.Wi + ix) * CP + 2 * pr;
                 // the sums use the RAW input value (same mask / xhat as every consumer of them, bnbwd_apply): the ring holds it
                 const bf16* rp = Rin + ((size_t)(own_lo - bd.i_lo) * a.Wi + ix) * CP + 2 * pr;
-                auto finish = [&](float acc0, float acc1) {       // (+ existing share), store, BatchNorm-backward sums of the input
-                    if (a.accumulate) { const float2 e = unpack2(*reinterpret_cast<const uint32_t*>(gp)); acc0 += e.x; acc1 += e.y; }
+                // (+ existing share: `ex`, loaded by the caller one row ahead), store, BatchNorm-backward sums of the input
+                auto finish = [&](float acc0, float acc1, uint32_t ex) {
+                    if (a.accumulate) { const float2 e = unpack2(ex); acc0 += e.x; acc1 += e.y; }
                     const uint32_t pk = pack2(acc0, acc1);
                     *reinterpret_cast<uint32_t*>(gp) = pk;
                     if (want_sums) {
@@ -957,7 +958,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                         dw_mac_row<true>(A, w0 + 6, w1 + 6, acc0, acc1);
                         dw_mac_row<true>(B, w0 + 3, w1 + 3, acc0, acc1);
                         dw_mac_row<true>(C, w0, w1, acc0, acc1);
-                        finish(acc0, acc1);
+                        finish(acc0, acc1, a.accumulate ? *reinterpret_cast<const uint32_t*>(gp) : 0u);
                     };
                     const int nown = own_hi - own_lo;
                     const bf16* dwin = Pdr + ix * CP + 2 * pr;
@@ -983,7 +984,10 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                         wb0[ky] = xe ? w0[ky * 3 + 2] : 0.f;         wb1[ky] = xe ? w1[ky * 3 + 2] : 0.f;
                     }
                     const bf16* pa = Pdr + cA * CP + 2 * pr; const bf16* pb = Pdr + cB * CP + 2 * pr;
+                    // the existing share of row iy + 1 is requested before row iy is computed (a dependent global load per row otherwise)
+                    uint32_t ex_cur = (a.accumulate && own_lo < own_hi) ? *reinterpret_cast<const uint32_t*>(gp) : 0u;
                     for (int iy = own_lo; iy < own_hi; ++iy) {
+                        const uint32_t ex_next = (a.accumulate && iy + 1 < own_hi) ? *reinterpret_cast<const uint32_t*>(gp + a.Wi * CP) : 0u;
                         const int ys = iy + a.pad_t;
                         float acc0, acc1;
                         if ((ys & 1) == 0) {                      // ky = 0 at dR row ys/2, ky = 2 at dR row ys/2 - 1
@@ -998,7 +1002,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_kernel(const DwArgs a) {
                             acc0 = fmaf(a1.x, wa0[1], b1.x * wb0[1]);
                             acc1 = fmaf(a1.y, wa1[1], b1.y * wb1[1]);
                         }
-                        finish(acc0, acc1);
+                        finish(acc0, acc1, ex_cur);
+                        ex_cur = ex_next;
                     }
                 }
             }

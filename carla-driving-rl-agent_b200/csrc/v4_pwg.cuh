@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_fwd_kernel(const PwFwdArgs a
             // staged rows -> HBM: 16-byte chunks (+ 4-byte pairs where the stored columns end inside a chunk)
             bf16* orow = outp + ((size_t)t * Rt + r0) * cpo + slot0;
             if (cc < nch) {
+#pragma unroll 4
                 for (int r = crl; r < rows; r += 8)
                     *reinterpret_cast<uint4*>(orow + (size_t)r * cpo + cc * 8) = *reinterpret_cast<const uint4*>(St + r * stw + cc * 8);
             } else if (cc == nch && ntail > 0) {
@@ -525,7 +526,9 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_dgrad_kernel(const PwBwdArgs
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, rows = min(kGRows, Rt - r0);
             const size_t rowbase = (size_t)t * Rt + r0;
+            if (et == 0 && it == 5) PWG_TS(12);
             mbar_wait(&tm_full[b], (it >> 1) & 1);
+            if (et == 0 && it == 5) PWG_TS(13);
             tc_fence_after();
             named_bar_sync(1, kGEpiThreads);
             const uint32_t taddr = tmem + ((uint32_t)(32 * lg) << 16) + (uint32_t)(b * kGRows);
@@ -542,20 +545,36 @@ __global__ void __launch_bounds__(kGThreads, 1) pwg_dgrad_kernel(const PwBwdArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[b]);
             named_bar_sync(1, kGEpiThreads);
+            if (et == 0 && it == 5) PWG_TS(14);
             if (cc < nch) {
                 bf16* grow = gout + rowbase * cp + slot0 + cc * 8;
-                for (int r = crl; r < rows; r += 8) {
-                    uint4 v = *reinterpret_cast<const uint4*>(St + r * stw + cc * 8);
-                    if (acc) {                          // second consumer of the tensor: add to the share already written
-                        const uint4 ex = ldg_cg16(grow + (size_t)r * cp);
-                        uint32_t* w = reinterpret_cast<uint32_t*>(&v); const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ex);
+                // four rows per round, every load of the round issued before the first use (the existing-share loads are L2 round trips)
+                for (int rb = crl; rb < rows; rb += 32) {
+                    uint4 v[4], ex[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { const float2 x = unpack2(w[k]), y = unpack2(ew[k]); w[k] = pack2(x.x + y.x, x.y + y.y); }
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + 8 * u;
+                        v[u] = make_uint4(0, 0, 0, 0); ex[u] = v[u];
+                        if (r < rows) {
+                            v[u] = *reinterpret_cast<const uint4*>(St + r * stw + cc * 8);
+                            if (acc) ex[u] = ldg_cg16(grow + (size_t)r * cp);     // second consumer of the tensor: add to the share already written
+                        }
                     }
-                    *reinterpret_cast<uint4*>(grow + (size_t)r * cp) = v;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + 8 * u;
+                        if (r >= rows) continue;
+                        if (acc) {
+                            uint32_t* w = reinterpret_cast<uint32_t*>(&v[u]); const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ex[u]);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { const float2 x = unpack2(w[k]), y = unpack2(ew[k]); w[k] = pack2(x.x + y.x, x.y + y.y); }
+                        }
+                        *reinterpret_cast<uint4*>(grow + (size_t)r * cp) = v[u];
+                    }
                 }
             }
             r0 += kGRows; if (r0 >= Rt) { r0 = 0; ++t; }
+            if (et == 0 && it == 5) PWG_TS(15);
         }
     }
     tc_fence_before();

@@ -20,6 +20,7 @@ for B in (512,):
     print('B =', B, '(head conv = last pwg_fwd launch, block (0,0))')
     for i, n in enumerate(names):
         print(f'  {n:28s} {(t[i] - t[0]) / 1e3:8.2f} us')
+    print('  pwg_dgrad (last launch = first stage-3 layer of the backward... see note), tile 5 epilogue: loop top %.2f, accumulator ready %.2f, staged %.2f, copied out %.2f (us, same clock as above)' % tuple((t[i] - t[0]) / 1e3 for i in (12, 13, 14, 15)))
     names3 = ['start', 'prologue done', 'pdl_wait done', 'first full (transform)', 'first stg_full (MMA)', 'first tm_full (epi)', 'tile 20: epilogue channel loop done', 'last tile done (epi)', 'roles joined', 'dW flush done', 'MMA tile 8 staged', 'BN param grads done']
     print('fused backward, last launch (s1.u0.pw1), block 0')
     for i, n in enumerate(names3):
