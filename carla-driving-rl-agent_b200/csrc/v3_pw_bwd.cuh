@@ -41,7 +41,7 @@ constexpr int kBfTransformThreads = kBfTransformWarps * 32, kBfEpilogueThreads =
 constexpr int kBfGroupWarps = 4, kBfGroupThreads = kBfGroupWarps * 32;     // one epilogue GROUP (4 warps = the 4 TMEM lane blocks) per tile; two groups alternate tiles
 
 struct PwBfSmem {
-    int maps, w, dr, xs, st, st2, ring, total;
+    int maps, mdesc, w, dr, xs, st, st2, ring, total;
     int stage_bytes, dr_bytes, xs_bytes, w_bytes;
     int o_dout, o_out, o_src[kMaxSrc], o_x1, o_ge[kMaxSrc], st_off[kMaxSrc];
     int mbk, np16, nkb, cols_dw, tmem_cols;
@@ -69,6 +69,7 @@ inline __host__ __device__ PwBfSmem pw_bf_smem(int R, int nsrc, const int* cps, 
     s.xs_bytes = s.mbk * 2 * R * 128;
     off = 1024;                                         // mbarriers + TMEM slot
     s.maps = off; off += 2 * 256 * 4;                   // logical row / column maps of the weight-gradient flush
+    s.mdesc = off; off += 96 * 8;                       // the MMA issuer's precomputed shared-memory descriptors
     off = (off + 1023) & ~1023;
     s.w = off; off += s.w_bytes;
     s.dr = off; off += 2 * s.dr_bytes;
@@ -192,6 +193,22 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
         if (lane == 0) {
             const uint32_t idesc_d = umma_idesc(128, R, 0, 0), idesc_w = umma_idesc(128, L.np16, 1, 1);
             const uint32_t wa = smem_u32(Ws);
+            // Every operand address is one of a few fixed ones (resident weights, two staging buffers): the descriptors are built
+            // ONCE into a private table, so a tile costs 2 shared loads + 1 tcgen05.mma per K step (a lone warp issues dependent
+            // instructions ~5 cycles apart: building descriptors in the loop made the issue 0.9 us per tile, next to a 1.1 us transform).
+            // Table: [0,16) weights (dgrad A), [16 + 16 b, +16) dR K-major (dgrad B), [48 + 8 b, +8) act(x) MN-major (wgrad A),
+            // [64 + 8 b, +8) dR MN-major (wgrad B).  The launcher guarantees one 128-row weight block (mbk == 1).
+            uint64_t* md = reinterpret_cast<uint64_t*>(smem + L.mdesc);
+            const int nks = L.np16 >> 4;
+            for (int ks = 0; ks < nks; ++ks) md[ks] = umma_desc(wa + (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u, 16, 1024);
+            for (int b = 0; b < 2; ++b) {
+                const uint32_t ra = smem_u32(smem + L.dr + (size_t)b * L.dr_bytes), xa = smem_u32(smem + L.xs + (size_t)b * L.xs_bytes);
+                for (int ks = 0; ks < nks; ++ks) md[16 + 16 * b + ks] = umma_desc(ra + (uint32_t)(ks >> 2) * (uint32_t)(R * 128) + (uint32_t)(ks & 3) * 32u, 16, 1024);
+                for (int ks = 0; ks < R / 16; ++ks) {
+                    md[48 + 8 * b + ks] = umma_desc(xa + (uint32_t)ks * 2048u, R * 128, 1024);
+                    md[64 + 8 * b + ks] = umma_desc(ra + (uint32_t)ks * 2048u, R * 128, 1024);
+                }
+            }
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, n = it >> 1;
                 if (it == 20) BF_TS(18);
@@ -201,20 +218,12 @@ __global__ void __launch_bounds__(kBfThreads, 1) pw_bwd_fused_kernel(const PwBwd
                 mbar_wait(&tm_empty[b], (n & 1) ^ 1);
                 if (it == 20) BF_TS(20);
                 tc_fence_after();
-                const uint32_t ra = smem_u32(smem + L.dr + (size_t)b * L.dr_bytes), xa = smem_u32(smem + L.xs + (size_t)b * L.xs_bytes);
-                for (int mb = 0; mb < L.mbk; ++mb)
-                    for (int ks = 0; ks < (L.np16 >> 4); ++ks) {
-                        const int kb = ks >> 2;
-                        umma_bf16(tmem + (uint32_t)(L.cols_dw + (b * L.mbk + mb) * R),
-                                  umma_desc(wa + (uint32_t)(mb * L.nkb + kb) * 16384u + (uint32_t)(ks & 3) * 32u, 16, 1024),
-                                  umma_desc(ra + (uint32_t)kb * (uint32_t)(R * 128) + (uint32_t)(ks & 3) * 32u, 16, 1024), idesc_d, ks > 0);
-                    }
+                const uint64_t* dB = md + 16 + 16 * b;
+                const uint32_t tacc = tmem + (uint32_t)(L.cols_dw + b * R);
+                for (int ks = 0; ks < nks; ++ks) umma_bf16(tacc, md[ks], dB[ks], idesc_d, ks > 0);
                 umma_commit(&tm_full[b]);
-                for (int mb = 0; mb < L.mbk; ++mb)
 #pragma unroll
-                    for (int ks = 0; ks < R / 16; ++ks)
-                        umma_bf16(tmem + (uint32_t)(mb * L.np16), umma_desc(xa + (uint32_t)mb * 2u * R * 128u + (uint32_t)ks * 2048u, R * 128, 1024),
-                                  umma_desc(ra + (uint32_t)ks * 2048u, R * 128, 1024), idesc_w, it > 0 || ks > 0);
+                for (int ks = 0; ks < R / 16; ++ks) umma_bf16(tmem, md[48 + 8 * b + ks], md[64 + 8 * b + ks], idesc_w, it > 0 || ks > 0);
                 umma_commit(&stg_empty[b]);
                 if (it == 20) BF_TS(21);
             }
