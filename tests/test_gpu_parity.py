@@ -240,6 +240,34 @@ def test_full_size_properties_bf16(built_libs, params):
     assert losses[-1] < losses[0]
 
 
+def test_full_size_permutation_and_repeatability_bf16(built_libs):
+    """BASELINE config 2 minibatch (B = 512, 90x120, bf16), whole policy pass on the trained stage-s5 weights (a freshly
+    initialised tower amplifies a single bf16 rounding flip ~30x per unit -- profiles/dbg_repeat.py -- so only a trained
+    network has a meaningful end-to-end tolerance): (a) the same step twice gives the same loss and
+    gradients up to the order of the fp32 / fp64 atomics; (b) permuting the samples of the minibatch (observations and PPO
+    batch alike) changes neither: BatchNorm statistics, the loss and every parameter gradient are sums over the batch.  The
+    permutation moves every sample into another 128-row tile, another CTA and another ring slot of every kernel on the path,
+    so a tile-, band- or slot-dependent error shows up here at the size the bench runs."""
+    B = 512
+    dyn, pol, val = C.trained_params(torch.float64)
+    eng = _engine(B, 'bf16')
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = _dev(C.synthetic_obs(B, H, W, seed=61)), _dev(C.synthetic_batch(B, seed=62))
+    l0 = C.policy_step_engine(eng, obs, bt)[0].item()
+    gd0, gp0 = eng.g_dyn.clone(), eng.g_pol.clone()
+    l1 = C.policy_step_engine(eng, obs, bt)[0].item()
+    rep_d, rep_p = C.rel_l2(eng.g_dyn, gd0), C.rel_l2(eng.g_pol, gp0)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(7)).cuda()
+    obs_p = {k: v[perm].contiguous() for k, v in obs.items()}
+    bt_p = {k: v[perm].contiguous() for k, v in bt.items()}
+    l2 = C.policy_step_engine(eng, obs_p, bt_p)[0].item()
+    prm_d, prm_p = C.rel_l2(eng.g_dyn, gd0), C.rel_l2(eng.g_pol, gp0)
+    print(f'repeat: loss {l0:.7f} / {l1:.7f}, g_dyn {rep_d:.2e}, g_pol {rep_p:.2e};  permuted: loss {l2:.7f}, g_dyn {prm_d:.2e}, g_pol {prm_p:.2e}')
+    # measured on B200: repeat g_dyn 2.3e-5 / g_pol 2.6e-7, permuted 3.5e-5 / 2.7e-7, loss equal to 1e-7 (order of the fp32 / fp64
+    # atomics in the sums and weight gradients); the bounds leave ~30x
+    assert abs(l1 - l0) <= 1e-5 * abs(l0) and rep_d < 1e-3 and rep_p < 1e-4
+    assert abs(l2 - l0) <= 1e-5 * abs(l0) and prm_d < 1e-3 and prm_p < 1e-4
+
 def test_stem_backward_tensor_core_vs_cuda_core(built_libs, params):
     """the one-pass tensor-core stem backward (max-pool backward + BN backward folded into the weight gradient by
     linearity, v2_stem.cuh) against the CUDA-core kernels that materialise every intermediate, on identical inputs"""
