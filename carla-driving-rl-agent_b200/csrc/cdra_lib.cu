@@ -506,16 +506,22 @@ static int run_head(bool policy, cdra_plan_t* plan, const float* params, float* 
         b.dgamma = grads + g; b.dbeta = grads + be; b.B = B; b.C = C;
         CDRA_LAUNCH(bn1d_bwd_kernel, dim3(cdiv(C, 32)), dim3(256), 0, st, b);
     };
+    // the Dense weight / bias gradients are leaves: they run on the plan's side stream next to the chain that produces d x512
+    RunCtx c{&p, ws, params, state, grads, st, training};
+    cudaStream_t sd = side_stream(c);
     act(false, pre2, da2, dpre2, (long long)B * kHU);
-    gemm(st, true, false, n2, kHU, dpre2, kHU, grads + h.d2_w, kHU, nullptr, kHU, kHU, B, false);
-    colsum(st, dpre2, kHU, B, kHU, grads + h.d2_b, false);
+    side_fork(c, sd);
+    gemm(sd, true, false, n2, kHU, dpre2, kHU, grads + h.d2_w, kHU, nullptr, kHU, kHU, B, false);
+    colsum(sd, dpre2, kHU, B, kHU, grads + h.d2_b, false);
     gemm(st, false, true, dpre2, kHU, params + h.d2_w, kHU, dn2, kHU, nullptr, B, kHU, kHU, false);
     bn_bwd(a1, dn2, da1, st2, kHU, h.bn2_g, h.bn2_be);
     act(false, pre1, da1, dpre1, (long long)B * kHU);
-    gemm(st, true, false, n1, 512, dpre1, kHU, grads + h.d1_w, kHU, nullptr, 512, kHU, B, false);
-    colsum(st, dpre1, kHU, B, kHU, grads + h.d1_b, false);
+    side_fork(c, sd);
+    gemm(sd, true, false, n1, 512, dpre1, kHU, grads + h.d1_w, kHU, nullptr, 512, kHU, B, false);
+    colsum(sd, dpre1, kHU, B, kHU, grads + h.d1_b, false);
     gemm(st, false, true, dpre1, kHU, params + h.d1_w, kHU, dn1, 512, nullptr, B, 512, kHU, false);
     bn_bwd(x512, dn1, d_x512, st1, 512, h.bn1_g, h.bn1_be);
+    side_join(c, sd);
     return check_launch("head fwd/bwd");
 }
 

@@ -17,7 +17,7 @@ inline __host__ __device__ PwFwdTcSmem pw_fwd_tc_smem(int KP, int NPall, int cpo
     PwFwdTcSmem s;
     s.nkb = (KP + 63) / 64; s.np = (NPall + 15) & ~15; s.lds = pad_ld(cpo);
     s.tmem_cols = 32; while (s.tmem_cols < s.np) s.tmem_cols *= 2;
-    int off = 128;                                     // mbarriers (8 TMA + 1 MMA) + TMEM slot
+    int off = 384;                                     // mbarriers (8 TMA + 1 MMA) + TMEM slot; [128, 384): the MMA issuer's descriptor table
     s.aff = off; off += s.nkb * 64 * 8;
     s.bias = off; off += s.np * 4;
     off = (off + 1023) & ~1023;
@@ -82,6 +82,16 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
     const uint32_t tmem = *s_tmem;
     const uint32_t idesc = umma_idesc(128, L.np, 0, 0);
 
+    // the operand addresses never change: descriptors built once (the issuing thread is on every tile's critical path)
+    uint64_t* s_md = reinterpret_cast<uint64_t*>(smem + 128);
+    if (tid == 0) {
+        const uint32_t aa = smem_u32(As), wa = smem_u32(Ws);
+        for (int kb = 0; kb < L.nkb; ++kb)
+            for (int ks = 0; ks < 4; ++ks) {
+                s_md[2 * (4 * kb + ks)] = umma_desc(aa + kb * R * 128 + ks * 32, 16, 1024);
+                s_md[2 * (4 * kb + ks) + 1] = umma_desc(wa + kb * L.np * 128 + ks * 32, 16, 1024);
+            }
+    }
     auto issue = [&](int tile, int buf) {
         const int t = tile / tps, r0 = (tile - t * tps) * R, rows = min(R, a.Rt - r0);
         unsigned char* dst = raw + (size_t)buf * L.raw_stride;
@@ -182,12 +192,7 @@ __global__ void __launch_bounds__(NT, 1) pw_fwd_tc_kernel(const PwFwdArgs a) {
         if (it == 2) TC_TS(5);
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t aa = smem_u32(As), wa = smem_u32(Ws);
-            for (int kb = 0; kb < L.nkb; ++kb)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16(tmem, umma_desc(aa + kb * R * 128 + ks * 32, 16, 1024), umma_desc(wa + kb * L.np * 128 + ks * 32, 16, 1024),
-                              idesc, kb > 0 || ks > 0);
+            for (int q = 0; q < 4 * L.nkb; ++q) umma_bf16(tmem, s_md[2 * q], s_md[2 * q + 1], idesc, q > 0);
             umma_commit(mma_done);
         }
         mbar_wait(mma_done, it & 1);
