@@ -233,13 +233,9 @@ def run_b200(args):
         ret, adv = eng.gae(roll['rewards'], roll['values_be'], roll['last_be'], 0.9999, 0.999, 2.0)
         state['ret'], state['adv'] = ret.view(N, 2), adv.view(N, 1)
 
-    def gather(idx, what):
-        for k in keys:
-            eng.gather_rows(roll[k], idx, mb[k])
-        if what == 'policy':
-            eng.gather_rows(state['adv'], idx, mb['adv'])
-        else:
-            eng.gather_rows(state['ret'], idx, mb['returns'])
+    def gather(idx, what):              # the whole minibatch in one launch (cdra_gather_rows_multi), like CARLANetwork.gather_device
+        extra = ('adv', 'adv') if what == 'policy' else ('ret', 'returns')
+        eng.gather_rows_multi([roll[k] for k in keys] + [state[extra[0]]], idx, [mb[k] for k in keys] + [mb[extra[1]]])
 
     from cdra.parallel import GradSync
     sync = GradSync(eng)            # the library's own NCCL communicator: cdra_allreduce_grads on the compute stream

@@ -52,6 +52,7 @@ _SIGNATURES = {
                                  C.c_float, C.c_int64, C.c_float, _P, _P]),
     'cdra_grad_norms': (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_float, _P, _P]),
     'cdra_gather_rows': (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
+    'cdra_gather_rows_multi': (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
     'cdra_comm_unique_id': (C.c_int, [_P]),
     'cdra_comm_create': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     'cdra_comm_destroy': (None, [_P]),

@@ -223,6 +223,20 @@ class Engine:
                                                       float(grad_scale), p(out), self._stream()), 'grad_norms')
         return out.sqrt_()
 
+    def gather_rows_multi(self, srcs, index, outs):
+        """dst[k][i] = src[k][index[i]] for every tensor of a minibatch in one launch (same index vector)"""
+        n = len(srcs)
+        if n > 12:
+            for a, b in ((srcs[:12], outs[:12]), (srcs[12:], outs[12:])):
+                self.gather_rows_multi(a, index, b)
+            return outs
+        PA = C.c_void_p * n
+        sp = PA(*[t.data_ptr() for t in srcs]); dp = PA(*[t.data_ptr() for t in outs])
+        rb = (C.c_int64 * n)(*[t[0].numel() * t.element_size() for t in srcs])
+        _lib.check(self.lib, self.lib.cdra_gather_rows_multi(sp, dp, rb, n, _lib.ptr(index), index.numel(), self._stream()),
+                   'gather_rows_multi')
+        return outs
+
     def gather_rows(self, src, index, out):
         row_bytes = src[0].numel() * src.element_size()
         p = _lib.ptr

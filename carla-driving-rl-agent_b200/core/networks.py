@@ -197,11 +197,8 @@ class CARLANetwork(Network):
     def gather_device(self, tensors: List[torch.Tensor], index: torch.Tensor) -> List[torch.Tensor]:
         """Minibatch gather (the tf.data slicing of rl/utils.py:365-393) with cdra_gather_rows: `tensors` are contiguous
         device tensors [N, ...], `index` an int64 device vector."""
-        out = []
-        for t in tensors:
-            dst = torch.empty((index.numel(),) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
-            out.append(self.engine.gather_rows(t, index, dst))
-        return out
+        out = [torch.empty((index.numel(),) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in tensors]
+        return self.engine.gather_rows_multi(tensors, index, out)            # one launch for the whole minibatch
 
     def gather(self, tensors: List[torch.Tensor], idx: np.ndarray) -> List[torch.Tensor]:
         index = torch.as_tensor(idx, dtype=torch.int64, device=self.device)

@@ -922,6 +922,23 @@ int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t r
     return check_launch("gather_rows");
 }
 
+int cdra_gather_rows_multi(const void* const* srcs, void* const* dsts, const int64_t* row_bytes, int n_tensors, const int64_t* index,
+                           int64_t n, void* stream) {
+    if (!srcs || !dsts || !row_bytes || !index || n < 1 || n_tensors < 1 || n_tensors > kGatherMax) return fail(CDRA_ERR_BADARG, "bad argument");
+    GatherMultiArgs a; memset(&a, 0, sizeof a);
+    a.index = index; a.n = n; a.nt = n_tensors;
+    int y = 0;
+    for (int k = 0; k < n_tensors; ++k) {
+        if (!srcs[k] || !dsts[k] || row_bytes[k] < 1) return fail(CDRA_ERR_BADARG, "bad argument");
+        a.src[k] = (const char*)srcs[k]; a.dst[k] = (char*)dsts[k]; a.row_bytes[k] = row_bytes[k];
+        int gy = (int)cdiv(row_bytes[k], 256 * 16 * 8); if (gy < 1) gy = 1; if (gy > 64) gy = 64;
+        a.y0[k] = y; y += gy;
+    }
+    a.y0[n_tensors] = y;
+    CDRA_LAUNCH(gather_rows_multi_kernel, dim3((unsigned)n, (unsigned)y), dim3(256), 0, (cudaStream_t)stream, a);
+    return check_launch("gather_rows_multi");
+}
+
 int cdra_debug_timeline(uint64_t* out64) {
     uint64_t* out32 = out64;
     if (!out32) return fail(CDRA_ERR_BADARG, "null argument");

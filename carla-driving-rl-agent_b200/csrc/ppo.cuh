@@ -337,4 +337,22 @@ CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) gather_rows_kernel(GatherArgs a) {
     }
 }
 
+// every tensor of a minibatch in ONE launch: blockIdx.y -> (tensor, column split of its row)
+constexpr int kGatherMax = 12;
+struct GatherMultiArgs { const char* src[kGatherMax]; char* dst[kGatherMax]; int64_t row_bytes[kGatherMax]; int y0[kGatherMax + 1]; const int64_t* index; int64_t n; int nt; };
+CDRA_KERNEL CDRA_LAUNCH_BOUNDS(256) gather_rows_multi_kernel(GatherMultiArgs a) {
+    int k = 0;
+    while (k + 1 < a.nt && (int)blockIdx.y >= a.y0[k + 1]) ++k;
+    const int64_t row = blockIdx.x, rb = a.row_bytes[k];
+    const int part = (int)blockIdx.y - a.y0[k], nparts = a.y0[k + 1] - a.y0[k];
+    const char* s = a.src[k] + a.index[row] * rb;
+    char* d = a.dst[k] + row * rb;
+    if ((rb & 15) == 0 && (((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+        const int64_t n16 = rb >> 4;
+        for (int64_t i = (int64_t)part * 256 + threadIdx.x; i < n16; i += (int64_t)nparts * 256) ((uint4*)d)[i] = ((const uint4*)s)[i];
+    } else {
+        for (int64_t i = (int64_t)part * 256 + threadIdx.x; i < rb; i += (int64_t)nparts * 256) d[i] = s[i];
+    }
+}
+
 }  // namespace cdra

@@ -176,6 +176,10 @@ int cdra_grad_norms(const float* grads, const int64_t* tensor_offsets, int n_ten
 
 /* utils.data_to_batches gather (rl/utils.py:365-393): dst[i] = src[index[i]] for rows of row_bytes. */
 int cdra_gather_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst, void* stream);
+/* The same for every tensor of a minibatch (state components, actions, advantages, ...) in ONE launch: srcs / dsts / row_bytes are
+ * HOST arrays of n_tensors (<= 12) device pointers / row sizes; all tensors are gathered with the same index vector. */
+int cdra_gather_rows_multi(const void* const* srcs, void* const* dsts, const int64_t* row_bytes, int n_tensors, const int64_t* index,
+                           int64_t n, void* stream);
 
 /* Data-parallel gradient exchange (nothing like it exists in the single-process reference): one NCCL sum
  * all-reduce of a flat fp32 gradient range per pass, enqueued on `stream` like every kernel of the library so that a whole

@@ -166,6 +166,13 @@ def test_gather_rows(eng):
     out = torch.empty(3, 5)
     eng.gather_rows(src, torch.tensor([8, 1, 4]), out)
     assert torch.equal(out, src[[8, 1, 4]])
+    # every tensor of a minibatch in one launch (ragged row sizes: 16-byte vector path, byte path, 4-byte rows)
+    srcs = [torch.arange(9 * 4096, dtype=torch.uint8).view(9, 4096).contiguous(), torch.randn(9, 5), torch.randn(9, 1), torch.randn(9, 4, 9)]
+    idx = torch.tensor([8, 1, 4, 4, 0], dtype=torch.int64)
+    outs = [torch.empty((5,) + tuple(t.shape[1:]), dtype=t.dtype) for t in srcs]
+    eng.gather_rows_multi(srcs, idx, outs)
+    for t, o in zip(srcs, outs):
+        assert torch.equal(o, t[idx])
 
 
 def test_policy_head_reparameterized_sample_gradient(eng, params):

@@ -199,6 +199,11 @@ def test_clip_adam_and_gather(built_libs):
     out = torch.empty(32, src.shape[1], dtype=torch.uint8, device='cuda')
     eng.gather_rows(src, idx, out)
     assert torch.equal(out, src[idx])
+    srcs = [src, torch.randn(64, 4, 9, device='cuda'), torch.randn(64, 1, device='cuda'), torch.randn(64, 2, device='cuda')]
+    outs = [torch.empty((32,) + tuple(t.shape[1:]), dtype=t.dtype, device='cuda') for t in srcs]
+    eng.gather_rows_multi(srcs, idx, outs)                # the whole minibatch in one launch
+    for t, o in zip(srcs, outs):
+        assert torch.equal(o, t[idx])
 
 
 def test_full_size_properties_bf16(built_libs, params):
