@@ -245,6 +245,27 @@ def test_full_size_properties_bf16(built_libs, params):
     assert losses[-1] < losses[0]
 
 
+def test_config4_value_pass_permutation_bf16(built_libs):
+    """The same permutation / repeatability property for the VALUE pass at the 180x240 geometry of BASELINE config 4
+    (B = 256 per launch): the row-banded depthwise / stem kernels and the 4x larger row counts of every GEMM launch."""
+    B, h, w = 256, 180, 240
+    dyn, pol, val = C.trained_params(torch.float64)
+    eng = _engine(B, 'bf16', h, w)
+    C.load_engine(eng, dyn, pol, val)
+    obs, bt = _dev(C.synthetic_obs(B, h, w, seed=71)), _dev(C.synthetic_batch(B, seed=72))
+    l0 = C.value_step_engine(eng, obs, bt)[0].item()
+    gd0, gv0 = eng.g_dyn.clone(), eng.g_val.clone()
+    l1 = C.value_step_engine(eng, obs, bt)[0].item()
+    rep_d, rep_v = C.rel_l2(eng.g_dyn, gd0), C.rel_l2(eng.g_val, gv0)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(9)).cuda()
+    l2 = C.value_step_engine(eng, {k: v[perm].contiguous() for k, v in obs.items()}, {k: v[perm].contiguous() for k, v in bt.items()})[0].item()
+    prm_d, prm_v = C.rel_l2(eng.g_dyn, gd0), C.rel_l2(eng.g_val, gv0)
+    print(f'repeat: loss {l0:.7f} / {l1:.7f}, g_dyn {rep_d:.2e}, g_val {rep_v:.2e};  permuted: loss {l2:.7f}, g_dyn {prm_d:.2e}, g_val {prm_v:.2e}')
+    assert torch.isfinite(eng.g_dyn).all() and eng.g_dyn.abs().max() > 0
+    assert abs(l1 - l0) <= 1e-5 * abs(l0) and rep_d < 1e-3 and rep_v < 1e-4
+    assert abs(l2 - l0) <= 1e-5 * abs(l0) and prm_d < 1e-3 and prm_v < 1e-4
+
+
 def test_full_size_permutation_and_repeatability_bf16(built_libs):
     """BASELINE config 2 minibatch (B = 512, 90x120, bf16), whole policy pass on the trained stage-s5 weights (a freshly
     initialised tower amplifies a single bf16 rounding flip ~30x per unit -- profiles/dbg_repeat.py -- so only a trained
