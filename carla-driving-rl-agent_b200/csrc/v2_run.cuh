@@ -518,7 +518,7 @@ inline bool try_pwg_dgrad(const RunCtx& c, PwBwdArgs& a, const PwDesc& hd) {
     if (a.x1) {
         PassBwdArgs q; q.x1 = a.x1; q.dx1 = a.dx1; q.x1cp = a.x1cp; q.x1map = a.x1map; q.x1aff = a.x1aff; q.x1bnp = a.x1bnp; q.x1bsum = a.x1bsum;
         q.x1clamp = a.x1clamp; q.dout[0] = a.dout[0]; q.dout[1] = a.dout[1]; q.cpo = a.cpo; q.ncopy = a.ncopy; q.copy_dst0 = a.copy_dst0; q.Rt = a.Rt;
-        q.rows_per_cta = 32;       // a thread walks its column serially (2-byte gathers): measured 47 / 33 / 46 / 82 us at 16 / 32 / 64 / 128 rows (stage 3)
+        q.rows_per_cta = 64;
         prof_bytes(4.0 * a.Rt * 2 * a.ncopy * 2 * 3);
         CDRA_LAUNCH_PDL(pass_bwd_kernel, dim3((a.Rt + q.rows_per_cta - 1) / q.rows_per_cta, kT), dim3(256), 0, c.stream, q);
     }

@@ -889,15 +889,29 @@ __global__ void __launch_bounds__(256) pass_bwd_kernel(const PassBwdArgs a) {
     const float4 sc = sum_consts(a.x1aff, a.x1bnp, (size_t)t * a.x1cp + s);
     const bool clamp = a.x1clamp != 0;
     float s1 = 0.f, s2 = 0.f;
-    const unsigned short* xr = reinterpret_cast<const unsigned short*>(a.x1);
-    unsigned short* dx = reinterpret_cast<unsigned short*>(a.dx1);
-    const unsigned short* sp = reinterpret_cast<const unsigned short*>(src);
-#pragma unroll 4
-    for (int r = r_lo; r < r_hi; ++r) {
-        const size_t row = (size_t)t * a.Rt + r;
-        const unsigned short g = sp ? sp[row * a.cpo] : (unsigned short)0;
-        dx[row * a.x1cp + s] = g;
-        sum_accum(__uint_as_float((uint32_t)g << 16), __uint_as_float((uint32_t)xr[row * a.x1cp + s] << 16), sc, clamp, s1, s2);
+    // __restrict__ + read-only loads: without them every row's loads wait behind the previous row's store (possible aliasing) and the
+    // column walk runs at one memory round trip (0.6 us) per row
+    const unsigned short* __restrict__ xr = reinterpret_cast<const unsigned short*>(a.x1) + (size_t)t * a.Rt * a.x1cp + s;
+    unsigned short* __restrict__ dx = reinterpret_cast<unsigned short*>(a.dx1) + (size_t)t * a.Rt * a.x1cp + s;
+    const unsigned short* __restrict__ sp = src ? reinterpret_cast<const unsigned short*>(src) + (size_t)t * a.Rt * a.cpo : xr;
+    const int sps = src ? a.cpo : a.x1cp;               // (no source: read x1 again and discard -> no per-row branch on the pointer)
+    const bool has = src != nullptr;
+    for (int rb = r_lo; rb < r_hi; rb += 8) {
+        unsigned short g[8], x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = min(rb + u, r_hi - 1);
+            g[u] = __ldg(sp + (size_t)r * sps); x[u] = __ldg(xr + (size_t)r * a.x1cp);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = rb + u;
+            if (r < r_hi) {
+                const unsigned short gv = has ? g[u] : (unsigned short)0;
+                dx[(size_t)r * a.x1cp] = gv;
+                sum_accum(__uint_as_float((uint32_t)gv << 16), __uint_as_float((uint32_t)x[u] << 16), sc, clamp, s1, s2);
+            }
+        }
     }
     if (a.x1bsum && (s1 != 0.f || s2 != 0.f)) {
         double2* dst = a.x1bsum + (size_t)t * a.x1cp + s;
